@@ -1,0 +1,386 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path (contract: see the task statement / DESIGN.md "Measurement").
+
+  python bench.py --gpus N --steps K --warmup W            (N>1: launched by torch.distributed.run)
+  python bench.py --impl reference --gpus N --steps K --warmup W
+
+Workload (BASELINE.json configs[1]): CIFAR-100 ResNet-110 (`resnet-110-fc`, the variant that emits
+100-d embeddings), cosine loss against embeddings/cifar100.unitsphere (fixture copy), SGD momentum
+0.9 + clipnorm 10 + L2, batch 128 per GPU, synthetic N(0,1) 32x32x3 images.  One step = forward +
+backward + (all-reduce) + clip + SGD.  Weak scaling: the per-GPU batch is fixed.
+
+Printed JSON (one line, rank 0): metric/value = images/s with the batch resident in HBM; e2e = the
+same through Engine.train_step with pinned-host inputs (H2D inside the timed region) and a D2H read
+of the loss every step; roofline = dominant training kernel class (per-op CUDA-event times from
+se_run_ops_timed); retrieval = all-pairs distance N=50000, D=100 in Gpairs/s with its HBM roofline;
+cpu_baseline = the float32 CPU restatement of the Keras reference (oracle/) timed on the host cores.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+ARCH = 'resnet-110-fc'
+PER_GPU_BATCH = 128
+METRIC = 'images/sec training ResNet-110 CIFAR-100 at 1/2/4/8 B200; retrieval Gpairs/s'
+
+
+def peaks():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return {'hbm_gbs': d['hbm_gbs'], 'tflops_burst': d['bf16_tflops'], 'tflops_sustained': d['bf16_tflops_sustained'],
+                'source': 'measured (MEASURED_PEAKS.json)'}
+    return {'hbm_gbs': 6650.0, 'tflops_burst': 1590.0, 'tflops_sustained': 1400.0, 'source': 'fallback (B200_PROFILING.md)'}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = 'clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,' \
+        'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
+                                          '--format=csv,noheader,nounits', '-lms', '200'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(',')])
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except (ValueError, IndexError):
+                continue
+            for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), r[3:7]):
+                if v.lower().startswith('active'):
+                    reasons.add(name)
+        return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': max(mx) if mx else None,
+                'reasons': sorted(reasons), 'samples': len(sm)}
+
+
+# ----------------------------------------------------------------------------------------------- CPU arm
+def cpu_reference_arm(steps, warmup, sample_batch=None, budget_s=150.0):
+    """The reference's training step restated on the CPU (oracle/, float32, all host threads).  Keras/TF are
+    not installable, so this is kind='port'.  Returns (images/s, ms per step, info)."""
+    import torch
+    from oracle import models as omodels
+    from oracle import train as otrain
+    emb = np.load(os.path.join(ROOT, 'tests', 'golden', 'class_matrices.npz'))['cifar100_embedding']
+    cores = torch.get_num_threads()
+    om = omodels.build_network(100, ARCH, input_channels=3, seed=0)
+    otrain.cast_model(om, torch.float32)
+    vel = otrain.make_velocity(om)
+    emb_t = torch.as_tensor(emb.astype(np.float32))
+    g = torch.Generator().manual_seed(1000)
+    B = sample_batch or PER_GPU_BATCH
+
+    def one(bsz):
+        x = torch.randn(bsz, 32, 32, 3, generator=g)
+        y = torch.randint(0, 100, (bsz,), generator=g)
+        t0 = time.perf_counter()
+        otrain.train_step(om, x, y, emb_t, vel, 0.1)
+        return time.perf_counter() - t0
+
+    t_first = one(B)                                    # also the first warm-up step
+    # keep the whole run inside the budget: shrink the per-step sample if a full batch is too slow
+    total_steps = steps + max(warmup - 1, 0)
+    if sample_batch is None and t_first * total_steps > budget_s:
+        B = max(8, int(PER_GPU_BATCH * budget_s / (t_first * total_steps)) // 8 * 8)
+    for _ in range(max(warmup - 1, 0)):
+        one(B)
+    ts = [one(B) for _ in range(steps)]
+    ms = 1000.0 * float(np.mean(ts))
+    return B / (ms / 1000.0), ms, {'cores': cores, 'sample_batch': B}
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    ips, ms, info = cpu_reference_arm(args.steps, args.warmup)
+    line = {
+        'impl': 'reference', 'metric': METRIC, 'value': ips, 'unit': 'images/s', 'n_gpus': args.gpus, 'steps': args.steps,
+        'warmup': args.warmup, 'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+        'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': 'CIFAR-100 %s cosine loss, SGD momentum+clipnorm+L2, synthetic 32x32x3' % ARCH,
+                   'per_step_images': info['sample_batch']},
+        'cpu_baseline': {'value': ips, 'unit': 'images/s', 'cores': info['cores'], 'kind': 'port',
+                         'sample': '%d steps of %d images (float32 torch-CPU restatement of the Keras reference; '
+                                   'Keras/TF not installable)' % (args.steps, info['sample_batch'])},
+        'e2e': {'value': ips, 'unit': 'images/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+    }
+    print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------------------------- GPU arm
+def op_category(op, L):
+    i = op.i
+    names = {L.OP_CONV_FWD: 'conv_fwd', L.OP_CONV_DGRAD: 'conv_dgrad', L.OP_CONV_WGRAD: 'conv_wgrad'}
+    if op.opcode in names:
+        key = '%s %dx%d s%d %d->%d @%dx%d' % (names[op.opcode], i[5], i[6], i[7], i[3], i[4], i[1], i[2])
+        flops = 2.0 * i[0] * i[10] * i[11] * i[4] * i[5] * i[6] * i[3]
+        return key, flops, 0.0
+    bn = {L.OP_BN_STATS: ('bn_stats', 1), L.OP_BN_FWD_TRAIN: ('bn_fwd', 2), L.OP_BN_BWD: ('bn_bwd', 7)}
+    if op.opcode in bn:
+        nm, passes = bn[op.opcode]
+        return '%s C=%d rows=%d' % (nm, i[0], i[1]), 0.0, 4.0 * i[0] * i[1] * passes
+    other = {L.OP_HEAD: 'embed_head', L.OP_SGD_PREPARE: 'sgd_prepare', L.OP_SGD_APPLY: 'sgd_apply', L.OP_MEMSET: 'memset',
+             L.OP_GAP_FWD: 'gap_fwd', L.OP_GAP_BWD: 'gap_bwd', L.OP_SHORTCUT_BWD: 'shortcut_bwd', L.OP_ADD_BWD: 'add_bwd',
+             L.OP_ADD_FWD: 'add_fwd', L.OP_XENT: 'softmax_xent'}
+    return other.get(op.opcode, 'op%d' % op.opcode), 0.0, 0.0
+
+
+def profile_step(eng, L, pk):
+    """Per-op device times of one training step (eager, CUDA-event pair per op) -> dominant kernel class."""
+    import ctypes
+    arr = eng.plans['step']
+    n = len(arr)
+    ms = (ctypes.c_float * n)()
+    for _ in range(2):
+        L.check(eng.lib.se_run_ops_timed(arr, n, eng.mode, L.stream_ptr(), ms), 'se_run_ops_timed')
+    cats = {}
+    for k in range(n):
+        key, flops, byts = op_category(arr[k], L)
+        c = cats.setdefault(key, {'ms': 0.0, 'n': 0, 'flops': flops, 'bytes': byts})
+        c['ms'] += ms[k]
+        c['n'] += 1
+    total = sum(c['ms'] for c in cats.values())
+    top = sorted(cats.items(), key=lambda kv: -kv[1]['ms'])
+    name, c = top[0]
+    avg_s = c['ms'] / c['n'] / 1000.0
+    if c['flops'] > 0:
+        achieved = c['flops'] / avg_s / 1e12
+        roof = {'bound': 'tensor', 'kernel': name, 'achieved': achieved, 'peak': pk['tflops_sustained'], 'unit': 'TFLOP/s',
+                'frac': achieved / pk['tflops_sustained'], 'traffic': None}
+    else:
+        achieved = c['bytes'] / avg_s / 1e9 if c['bytes'] else 0.0
+        roof = {'bound': 'hbm', 'kernel': name, 'achieved': achieved, 'peak': pk['hbm_gbs'], 'unit': 'GB/s',
+                'frac': achieved / pk['hbm_gbs'], 'traffic': None}
+    roof.update({'avg_launch_us': 1e6 * avg_s, 'launches_per_step': c['n'], 'share_of_step': c['ms'] / total,
+                 'peak_source': pk['source'] + ', sustained bf16' if c['flops'] > 0 else pk['source']})
+    breakdown = [{'kernel': k, 'ms_per_step': v['ms'], 'launches': v['n'], 'share': v['ms'] / total} for k, v in top[:12]]
+    conv_flops = sum(v['flops'] * v['n'] for v in cats.values())
+    return roof, breakdown, total, conv_flops
+
+
+def bench_retrieval(L, rank, world, dev, n, d, reps, mode):
+    """All-pairs distance (evaluate_retrieval.py:56-63), rows sharded over ranks, no exchange step."""
+    import torch
+    from semantic_embeddings_b200.evaluate_retrieval import pairwise_distances
+    rng = np.random.RandomState(0)
+    f = rng.randn(n, d).astype(np.float32)
+    f /= np.linalg.norm(f, axis=-1, keepdims=True)
+    fd = torch.from_numpy(f).to(dev)
+    rows = (n + world - 1) // world
+    r0 = rank * rows
+    rows = max(0, min(rows, n - r0))
+    out = torch.empty((rows, n), dtype=torch.float32, device=dev)
+    for _ in range(2):
+        pairwise_distances(None, False, r0, rows, mode, out=out, feat_dev=fd)
+    torch.cuda.synchronize(dev)
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
+    for a, b in evs:
+        a.record()
+        pairwise_distances(None, False, r0, rows, mode, out=out, feat_dev=fd)
+        b.record()
+    torch.cuda.synchronize(dev)
+    ms = float(np.mean([a.elapsed_time(b) for a, b in evs]))
+    chk = float(out[0, :8].sum().item())
+    return ms, rows, chk
+
+
+def run_native(args):
+    import torch
+    import torch.distributed as dist
+    from semantic_embeddings_b200 import _lib as L
+    from semantic_embeddings_b200 import utils
+    from semantic_embeddings_b200.engine import Engine
+
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    if world != args.gpus:
+        raise SystemExit('--gpus %d but WORLD_SIZE=%d (launch N>1 with torch.distributed.run)' % (args.gpus, world))
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        dist.init_process_group('nccl', device_id=dev)
+    L.load()
+    pk = peaks()
+    mode = L.SE_MODE_TF32 if args.mode == 'tf32' else L.SE_MODE_F32
+    caps = L.load().se_tc_capabilities()
+    emb = np.load(os.path.join(ROOT, 'tests', 'golden', 'class_matrices.npz'))['cifar100_embedding']
+    B = args.batch
+    graph = utils.build_network(100, ARCH, input_channels=3)
+    eng = Engine(graph, B, emb, mode=mode, device=str(dev), world_size=world, use_cuda_graph=not args.no_graph)
+    eng.set_lr(0.1)
+
+    # synthetic data: N(0,1) images, seed 1000+rank; a small pool cycled through
+    gen = torch.Generator().manual_seed(1000 + rank)
+    pool = 4
+    xs_host = [torch.randn(B, 32, 32, 3, generator=gen).pin_memory() for _ in range(pool)]
+    ys_host = [torch.randint(0, 100, (B,), generator=gen, dtype=torch.int32).pin_memory() for _ in range(pool)]
+    xs_dev = [x.to(dev) for x in xs_host]
+    ys_dev = [y.to(dev) for y in ys_host]
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize(dev)
+
+    def timed(loader, steps, read_loss):
+        barrier()
+        t0 = torch.cuda.Event(enable_timing=True)
+        t1 = torch.cuda.Event(enable_timing=True)
+        t0.record()
+        last = None
+        for s in range(steps):
+            loader(s)
+            eng.train_step()
+            if read_loss:
+                last = eng.metrics()['loss']
+        t1.record()
+        torch.cuda.synchronize(dev)
+        ms = t0.elapsed_time(t1)
+        barrier()
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, last
+
+    resident = lambda s: eng.load_batch(xs_dev[s % pool], ys_dev[s % pool])
+    from_host = lambda s: eng.load_batch(xs_host[s % pool], ys_host[s % pool])
+
+    launches_per_step = eng.launches_per_step() if rank == 0 or True else 0
+    timed(resident, args.warmup, False)                      # warm-up (also captures the CUDA graphs)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ms_res, _ = timed(resident, args.steps, False)
+    ms_e2e, last_loss = timed(from_host, args.steps, True)
+    clocks = sampler.stop() if rank == 0 else None
+
+    gb = B * world
+    value = gb * args.steps / (ms_res / 1000.0)
+    e2e = gb * args.steps / (ms_e2e / 1000.0)
+
+    roof, breakdown, prof_total, conv_flops = (None, None, None, None)
+    if rank == 0:
+        roof, breakdown, prof_total, conv_flops = profile_step(eng, L, pk)
+
+    retrieval = None
+    if not args.skip_retrieval:
+        n, d = args.retrieval_n, 100
+        ms_r, rows, chk = bench_retrieval(L, rank, world, dev, n, d, 5, mode)
+        if world > 1:
+            t = torch.tensor([ms_r], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms_r = float(t.item())
+        pairs = float(n) * n
+        gpairs = pairs / (ms_r / 1000.0) / 1e9
+        per_gpu_bytes = 4.0 * rows * n + 4.0 * n * d        # algorithmic: write the row block once, read F once
+        ach = per_gpu_bytes / (ms_r / 1000.0) / 1e9
+        retrieval = {'value': gpairs, 'unit': 'Gpairs/s', 'N': n, 'D': d, 'ms': ms_r, 'rows_per_gpu': rows,
+                     'roofline': {'bound': 'hbm', 'kernel': 'pairwise_dist', 'achieved': ach, 'peak': pk['hbm_gbs'],
+                                  'unit': 'GB/s', 'frac': ach / pk['hbm_gbs'], 'traffic': None,
+                                  'algorithmic_bytes_per_launch': per_gpu_bytes, 'peak_source': pk['source']},
+                     'arithmetic': 'tcgen05 3xTF32' if (mode == L.SE_MODE_TF32 and caps & 8) else 'fp32 FFMA'}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.skip_cpu_baseline:
+        ips, ms_cpu, info = cpu_reference_arm(steps=3, warmup=1, budget_s=25.0)
+        cpu = {'value': ips, 'unit': 'images/s', 'cores': info['cores'], 'kind': 'port',
+               'sample': '3 timed steps of %d images after 1 warm-up (float32 torch-CPU restatement of the Keras '
+                         'reference training step; Keras/TF not installable)' % info['sample_batch']}
+
+    if rank == 0:
+        conv_train_flops_per_img = 3 * 2 * graph.conv_macs_per_image()
+        tc = bool(mode == L.SE_MODE_TF32 and (caps & 7))
+        line = {
+            'metric': METRIC, 'value': value, 'unit': 'images/s', 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
+            'ms_per_step': ms_res / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+            'dtype': 'tf32' if tc else 'f32', 'data': 'synthetic',
+            'config': {'workload': 'CIFAR-100 ResNet-110 (%s) cosine loss vs cifar100.unitsphere, SGD momentum 0.9 + '
+                                   'clipnorm 10 + L2 2e-4, batch %d/GPU, synthetic 32x32x3' % (ARCH, B),
+                       'per_gpu_batch': B, 'global_batch': gb, 'parallelism': 'dp%d' % world,
+                       'arith_mode': args.mode, 'tc_capabilities': caps, 'cuda_graph': not args.no_graph,
+                       'l2_policy': 'activations+gradients touched per step (~%.1f GB) exceed the 126 MB L2; '
+                                    'retrieval output 10 GB' % (eng_bytes(eng) / 1e9)},
+            'e2e': {'value': e2e, 'unit': 'images/s', 'ms_per_step': ms_e2e / args.steps,
+                    'h2d_bytes_per_step': int(xs_host[0].numel() * 4 + ys_host[0].numel() * 4),
+                    'd2h_bytes_per_step': int(B * 8), 'last_loss': last_loss},
+            'gpu_launches': int(launches_per_step * args.steps),
+            'launches_per_step': int(launches_per_step),
+            'roofline': roof, 'breakdown': breakdown,
+            'conv_flop_roofline': {'train_gflop_per_image': conv_train_flops_per_img / 1e9,
+                                   'achieved_tflops': value * conv_train_flops_per_img / 1e12 / world,
+                                   'frac_of_bf16_sustained_peak': value * conv_train_flops_per_img / 1e12 / world / pk['tflops_sustained']},
+            'retrieval': retrieval, 'cpu_baseline': cpu, 'clocks': clocks, 'peaks': pk,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def eng_bytes(eng):
+    tot = 0
+    for d in (eng.act, eng.grad):
+        for t in d.values():
+            tot += t.numel() * 4
+    return tot
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=30)
+    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--impl', default='native', choices=['native', 'reference'])
+    ap.add_argument('--mode', default='tf32', choices=['tf32', 'f32'])
+    ap.add_argument('--batch', type=int, default=PER_GPU_BATCH)
+    ap.add_argument('--retrieval-n', type=int, default=50000)
+    ap.add_argument('--skip-retrieval', action='store_true')
+    ap.add_argument('--skip-cpu-baseline', action='store_true')
+    ap.add_argument('--no-graph', action='store_true')
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    if args.impl == 'reference':
+        run_reference(args)
+    else:
+        run_native(args)
+
+
+if __name__ == '__main__':
+    main()

@@ -1,0 +1,217 @@
+/* se_b200.h -- C ABI of the B200-native hot path of cvjena/semantic-embeddings.
+ *
+ * The reference (/root/reference, pure Python on Keras 2.2 / TF 1.x) has no FFI layer: its
+ * device work is whatever the Keras graph of learn_image_embeddings.py and the numpy calls of
+ * evaluate_retrieval.py:56-67 dispatch to cuDNN/cuBLAS/BLAS.  Each entry point below replaces
+ * one group of those graph ops; the comment on each names the reference lines it stands for.
+ * The host side (the semantic_embeddings_b200 package) binds this file with ctypes; INTEGRATION.md shows
+ * the binding a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes; no torch / C++ types.
+ *   - every function returns 0 on success, <0 on error (SE_ERR_*); se_last_error() gives the
+ *     message of the calling thread's last failure.
+ *   - device pointers are caller-owned (PyTorch tensors are used as containers); the library
+ *     never allocates or frees device memory.  Kernels that need scratch take it explicitly.
+ *   - `stream` is a cudaStream_t; all calls are asynchronous w.r.t. the host and capturable
+ *     into a CUDA graph.
+ *   - activations are float32 NHWC; conv kernels are float32 HWIO (Keras layout); dense
+ *     kernels are (in,out).  `mode` selects the arithmetic of contraction kernels:
+ *     SE_MODE_F32 = fp32 FFMA (parity mode), SE_MODE_TF32 = tcgen05 kind::tf32, fp32
+ *     accumulate in TMEM (fast mode; falls back to F32 for shapes the tensor path does not
+ *     cover -- never to the CPU).
+ */
+#ifndef SE_B200_H
+#define SE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SE_OK 0
+#define SE_ERR_ARG (-1)
+#define SE_ERR_CUDA (-2)
+#define SE_ERR_UNSUPPORTED (-3)
+
+#define SE_MODE_F32 0
+#define SE_MODE_TF32 1
+
+/* head variants: learn_image_embeddings.py --loss (lines 62, 127-130, 164-171) */
+#define SE_LOSS_INV_CORR 0     /* l2norm wrapper + 1 - <t,x>      */
+#define SE_LOSS_UNNORM_CORR 1  /* no wrapper     + 1 - <t,z>      */
+#define SE_LOSS_MSE 2          /* no wrapper     + sum (z-t)^2    */
+
+/* pairwise modes: evaluate_retrieval.py:57-62 */
+#define SE_PDIST_SQEUCLID 0    /* A + B - 2 F F^T                 */
+#define SE_PDIST_NEGDOT 1      /* -(F F^T)  (caller passes normalised F, or sets normalize=1) */
+
+const char* se_version(void);
+const char* se_last_error(void);
+/* number of kernel launches issued by this library since load (for bench.py's gpu_launches) */
+int64_t se_launch_count(void);
+int se_device_sm_count(void);
+/* bit mask of the tcgen05 kernels compiled in: 1 conv fwd, 2 conv dgrad, 4 conv wgrad, 8 pairwise */
+int se_tc_capabilities(void);
+
+/* ------------------------------------------------------------------ convolution / dense
+ * Conv2D of models/cifar_resnet.py:96-105,218, models/plainnet.py:52,70,
+ * models/wide_residual_network.py:9,20,28,31,46,53 and keras.applications.ResNet50 (utils.py:237).
+ * Explicit zero padding (pad_t, pad_l) and output size: the host computes TF 'SAME'
+ * (pad_before = total//2, so k=3,s=2 on an even input gives pad 0 before / 1 after). */
+typedef struct {
+  int32_t N, H, W, Cin;   /* input  NHWC */
+  int32_t Cout, kh, kw;   /* kernel HWIO */
+  int32_t stride;
+  int32_t pad_t, pad_l;
+  int32_t Ho, Wo;         /* output NHWC = (N, Ho, Wo, Cout) */
+} se_conv_desc;
+
+/* y = conv(x, w) [+ bias] [+ residual] [relu]; optionally accumulates per-channel
+ * sum(y) and sum(y^2) (of the stored values) into stats[0:Cout], stats[Cout:2Cout]
+ * (float64, caller zeroes) -- the BatchNormalization statistics of the next layer. */
+int se_conv2d_fwd(const se_conv_desc* d, const float* x, const float* w, const float* bias,
+                  const float* residual, float* y, int relu, double* stats, int mode, void* stream);
+/* dx = beta*dx + conv^T(dy, w)   (gradient wrt the input; autodiff of the above) */
+int se_conv2d_dgrad(const se_conv_desc* d, const float* dy, const float* w, float* dx, float beta,
+                    int mode, void* stream);
+/* dw += x (*) dy ; dbias += sum_pixels dy   (dbias may be NULL). Accumulates: caller zeroes. */
+int se_conv2d_wgrad(const se_conv_desc* d, const float* x, const float* dy, float* dw, float* dbias,
+                    int mode, void* stream);
+/* Dense (models/cifar_resnet.py:233, plainnet.py:67,76, wide_residual_network.py:96, utils.py:242,
+ * learn_image_embeddings.py:44): y = x W + b as a 1x1 convolution over a (B,1,1,Cin) tensor. */
+int se_dense_fwd(const float* x, const float* w, const float* bias, float* y, int B, int Cin, int Cout,
+                 int relu, double* stats, int mode, void* stream);
+int se_dense_bwd(const float* x, const float* w, const float* dy, float* dx, float beta, float* dw,
+                 float* dbias, int B, int Cin, int Cout, int mode, void* stream);
+
+/* ------------------------------------------------------------------ batch normalisation
+ * keras.layers.BatchNormalization (cifar_resnet.py:100,107,220; plainnet.py:53,68,71;
+ * wide_residual_network.py:14,25,44,51,91; learn_image_embeddings.py:43), fused with the
+ * Activation('relu') / layers.add / AveragePooling2D+ChannelPadding shortcut that follow it
+ * (cifar_resnet.py:101,117-124). rows = N*H*W. */
+typedef struct {
+  const float* ptr;       /* NULL = no residual */
+  int32_t C;              /* channels of the residual tensor (<= C of the BN output) */
+  int32_t pad_lo;         /* ChannelPadding: residual channel c lands on output channel c+pad_lo */
+  int32_t pool;           /* 1 = same resolution, 2 = 2x2 average pool of a (N,2H,2W,C) tensor */
+  int32_t H, W;           /* spatial size of the BN output (needed when pool == 2) */
+} se_residual;
+
+/* accumulate sum(x), sum(x^2) per channel into stats (float64 [2C], caller zeroes) */
+int se_bn_stats(const float* x, int64_t rows, int C, double* stats, void* stream);
+/* training mode: mean/var (biased) from `stats`; y = relu?( gamma*(x-mean)*rsqrt(var+eps)+beta + res );
+ * writes save_mean/save_invstd [C] for the backward pass and updates moving statistics
+ * (moving = moving*momentum + batch*(1-momentum); variance fed as var*n/(n-(1+eps))). */
+int se_bn_fwd_train(const float* x, int64_t rows, int C, const double* stats, const float* gamma,
+                    const float* beta, float eps, float momentum, float* moving_mean, float* moving_var,
+                    float* save_mean, float* save_invstd, const se_residual* res, int relu, float* y,
+                    void* stream);
+/* inference mode (learn_image_embeddings.py:271 predict_generator): moving statistics */
+int se_bn_fwd_infer(const float* x, int64_t rows, int C, const float* gamma, const float* beta,
+                    const float* moving_mean, const float* moving_var, float eps, const se_residual* res,
+                    int relu, float* y, void* stream);
+/* backward of se_bn_fwd_train.  dout = gradient wrt y; `y` is needed when relu != 0 (mask y > 0).
+ *   g  = dout * (y > 0)                                  (relu)          [also the residual gradient]
+ *   dgamma += sum g*xhat ; dbeta += sum g                 (accumulate: caller zeroes)
+ *   dx = beta_dx*dx + gamma*invstd*(g - mean(g) - xhat*mean(g*xhat)) [* (x > 0) if relu_in]
+ *   dres = beta_res*dres + g      (same-resolution residual only; NULL to skip)
+ * scratch: float64 [2C], caller zeroes. relu_in: x itself is a relu output (plainnet.py:52-53). */
+int se_bn_bwd(const float* x, const float* y, const float* dout, int64_t rows, int C, const float* gamma,
+              const float* save_mean, const float* save_invstd, int relu, int relu_in, float* dx,
+              float beta_dx, float* dres, float beta_res, float* dgamma, float* dbeta, double* scratch,
+              void* stream);
+/* gradient of the pooled / channel-padded shortcut (cifar_resnet.py:117-121):
+ * dsrc[n,2h+i,2w+j,c] = beta*dsrc + 0.25 * g[n,h,w,c+pad_lo], g = dout*(y>0) if relu. */
+int se_shortcut_bwd(const float* dout, const float* y, int relu, int N, int H, int W, int C,
+                    const se_residual* res, float* dsrc, float beta, void* stream);
+
+/* ------------------------------------------------------------------ pooling / elementwise */
+int se_avgpool2_fwd(const float* x, float* y, int N, int H, int W, int C, void* stream);       /* plainnet.py:59 */
+int se_avgpool2_bwd(const float* dy, float* dx, float beta, int N, int H, int W, int C, void* stream);
+int se_maxpool_fwd(const float* x, float* y, int N, int H, int W, int C, int k, int stride, int pad_t,
+                   int pad_l, int Ho, int Wo, void* stream);                                    /* ResNet-50 pool1 */
+int se_maxpool_bwd(const float* x, const float* y, const float* dy, float* dx, int N, int H, int W, int C,
+                   int k, int stride, int pad_t, int pad_l, int Ho, int Wo, void* stream);
+int se_gap_fwd(const float* x, float* y, int N, int HW, int C, void* stream);                  /* cifar_resnet.py:228 */
+int se_gap_bwd(const float* dy, float* dx, float beta, int N, int HW, int C, void* stream);
+/* y = a + b [relu]; backward: da = beta*da + g, db likewise, g = dy*(y>0)  (wide_residual_network.py:34,56) */
+int se_add_fwd(const float* a, const float* b, float* y, int64_t n, int relu, void* stream);
+int se_add_bwd(const float* dy, const float* y, int relu, float* da, float beta_a, float* db, float beta_b,
+               int64_t n, void* stream);
+/* y = relu(x) ; dx = beta*dx + dy*(y>0)  (learn_image_embeddings.py:42) */
+int se_relu_fwd(const float* x, float* y, int64_t n, void* stream);
+int se_relu_bwd(const float* dy, const float* y, float* dx, float beta, int64_t n, void* stream);
+
+/* ------------------------------------------------------------------ embedding head (north-star item)
+ * One fused kernel for utils.l2norm (utils.py:125-127), the target gather E[y]
+ * (learn_image_embeddings.py:48-50), utils.inv_correlation / squared_distance (utils.py:34-46),
+ * the metric utils.nn_accuracy (utils.py:57-100, k<=1) and the backward pass of all of it.
+ *   z [B,ldz] raw network output; E [C,ldE] class matrix (fp32); labels int32 [B]
+ *   x_out [B,ldz]  = wrapped output (l2norm(z) for INV_CORR, z otherwise)   (may be NULL)
+ *   loss [B], acc [B] per-sample loss and 0/1 accuracy                       (may be NULL)
+ *   dz [B,ldz]     = d( loss_scale * sum_b loss_b )/dz + Jx^T extra_dx, where extra_dx [B,ldz]
+ *                    (may be NULL) is a gradient wrt x_out coming from the classifier branch
+ *                    (learn_image_embeddings.py:34-44, --cls_weight)        (dz may be NULL)
+ * loss_scale is 1/global_batch for Keras' mean-over-batch. */
+int se_embed_head_fwd_bwd(const float* z, int ldz, const int32_t* labels, const float* E, int ldE, int B,
+                          int D, int C, int loss_kind, float loss_scale, const float* extra_dx,
+                          float* x_out, float* loss, float* acc, float* dz, void* stream);
+/* softmax + Keras categorical_crossentropy (clip 1e-7) + argmax accuracy + backward
+ * (learn_image_embeddings.py:44,230-231): dlogits = scale * dCE/dlogits. */
+int se_softmax_xent_fwd_bwd(const float* logits, int ld, const int32_t* labels, int B, int C, float scale,
+                            float* prob, float* loss, float* acc, float* dlogits, void* stream);
+
+/* ------------------------------------------------------------------ optimizer
+ * keras.optimizers.SGD(lr, momentum, decay, nesterov, clipnorm) + kernel_regularizer=l2(.)
+ * (learn_image_embeddings.py:229-236; cifar_resnet.py:152; plainnet.py:8) over ONE flat fp32
+ * parameter / gradient / velocity buffer.  Segments give the L2 coefficient of a range.
+ *   pass 1: g += 2*lambda*p on regularised ranges; out[0] = sum g^2, out[1] = sum lambda*p^2
+ *   pass 2: scale = clipnorm/norm if norm >= clipnorm; v = m*v - lr*g*scale; p += v
+ *           (nesterov: p += m*v - lr*g*scale)
+ * `out` is float64[2] device memory (caller zeroes before pass 1). */
+typedef struct {
+  int64_t begin, end;     /* element range [begin,end) of the flat buffer */
+  float l2;               /* lambda */
+} se_l2_segment;
+int se_sgd_step(float* p, float* g, float* v, int64_t n, const se_l2_segment* segs, int nsegs, float lr,
+                float momentum, int nesterov, float clipnorm, double* out, void* stream);
+/* the two passes separately (data-parallel runs all-reduce g between nothing and pass 1) */
+int se_sgd_prepare(const float* p, float* g, int64_t n, const se_l2_segment* segs, int nsegs, double* out,
+                   void* stream);
+int se_sgd_apply(float* p, const float* g, float* v, int64_t n, float lr, float momentum, int nesterov,
+                 float clipnorm, const double* out, void* stream);
+
+/* same as se_sgd_apply with the learning rate read from device memory (float[1]) at run time, so
+ * that a CUDA-graph-captured step follows the SGDR schedule (sgdr_callback.py:75-87) without re-capture */
+int se_sgd_apply_devlr(float* p, const float* g, float* v, int64_t n, const float* lr_dev, float momentum,
+                       int nesterov, float clipnorm, const double* out, void* stream);
+
+/* ------------------------------------------------------------------ retrieval
+ * evaluate_retrieval.py:56-63: rows [row0,row0+rows) of the N x N distance matrix of F [N,ldF]
+ * (fp32, D columns) against all N columns; out [rows, ldout].  normalize=1 applies line 58
+ * (F /= ||F||) on the fly without mutating F.  `workspace` (device, >= se_pairwise_workspace_bytes)
+ * holds the row norms and, for the tensor-core path, the split operands. */
+int64_t se_pairwise_workspace_bytes(int N, int D, int mode);
+int se_pairwise_dist(const float* F, int ldF, int N, int D, int row0, int rows, int pdist_mode,
+                     int normalize, float* out, int64_t ldout, void* workspace, int mode, void* stream);
+
+/* ------------------------------------------------------------------ plan runner
+ * Runs a host-built array of ops (one training step is ~900 launches) in one call so that
+ * neither Python nor ctypes sits between launches.  Each op is an opcode plus the argument
+ * block of the entry point above it maps to (see semantic_embeddings_b200/engine.py). */
+typedef struct {
+  int32_t opcode;
+  int32_t i[15];
+  float f[8];
+  void* p[16];
+} se_op;
+int se_run_ops(const se_op* ops, int n, int mode, void* stream);
+/* profiling variant (bench.py): eager, a CUDA-event pair around every op, per-op device milliseconds */
+int se_run_ops_timed(const se_op* ops, int n, int mode, void* stream, float* ms_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SE_B200_H */

@@ -199,3 +199,13 @@ def sgdr_lr_sequence(num_epochs, min_lr=1e-6, max_lr=0.1, base=12, mul=2):
 
 def sgdr_default_epochs(base=12, mul=2):
     return sum(base * (mul ** i) for i in range(5))      # utils.py:367
+
+
+def cast_model(model, dtype, cls=None):
+    """In-place dtype change of every weight (float32 for the timed CPU baseline of bench.py)."""
+    for k in list(model.params.keys()):
+        model.params[k] = model.params[k].to(dtype)
+    if cls is not None:
+        for k in list(cls.params.keys()):
+            cls.params[k] = cls.params[k].to(dtype)
+    return model

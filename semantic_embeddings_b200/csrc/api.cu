@@ -1,0 +1,270 @@
+// C-ABI glue: error state, launch counter, conv/dense dispatch between the arithmetic modes,
+// and the plan runner (se_run_ops) that issues a whole training step without returning to Python.
+#include <stdarg.h>
+#include <string.h>
+
+#include <atomic>
+
+#include "common.cuh"
+#include "opcodes.h"
+
+namespace se {
+
+static thread_local char g_err[512] = "";
+static std::atomic<long long> g_launches{0};
+static int g_sms = 0;
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+int sm_count() {
+  if (g_sms == 0) {
+    int dev = 0, n = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess &&
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0)
+      g_sms = n;
+    else
+      g_sms = 148;
+  }
+  return g_sms;
+}
+
+// conv_simt.cu
+int conv_fwd_simt(const se_conv_desc*, const float*, const float*, const float*, const float*, float*, int, double*, cudaStream_t);
+int conv_dgrad_simt(const se_conv_desc*, const float*, const float*, float*, float, cudaStream_t);
+int conv_wgrad_simt(const se_conv_desc*, const float*, const float*, float*, float*, cudaStream_t);
+// conv_tc.cu (tcgen05 kind::tf32); each returns SE_ERR_UNSUPPORTED for shapes it does not cover
+int conv_fwd_tc(const se_conv_desc*, const float*, const float*, const float*, const float*, float*, int, double*, cudaStream_t);
+int conv_dgrad_tc(const se_conv_desc*, const float*, const float*, float*, float, cudaStream_t);
+int conv_wgrad_tc(const se_conv_desc*, const float*, const float*, float*, float*, cudaStream_t);
+
+static int check_desc(const se_conv_desc* d) {
+  if (!d) { set_error("null conv descriptor"); return SE_ERR_ARG; }
+  if (d->N <= 0 || d->H <= 0 || d->W <= 0 || d->Cin <= 0 || d->Cout <= 0 || d->kh <= 0 || d->kw <= 0 ||
+      d->stride <= 0 || d->Ho <= 0 || d->Wo <= 0 || d->pad_t < 0 || d->pad_l < 0) {
+    set_error("invalid conv descriptor");
+    return SE_ERR_ARG;
+  }
+  // the last window must start inside the (top/left padded) input
+  if ((d->Ho - 1) * d->stride - d->pad_t >= d->H || (d->Wo - 1) * d->stride - d->pad_l >= d->W) {
+    set_error("conv output size inconsistent with input/stride/padding");
+    return SE_ERR_ARG;
+  }
+  return SE_OK;
+}
+
+}  // namespace se
+
+using namespace se;
+
+extern "C" const char* se_version(void) { return "se_b200 0.1 (sm_100a)"; }
+extern "C" const char* se_last_error(void) { return g_err; }
+extern "C" int64_t se_launch_count(void) { return g_launches.load(); }
+extern "C" int se_device_sm_count(void) { return sm_count(); }
+namespace se { int tc_capabilities(); }
+extern "C" int se_tc_capabilities(void) { return se::tc_capabilities(); }
+
+extern "C" int se_conv2d_fwd(const se_conv_desc* d, const float* x, const float* w, const float* bias,
+                             const float* residual, float* y, int relu, double* stats, int mode, void* stream) {
+  int rc = check_desc(d);
+  if (rc) return rc;
+  SE_REQUIRE(x && w && y, "null pointer");
+  if (mode == SE_MODE_TF32) {
+    rc = conv_fwd_tc(d, x, w, bias, residual, y, relu, stats, as_stream(stream));
+    if (rc != SE_ERR_UNSUPPORTED) return rc;
+  }
+  return conv_fwd_simt(d, x, w, bias, residual, y, relu, stats, as_stream(stream));
+}
+
+extern "C" int se_conv2d_dgrad(const se_conv_desc* d, const float* dy, const float* w, float* dx, float beta, int mode,
+                               void* stream) {
+  int rc = check_desc(d);
+  if (rc) return rc;
+  SE_REQUIRE(dy && w && dx, "null pointer");
+  if (mode == SE_MODE_TF32) {
+    rc = conv_dgrad_tc(d, dy, w, dx, beta, as_stream(stream));
+    if (rc != SE_ERR_UNSUPPORTED) return rc;
+  }
+  return conv_dgrad_simt(d, dy, w, dx, beta, as_stream(stream));
+}
+
+extern "C" int se_conv2d_wgrad(const se_conv_desc* d, const float* x, const float* dy, float* dw, float* dbias, int mode,
+                               void* stream) {
+  int rc = check_desc(d);
+  if (rc) return rc;
+  SE_REQUIRE(x && dy && dw, "null pointer");
+  if (mode == SE_MODE_TF32) {
+    rc = conv_wgrad_tc(d, x, dy, dw, dbias, as_stream(stream));
+    if (rc != SE_ERR_UNSUPPORTED) return rc;
+  }
+  return conv_wgrad_simt(d, x, dy, dw, dbias, as_stream(stream));
+}
+
+static se_conv_desc dense_desc(int B, int Cin, int Cout) {
+  se_conv_desc d;
+  d.N = B; d.H = 1; d.W = 1; d.Cin = Cin; d.Cout = Cout; d.kh = 1; d.kw = 1; d.stride = 1; d.pad_t = 0; d.pad_l = 0;
+  d.Ho = 1; d.Wo = 1;
+  return d;
+}
+
+extern "C" int se_dense_fwd(const float* x, const float* w, const float* bias, float* y, int B, int Cin, int Cout,
+                            int relu, double* stats, int mode, void* stream) {
+  se_conv_desc d = dense_desc(B, Cin, Cout);
+  return se_conv2d_fwd(&d, x, w, bias, nullptr, y, relu, stats, mode, stream);
+}
+
+extern "C" int se_dense_bwd(const float* x, const float* w, const float* dy, float* dx, float beta, float* dw,
+                            float* dbias, int B, int Cin, int Cout, int mode, void* stream) {
+  se_conv_desc d = dense_desc(B, Cin, Cout);
+  int rc = SE_OK;
+  if (dx) rc = se_conv2d_dgrad(&d, dy, w, dx, beta, mode, stream);
+  if (rc) return rc;
+  if (dw) rc = se_conv2d_wgrad(&d, x, dy, dw, dbias, mode, stream);
+  return rc;
+}
+
+// ---------------------------------------------------------------------------------------- plan runner
+static se_conv_desc desc_from(const int32_t* i) {
+  se_conv_desc d;
+  d.N = i[0]; d.H = i[1]; d.W = i[2]; d.Cin = i[3]; d.Cout = i[4]; d.kh = i[5]; d.kw = i[6]; d.stride = i[7];
+  d.pad_t = i[8]; d.pad_l = i[9]; d.Ho = i[10]; d.Wo = i[11];
+  return d;
+}
+
+extern "C" int se_sgd_apply_devlr(float* p, const float* g, float* v, int64_t n, const float* lr_dev, float momentum,
+                                  int nesterov, float clipnorm, const double* out, void* stream);
+
+extern "C" int se_run_ops(const se_op* ops, int n, int mode, void* stream) {
+  SE_REQUIRE(ops && n >= 0, "bad arguments");
+  for (int k = 0; k < n; ++k) {
+    const se_op& o = ops[k];
+    const int32_t* i = o.i;
+    const float* f = o.f;
+    void* const* p = o.p;
+    int rc = SE_OK;
+    switch (o.opcode) {
+      case SE_OP_CONV_FWD: {
+        se_conv_desc d = desc_from(i);
+        rc = se_conv2d_fwd(&d, (const float*)p[0], (const float*)p[1], (const float*)p[2], (const float*)p[3],
+                           (float*)p[4], i[12], (double*)p[5], i[13] >= 0 ? i[13] : mode, stream);
+        break;
+      }
+      case SE_OP_CONV_DGRAD: {
+        se_conv_desc d = desc_from(i);
+        rc = se_conv2d_dgrad(&d, (const float*)p[0], (const float*)p[1], (float*)p[2], f[0], i[13] >= 0 ? i[13] : mode, stream);
+        break;
+      }
+      case SE_OP_CONV_WGRAD: {
+        se_conv_desc d = desc_from(i);
+        rc = se_conv2d_wgrad(&d, (const float*)p[0], (const float*)p[1], (float*)p[2], (float*)p[3], i[13] >= 0 ? i[13] : mode, stream);
+        break;
+      }
+      case SE_OP_BN_STATS:
+        rc = se_bn_stats((const float*)p[0], i[1], i[0], (double*)p[1], stream);
+        break;
+      case SE_OP_BN_FWD_TRAIN:
+      case SE_OP_BN_FWD_INFER: {
+        se_residual r;
+        r.ptr = (const float*)p[8]; r.C = i[3]; r.pad_lo = i[4]; r.pool = i[5]; r.H = i[6]; r.W = i[7];
+        if (o.opcode == SE_OP_BN_FWD_TRAIN)
+          rc = se_bn_fwd_train((const float*)p[0], i[1], i[0], (const double*)p[1], (const float*)p[2], (const float*)p[3],
+                               f[0], f[1], (float*)p[4], (float*)p[5], (float*)p[6], (float*)p[7], &r, i[2], (float*)p[9], stream);
+        else
+          rc = se_bn_fwd_infer((const float*)p[0], i[1], i[0], (const float*)p[2], (const float*)p[3], (const float*)p[4],
+                               (const float*)p[5], f[0], &r, i[2], (float*)p[9], stream);
+        break;
+      }
+      case SE_OP_BN_BWD:
+        rc = se_bn_bwd((const float*)p[0], (const float*)p[1], (const float*)p[2], i[1], i[0], (const float*)p[3],
+                       (const float*)p[4], (const float*)p[5], i[2], i[3], (float*)p[6], f[0], (float*)p[7], f[1],
+                       (float*)p[8], (float*)p[9], (double*)p[10], stream);
+        break;
+      case SE_OP_SHORTCUT_BWD: {
+        se_residual r;
+        r.ptr = (const float*)p[2]; r.C = i[5]; r.pad_lo = i[6]; r.pool = i[7]; r.H = i[1]; r.W = i[2];
+        rc = se_shortcut_bwd((const float*)p[0], (const float*)p[1], i[4], i[0], i[1], i[2], i[3], &r, (float*)p[2], f[0], stream);
+        break;
+      }
+      case SE_OP_AVGPOOL_FWD:
+        rc = se_avgpool2_fwd((const float*)p[0], (float*)p[1], i[0], i[1], i[2], i[3], stream);
+        break;
+      case SE_OP_AVGPOOL_BWD:
+        rc = se_avgpool2_bwd((const float*)p[0], (float*)p[1], f[0], i[0], i[1], i[2], i[3], stream);
+        break;
+      case SE_OP_MAXPOOL_FWD:
+        rc = se_maxpool_fwd((const float*)p[0], (float*)p[1], i[0], i[1], i[2], i[3], i[4], i[5], i[6], i[7], i[8], i[9], stream);
+        break;
+      case SE_OP_MAXPOOL_BWD:
+        rc = se_maxpool_bwd((const float*)p[0], (const float*)p[1], (const float*)p[2], (float*)p[3], i[0], i[1], i[2],
+                            i[3], i[4], i[5], i[6], i[7], i[8], i[9], stream);
+        break;
+      case SE_OP_GAP_FWD:
+        rc = se_gap_fwd((const float*)p[0], (float*)p[1], i[0], i[1], i[2], stream);
+        break;
+      case SE_OP_GAP_BWD:
+        rc = se_gap_bwd((const float*)p[0], (float*)p[1], f[0], i[0], i[1], i[2], stream);
+        break;
+      case SE_OP_ADD_FWD:
+        rc = se_add_fwd((const float*)p[0], (const float*)p[1], (float*)p[2], i[1], i[0], stream);
+        break;
+      case SE_OP_ADD_BWD:
+        rc = se_add_bwd((const float*)p[0], (const float*)p[1], i[0], (float*)p[2], f[0], (float*)p[3], f[1], i[1], stream);
+        break;
+      case SE_OP_HEAD:
+        rc = se_embed_head_fwd_bwd((const float*)p[0], i[0], (const int32_t*)p[1], (const float*)p[2], i[1], i[2], i[3],
+                                   i[4], i[5], f[0], (const float*)p[3], (float*)p[4], (float*)p[5], (float*)p[6],
+                                   (float*)p[7], stream);
+        break;
+      case SE_OP_XENT:
+        rc = se_softmax_xent_fwd_bwd((const float*)p[0], i[0], (const int32_t*)p[1], i[1], i[2], f[0], (float*)p[2],
+                                     (float*)p[3], (float*)p[4], (float*)p[5], stream);
+        break;
+      case SE_OP_MEMSET: {
+        cudaError_t e = cudaMemsetAsync(p[0], 0, (size_t)(uintptr_t)p[1], as_stream(stream));
+        if (e != cudaSuccess) { set_error("memset: %s", cudaGetErrorString(e)); rc = SE_ERR_CUDA; }
+        break;
+      }
+      case SE_OP_SGD_PREPARE:
+        rc = se_sgd_prepare((const float*)p[0], (float*)p[1], (int64_t)(uintptr_t)p[2], (const se_l2_segment*)p[3], i[0],
+                            (double*)p[4], stream);
+        break;
+      case SE_OP_SGD_APPLY:
+        rc = se_sgd_apply_devlr((float*)p[0], (const float*)p[1], (float*)p[5], (int64_t)(uintptr_t)p[2], (const float*)p[3],
+                                f[0], i[0], f[1], (const double*)p[4], stream);
+        break;
+      default:
+        set_error("se_run_ops: unknown opcode %d at index %d", o.opcode, k);
+        return SE_ERR_ARG;
+    }
+    if (rc != SE_OK) return rc;
+  }
+  return SE_OK;
+}
+
+
+// Profiling variant used by bench.py: runs the ops eagerly with a CUDA-event pair around each one and
+// returns the per-op device time in milliseconds (ms_out[n]).  Not capturable.
+extern "C" int se_run_ops_timed(const se_op* ops, int n, int mode, void* stream, float* ms_out) {
+  SE_REQUIRE(ops && ms_out && n >= 0, "bad arguments");
+  cudaStream_t st = as_stream(stream);
+  cudaEvent_t* ev = new cudaEvent_t[2 * (size_t)n];
+  for (int k = 0; k < 2 * n; ++k) cudaEventCreate(&ev[k]);
+  int rc = SE_OK;
+  for (int k = 0; k < n && rc == SE_OK; ++k) {
+    cudaEventRecord(ev[2 * k], st);
+    rc = se_run_ops(ops + k, 1, mode, stream);
+    cudaEventRecord(ev[2 * k + 1], st);
+  }
+  cudaStreamSynchronize(st);
+  for (int k = 0; k < n; ++k) {
+    ms_out[k] = 0.f;
+    if (rc == SE_OK) cudaEventElapsedTime(&ms_out[k], ev[2 * k], ev[2 * k + 1]);
+  }
+  for (int k = 0; k < 2 * n; ++k) cudaEventDestroy(ev[k]);
+  delete[] ev;
+  return rc;
+}

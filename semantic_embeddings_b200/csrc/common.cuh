@@ -1,0 +1,84 @@
+// Shared helpers of the se_b200 CUDA library (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/se_b200.h"
+
+namespace se {
+
+void set_error(const char* fmt, ...);
+void count_launch(int n = 1);
+int sm_count();
+
+inline int check_launch(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_error("%s: %s", what, cudaGetErrorString(e));
+    return SE_ERR_CUDA;
+  }
+  count_launch();
+  return SE_OK;
+}
+
+#define SE_REQUIRE(cond, msg)                                \
+  do {                                                       \
+    if (!(cond)) {                                           \
+      se::set_error("%s: requirement failed: %s", __func__, msg); \
+      return SE_ERR_ARG;                                     \
+    }                                                        \
+  } while (0)
+
+inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+
+template <typename T>
+__host__ __device__ inline T ceil_div(T a, T b) { return (a + b - 1) / b; }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// 128-bit streaming load/store (read-once / write-once data: keep L1 for reused tiles)
+__device__ __forceinline__ float4 ldg_nc_f4(const float* p) {
+  float4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+               : "l"(p));
+  return r;
+}
+
+constexpr int BK = 16;
+
+// One BK-deep rank update of the TMxTN register tile from the smem tiles.
+template <int BM, int BN, int TM, int TN>
+__device__ __forceinline__ void tile_fma(const float (*As)[BM + 4], const float (*Bs)[BN + 4], int tm, int tn,
+                                         float (&acc)[TM][TN]) {
+#pragma unroll
+  for (int k = 0; k < BK; ++k) {
+    float a[TM], b[TN];
+#pragma unroll
+    for (int i = 0; i < TM; ++i) a[i] = As[k][tm * TM + i];
+#pragma unroll
+    for (int j = 0; j < TN; ++j) b[j] = Bs[k][tn * TN + j];
+#pragma unroll
+    for (int i = 0; i < TM; ++i)
+#pragma unroll
+      for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+  }
+}
+
+
+}  // namespace se

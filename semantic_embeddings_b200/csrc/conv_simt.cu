@@ -1,0 +1,552 @@
+// fp32 FFMA convolution kernels ("parity mode", SE_MODE_F32) -- implicit GEMM over NHWC / HWIO.
+//
+// These are the exact-fp32 counterpart of the tcgen05 path (conv_tc.cu) and the fallback for the
+// shapes that path does not cover (Cin=3 stem, stride-2 layers, 7x7, dense layers).  They stand for
+// the Conv2D / Dense ops of the reference graph (models/cifar_resnet.py:96-105,218,233;
+// models/plainnet.py:52,67,70,76; models/wide_residual_network.py:9-53,96) and their autodiff
+// gradients (learn_image_embeddings.py:238).
+//
+//   forward : Y[m, co]   = sum_{tap,ci} X[pix(m,tap), ci] * W[tap, ci, co]      M = N*Ho*Wo
+//   dgrad   : dX[m, ci]  = sum_{tap,co} dY[opix(m,tap), co] * W[tap, ci, co]    M = N*H*W
+//   wgrad   : dW[tap,ci,co] = sum_m X[pix(m,tap), ci] * dY[m, co]               reduction over pixels
+#include "common.cuh"
+
+namespace se {
+
+struct ConvP {
+  int N, H, W, Cin, Cout, kh, kw, stride, pad_t, pad_l, Ho, Wo;
+};
+
+static ConvP to_p(const se_conv_desc* d) {
+  ConvP p;
+  p.N = d->N; p.H = d->H; p.W = d->W; p.Cin = d->Cin; p.Cout = d->Cout; p.kh = d->kh; p.kw = d->kw;
+  p.stride = d->stride; p.pad_t = d->pad_t; p.pad_l = d->pad_l; p.Ho = d->Ho; p.Wo = d->Wo;
+  return p;
+}
+
+// ---------------------------------------------------------------------------------------- forward
+template <int BM, int BN, int TM, int TN, bool VEC>
+__global__ void __launch_bounds__((BM / TM) * (BN / TN))
+conv_fwd_kernel(ConvP p, const float* __restrict__ x, const float* __restrict__ w,
+                const float* __restrict__ bias, const float* __restrict__ residual, float* __restrict__ y,
+                int relu, double* __restrict__ stats) {
+  constexpr int NT = (BM / TM) * (BN / TN);
+  constexpr int CG = BN / TN;  // threads along the channel dimension
+  __shared__ __align__(16) float As[BK][BM + 4];
+  __shared__ __align__(16) float Bs[BK][BN + 4];
+  __shared__ long long row_off[BM];
+  __shared__ int row_h0[BM], row_w0[BM];
+  __shared__ double s_sum[BN], s_sq[BN];
+
+  const int tid = threadIdx.x;
+  const int tn = tid % CG, tm = tid / CG;
+  const long long M = (long long)p.N * p.Ho * p.Wo;
+  const long long m0 = (long long)blockIdx.x * BM;
+  const int n0 = blockIdx.y * BN;
+
+  for (int r = tid; r < BM; r += NT) {
+    long long m = m0 + r;
+    if (m < M) {
+      int ow = (int)(m % p.Wo);
+      long long t = m / p.Wo;
+      int oh = (int)(t % p.Ho);
+      int n = (int)(t / p.Ho);
+      int h0 = oh * p.stride - p.pad_t, w0 = ow * p.stride - p.pad_l;
+      row_h0[r] = h0;
+      row_w0[r] = w0;
+      row_off[r] = (((long long)n * p.H + h0) * p.W + w0) * p.Cin;
+    } else {
+      row_h0[r] = -(1 << 28);
+      row_w0[r] = -(1 << 28);
+      row_off[r] = 0;
+    }
+  }
+  if (tid < BN) { s_sum[tid] = 0.0; s_sq[tid] = 0.0; }
+  __syncthreads();
+
+  float acc[TM][TN];
+#pragma unroll
+  for (int i = 0; i < TM; ++i)
+#pragma unroll
+    for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+
+  const int taps = p.kh * p.kw;
+  for (int tap = 0; tap < taps; ++tap) {
+    const int fr = tap / p.kw, fs = tap % p.kw;
+    const long long tap_off = ((long long)fr * p.W + fs) * p.Cin;
+    for (int ci0 = 0; ci0 < p.Cin; ci0 += BK) {
+      if (VEC) {
+        for (int idx = tid; idx < BM * (BK / 4); idx += NT) {
+          int row = idx / (BK / 4), kq = idx % (BK / 4);
+          int ih = row_h0[row] + fr, iw = row_w0[row] + fs;
+          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (ih >= 0 && ih < p.H && iw >= 0 && iw < p.W && ci0 + 4 * kq < p.Cin)
+            v = *reinterpret_cast<const float4*>(x + row_off[row] + tap_off + ci0 + 4 * kq);
+          As[4 * kq + 0][row] = v.x; As[4 * kq + 1][row] = v.y;
+          As[4 * kq + 2][row] = v.z; As[4 * kq + 3][row] = v.w;
+        }
+        for (int idx = tid; idx < BK * (BN / 4); idx += NT) {
+          int k = idx / (BN / 4), nq = idx % (BN / 4);
+          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (ci0 + k < p.Cin && n0 + 4 * nq < p.Cout)
+            v = *reinterpret_cast<const float4*>(w + ((long long)tap * p.Cin + ci0 + k) * p.Cout + n0 + 4 * nq);
+          *reinterpret_cast<float4*>(&Bs[k][4 * nq]) = v;
+        }
+      } else {
+        for (int idx = tid; idx < BM * BK; idx += NT) {
+          int row = idx / BK, k = idx % BK;
+          int ih = row_h0[row] + fr, iw = row_w0[row] + fs;
+          float v = 0.f;
+          if (ih >= 0 && ih < p.H && iw >= 0 && iw < p.W && ci0 + k < p.Cin)
+            v = x[row_off[row] + tap_off + ci0 + k];
+          As[k][row] = v;
+        }
+        for (int idx = tid; idx < BK * BN; idx += NT) {
+          int k = idx / BN, n = idx % BN;
+          float v = 0.f;
+          if (ci0 + k < p.Cin && n0 + n < p.Cout) v = w[((long long)tap * p.Cin + ci0 + k) * p.Cout + n0 + n];
+          Bs[k][n] = v;
+        }
+      }
+      __syncthreads();
+      tile_fma<BM, BN, TM, TN>(As, Bs, tm, tn, acc);
+      __syncthreads();
+    }
+  }
+
+  // epilogue: bias, residual, relu, store, BatchNorm statistics of the stored values
+  float csum[TN], csq[TN];
+#pragma unroll
+  for (int j = 0; j < TN; ++j) { csum[j] = 0.f; csq[j] = 0.f; }
+#pragma unroll
+  for (int i = 0; i < TM; ++i) {
+    long long m = m0 + tm * TM + i;
+    if (m >= M) continue;
+#pragma unroll
+    for (int j = 0; j < TN; ++j) {
+      int co = n0 + tn * TN + j;
+      if (co >= p.Cout) continue;
+      float v = acc[i][j];
+      if (bias) v += bias[co];
+      if (residual) v += residual[m * p.Cout + co];
+      if (relu) v = fmaxf(v, 0.f);
+      y[m * p.Cout + co] = v;
+      csum[j] += v;
+      csq[j] += v * v;
+    }
+  }
+  if (stats) {
+    // lanes that share `tn` own the same channels: reduce them with shuffles first (CG divides 32)
+#pragma unroll
+    for (int j = 0; j < TN; ++j) {
+      float a = csum[j], b = csq[j];
+      for (int o = CG; o < 32; o <<= 1) {
+        a += __shfl_xor_sync(0xffffffffu, a, o);
+        b += __shfl_xor_sync(0xffffffffu, b, o);
+      }
+      if ((tid & 31) < CG) {
+        atomicAdd(&s_sum[tn * TN + j], (double)a);
+        atomicAdd(&s_sq[tn * TN + j], (double)b);
+      }
+    }
+    __syncthreads();
+    if (tid < BN && n0 + tid < p.Cout) {
+      atomicAdd(&stats[n0 + tid], s_sum[tid]);
+      atomicAdd(&stats[p.Cout + n0 + tid], s_sq[tid]);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------- dgrad
+template <int BM, int BN, int TM, int TN, bool VEC>
+__global__ void __launch_bounds__((BM / TM) * (BN / TN))
+conv_dgrad_kernel(ConvP p, const float* __restrict__ dy, const float* __restrict__ w, float* __restrict__ dx,
+                  float beta) {
+  constexpr int NT = (BM / TM) * (BN / TN);
+  constexpr int CG = BN / TN;
+  __shared__ __align__(16) float As[BK][BM + 4];
+  __shared__ __align__(16) float Bs[BK][BN + 4];
+  __shared__ int row_n[BM], row_h[BM], row_w[BM];
+
+  const int tid = threadIdx.x;
+  const int tn = tid % CG, tm = tid / CG;
+  const long long M = (long long)p.N * p.H * p.W;
+  const long long m0 = (long long)blockIdx.x * BM;
+  const int n0 = blockIdx.y * BN;  // input-channel tile
+
+  for (int r = tid; r < BM; r += NT) {
+    long long m = m0 + r;
+    if (m < M) {
+      row_w[r] = (int)(m % p.W);
+      long long t = m / p.W;
+      row_h[r] = (int)(t % p.H);
+      row_n[r] = (int)(t / p.H);
+    } else {
+      row_n[r] = -1; row_h[r] = 0; row_w[r] = 0;
+    }
+  }
+  __syncthreads();
+
+  float acc[TM][TN];
+#pragma unroll
+  for (int i = 0; i < TM; ++i)
+#pragma unroll
+    for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+
+  const int taps = p.kh * p.kw;
+  for (int tap = 0; tap < taps; ++tap) {
+    const int fr = tap / p.kw, fs = tap % p.kw;
+    for (int co0 = 0; co0 < p.Cout; co0 += BK) {
+      // A[m, k=co] = dy[n, (ih+pad_t-fr)/s, (iw+pad_l-fs)/s, co] when divisible and in range
+      if (VEC) {
+        for (int idx = tid; idx < BM * (BK / 4); idx += NT) {
+          int row = idx / (BK / 4), kq = idx % (BK / 4);
+          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+          int n = row_n[row];
+          int th = row_h[row] + p.pad_t - fr, tw = row_w[row] + p.pad_l - fs;
+          if (n >= 0 && th >= 0 && tw >= 0 && (th % p.stride) == 0 && (tw % p.stride) == 0 && co0 + 4 * kq < p.Cout) {
+            int oh = th / p.stride, ow = tw / p.stride;
+            if (oh < p.Ho && ow < p.Wo)
+              v = *reinterpret_cast<const float4*>(dy + (((long long)n * p.Ho + oh) * p.Wo + ow) * p.Cout + co0 + 4 * kq);
+          }
+          As[4 * kq + 0][row] = v.x; As[4 * kq + 1][row] = v.y;
+          As[4 * kq + 2][row] = v.z; As[4 * kq + 3][row] = v.w;
+        }
+        // B[k=co, n=ci] = w[tap, ci, co]
+        for (int idx = tid; idx < BN * (BK / 4); idx += NT) {
+          int n = idx / (BK / 4), kq = idx % (BK / 4);
+          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (n0 + n < p.Cin && co0 + 4 * kq < p.Cout)
+            v = *reinterpret_cast<const float4*>(w + ((long long)tap * p.Cin + n0 + n) * p.Cout + co0 + 4 * kq);
+          Bs[4 * kq + 0][n] = v.x; Bs[4 * kq + 1][n] = v.y;
+          Bs[4 * kq + 2][n] = v.z; Bs[4 * kq + 3][n] = v.w;
+        }
+      } else {
+        for (int idx = tid; idx < BM * BK; idx += NT) {
+          int row = idx / BK, k = idx % BK;
+          float v = 0.f;
+          int n = row_n[row];
+          int th = row_h[row] + p.pad_t - fr, tw = row_w[row] + p.pad_l - fs;
+          if (n >= 0 && th >= 0 && tw >= 0 && (th % p.stride) == 0 && (tw % p.stride) == 0 && co0 + k < p.Cout) {
+            int oh = th / p.stride, ow = tw / p.stride;
+            if (oh < p.Ho && ow < p.Wo) v = dy[(((long long)n * p.Ho + oh) * p.Wo + ow) * p.Cout + co0 + k];
+          }
+          As[k][row] = v;
+        }
+        for (int idx = tid; idx < BN * BK; idx += NT) {
+          int n = idx / BK, k = idx % BK;
+          float v = 0.f;
+          if (n0 + n < p.Cin && co0 + k < p.Cout) v = w[((long long)tap * p.Cin + n0 + n) * p.Cout + co0 + k];
+          Bs[k][n] = v;
+        }
+      }
+      __syncthreads();
+      tile_fma<BM, BN, TM, TN>(As, Bs, tm, tn, acc);
+      __syncthreads();
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < TM; ++i) {
+    long long m = m0 + tm * TM + i;
+    if (m >= M) continue;
+#pragma unroll
+    for (int j = 0; j < TN; ++j) {
+      int ci = n0 + tn * TN + j;
+      if (ci >= p.Cin) continue;
+      float v = acc[i][j];
+      if (beta != 0.f) v += beta * dx[m * p.Cin + ci];
+      dx[m * p.Cin + ci] = v;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------- wgrad (generic)
+// M' = kh*kw*Cin (flattened kk), N' = Cout, reduction over output pixels split across blockIdx.z.
+template <int BM, int BN, int TM, int TN>
+__global__ void __launch_bounds__((BM / TM) * (BN / TN))
+conv_wgrad_kernel(ConvP p, const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ dw,
+                  float* __restrict__ dbias, long long pix_per_split) {
+  constexpr int NT = (BM / TM) * (BN / TN);
+  constexpr int CG = BN / TN;
+  __shared__ __align__(16) float As[BK][BM + 4];
+  __shared__ __align__(16) float Bs[BK][BN + 4];
+  __shared__ long long pix_off[BK];
+  __shared__ int pix_h0[BK], pix_w0[BK];
+  __shared__ int kk_tap_off[BM], kk_r[BM], kk_s[BM];
+
+  const int tid = threadIdx.x;
+  const int tn = tid % CG, tm = tid / CG;
+  const int KK = p.kh * p.kw * p.Cin;
+  const int m0 = blockIdx.x * BM;  // kk tile
+  const int n0 = blockIdx.y * BN;  // cout tile
+  const long long P = (long long)p.N * p.Ho * p.Wo;
+  const long long pbeg = (long long)blockIdx.z * pix_per_split;
+  const long long pend = min(P, pbeg + pix_per_split);
+
+  for (int r = tid; r < BM; r += NT) {
+    int kk = m0 + r;
+    if (kk < KK) {
+      int tap = kk / p.Cin, ci = kk % p.Cin;
+      int fr = tap / p.kw, fs = tap % p.kw;
+      kk_r[r] = fr; kk_s[r] = fs;
+      kk_tap_off[r] = (fr * p.W + fs) * p.Cin + ci;
+    } else {
+      kk_r[r] = 1 << 28; kk_s[r] = 1 << 28; kk_tap_off[r] = 0;
+    }
+  }
+  float acc[TM][TN];
+#pragma unroll
+  for (int i = 0; i < TM; ++i)
+#pragma unroll
+    for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+  float bsum = 0.f;
+  const bool do_bias = (dbias != nullptr) && blockIdx.x == 0 && tid < BN;
+
+  for (long long pc = pbeg; pc < pend; pc += BK) {
+    __syncthreads();
+    if (tid < BK) {
+      long long m = pc + tid;
+      if (m < pend) {
+        int ow = (int)(m % p.Wo);
+        long long t = m / p.Wo;
+        int oh = (int)(t % p.Ho);
+        int n = (int)(t / p.Ho);
+        int h0 = oh * p.stride - p.pad_t, w0 = ow * p.stride - p.pad_l;
+        pix_h0[tid] = h0; pix_w0[tid] = w0;
+        pix_off[tid] = (((long long)n * p.H + h0) * p.W + w0) * p.Cin;
+      } else {
+        pix_h0[tid] = -(1 << 28); pix_w0[tid] = -(1 << 28); pix_off[tid] = 0;
+      }
+    }
+    __syncthreads();
+    for (int idx = tid; idx < BK * BM; idx += NT) {
+      int k = idx / BM, mm = idx % BM;
+      int ih = pix_h0[k] + kk_r[mm], iw = pix_w0[k] + kk_s[mm];
+      float v = 0.f;
+      if (ih >= 0 && ih < p.H && iw >= 0 && iw < p.W) v = x[pix_off[k] + kk_tap_off[mm]];
+      As[k][mm] = v;
+    }
+    for (int idx = tid; idx < BK * BN; idx += NT) {
+      int k = idx / BN, n = idx % BN;
+      float v = 0.f;
+      if (pc + k < pend && n0 + n < p.Cout) v = dy[(pc + k) * p.Cout + n0 + n];
+      Bs[k][n] = v;
+    }
+    __syncthreads();
+    tile_fma<BM, BN, TM, TN>(As, Bs, tm, tn, acc);
+    if (do_bias) {
+#pragma unroll
+      for (int k = 0; k < BK; ++k) bsum += Bs[k][tid];
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < TM; ++i) {
+    int kk = m0 + tm * TM + i;
+    if (kk >= KK) continue;
+#pragma unroll
+    for (int j = 0; j < TN; ++j) {
+      int co = n0 + tn * TN + j;
+      if (co < p.Cout) atomicAdd(&dw[(long long)kk * p.Cout + co], acc[i][j]);
+    }
+  }
+  if (do_bias && n0 + tid < p.Cout) atomicAdd(&dbias[n0 + tid], bsum);
+}
+
+// ---------------------------------------------------------------------------------------- wgrad 3x3 stride 1 'same'
+// One CTA walks over (image, row-band) tiles with the 9 x CI_T x CO_T partial sums of its
+// (ci, co) pairs in registers: per pixel it reads 3 new x values per ci and 1 dy value per co
+// from shared memory for 9 FMAs per pair (sliding 3x3 window), then adds the result into dW once.
+template <int CI_T, int CO_T>
+__global__ void __launch_bounds__(256)
+conv_wgrad3x3_kernel(ConvP p, const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ dw,
+                     float* __restrict__ dbias, int TH, int tiles_per_img, int num_tiles) {
+  constexpr int CIT = 16 * CI_T, COT = 16 * CO_T;
+  extern __shared__ __align__(16) float smem[];
+  const int W = p.W, H = p.H;
+  float* xs = smem;                                   // [(TH+2)][(W+2)][CIT]
+  float* ds = smem + (TH + 2) * (W + 2) * CIT;        // [TH][W][COT]
+  const int tid = threadIdx.x;
+  const int tco = tid & 15, tci = tid >> 4;
+  const int ci0 = blockIdx.y * CIT, co0 = blockIdx.z * COT;
+
+  float acc[3][3][CI_T][CO_T];
+#pragma unroll
+  for (int r = 0; r < 3; ++r)
+#pragma unroll
+    for (int s = 0; s < 3; ++s)
+#pragma unroll
+      for (int a = 0; a < CI_T; ++a)
+#pragma unroll
+        for (int b = 0; b < CO_T; ++b) acc[r][s][a][b] = 0.f;
+  float bacc[CO_T];
+#pragma unroll
+  for (int b = 0; b < CO_T; ++b) bacc[b] = 0.f;
+
+  for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    const int n = tile / tiles_per_img;
+    const int h0 = (tile % tiles_per_img) * TH;
+    const int th = min(TH, H - h0);
+    __syncthreads();
+    // x halo band: rows h0-1 .. h0+th, cols -1 .. W, zero outside the image ('same' padding)
+    const int xq = CIT / 4;
+    for (int idx = tid; idx < (th + 2) * (W + 2) * xq; idx += 256) {
+      int q = idx % xq;
+      int t = idx / xq;
+      int cw = t % (W + 2), rh = t / (W + 2);
+      int ih = h0 + rh - 1, iw = cw - 1;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (ih >= 0 && ih < H && iw >= 0 && iw < W)
+        v = *reinterpret_cast<const float4*>(x + (((long long)n * H + ih) * W + iw) * p.Cin + ci0 + 4 * q);
+      *reinterpret_cast<float4*>(xs + (rh * (W + 2) + cw) * CIT + 4 * q) = v;
+    }
+    const int dq = COT / 4;
+    for (int idx = tid; idx < th * W * dq; idx += 256) {
+      int q = idx % dq;
+      int t = idx / dq;
+      float4 v = *reinterpret_cast<const float4*>(dy + (((long long)n * H + h0) * W + t) * p.Cout + co0 + 4 * q);
+      *reinterpret_cast<float4*>(ds + t * COT + 4 * q) = v;
+    }
+    __syncthreads();
+    for (int h = 0; h < th; ++h) {
+      float win[3][2][CI_T];  // previous two columns of the three halo rows
+#pragma unroll
+      for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int a = 0; a < CI_T; ++a) {
+          win[r][0][a] = xs[((h + r) * (W + 2) + 0) * CIT + tci + 16 * a];
+          win[r][1][a] = xs[((h + r) * (W + 2) + 1) * CIT + tci + 16 * a];
+        }
+      for (int wcol = 0; wcol < W; ++wcol) {
+        float d[CO_T];
+#pragma unroll
+        for (int b = 0; b < CO_T; ++b) d[b] = ds[(h * W + wcol) * COT + tco + 16 * b];
+        if (tci == 0) {
+#pragma unroll
+          for (int b = 0; b < CO_T; ++b) bacc[b] += d[b];
+        }
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+          float xc[CI_T];
+#pragma unroll
+          for (int a = 0; a < CI_T; ++a) xc[a] = xs[((h + r) * (W + 2) + wcol + 2) * CIT + tci + 16 * a];
+#pragma unroll
+          for (int a = 0; a < CI_T; ++a)
+#pragma unroll
+            for (int b = 0; b < CO_T; ++b) {
+              acc[r][0][a][b] = fmaf(win[r][0][a], d[b], acc[r][0][a][b]);
+              acc[r][1][a][b] = fmaf(win[r][1][a], d[b], acc[r][1][a][b]);
+              acc[r][2][a][b] = fmaf(xc[a], d[b], acc[r][2][a][b]);
+            }
+#pragma unroll
+          for (int a = 0; a < CI_T; ++a) { win[r][0][a] = win[r][1][a]; win[r][1][a] = xc[a]; }
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < 3; ++r)
+#pragma unroll
+    for (int s = 0; s < 3; ++s)
+#pragma unroll
+      for (int a = 0; a < CI_T; ++a)
+#pragma unroll
+        for (int b = 0; b < CO_T; ++b) {
+          int ci = ci0 + tci + 16 * a, co = co0 + tco + 16 * b;
+          atomicAdd(&dw[((long long)(r * 3 + s) * p.Cin + ci) * p.Cout + co], acc[r][s][a][b]);
+        }
+  if (dbias != nullptr && tci == 0 && blockIdx.y == 0) {
+#pragma unroll
+    for (int b = 0; b < CO_T; ++b) atomicAdd(&dbias[co0 + tco + 16 * b], bacc[b]);
+  }
+}
+
+// ---------------------------------------------------------------------------------------- launchers
+template <int BM, int BN, int TM, int TN>
+static int launch_fwd(const ConvP& p, const float* x, const float* w, const float* bias, const float* residual,
+                      float* y, int relu, double* stats, cudaStream_t st) {
+  long long M = (long long)p.N * p.Ho * p.Wo;
+  dim3 grid((unsigned)ceil_div<long long>(M, BM), (unsigned)ceil_div(p.Cout, BN));
+  bool vec = (p.Cin % 4 == 0) && (p.Cout % 4 == 0);
+  if (vec)
+    conv_fwd_kernel<BM, BN, TM, TN, true><<<grid, (BM / TM) * (BN / TN), 0, st>>>(p, x, w, bias, residual, y, relu, stats);
+  else
+    conv_fwd_kernel<BM, BN, TM, TN, false><<<grid, (BM / TM) * (BN / TN), 0, st>>>(p, x, w, bias, residual, y, relu, stats);
+  return check_launch("conv_fwd_kernel");
+}
+
+int conv_fwd_simt(const se_conv_desc* d, const float* x, const float* w, const float* bias, const float* residual,
+                  float* y, int relu, double* stats, cudaStream_t st) {
+  ConvP p = to_p(d);
+  if (p.Cout <= 16) return launch_fwd<128, 16, 4, 2>(p, x, w, bias, residual, y, relu, stats, st);
+  if (p.Cout <= 32) return launch_fwd<128, 32, 4, 4>(p, x, w, bias, residual, y, relu, stats, st);
+  return launch_fwd<64, 64, 4, 4>(p, x, w, bias, residual, y, relu, stats, st);
+}
+
+template <int BM, int BN, int TM, int TN>
+static int launch_dgrad(const ConvP& p, const float* dy, const float* w, float* dx, float beta, cudaStream_t st) {
+  long long M = (long long)p.N * p.H * p.W;
+  dim3 grid((unsigned)ceil_div<long long>(M, BM), (unsigned)ceil_div(p.Cin, BN));
+  bool vec = (p.Cout % 4 == 0);
+  if (vec)
+    conv_dgrad_kernel<BM, BN, TM, TN, true><<<grid, (BM / TM) * (BN / TN), 0, st>>>(p, dy, w, dx, beta);
+  else
+    conv_dgrad_kernel<BM, BN, TM, TN, false><<<grid, (BM / TM) * (BN / TN), 0, st>>>(p, dy, w, dx, beta);
+  return check_launch("conv_dgrad_kernel");
+}
+
+int conv_dgrad_simt(const se_conv_desc* d, const float* dy, const float* w, float* dx, float beta, cudaStream_t st) {
+  ConvP p = to_p(d);
+  if (p.Cin <= 16) return launch_dgrad<128, 16, 4, 2>(p, dy, w, dx, beta, st);
+  if (p.Cin <= 32) return launch_dgrad<128, 32, 4, 4>(p, dy, w, dx, beta, st);
+  return launch_dgrad<64, 64, 4, 4>(p, dy, w, dx, beta, st);
+}
+
+template <int CI_T, int CO_T>
+static int launch_wgrad3x3(const ConvP& p, const float* x, const float* dy, float* dw, float* dbias, cudaStream_t st) {
+  constexpr int CIT = 16 * CI_T, COT = 16 * CO_T;
+  int TH = max(1, 128 / p.W);
+  if (TH > p.H) TH = p.H;
+  size_t smem = ((size_t)(TH + 2) * (p.W + 2) * CIT + (size_t)TH * p.W * COT) * sizeof(float);
+  int tiles_per_img = ceil_div(p.H, TH);
+  int num_tiles = p.N * tiles_per_img;
+  int cy = p.Cin / CIT, cz = p.Cout / COT;
+  int gx = min(num_tiles, max(1, (2 * sm_count()) / (cy * cz)));
+  auto kern = conv_wgrad3x3_kernel<CI_T, CO_T>;
+  if (smem > 48 * 1024) {
+    if (smem > 200 * 1024) return SE_ERR_UNSUPPORTED;
+    static int configured = 0;   // per instantiation; set once, outside any later graph capture
+    if (configured < (int)smem) {
+      cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      configured = (int)smem;
+    }
+  }
+  kern<<<dim3(gx, cy, cz), 256, smem, st>>>(p, x, dy, dw, dbias, TH, tiles_per_img, num_tiles);
+  return check_launch("conv_wgrad3x3_kernel");
+}
+
+int conv_wgrad_simt(const se_conv_desc* d, const float* x, const float* dy, float* dw, float* dbias, cudaStream_t st) {
+  ConvP p = to_p(d);
+  const bool same3x3 = p.kh == 3 && p.kw == 3 && p.stride == 1 && p.pad_t == 1 && p.pad_l == 1 && p.Ho == p.H &&
+                       p.Wo == p.W && (p.Cin % 16 == 0) && (p.Cout % 16 == 0);
+  if (same3x3) {
+    int rc;
+    if (p.Cin % 32 == 0 && p.Cout % 32 == 0) rc = launch_wgrad3x3<2, 2>(p, x, dy, dw, dbias, st);
+    else if (p.Cout % 32 == 0) rc = launch_wgrad3x3<1, 2>(p, x, dy, dw, dbias, st);
+    else if (p.Cin % 32 == 0) rc = launch_wgrad3x3<2, 1>(p, x, dy, dw, dbias, st);
+    else rc = launch_wgrad3x3<1, 1>(p, x, dy, dw, dbias, st);
+    if (rc != SE_ERR_UNSUPPORTED) return rc;
+  }
+  constexpr int BM = 64, BN = 64, TM = 4, TN = 4;
+  const int KK = p.kh * p.kw * p.Cin;
+  long long P = (long long)p.N * p.Ho * p.Wo;
+  int gx = ceil_div(KK, BM), gy = ceil_div(p.Cout, BN);
+  // split the pixel reduction so that the grid fills the machine about twice
+  long long want = max(1LL, (long long)(2 * sm_count()) / ((long long)gx * gy));
+  long long splits = min(want, ceil_div<long long>(P, 4 * BK));
+  long long per = ceil_div<long long>(ceil_div<long long>(P, splits), BK) * BK;
+  splits = ceil_div<long long>(P, per);
+  conv_wgrad_kernel<BM, BN, TM, TN><<<dim3(gx, gy, (unsigned)splits), (BM / TM) * (BN / TN), 0, st>>>(p, x, dy, dw, dbias, per);
+  return check_launch("conv_wgrad_kernel");
+}
+
+}  // namespace se

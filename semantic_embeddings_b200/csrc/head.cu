@@ -1,0 +1,212 @@
+// The embedding head as ONE fused kernel (north-star item): L2-normalise, gather t = E[label],
+// 1 - <t,x> (or squared distance) loss, nearest-class accuracy over the whole class matrix, and the
+// backward pass -- one warp per sample row, warp-shuffle reductions, 128-bit coalesced loads.
+//
+// Replaces these graph ops of the reference:
+//   utils.l2norm              utils.py:125-127      x = z * rsqrt(max(sum z^2, 1e-12))
+//   transform_inputs          learn_image_embeddings.py:48-50   (host gather E[y], now in-kernel)
+//   utils.inv_correlation     utils.py:44-46        1 - sum_d t*x
+//   utils.squared_distance    utils.py:34-36        sum_d (x-t)^2
+//   utils.nn_accuracy         utils.py:57-100       |max_c <x,E_c> - <x,t>| < 1e-6  (k<=1)
+//   + TF autodiff of the above (learn_image_embeddings.py:238)
+// and Activation('softmax') + categorical_crossentropy of the classifier branch
+// (learn_image_embeddings.py:44,230-231).
+#include <float.h>
+
+#include "common.cuh"
+
+namespace se {
+
+constexpr int HEAD_WARPS = 4;
+
+template <bool VEC>
+__device__ __forceinline__ float warp_dot(const float* __restrict__ a_smem, const float* __restrict__ b_gmem, int D,
+                                          int lane) {
+  float s = 0.f;
+  if (VEC) {
+    for (int i = lane; i < (D >> 2); i += 32) {
+      float4 b = *reinterpret_cast<const float4*>(b_gmem + 4 * i);
+      float4 a = *reinterpret_cast<const float4*>(a_smem + 4 * i);
+      s = fmaf(a.x, b.x, s); s = fmaf(a.y, b.y, s); s = fmaf(a.z, b.z, s); s = fmaf(a.w, b.w, s);
+    }
+  } else {
+    for (int i = lane; i < D; i += 32) s = fmaf(a_smem[i], b_gmem[i], s);
+  }
+  return warp_sum(s);
+}
+
+template <bool VEC>
+__global__ void __launch_bounds__(HEAD_WARPS * 32)
+embed_head_kernel(const float* __restrict__ z, int ldz, const int* __restrict__ labels, const float* __restrict__ E,
+                  int ldE, int B, int D, int C, int loss_kind, float loss_scale, const float* __restrict__ extra_dx,
+                  float* __restrict__ x_out, float* __restrict__ loss, float* __restrict__ acc, float* __restrict__ dz) {
+  extern __shared__ __align__(16) float smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int Dp = (D + 3) & ~3;
+  float* xs = smem + warp * Dp;  // this warp's row (wrapped output x)
+  const int row = blockIdx.x * HEAD_WARPS + warp;
+  if (row >= B) return;
+  const float* zr = z + (long long)row * ldz;
+
+  // ---- load z, sum of squares
+  float ss = 0.f;
+  if (VEC) {
+    for (int i = lane; i < (D >> 2); i += 32) {
+      float4 v = ldg_nc_f4(zr + 4 * i);
+      *reinterpret_cast<float4*>(xs + 4 * i) = v;
+      ss += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+    }
+  } else {
+    for (int i = lane; i < D; i += 32) { float v = zr[i]; xs[i] = v; ss += v * v; }
+  }
+  ss = warp_sum(ss);
+  float inv = 1.f;
+  bool clamped = false;
+  if (loss_kind == SE_LOSS_INV_CORR) {
+    clamped = !(ss >= 1e-12f);
+    inv = rsqrtf(fmaxf(ss, 1e-12f));
+    __syncwarp();
+    for (int i = lane; i < D; i += 32) xs[i] *= inv;
+  }
+  __syncwarp();
+  if (x_out) {
+    float* xo = x_out + (long long)row * ldz;
+    if (VEC) {
+      for (int i = lane; i < (D >> 2); i += 32)
+        *reinterpret_cast<float4*>(xo + 4 * i) = *reinterpret_cast<const float4*>(xs + 4 * i);
+    } else {
+      for (int i = lane; i < D; i += 32) xo[i] = xs[i];
+    }
+  }
+
+  // ---- loss against the target row
+  const int lab = labels[row];
+  const float* t = E + (long long)lab * ldE;
+  float true_sim = warp_dot<VEC>(xs, t, D, lane);
+  float xnorm2 = (loss_kind == SE_LOSS_INV_CORR) ? ss * inv * inv : ss;
+  float l;
+  float true_dist = 0.f;
+  if (loss_kind == SE_LOSS_MSE) {
+    float s = 0.f;
+    for (int i = lane; i < D; i += 32) { float d = xs[i] - t[i]; s = fmaf(d, d, s); }
+    true_dist = warp_sum(s);
+    l = true_dist;
+  } else {
+    l = 1.f - true_sim;
+  }
+  if (loss && lane == 0) loss[row] = l;
+
+  // ---- accuracy: nearest class over the whole class matrix (utils.py:73-93)
+  if (acc) {
+    float best = (loss_kind == SE_LOSS_MSE) ? FLT_MAX : -FLT_MAX;
+    for (int c = 0; c < C; ++c) {
+      const float* e = E + (long long)c * ldE;
+      float sim = warp_dot<VEC>(xs, e, D, lane);
+      if (loss_kind == SE_LOSS_MSE) {
+        float en = warp_dot<VEC>(e, e, D, lane);  // centroids_norm (utils.py:76)
+        float dist = xnorm2 + en - 2.f * sim;
+        best = fminf(best, dist);
+      } else {
+        best = fmaxf(best, sim);
+      }
+    }
+    float ref = (loss_kind == SE_LOSS_MSE) ? true_dist : true_sim;
+    if (lane == 0) acc[row] = (fabsf(best - ref) < 1e-6f) ? 1.f : 0.f;
+  }
+
+  // ---- backward
+  if (dz) {
+    float* dzr = dz + (long long)row * ldz;
+    const float* ex = extra_dx ? extra_dx + (long long)row * ldz : nullptr;
+    if (loss_kind == SE_LOSS_INV_CORR) {
+      // g = dL/dx = -scale*t + extra ; dz = inv * (g - x <x,g>)   (only inv*g when the clamp is active)
+      float xg = 0.f;
+      for (int i = lane; i < D; i += 32) {
+        float g = -loss_scale * t[i] + (ex ? ex[i] : 0.f);
+        xg = fmaf(xs[i], g, xg);
+      }
+      xg = warp_sum(xg);
+      if (clamped) xg = 0.f;
+      for (int i = lane; i < D; i += 32) {
+        float g = -loss_scale * t[i] + (ex ? ex[i] : 0.f);
+        dzr[i] = inv * (g - xs[i] * xg);
+      }
+    } else if (loss_kind == SE_LOSS_UNNORM_CORR) {
+      for (int i = lane; i < D; i += 32) dzr[i] = -loss_scale * t[i] + (ex ? ex[i] : 0.f);
+    } else {
+      for (int i = lane; i < D; i += 32) dzr[i] = 2.f * loss_scale * (xs[i] - t[i]) + (ex ? ex[i] : 0.f);
+    }
+  }
+}
+
+// softmax + Keras categorical_crossentropy(prob) + arg-max accuracy + backward; one warp per row.
+__global__ void __launch_bounds__(HEAD_WARPS * 32)
+softmax_xent_kernel(const float* __restrict__ logits, int ld, const int* __restrict__ labels, int B, int C, float scale,
+                    float* __restrict__ prob, float* __restrict__ loss, float* __restrict__ acc,
+                    float* __restrict__ dlogits) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row = blockIdx.x * HEAD_WARPS + warp;
+  if (row >= B) return;
+  const float* lr = logits + (long long)row * ld;
+  float m = -FLT_MAX;
+  int arg = 0;
+  for (int i = lane; i < C; i += 32) { float v = lr[i]; if (v > m) { m = v; arg = i; } }
+  // warp arg-max with lowest-index tie-break (np.argmax semantics)
+  for (int o = 16; o > 0; o >>= 1) {
+    float om = __shfl_xor_sync(0xffffffffu, m, o);
+    int oa = __shfl_xor_sync(0xffffffffu, arg, o);
+    if (om > m || (om == m && oa < arg)) { m = om; arg = oa; }
+  }
+  float s = 0.f;
+  for (int i = lane; i < C; i += 32) s += expf(lr[i] - m);
+  s = warp_sum(s);
+  const float invs = 1.f / s;
+  const int lab = labels[row];
+  const float py = expf(lr[lab] - m) * invs;
+  // Keras: p /= sum(p); p = clip(p, 1e-7, 1-1e-7); loss = -log p_y.  Gradient is zero where the clip is active.
+  const float lo = 1e-7f, hi = 1.f - 1e-7f;
+  const float pyc = fminf(fmaxf(py, lo), hi);
+  if (lane == 0) {
+    if (loss) loss[row] = -logf(pyc);
+    if (acc) acc[row] = (arg == lab) ? 1.f : 0.f;
+  }
+  const bool live = (py >= lo) && (py <= hi);
+  for (int i = lane; i < C; i += 32) {
+    float p = expf(lr[i] - m) * invs;
+    if (prob) prob[(long long)row * ld + i] = p;
+    if (dlogits) dlogits[(long long)row * ld + i] = live ? scale * (p - (i == lab ? 1.f : 0.f)) : 0.f;
+  }
+}
+
+}  // namespace se
+
+using namespace se;
+
+extern "C" int se_embed_head_fwd_bwd(const float* z, int ldz, const int32_t* labels, const float* E, int ldE, int B,
+                                     int D, int C, int loss_kind, float loss_scale, const float* extra_dx, float* x_out,
+                                     float* loss, float* acc, float* dz, void* stream) {
+  SE_REQUIRE(z && labels && E && B > 0 && D > 0 && C > 0, "bad arguments");
+  SE_REQUIRE(ldz >= D && ldE >= D, "leading dimension smaller than D");
+  SE_REQUIRE(loss_kind >= 0 && loss_kind <= 2, "unknown loss kind");
+  const int Dp = (D + 3) & ~3;
+  size_t smem = (size_t)HEAD_WARPS * Dp * sizeof(float);
+  SE_REQUIRE(smem <= 48 * 1024, "D too large for the fused head (max 3072)");
+  auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+  bool vec = (D % 4 == 0) && (ldz % 4 == 0) && (ldE % 4 == 0) && al16(z) && al16(E) && (!x_out || al16(x_out));
+  int grid = ceil_div(B, HEAD_WARPS);
+  if (vec)
+    embed_head_kernel<true><<<grid, HEAD_WARPS * 32, smem, as_stream(stream)>>>(z, ldz, labels, E, ldE, B, D, C, loss_kind,
+                                                                                loss_scale, extra_dx, x_out, loss, acc, dz);
+  else
+    embed_head_kernel<false><<<grid, HEAD_WARPS * 32, smem, as_stream(stream)>>>(z, ldz, labels, E, ldE, B, D, C, loss_kind,
+                                                                                 loss_scale, extra_dx, x_out, loss, acc, dz);
+  return check_launch("embed_head_kernel");
+}
+
+extern "C" int se_softmax_xent_fwd_bwd(const float* logits, int ld, const int32_t* labels, int B, int C, float scale,
+                                       float* prob, float* loss, float* acc, float* dlogits, void* stream) {
+  SE_REQUIRE(logits && labels && B > 0 && C > 0 && ld >= C, "bad arguments");
+  softmax_xent_kernel<<<ceil_div(B, HEAD_WARPS), HEAD_WARPS * 32, 0, as_stream(stream)>>>(logits, ld, labels, B, C, scale,
+                                                                                         prob, loss, acc, dlogits);
+  return check_launch("softmax_xent_kernel");
+}

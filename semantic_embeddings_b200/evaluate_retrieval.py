@@ -1,0 +1,93 @@
+"""Host-side mirror of the reference's evaluate_retrieval.pairwise_retrieval (evaluate_retrieval.py:22-73)
+on top of the CUDA all-pairs distance kernel (se_pairwise_dist).
+
+Same signature, accepted input forms, id mapping, error and -- for drop-in fidelity -- the same side
+effect (with normalize=True a caller-supplied ndarray is L2-normalised in place, evaluate_retrieval.py:58).
+The distance matrix (lines 56-63) is computed by the hand-written kernel; the ranking (line 67) is the
+"next" row of the scope table and is currently a device-side stable sort of each
+row block (ascending distance, ties by ascending index).
+"""
+import pickle
+
+import numpy as np
+
+from . import _lib
+
+
+def _features_to_array(features):
+    """evaluate_retrieval.py:43-54."""
+    if isinstance(features, str):
+        with open(features, 'rb') as feat_dump:
+            features = pickle.load(feat_dump)
+    if isinstance(features, dict):
+        if 'feat' in features:
+            features = features['feat']
+        ind2id = np.array(list(features.keys()))
+        features = np.stack(list(features.values()))
+        if features.ndim > 2:
+            raise ValueError('Feature matrix must be 2-dimensional. Actual shape: {}'.format(features.shape))
+    else:
+        ind2id = None
+    return features, ind2id
+
+
+def pairwise_distances(features, normalize=False, row0=0, rows=None, mode=None, device=None, out=None, feat_dev=None):
+    """Rows [row0, row0+rows) of the N x N distance matrix as a CUDA tensor (float32).
+
+    normalize=True : -F^ F^T with F^ = F/||F||        (evaluate_retrieval.py:57-59)
+    normalize=False: sq_i + sq_j - 2 F F^T            (evaluate_retrieval.py:61-62)
+    `mode`: _lib.SE_MODE_F32 (exact fp32 FFMA) or SE_MODE_TF32 (tcgen05 3xTF32, default)."""
+    import torch
+    if feat_dev is None:
+        f = np.ascontiguousarray(np.asarray(features, dtype=np.float32))
+        if f.ndim != 2:
+            raise ValueError('Feature matrix must be 2-dimensional. Actual shape: {}'.format(f.shape))
+        dev = torch.device(device or 'cuda')
+        feat_dev = torch.from_numpy(f).to(dev)
+    N, D = feat_dev.shape
+    rows = N - row0 if rows is None else rows
+    mode = _lib.SE_MODE_TF32 if mode is None else mode
+    lib = _lib.load()
+    ws = torch.empty(int(lib.se_pairwise_workspace_bytes(N, D, mode)), dtype=torch.uint8, device=feat_dev.device)
+    if out is None:
+        out = torch.empty((rows, N), dtype=torch.float32, device=feat_dev.device)
+    pmode = _lib.SE_PDIST_NEGDOT if normalize else _lib.SE_PDIST_SQEUCLID
+    with torch.cuda.device(feat_dev.device):
+        _lib.call('se_pairwise_dist', feat_dev.data_ptr(), feat_dev.stride(0), N, D, row0, rows, pmode,
+                  1 if normalize else 0, out.data_ptr(), out.stride(0), ws.data_ptr(), mode, _lib.stream_ptr())
+    return out
+
+
+def pairwise_ranking(features, normalize=False, block_rows=4096, mode=None, device=None, topk=None):
+    """int64 ndarray (N, N) -- or (N, topk) -- of database indices sorted by ascending distance per query."""
+    import torch
+    f = np.ascontiguousarray(np.asarray(features, dtype=np.float32))
+    dev = torch.device(device or 'cuda')
+    fd = torch.from_numpy(f).to(dev)
+    N = f.shape[0]
+    k = N if topk is None else min(topk, N)
+    ranking = np.empty((N, k), dtype=np.int64)
+    buf = torch.empty((min(block_rows, N), N), dtype=torch.float32, device=dev)
+    for r0 in range(0, N, block_rows):
+        r = min(block_rows, N - r0)
+        d = pairwise_distances(None, normalize, r0, r, mode, out=buf[:r], feat_dev=fd)
+        idx = torch.sort(d, dim=-1, stable=True).indices[:, :k]
+        ranking[r0:r0 + r] = idx.cpu().numpy()
+    return ranking
+
+
+def pairwise_retrieval(features, normalize=False, return_generator=True):
+    """Uses each image as query and retrieves its nearest neighbors (evaluate_retrieval.py:22-73).
+
+    features: 2-d array | dict id -> vector | dict with key 'feat' | path to a pickle of one of those.
+    Returns a generator of (id, ranked id list) tuples, or a dict when return_generator is False."""
+    features, ind2id = _features_to_array(features)
+    ranking = pairwise_ranking(features, normalize)
+    if normalize and isinstance(features, np.ndarray) and features.dtype.kind == 'f':
+        # the reference normalises its argument in place (line 58); keep the caller-visible side effect
+        features /= np.linalg.norm(features, axis=-1, keepdims=True)
+    if ind2id is not None:
+        gen = ((ind2id[i], ind2id[ret].tolist()) for i, ret in enumerate(ranking))
+    else:
+        gen = ((i, ret.tolist()) for i, ret in enumerate(ranking))
+    return gen if return_generator else dict(gen)

@@ -1,0 +1,216 @@
+"""CPU tests (`-m "not gpu"`): the C-ABI library loads and exports what include/se_b200.h declares, the host
+layer (graph builders, schedules, plans, DP plumbing) matches the fixtures recorded from the reference."""
+import json
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+G = os.path.join(ROOT, 'tests', 'golden')
+
+
+@pytest.fixture(scope='session')
+def built_lib():
+    from semantic_embeddings_b200 import _lib
+    if not os.path.exists(_lib.LIB_PATH):
+        import __graft_entry__ as ge
+        ge.build()
+    return _lib
+
+
+def test_library_exports_every_declared_symbol(built_lib):
+    hdr = open(os.path.join(ROOT, 'include', 'se_b200.h')).read()
+    hdr = re.sub(r'/\*.*?\*/', '', hdr, flags=re.S)
+    declared = set(re.findall(r'\b(se_[a-z0-9_]+)\s*\(', hdr))
+    assert len(declared) >= 30
+    lib = built_lib.load()
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert declared == set(built_lib.exported_symbols()), declared ^ set(built_lib.exported_symbols())
+    assert lib.se_version().decode().startswith('se_b200')
+
+
+def test_product_path_has_no_oracle_or_cpu_fallback():
+    pkg = os.path.join(ROOT, 'semantic_embeddings_b200')
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith('.py'):
+                src = open(os.path.join(dirpath, f)).read()
+                assert 'import oracle' not in src and 'from oracle' not in src, f
+    from semantic_embeddings_b200 import _lib
+    saved = _lib.LIB_PATH
+    try:
+        _lib.LIB_PATH = saved + '.missing'
+        _lib._lib = None
+        with pytest.raises(_lib.SeError):
+            _lib.load()
+    finally:
+        _lib.LIB_PATH = saved
+        _lib._lib = None
+
+
+def test_same_padding():
+    from semantic_embeddings_b200.graph import same_pad
+    assert same_pad(32, 3, 1) == (1, 1, 32)
+    assert same_pad(32, 3, 2) == (0, 1, 16)       # TF SAME is asymmetric for stride 2
+    assert same_pad(32, 1, 2) == (0, 0, 16)
+    assert same_pad(7, 3, 2) == (1, 1, 4)
+
+
+@pytest.mark.parametrize('tag', ['simple', 'resnet-110-fc', 'resnet-110', 'resnet-32', 'wrn-28-10'])
+def test_graph_builders_match_reference_layer_trace(tag):
+    """Layer names, kernel sizes, strides, padding, bias, L2, BN hyper-parameters and output shapes of the product's
+    graphs vs the trace recorded from the reference's own model builders (make_golden.py)."""
+    from semantic_embeddings_b200 import utils
+    with open(os.path.join(G, 'arch_%s.json' % tag)) as f:
+        meta = json.load(f)
+    g = utils.build_network(meta['dim'], meta['architecture'], input_channels=3)
+    nodes = {n.name: n for n in g.nodes}
+    convs = [t for t in meta['trace'] if t['class'] == 'Conv2D']
+    assert len(convs) == sum(1 for n in g.nodes if n.op == 'conv')
+    for t in convs:
+        n = nodes[t['name']]
+        assert n.attrs['k'] == t['kernel_size'][0] == t['kernel_size'][1]
+        assert n.attrs['stride'] == t['strides'][0]
+        assert n.attrs['use_bias'] == t['use_bias']
+        assert list(n.output.shape) == t['out_shape'], (t['name'], n.output.shape, t['out_shape'])
+        assert g.params[t['name'] + '/kernel'].l2 == t['l2']
+        assert g.params[t['name'] + '/kernel'].init == t['kernel_initializer']
+        assert n.attrs['relu'] == (t['activation'] == 'relu')
+    bns = [t for t in meta['trace'] if t['class'] == 'BatchNormalization' and t['name'] in nodes]
+    assert len(bns) == sum(1 for n in g.nodes if n.op == 'bn')
+    for t in bns:
+        n = nodes[t['name']]
+        assert abs(n.attrs['momentum'] - t['momentum']) < 1e-12 and abs(n.attrs['eps'] - t['epsilon']) < 1e-12
+        assert g.params[t['name'] + '/gamma'].init == t['gamma_initializer']
+    for t in meta['trace']:
+        if t['class'] == 'Dense' and t['name'] in nodes:
+            assert nodes[t['name']].output.shape == (t['units'],)
+            assert g.params[t['name'] + '/kernel'].l2 == t['l2']
+    last = [t for t in meta['trace'] if t['class'] == 'Lambda'][0]
+    assert list(g.output.shape) == last['out_shape']
+
+
+def test_model_sizes_match_survey():
+    from semantic_embeddings_b200 import utils
+    g = utils.build_network(100, 'resnet-110-fc')
+    assert sum(1 for n in g.nodes if n.op == 'conv') == 109
+    assert abs(g.conv_macs_per_image() / 1e6 - 252.89) < 0.01
+    g = utils.build_network(100, 'simple')
+    assert abs(g.conv_macs_per_image() / 1e6 - 247.14) < 0.01
+    g = utils.build_network(100, 'wrn-28-10')
+    assert abs(g.conv_macs_per_image() / 1e6 - 5243.3) < 0.1
+    assert abs(g.num_params() / 1e6 - 36.5) < 0.1
+    g = utils.build_network(555, 'resnet-50')
+    assert sum(1 for n in g.nodes if n.op == 'conv') == 53
+
+
+def test_build_network_errors_like_reference():
+    from semantic_embeddings_b200 import utils
+    with pytest.raises(ValueError, match='Unknown network architecture'):
+        utils.build_network(10, 'no-such-net')                          # utils.py:276
+    with pytest.raises(NotImplementedError):
+        utils.build_network(10, 'pyramidnet-272-200')
+    with pytest.raises(ValueError, match='Unknown learning rate schedule'):
+        utils.get_lr_schedule('nope', 1, 1, {})                         # utils.py:397-399
+
+
+def test_sgdr_matches_reference_fixture():
+    from semantic_embeddings_b200 import utils
+    with open(os.path.join(G, 'sgdr_ref.json')) as f:
+        ref = json.load(f)
+    for tag in ('default', 'short'):
+        cbs, num_epochs = utils.get_lr_schedule('SGDR', 50000, 128, dict(ref[tag]['args']))
+        assert num_epochs == ref[tag]['num_epochs']
+        s = cbs[0]
+        s.on_train_begin()
+        seq = []
+        for ep in range(num_epochs):
+            seq.append(s.lr)
+            s.on_epoch_end(ep, {})
+        np.testing.assert_allclose(seq, ref[tag]['lr'], rtol=1e-14)
+
+
+def test_engine_builds_plans_without_a_gpu(built_lib):
+    """device='cpu' allocates host tensors and builds the launch plans only (nothing is executed)."""
+    from semantic_embeddings_b200 import utils
+    from semantic_embeddings_b200.engine import Engine
+    L = built_lib
+    emb = np.load(os.path.join(G, 'class_matrices.npz'))['cifar100_embedding']
+    for arch, cls_w in (('resnet-110-fc', 0.0), ('simple', 0.0), ('wrn-28-10', 0.1), ('resnet-110-fc', 0.1)):
+        g = utils.build_network(100, arch)
+        eng = Engine(g, 2, emb, cls_weight=cls_w, num_classes=100, device='cpu', use_cuda_graph=False)
+        fwd, bwd = eng.plans['fwd'], eng.plans['bwd']
+        nconv = sum(1 for n in eng.nodes if n.op in ('conv', 'dense'))
+        assert sum(1 for o in fwd if o.opcode == L.OP_CONV_FWD) == nconv
+        assert sum(1 for o in bwd if o.opcode == L.OP_CONV_WGRAD) == nconv
+        # every conv but the stem (whose input is the image) needs a data gradient
+        assert sum(1 for o in bwd if o.opcode == L.OP_CONV_DGRAD) == nconv - 1
+        nbn = sum(1 for n in eng.nodes if n.op == 'bn')
+        assert sum(1 for o in fwd if o.opcode == L.OP_BN_FWD_TRAIN) == nbn
+        assert sum(1 for o in bwd if o.opcode == L.OP_BN_BWD) == nbn
+        assert sum(1 for o in fwd if o.opcode == L.OP_HEAD) == 1
+        assert sum(1 for o in bwd if o.opcode == L.OP_HEAD) == (1 if cls_w > 0 else 0)
+        # L2 segments cover exactly the regularised kernels
+        reg = sum(int(np.prod(p.shape)) for p in eng.pspecs.values() if p.trainable and p.l2 > 0)
+        covered = sum(e - b for b, e, _ in eng.segments)
+        assert reg <= covered <= reg + 4 * len(eng.pspecs)
+        w = eng.get_weights() if False else None
+    # weight I/O round trip keeps Keras names and layouts
+    g = utils.build_network(100, 'resnet-32')
+    eng = Engine(g, 2, np.eye(64), device='cpu', use_cuda_graph=False)
+    ws = g.init_weights(3)
+    eng.set_weights(ws)
+    v = eng._pview('res2-1x/kernel')
+    assert tuple(v.shape) == (3, 3, 16, 32)
+    np.testing.assert_array_equal(v.numpy(), ws['res2-1x/kernel'])
+    with pytest.raises(KeyError):
+        eng.set_weights({'nope/kernel': np.zeros(1)})
+    with pytest.raises(ValueError):
+        Engine(utils.build_network(100, 'resnet-110'), 2, emb, device='cpu')     # 64-d output vs 100-d classes
+
+
+def test_shard_helpers():
+    from semantic_embeddings_b200.parallel import shard_batch, shard_rows
+    assert [shard_rows(50000, 8, r) for r in (0, 7)] == [(0, 6250), (43750, 6250)]
+    assert [shard_rows(10, 4, r) for r in range(4)] == [(0, 3), (3, 3), (6, 3), (9, 1)]
+    assert shard_rows(2, 4, 3) == (2, 0)
+    assert [shard_batch(10, 4, r) for r in range(4)] == [(0, 2), (2, 2), (4, 2), (6, 4)]   # last tower takes the rest
+
+
+_GLOO_WORKER = r'''
+import os, sys
+sys.path.insert(0, %(root)r)
+import torch, torch.distributed as dist
+from semantic_embeddings_b200.parallel import init_process_group, allreduce_gradients, broadcast_parameters, shard_rows
+rank, world = init_process_group('gloo')
+assert world == 2
+flat = torch.arange(10, dtype=torch.float32) * (rank + 1)
+allreduce_gradients(flat)
+assert torch.equal(flat, torch.arange(10, dtype=torch.float32) * 3), flat
+w = torch.full((5,), float(rank + 7))
+broadcast_parameters([w], src=0)
+assert torch.equal(w, torch.full((5,), 7.0))
+# row-sharded retrieval: the shards tile [0, N) exactly once
+r0, rows = shard_rows(1001, world, rank)
+t = torch.zeros(1001); t[r0:r0 + rows] = 1
+dist.all_reduce(t)
+assert torch.equal(t, torch.ones(1001))
+dist.destroy_process_group()
+print('rank', rank, 'ok')
+'''
+
+
+def test_data_parallel_plumbing_gloo_world2(tmp_path):
+    script = tmp_path / 'worker.py'
+    script.write_text(_GLOO_WORKER % {'root': ROOT})
+    env = dict(os.environ, MASTER_ADDR='127.0.0.1')
+    out = subprocess.run([sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node=2',
+                          '--master-addr', '127.0.0.1', '--master-port', '29533', str(script)],
+                         capture_output=True, text=True, timeout=300, env=env)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert 'rank 0 ok' in out.stdout and 'rank 1 ok' in out.stdout

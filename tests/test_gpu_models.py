@@ -1,0 +1,228 @@
+"""GPU parity tests of whole training steps (engine + C-ABI library) against the CPU oracle, and of the
+forward pass against the fixtures produced by the reference's own model-building code
+(tests/golden/arch_*.npz, see make_golden.py).
+
+North-star tolerance (BASELINE.json): embeddings and loss within 1e-4 relative of the reference
+semantics in parity mode (SE_MODE_F32).  Gradients / updated weights are compared per tensor by
+relative L2 error.
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+G = os.path.join(os.path.dirname(__file__), 'golden')
+REPORT = os.path.join(os.path.dirname(os.path.dirname(__file__)), 'gpurun_out', 'parity_models.jsonl')
+
+
+def report(name, **vals):
+    try:
+        os.makedirs(os.path.dirname(REPORT), exist_ok=True)
+        with open(REPORT, 'a') as f:
+            f.write(json.dumps(dict(test=name, **vals)) + '\n')
+    except OSError:
+        pass
+
+
+def rel_l2(a, b):
+    a = np.asarray(a, np.float64).ravel()
+    b = np.asarray(b, np.float64).ravel()
+    return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-30))
+
+
+def rel_max(a, b):
+    a = np.asarray(a, np.float64)
+    b = np.asarray(b, np.float64)
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-30))
+
+
+def class_matrix(key='cifar100'):
+    return np.load(os.path.join(G, 'class_matrices.npz'))[key + '_embedding']
+
+
+def oracle_weights_np(m, cls=None):
+    w = {k: v.numpy().astype(np.float32) for k, v in m.params.items()}
+    if cls is not None:
+        w.update({k: v.numpy().astype(np.float32) for k, v in cls.params.items()})
+    return w
+
+
+def to_f32_exact(m, cls=None):
+    """Round the oracle's float64 weights to float32 values so both sides start from identical numbers."""
+    for v in m.params.values():
+        v.copy_(v.float().double())
+    if cls is not None:
+        for v in cls.params.values():
+            v.copy_(v.float().double())
+
+
+@pytest.mark.parametrize('tag', ['simple', 'resnet-110-fc', 'resnet-110', 'resnet-32', 'wrn-28-10'])
+def test_forward_matches_reference_graph_fixture(tag):
+    """Engine forward (training-mode BN) vs the output of the reference's own graph code on the same weights."""
+    from oracle import models as omodels
+    from oracle import train as otrain
+    from semantic_embeddings_b200 import utils
+    from semantic_embeddings_b200.engine import Engine
+    with open(os.path.join(G, 'arch_%s.json' % tag)) as f:
+        meta = json.load(f)
+    d = np.load(os.path.join(G, 'arch_%s.npz' % tag))
+    s = meta['seeds']
+    om = omodels.build_network(meta['dim'], meta['architecture'], input_channels=3, seed=s['build'])
+    omodels.randomize(om, seed=s['randomize'])
+    cls = None
+    if meta['with_cls']:
+        cls = otrain.ClsHead(meta['dim'], 100, seed=s['cls'])
+        omodels.randomize(cls.params, seed=s['cls_rand'])
+    graph = utils.build_network(meta['dim'], meta['architecture'], input_channels=3)
+    B = meta['batch']
+    emb = class_matrix('cifar100') if meta['dim'] == 100 else np.eye(meta['dim'])
+    eng = Engine(graph, B, emb, loss='inv_corr', cls_weight=0.5 if cls is not None else 0.0, num_classes=100,
+                 use_cuda_graph=False)
+    eng.set_weights(oracle_weights_np(om, cls))
+    eng.load_batch(torch.from_numpy(d['x'].astype(np.float32)), torch.zeros(B, dtype=torch.int64))
+    eng._run('fwd')
+    z = eng.act[graph.output.name].cpu().numpy()
+    x_out = eng.act['head_out'].cpu().numpy()
+    e_z, e_e = rel_max(z, d['z']), rel_max(x_out, d['emb'])
+    e_p = 0.0
+    if cls is not None:
+        e_p = rel_max(eng.act['prob_out'].cpu().numpy(), d['prob'])
+    report('forward_fixture', tag=tag, z=e_z, emb=e_e, prob=e_p)
+    assert e_z < 1e-4 and e_e < 1e-4 and e_p < 1e-4, (e_z, e_e, e_p)
+
+
+STEP_CASES = [
+    # tag, arch, D/emb key, batch, loss, cls_weight, nesterov
+    ('simple', 'simple', 'cifar100', 8, 'inv_corr', 0.0, False),
+    ('resnet-32', 'resnet-32', None, 8, 'inv_corr', 0.0, False),
+    ('resnet-110-fc', 'resnet-110-fc', 'cifar100', 8, 'inv_corr', 0.0, False),
+    ('resnet-110-fc-cls', 'resnet-110-fc', 'cifar100', 8, 'inv_corr', 0.1, True),
+    ('simple-mse', 'simple', 'cifar100', 6, 'mse', 0.0, False),
+    ('wrn-28-10-cls', 'wrn-28-10', 'cifar100', 4, 'inv_corr', 0.1, False),
+]
+
+
+@pytest.mark.parametrize('case', STEP_CASES, ids=lambda c: c[0])
+def test_two_training_steps_match_oracle(case):
+    """Two consecutive optimizer steps (so that momentum and BN moving statistics are exercised)."""
+    from oracle import models as omodels
+    from oracle import train as otrain
+    from semantic_embeddings_b200 import utils
+    from semantic_embeddings_b200.engine import Engine
+    tag, arch, key, B, loss, cls_weight, nesterov = case
+    emb = class_matrix(key) if key else np.eye(64)
+    C, D = emb.shape
+    om = omodels.build_network(D, arch, input_channels=3, seed=21)
+    omodels.randomize(om, seed=22)
+    cls = None
+    if cls_weight > 0:
+        cls = otrain.ClsHead(D, C, seed=23)
+        omodels.randomize(cls.params, seed=24)
+    to_f32_exact(om, cls)
+    graph = utils.build_network(D, arch, input_channels=3)
+    eng = Engine(graph, B, emb, loss=loss, cls_weight=cls_weight, num_classes=C, nesterov=nesterov, clipnorm=10.0,
+                 use_cuda_graph=(tag == 'resnet-110-fc'))
+    eng.set_weights(oracle_weights_np(om, cls))
+    vel = otrain.make_velocity(om, cls if cls_weight > 0 else None)
+    emb_t = torch.as_tensor(emb.astype(np.float32)).double()
+    g = torch.Generator().manual_seed(31)
+    lr = 0.05
+    errs = {}
+    for step in range(2):
+        x = torch.randn(B, 32, 32, 3, generator=g, dtype=torch.float64).float()
+        y = torch.randint(0, C, (B,), generator=g)
+        obj, grads, norm = otrain.train_step(om, x.double(), y, emb_t, vel, lr, loss, cls, cls_weight, nesterov, 10.0)
+        eng.train_step(x, y, lr=lr)
+        m = eng.metrics()
+        gn, reg = eng.grad_norm_and_reg()
+        e = {
+            'loss': abs(m['loss'] - float(obj['embed_loss'])) / max(1.0, abs(float(obj['embed_loss']))),
+            'emb': rel_max(eng.act['head_out'].cpu().numpy(), obj['emb'].detach().numpy()),
+            'acc': abs(m['acc'] - float(obj['acc'].mean())),
+            'gnorm': abs(gn - norm) / norm,
+            'reg': abs(reg - float(obj['reg'])) / max(float(obj['reg']), 1e-12),
+        }
+        if cls_weight > 0:
+            e['cls_loss'] = abs(m['cls_loss'] - float(obj['cls_loss'])) / max(1.0, abs(float(obj['cls_loss'])))
+        # gradients (the engine's G holds grad + 2*lambda*W after the optimizer's first pass)
+        eg = eng.get_grads()
+        worst_g, worst_name = 0.0, ''
+        allp = dict(om.params)
+        if cls is not None:
+            allp.update(cls.params)
+        gl2 = dict(om.l2)
+        if cls is not None and cls_weight > 0:
+            gl2.update(cls.l2)
+        num = den = 0.0
+        for name, gr in grads.items():
+            a = eg[name].astype(np.float64)
+            b = gr.numpy()
+            num += float(((a - b) ** 2).sum())
+            den += float((b ** 2).sum())
+            r = rel_l2(a, b) if np.linalg.norm(b) > 1e-6 * norm else 0.0
+            if r > worst_g:
+                worst_g, worst_name = r, name
+        e['grad_global'] = float(np.sqrt(num / den))
+        e['grad_worst'] = worst_g
+        ew = eng.get_weights()
+        e['weights'] = max(rel_l2(ew[n], allp[n].numpy()) for n in allp)
+        errs[step] = e
+        report('train_step', case=tag, step=step, worst_grad_tensor=worst_name, **e)
+    for step, e in errs.items():
+        assert e['loss'] < 1e-4 and e['emb'] < 1e-4, (step, e)
+        assert e['gnorm'] < 1e-3 and e['reg'] < 1e-5, (step, e)
+        assert e['grad_global'] < 2e-3, (step, e)
+        assert e['weights'] < 1e-4, (step, e)
+        assert e['acc'] <= 1.0 / B + 1e-9, (step, e)
+
+
+def test_inference_uses_moving_statistics():
+    from oracle import models as omodels
+    from oracle import train as otrain
+    from semantic_embeddings_b200 import utils
+    from semantic_embeddings_b200.engine import Engine
+    emb = class_matrix('cifar100')
+    om = omodels.build_network(100, 'resnet-32' if False else 'simple', input_channels=3, seed=5)
+    omodels.randomize(om, seed=6)
+    to_f32_exact(om)
+    graph = utils.build_network(100, 'simple', input_channels=3)
+    B = 4
+    eng = Engine(graph, B, emb, use_cuda_graph=False)
+    eng.set_weights(oracle_weights_np(om))
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(B, 32, 32, 3, generator=g, dtype=torch.float64).float()
+    with torch.no_grad():
+        ref = otrain.head_forward(om.forward(x.double(), training=False), 'inv_corr').numpy()
+    got = eng.predict(x)
+    assert rel_max(got, ref) < 1e-4
+
+
+def test_fast_mode_error_is_reported_not_hidden():
+    """SE_MODE_TF32 (tensor-core inputs with a 10-bit mantissa) is not expected to meet 1e-4; its measured
+    deviation from the oracle is recorded so that DESIGN.md can quote it."""
+    from oracle import models as omodels
+    from oracle import train as otrain
+    from semantic_embeddings_b200 import _lib, utils
+    from semantic_embeddings_b200.engine import Engine
+    emb = class_matrix('cifar100')
+    om = omodels.build_network(100, 'resnet-110-fc', input_channels=3, seed=41)
+    to_f32_exact(om)
+    graph = utils.build_network(100, 'resnet-110-fc', input_channels=3)
+    B = 8
+    eng = Engine(graph, B, emb, mode=_lib.SE_MODE_TF32, use_cuda_graph=False)
+    eng.set_weights(oracle_weights_np(om))
+    g = torch.Generator().manual_seed(2)
+    x = torch.randn(B, 32, 32, 3, generator=g, dtype=torch.float64).float()
+    y = torch.randint(0, 100, (B,), generator=g)
+    emb_t = torch.as_tensor(emb.astype(np.float32)).double()
+    obj = otrain.train_objective(om, x.double(), y, emb_t)
+    eng.load_batch(x, y)
+    eng._run('fwdbwd', graph=False)
+    e_emb = rel_max(eng.act['head_out'].cpu().numpy(), obj['emb'].detach().numpy())
+    e_loss = abs(eng.metrics()['loss'] - float(obj['embed_loss']))
+    report('fast_mode', emb=e_emb, loss=e_loss)
+    assert e_emb < 5e-2 and e_loss < 5e-2

@@ -1,0 +1,495 @@
+"""GPU parity tests of the individual C-ABI entry points against the CPU oracle (float64).
+
+Run on the B200 box with `pytest -m gpu`.  Every call goes through include/se_b200.h via ctypes
+(semantic_embeddings_b200._lib); the oracle (oracle/) is only the checker.
+Tolerances: fp32 kernels vs a float64 oracle -> relative error (max-norm scaled) <= 2e-5 per op;
+integer outputs (accuracy flags, rankings on tie-free inputs) bit-exact.
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+G = os.path.join(os.path.dirname(__file__), 'golden')
+REPORT = os.path.join(os.path.dirname(os.path.dirname(__file__)), 'gpurun_out', 'parity_ops.jsonl')
+
+
+def _lib():
+    from semantic_embeddings_b200 import _lib as L
+    L.load()
+    return L
+
+
+def dev(a, dtype=torch.float32):
+    return torch.as_tensor(np.ascontiguousarray(a)).to(dtype).cuda()
+
+
+def relerr(got, ref):
+    got = np.asarray(got, dtype=np.float64)
+    ref = np.asarray(ref, dtype=np.float64)
+    return float(np.abs(got - ref).max() / max(np.abs(ref).max(), 1e-30))
+
+
+def report(name, **vals):
+    try:
+        os.makedirs(os.path.dirname(REPORT), exist_ok=True)
+        with open(REPORT, 'a') as f:
+            f.write(json.dumps(dict(test=name, **vals)) + '\n')
+    except OSError:
+        pass
+
+
+def sptr():
+    return _lib().stream_ptr()
+
+
+CONV_CASES = [
+    # N, H, W, Cin, Cout, k, stride, padding, bias
+    (4, 32, 32, 3, 16, 3, 1, 'same', True),      # stem
+    (4, 32, 32, 16, 16, 3, 1, 'same', True),     # ResNet-110 stage 1
+    (4, 32, 32, 16, 32, 3, 2, 'same', True),     # stride-2, asymmetric SAME padding (0,1)
+    (4, 16, 16, 32, 32, 3, 1, 'same', True),
+    (3, 8, 8, 64, 64, 3, 1, 'same', False),
+    (2, 16, 16, 16, 160, 1, 2, 'same', False),   # WRN 1x1/2 skip
+    (2, 18, 18, 3, 64, 7, 2, (3, 3, 3, 3), True),  # ResNet-50 stem geometry
+    (2, 9, 7, 8, 24, 3, 1, 'same', True),        # ragged sizes, odd channels-of-4
+    (5, 1, 1, 64, 100, 1, 1, 'valid', True),     # dense 64 -> 100
+    (3, 1, 1, 20, 555, 1, 1, 'valid', True),     # dense -> 555 (not a multiple of 4)
+    (2, 12, 12, 32, 64, 3, 1, 'same', True),     # wgrad <2,2> register tile
+]
+
+
+@pytest.mark.parametrize('case', CONV_CASES, ids=lambda c: 'x'.join(str(v) for v in c[:7]))
+@pytest.mark.parametrize('mode', [0, 1], ids=['f32', 'tf32'])
+def test_conv_fwd_dgrad_wgrad(case, mode):
+    from oracle import nn as onn
+    from semantic_embeddings_b200.graph import same_pad
+    L = _lib()
+    N, H, W, Cin, Cout, k, stride, padding, use_bias = case
+    g = torch.Generator().manual_seed(hash(case[:7]) % 1000)
+    x = torch.randn(N, H, W, Cin, generator=g, dtype=torch.float64)
+    w = torch.randn(k, k, Cin, Cout, generator=g, dtype=torch.float64) * (1.0 / np.sqrt(k * k * Cin))
+    b = torch.randn(Cout, generator=g, dtype=torch.float64) if use_bias else None
+    x.requires_grad_(True)
+    w.requires_grad_(True)
+    if b is not None:
+        b.requires_grad_(True)
+    y = onn.conv2d(x, w, b, stride, padding)
+    dy = torch.randn(y.shape, generator=g, dtype=torch.float64)
+    grads = torch.autograd.grad(y, [x, w] + ([b] if b is not None else []), dy)
+    if padding == 'same':
+        pt, pl = same_pad(H, k, stride)[0], same_pad(W, k, stride)[0]
+    elif padding == 'valid':
+        pt = pl = 0
+    else:
+        pt, pl = padding[0], padding[2]
+    Ho, Wo = y.shape[1], y.shape[2]
+    d = L.ConvDesc(N, H, W, Cin, Cout, k, k, stride, pt, pl, Ho, Wo)
+    xd, wd, dyd = dev(x.detach()), dev(w.detach()), dev(dy)
+    bd = dev(b.detach()) if b is not None else None
+    yd = torch.empty(N, Ho, Wo, Cout, device='cuda')
+    stats = torch.zeros(2 * Cout, dtype=torch.float64, device='cuda')
+    L.call('se_conv2d_fwd', d, L.ptr(xd), L.ptr(wd), L.ptr(bd), None, L.ptr(yd), 0, L.ptr(stats), mode, sptr())
+    tol = 2e-5 if mode == 0 else 4e-3       # tf32 inputs: 10-bit mantissa
+    e_y = relerr(yd.cpu(), y.detach())
+    ys = y.detach().reshape(-1, Cout)
+    e_s = relerr(stats.cpu()[:Cout], ys.sum(0))
+    e_q = relerr(stats.cpu()[Cout:], (ys ** 2).sum(0))
+    dxd = torch.full((N, H, W, Cin), 7.0, device='cuda')
+    L.call('se_conv2d_dgrad', d, L.ptr(dyd), L.ptr(wd), L.ptr(dxd), 0.0, mode, sptr())
+    e_dx = relerr(dxd.cpu(), grads[0])
+    # beta = 1 accumulates
+    L.call('se_conv2d_dgrad', d, L.ptr(dyd), L.ptr(wd), L.ptr(dxd), 1.0, mode, sptr())
+    e_dx2 = relerr(dxd.cpu(), 2 * grads[0])
+    dwd = torch.zeros(k, k, Cin, Cout, device='cuda')
+    dbd = torch.zeros(Cout, device='cuda') if b is not None else None
+    L.call('se_conv2d_wgrad', d, L.ptr(xd), L.ptr(dyd), L.ptr(dwd), L.ptr(dbd), mode, sptr())
+    e_dw = relerr(dwd.cpu(), grads[1])
+    e_db = relerr(dbd.cpu(), grads[2]) if b is not None else 0.0
+    report('conv', case=str(case), mode=mode, y=e_y, sum=e_s, sumsq=e_q, dx=e_dx, dw=e_dw, db=e_db)
+    assert e_y < tol and e_dx < tol and e_dx2 < tol and e_dw < tol and e_db < tol, (e_y, e_dx, e_dx2, e_dw, e_db)
+    assert e_s < max(tol, 1e-4) and e_q < tol * 2, (e_s, e_q)
+
+
+def test_conv_epilogue_bias_relu_residual_stats():
+    from oracle import nn as onn
+    L = _lib()
+    g = torch.Generator().manual_seed(5)
+    N, H, W, Cin, Cout = 3, 8, 8, 16, 32
+    x = torch.randn(N, H, W, Cin, generator=g, dtype=torch.float64)
+    w = torch.randn(3, 3, Cin, Cout, generator=g, dtype=torch.float64) * 0.1
+    b = torch.randn(Cout, generator=g, dtype=torch.float64)
+    r = torch.randn(N, H, W, Cout, generator=g, dtype=torch.float64)
+    y = torch.relu(onn.conv2d(x, w, b, 1, 'same') + r)
+    d = L.ConvDesc(N, H, W, Cin, Cout, 3, 3, 1, 1, 1, H, W)
+    yd = torch.empty(N, H, W, Cout, device='cuda')
+    stats = torch.zeros(2 * Cout, dtype=torch.float64, device='cuda')
+    xd, wd, bd, rd = dev(x), dev(w), dev(b), dev(r)
+    L.call('se_conv2d_fwd', d, L.ptr(xd), L.ptr(wd), L.ptr(bd), L.ptr(rd), L.ptr(yd), 1, L.ptr(stats), 0, sptr())
+    assert relerr(yd.cpu(), y) < 2e-5
+    ys = y.reshape(-1, Cout)
+    assert relerr(stats.cpu()[:Cout], ys.sum(0)) < 1e-5
+    assert relerr(stats.cpu()[Cout:], (ys ** 2).sum(0)) < 1e-5
+
+
+def test_conv_rejects_bad_descriptor():
+    L = _lib()
+    d = L.ConvDesc(1, 8, 8, 4, 4, 3, 3, 1, 1, 1, 20, 8)      # Ho inconsistent
+    t = torch.zeros(8, device='cuda')
+    rc = L.load().se_conv2d_fwd(d, L.ptr(t), L.ptr(t), None, None, L.ptr(t), 0, None, 0, sptr())
+    assert rc == -1 and b'inconsistent' in L.load().se_last_error()
+
+
+BN_CASES = [
+    # rows-shape (N,H,W,C), relu, residual kind, relu_in
+    ((4, 8, 8, 16), True, None, False),
+    ((4, 8, 8, 16), True, 'same', False),
+    ((4, 8, 8, 32), True, 'poolpad', False),     # AvgPool2 + ChannelPadding(8,8) shortcut (cifar_resnet.py:117-121)
+    ((4, 8, 8, 64), False, None, True),          # plainnet: conv+relu -> BN
+    ((16, 1, 1, 512), False, None, True),        # fc512 + relu -> BN on a 2-d tensor
+    ((6, 1, 1, 555), False, None, False),        # C not a multiple of 4 (cls head BN on NABirds)
+    ((2, 5, 3, 24), True, 'same', False),
+]
+
+
+@pytest.mark.parametrize('case', BN_CASES, ids=lambda c: '%s-%s-%s' % ('x'.join(map(str, c[0])), c[2], c[3]))
+def test_bn_train_forward_backward(case):
+    from oracle import nn as onn
+    L = _lib()
+    (N, H, W, C), relu, reskind, relu_in = case
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn(N, H, W, C, generator=g, dtype=torch.float64) * 1.7 + 0.3
+    if relu_in:
+        x = torch.relu(x)
+    pre = x.clone().requires_grad_(True)     # gradient wrt the pre-relu tensor is what the kernel returns with relu_in
+    xin = torch.relu(pre) if relu_in else pre
+    if relu_in:
+        # make the relu mask well defined: pre == relu output, zeros stay zeros
+        pass
+    gamma = (torch.rand(C, generator=g, dtype=torch.float64) + 0.5).requires_grad_(True)
+    beta = (torch.randn(C, generator=g, dtype=torch.float64) * 0.1).requires_grad_(True)
+    eps, momentum = 1e-3, 0.99
+    res = None
+    rC, pad_lo, pool = 0, 0, 1
+    if reskind == 'same':
+        res = torch.randn(N, H, W, C, generator=g, dtype=torch.float64).requires_grad_(True)
+        rC = C
+        rterm = res
+    elif reskind == 'poolpad':
+        rC, pad_lo, pool = C // 2, C // 4, 2
+        res = torch.randn(N, 2 * H, 2 * W, rC, generator=g, dtype=torch.float64).requires_grad_(True)
+        rterm = onn.channel_pad(onn.avgpool2(res, 2), pad_lo, C - rC - pad_lo)
+    y, mean, var = onn.batchnorm_train(xin, gamma, beta, eps)
+    if res is not None:
+        y = y + rterm
+    if relu:
+        y = torch.relu(y)
+    dout = torch.randn(y.shape, generator=g, dtype=torch.float64)
+    wrt = [pre, gamma, beta] + ([res] if res is not None else [])
+    grads = torch.autograd.grad(y, wrt, dout)
+    rows = N * H * W
+    xd = dev(x)
+    stats = torch.zeros(2 * C, dtype=torch.float64, device='cuda')
+    L.call('se_bn_stats', L.ptr(xd), rows, C, L.ptr(stats), sptr())
+    xs = x.reshape(-1, C)
+    assert relerr(stats.cpu()[:C], xs.sum(0)) < 1e-5
+    assert relerr(stats.cpu()[C:], (xs ** 2).sum(0)) < 1e-5
+    gd, bd = dev(gamma.detach()), dev(beta.detach())
+    mm = torch.zeros(C, device='cuda')
+    mv = torch.ones(C, device='cuda')
+    sm = torch.empty(C, device='cuda')
+    si = torch.empty(C, device='cuda')
+    yd = torch.empty(N, H, W, C, device='cuda')
+    resd = dev(res.detach()) if res is not None else None
+    r = L.Residual(L.ptr(resd), rC, pad_lo, pool, H, W)
+    L.call('se_bn_fwd_train', L.ptr(xd), rows, C, L.ptr(stats), L.ptr(gd), L.ptr(bd), eps, momentum, L.ptr(mm), L.ptr(mv),
+           L.ptr(sm), L.ptr(si), r, int(relu), L.ptr(yd), sptr())
+    e_y = relerr(yd.cpu(), y.detach())
+    e_mean = relerr(sm.cpu(), mean.detach())
+    e_istd = relerr(si.cpu(), torch.rsqrt(var.detach() + eps))
+    e_mm = relerr(mm.cpu(), onn.moving_update(torch.zeros(C, dtype=torch.float64), mean.detach(), momentum))
+    e_mv = relerr(mv.cpu(), onn.moving_update(torch.ones(C, dtype=torch.float64),
+                                                onn.unbiased_var(var.detach(), rows, eps), momentum))
+    # backward
+    doutd = dev(dout)
+    dxd = torch.full((N, H, W, C), 3.0, device='cuda')
+    dgd = torch.zeros(C, device='cuda')
+    dbd = torch.zeros(C, device='cuda')
+    scratch = torch.zeros(2 * C, dtype=torch.float64, device='cuda')
+    dresd = None
+    if reskind == 'same':
+        dresd = torch.full((N, H, W, C), 5.0, device='cuda')
+    L.call('se_bn_bwd', L.ptr(xd), L.ptr(yd), L.ptr(doutd), rows, C, L.ptr(gd), L.ptr(sm), L.ptr(si), int(relu), int(relu_in),
+           L.ptr(dxd), 0.0, L.ptr(dresd), 0.0, L.ptr(dgd), L.ptr(dbd), L.ptr(scratch), sptr())
+    e_dx = relerr(dxd.cpu(), grads[0])
+    e_dg = relerr(dgd.cpu(), grads[1])
+    e_db = relerr(dbd.cpu(), grads[2])
+    e_dr = 0.0
+    if reskind == 'same':
+        e_dr = relerr(dresd.cpu(), grads[3])
+    elif reskind == 'poolpad':
+        dsrc = torch.full((N, 2 * H, 2 * W, rC), 9.0, device='cuda')
+        L.call('se_shortcut_bwd', L.ptr(doutd), L.ptr(yd), int(relu), N, H, W, C, r, L.ptr(dsrc), 0.0, sptr())
+        e_dr = relerr(dsrc.cpu(), grads[3])
+    report('bn', case=str(case), y=e_y, mean=e_mean, invstd=e_istd, dx=e_dx, dgamma=e_dg, dbeta=e_db, dres=e_dr)
+    assert max(e_y, e_mean, e_istd, e_mm, e_mv) < 2e-5, (e_y, e_mean, e_istd, e_mm, e_mv)
+    assert max(e_dx, e_dg, e_db, e_dr) < 5e-5, (e_dx, e_dg, e_db, e_dr)
+    # inference mode uses the moving statistics
+    yi = onn.batchnorm_infer(x, gamma.detach(), beta.detach(), mm.cpu().double(), mv.cpu().double(), eps)
+    if res is not None:
+        yi = yi + rterm.detach()
+    if relu:
+        yi = torch.relu(yi)
+    L.call('se_bn_fwd_infer', L.ptr(xd), rows, C, L.ptr(gd), L.ptr(bd), L.ptr(mm), L.ptr(mv), eps, r, int(relu), L.ptr(yd), sptr())
+    assert relerr(yd.cpu(), yi) < 2e-5
+
+
+def test_pools_and_elementwise():
+    from oracle import nn as onn
+    L = _lib()
+    g = torch.Generator().manual_seed(3)
+    N, H, W, C = 3, 8, 6, 20
+    x = torch.randn(N, H, W, C, generator=g, dtype=torch.float64, requires_grad=True)
+    xd = dev(x.detach())
+    # average pooling 2x2
+    y = onn.avgpool2(x)
+    dy = torch.randn(y.shape, generator=g, dtype=torch.float64)
+    (gx,) = torch.autograd.grad(y, x, dy)
+    yd = torch.empty(N, H // 2, W // 2, C, device='cuda')
+    L.call('se_avgpool2_fwd', L.ptr(xd), L.ptr(yd), N, H, W, C, sptr())
+    assert relerr(yd.cpu(), y.detach()) < 1e-6
+    dxd = torch.ones(N, H, W, C, device='cuda')
+    L.call('se_avgpool2_bwd', L.ptr(dev(dy)), L.ptr(dxd), 1.0, N, H, W, C, sptr())
+    assert relerr(dxd.cpu(), gx + 1.0) < 1e-6
+    # global average pooling
+    y = onn.gap(x)
+    dy = torch.randn(y.shape, generator=g, dtype=torch.float64)
+    (gx,) = torch.autograd.grad(y, x, dy)
+    yd = torch.empty(N, C, device='cuda')
+    L.call('se_gap_fwd', L.ptr(xd), L.ptr(yd), N, H * W, C, sptr())
+    assert relerr(yd.cpu(), y.detach()) < 1e-6
+    dxd = torch.empty(N, H, W, C, device='cuda')
+    L.call('se_gap_bwd', L.ptr(dev(dy)), L.ptr(dxd), 0.0, N, H * W, C, sptr())
+    assert relerr(dxd.cpu(), gx) < 1e-6
+    # max pooling 3x3 / 2 'valid'
+    y = onn.maxpool(x, 3, 2)
+    dy = torch.randn(y.shape, generator=g, dtype=torch.float64)
+    (gx,) = torch.autograd.grad(y, x, dy)
+    Ho, Wo = y.shape[1], y.shape[2]
+    yd = torch.empty(N, Ho, Wo, C, device='cuda')
+    L.call('se_maxpool_fwd', L.ptr(xd), L.ptr(yd), N, H, W, C, 3, 2, 0, 0, Ho, Wo, sptr())
+    assert relerr(yd.cpu(), y.detach()) == 0.0
+    dxd = torch.empty(N, H, W, C, device='cuda')
+    L.call('se_maxpool_bwd', L.ptr(xd), L.ptr(yd), L.ptr(dev(dy)), L.ptr(dxd), N, H, W, C, 3, 2, 0, 0, Ho, Wo, sptr())
+    assert relerr(dxd.cpu(), gx) < 1e-6
+    # add + relu
+    a = torch.randn(N, H, W, C, generator=g, dtype=torch.float64, requires_grad=True)
+    y = torch.relu(a + x)
+    dy = torch.randn(y.shape, generator=g, dtype=torch.float64)
+    ga, gx = torch.autograd.grad(y, [a, x], dy)
+    yd = torch.empty(N, H, W, C, device='cuda')
+    n = N * H * W * C
+    L.call('se_add_fwd', L.ptr(dev(a.detach())), L.ptr(xd), L.ptr(yd), n, 1, sptr())
+    assert relerr(yd.cpu(), y.detach()) < 1e-6
+    dad = torch.empty(N, H, W, C, device='cuda')
+    dbd = torch.ones(N, H, W, C, device='cuda')
+    L.call('se_add_bwd', L.ptr(dev(dy)), L.ptr(yd), 1, L.ptr(dad), 0.0, L.ptr(dbd), 1.0, n, sptr())
+    assert relerr(dad.cpu(), ga) < 1e-6 and relerr(dbd.cpu(), gx + 1.0) < 1e-6
+
+
+def _head_oracle(z, labels, emb, kind, scale, extra):
+    from oracle import nn as onn
+    from oracle import train as otrain
+    z = z.clone().requires_grad_(True)
+    x = otrain.head_forward(z, kind)
+    t = emb[labels]
+    ls = otrain.per_sample_loss(t, x, kind)
+    acc = onn.nn_accuracy(emb, t, x) if kind == 'mse' else onn.max_sim_acc(emb, t, x)
+    obj = scale * ls.sum()
+    if extra is not None:
+        obj = obj + (x * extra).sum()
+    (dz,) = torch.autograd.grad(obj, z)
+    return x.detach(), ls.detach(), acc, dz
+
+
+@pytest.mark.parametrize('shape', [(128, 100, 100, 'cifar100'), (32, 555, 555, 'nab'), (7, 100, 100, 'cifar100')],
+                         ids=['cifar-b128', 'nab-b32', 'ragged-b7'])
+@pytest.mark.parametrize('kind', ['inv_corr', 'unnorm_corr', 'mse'])
+@pytest.mark.parametrize('with_extra', [False, True], ids=['plain', 'extra_dx'])
+def test_embed_head_matches_oracle(shape, kind, with_extra):
+    L = _lib()
+    from semantic_embeddings_b200.engine import LOSS_KINDS
+    B, D, C, key = shape
+    emb64 = torch.as_tensor(np.load(os.path.join(G, 'class_matrices.npz'))[key + '_embedding'])
+    emb32 = emb64.float().double()                      # the kernel sees the fp32 cast (learn_image_embeddings.py feeds fp32)
+    g = torch.Generator().manual_seed(B + D)
+    z = torch.randn(B, D, generator=g, dtype=torch.float64)
+    labels = torch.randint(0, C, (B,), generator=g)
+    z[0] = emb32[labels[0]] * 2.5                       # exactly-correct sample: accuracy 1
+    if B > 4:
+        z[3] = 0.0                                      # sum z^2 < 1e-12 clamp (utils.py:127 / tf.nn.l2_normalize)
+        z[4] = z[4] * 1e-9
+    z = z.float().double()
+    scale = 1.0 / B
+    extra = torch.randn(B, D, generator=g, dtype=torch.float64).float().double() * 0.01 if with_extra else None
+    x_ref, ls_ref, acc_ref, dz_ref = _head_oracle(z, labels, emb32, kind, scale, extra)
+    zd, ed, ld = dev(z), dev(emb32), dev(labels, torch.int32)
+    exd = dev(extra) if with_extra else None
+    xo = torch.empty(B, D, device='cuda')
+    lo = torch.empty(B, device='cuda')
+    ao = torch.empty(B, device='cuda')
+    dzo = torch.empty(B, D, device='cuda')
+    L.call('se_embed_head_fwd_bwd', L.ptr(zd), D, L.ptr(ld), L.ptr(ed), D, B, D, C, LOSS_KINDS[kind], scale, L.ptr(exd),
+           L.ptr(xo), L.ptr(lo), L.ptr(ao), L.ptr(dzo), sptr())
+    e_x = relerr(xo.cpu(), x_ref)
+    e_l = float(np.abs(lo.cpu().numpy() - ls_ref.numpy()).max() / max(1.0, np.abs(ls_ref.numpy()).max()))
+    e_dz = relerr(dzo.cpu(), dz_ref)
+    # the 0/1 accuracy may legitimately differ only where |best - true| sits within fp32 noise of the 1e-6 threshold
+    acc_got = ao.cpu().numpy()
+    sim = (x_ref @ emb32.t()).numpy() if kind != 'mse' else None
+    mism = int((acc_got != acc_ref.numpy()).sum())
+    report('head', shape=str(shape), kind=kind, extra=with_extra, x=e_x, loss=e_l, dz=e_dz, acc_mismatch=mism)
+    assert e_x < 2e-6 and e_l < 2e-6, (e_x, e_l)
+    assert e_dz < 1e-5, e_dz
+    assert acc_got[0] == 1.0
+    assert mism <= max(1, B // 50), mism
+
+
+def test_embed_head_matches_reference_formulas_fixture():
+    """Fixture produced by the reference's own utils.l2norm / inv_correlation / nn_accuracy (make_golden.py)."""
+    L = _lib()
+    d = np.load(os.path.join(G, 'formulas_ref.npz'))
+    emb = np.load(os.path.join(G, 'class_matrices.npz'))['cifar100_embedding']
+    z = d['z'].astype(np.float32)
+    B, D = z.shape
+    zd, ed, ld = dev(z), dev(emb), dev(d['labels'], torch.int32)
+    xo = torch.empty(B, D, device='cuda')
+    lo = torch.empty(B, device='cuda')
+    ao = torch.empty(B, device='cuda')
+    L.call('se_embed_head_fwd_bwd', L.ptr(zd), D, L.ptr(ld), L.ptr(ed), D, B, D, 100, 0, 1.0 / B, None,
+           L.ptr(xo), L.ptr(lo), L.ptr(ao), None, sptr())
+    assert np.abs(xo.cpu().numpy() - d['l2norm']).max() < 2e-6
+    assert np.abs(lo.cpu().numpy() - d['inv_correlation']).max() < 2e-6
+    assert (ao.cpu().numpy() != d['max_sim_acc']).sum() <= 1
+
+
+def test_softmax_xent_matches_oracle():
+    from oracle import nn as onn
+    L = _lib()
+    g = torch.Generator().manual_seed(2)
+    B, C = 37, 100
+    logits = (torch.randn(B, C, generator=g, dtype=torch.float64) * 3).float().double()
+    labels = torch.randint(0, C, (B,), generator=g)
+    logits[1, labels[1]] = 40.0            # p_y > 1 - 1e-7: clip active, zero gradient
+    logits[2, labels[2]] = -40.0           # p_y < 1e-7
+    lg = logits.clone().requires_grad_(True)
+    prob = torch.softmax(lg, -1)
+    onehot = torch.nn.functional.one_hot(labels, C).double()
+    ce = onn.categorical_crossentropy(onehot, prob)
+    scale = 0.1 / B
+    (dl,) = torch.autograd.grad(scale * ce.sum(), lg)
+    ld, yd = dev(logits), dev(labels, torch.int32)
+    po = torch.empty(B, C, device='cuda')
+    lo = torch.empty(B, device='cuda')
+    ao = torch.empty(B, device='cuda')
+    do = torch.empty(B, C, device='cuda')
+    L.call('se_softmax_xent_fwd_bwd', L.ptr(ld), C, L.ptr(yd), B, C, scale, L.ptr(po), L.ptr(lo), L.ptr(ao), L.ptr(do), sptr())
+    assert relerr(po.cpu(), prob.detach()) < 2e-6
+    assert np.abs(lo.cpu().numpy() - ce.detach().numpy()).max() < 2e-5
+    assert relerr(do.cpu(), dl) < 2e-5
+    np.testing.assert_array_equal(ao.cpu().numpy(), (prob.argmax(-1) == labels).double().numpy())
+
+
+@pytest.mark.parametrize('nesterov', [False, True])
+@pytest.mark.parametrize('big_grad', [False, True], ids=['noclip', 'clip'])
+def test_sgd_step_matches_oracle(nesterov, big_grad):
+    from oracle import train as otrain
+    L = _lib()
+    g = torch.Generator().manual_seed(9)
+    n = 10007
+    p = torch.randn(n, generator=g, dtype=torch.float64).float().double()
+    gr = (torch.randn(n, generator=g, dtype=torch.float64) * (1.0 if big_grad else 0.01)).float().double()
+    v = (torch.randn(n, generator=g, dtype=torch.float64) * 0.1).float().double()
+    segs = [(0, 4000, 5e-4), (4000, 6000, 2e-4)]
+    gref = gr.clone()
+    reg = 0.0
+    for b, e, l in segs:
+        gref[b:e] += 2 * l * p[b:e]
+        reg += l * float((p[b:e] ** 2).sum())
+    P, Gd, V = {'w': p.clone()}, {'w': gref.clone()}, {'w': v.clone()}
+    norm = otrain.sgd_step(P, Gd, V, lr=0.05, momentum=0.9, nesterov=nesterov, clipnorm=10.0)
+    assert (norm >= 10.0) == big_grad
+    pd, gd, vd = dev(p), dev(gr), dev(v)
+    out = torch.zeros(2, dtype=torch.float64, device='cuda')
+    arr = (L.L2Segment * 2)()
+    for k, (b, e, l) in enumerate(segs):
+        arr[k].begin, arr[k].end, arr[k].l2 = b, e, l
+    L.call('se_sgd_step', L.ptr(pd), L.ptr(gd), L.ptr(vd), n, arr, 2, 0.05, 0.9, int(nesterov), 10.0, L.ptr(out), sptr())
+    o = out.cpu().numpy()
+    assert abs(np.sqrt(o[0]) - norm) / norm < 1e-6
+    assert abs(o[1] - reg) / reg < 1e-6
+    assert relerr(pd.cpu(), P['w']) < 2e-6
+    assert relerr(vd.cpu(), V['w']) < 2e-6
+
+
+@pytest.mark.parametrize('mode', [0, 1], ids=['f32', 'tf32x3'])
+def test_pairwise_matches_reference_rankings(mode):
+    """Distances vs the float64 oracle and rankings vs the fixture produced by the reference's own
+    evaluate_retrieval.pairwise_retrieval (bit-exact wherever the float64 gap exceeds the kernel error)."""
+    from oracle import retrieval as oret
+    L = _lib()
+    d = np.load(os.path.join(G, 'retrieval_ref.npz'))
+    for key, feat, normalize, pmode in (('rank_sq', d['feat'], 0, 0), ('rank_cos', d['feat'], 1, 1),
+                                        ('rank_sq_unit', d['feat_unit'], 0, 0)):
+        N, D = feat.shape
+        fd = dev(feat)
+        ws = torch.zeros(int(L.load().se_pairwise_workspace_bytes(N, D, mode)), dtype=torch.uint8, device='cuda')
+        out = torch.empty(N, N, device='cuda')
+        L.call('se_pairwise_dist', L.ptr(fd), D, N, D, 0, N, pmode, normalize, L.ptr(out), N, L.ptr(ws), mode, sptr())
+        got = out.cpu().numpy()
+        ref64 = oret.pairwise_dist64(feat, bool(normalize))
+        err = float(np.abs(got - ref64).max())
+        scale = float(np.abs(ref64).max())
+        rank_got = np.argsort(got, axis=-1, kind='stable')
+        rank_ref = d[key].astype(np.int64)
+        mism = rank_got != rank_ref
+        # positions whose float64 neighbours are further apart than 4x the kernel error must agree
+        d_sorted = np.take_along_axis(ref64, rank_ref, -1)
+        gap = np.minimum(np.diff(d_sorted, axis=-1, prepend=-np.inf), np.diff(d_sorted, axis=-1, append=np.inf))
+        unambiguous = gap > 4 * err + 1e-7 * scale
+        report('pairwise', key=key, mode=mode, max_abs_err=err, scale=scale, rank_mismatch=float(mism.mean()),
+               unambiguous=float(unambiguous.mean()))
+        assert err < 3e-6 * max(1.0, scale), err
+        assert not (mism & unambiguous).any()
+        assert unambiguous.mean() > 0.9
+    # row-block call (multi-GPU sharding unit): rows [64, 160)
+    feat = d['feat']
+    N, D = feat.shape
+    fd = dev(feat)
+    ws = torch.zeros(int(L.load().se_pairwise_workspace_bytes(N, D, mode)), dtype=torch.uint8, device='cuda')
+    full = torch.empty(N, N, device='cuda')
+    L.call('se_pairwise_dist', L.ptr(fd), D, N, D, 0, N, 0, 0, L.ptr(full), N, L.ptr(ws), mode, sptr())
+    blk = torch.empty(96, N, device='cuda')
+    L.call('se_pairwise_dist', L.ptr(fd), D, N, D, 64, 96, 0, 0, L.ptr(blk), N, L.ptr(ws), mode, sptr())
+    np.testing.assert_array_equal(blk.cpu().numpy(), full.cpu().numpy()[64:160])
+
+
+@pytest.mark.parametrize('mode', [0, 1], ids=['f32', 'tf32x3'])
+def test_pairwise_ragged_sizes(mode):
+    from oracle import retrieval as oret
+    L = _lib()
+    rng = np.random.RandomState(4)
+    for N, D in ((1, 5), (37, 3), (130, 64), (257, 100), (300, 129)):
+        feat = rng.randn(N, D).astype(np.float32)
+        fd = dev(feat)
+        ws = torch.zeros(int(L.load().se_pairwise_workspace_bytes(N, D, mode)), dtype=torch.uint8, device='cuda')
+        out = torch.full((N, N), np.nan, device='cuda')
+        L.call('se_pairwise_dist', L.ptr(fd), D, N, D, 0, N, 0, 0, L.ptr(out), N, L.ptr(ws), mode, sptr())
+        ref = oret.pairwise_dist64(feat, False)
+        got = out.cpu().numpy()
+        assert np.isfinite(got).all()
+        assert np.abs(got - ref).max() < 3e-6 * max(1.0, np.abs(ref).max()), (N, D)
