@@ -52,6 +52,8 @@ const char* se_last_error(void);
 /* number of kernel launches issued by this library since load (for bench.py's gpu_launches) */
 int64_t se_launch_count(void);
 int se_device_sm_count(void);
+/* one-time per-process setup (device query, shared-memory attributes); call before capturing CUDA graphs */
+int se_init(void);
 /* bit mask of the tcgen05 kernels compiled in: 1 conv fwd, 2 conv dgrad, 4 conv wgrad, 8 pairwise */
 int se_tc_capabilities(void);
 

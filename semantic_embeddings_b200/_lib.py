@@ -47,6 +47,7 @@ _SIGS = {
     'se_last_error': (c_char_p, []),
     'se_launch_count': (c_int64, []),
     'se_device_sm_count': (c_int, []),
+    'se_init': (c_int, []),
     'se_tc_capabilities': (c_int, []),
     'se_conv2d_fwd': (c_int, [POINTER(ConvDesc), _P, _P, _P, _P, _P, c_int, _P, c_int, _P]),
     'se_conv2d_dgrad': (c_int, [POINTER(ConvDesc), _P, _P, _P, c_float, c_int, _P]),

@@ -65,6 +65,16 @@ extern "C" const char* se_version(void) { return "se_b200 0.1 (sm_100a)"; }
 extern "C" const char* se_last_error(void) { return g_err; }
 extern "C" int64_t se_launch_count(void) { return g_launches.load(); }
 extern "C" int se_device_sm_count(void) { return sm_count(); }
+namespace se { int init_conv_simt(); int init_pairwise_tc(); int init_conv_tc(); }
+// One-time per-process setup that must not happen inside a CUDA-graph capture: device query and the
+// cudaFuncSetAttribute calls of every kernel that needs more than 48 KB of dynamic shared memory.
+extern "C" int se_init(void) {
+  sm_count();
+  int rc = se::init_conv_simt();
+  if (rc == SE_OK) rc = se::init_pairwise_tc();
+  if (rc == SE_OK) rc = se::init_conv_tc();
+  return rc;
+}
 namespace se { int tc_capabilities(); }
 extern "C" int se_tc_capabilities(void) { return se::tc_capabilities(); }
 

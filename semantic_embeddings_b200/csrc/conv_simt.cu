@@ -24,6 +24,9 @@ static ConvP to_p(const se_conv_desc* d) {
   return p;
 }
 
+constexpr size_t WGRAD3X3_MAX_SMEM = 160 * 1024;
+int init_conv_simt();
+
 // ---------------------------------------------------------------------------------------- forward
 template <int BM, int BN, int TM, int TN, bool VEC>
 __global__ void __launch_bounds__((BM / TM) * (BN / TN))
@@ -461,6 +464,16 @@ conv_wgrad3x3_kernel(ConvP p, const float* __restrict__ x, const float* __restri
 }
 
 // ---------------------------------------------------------------------------------------- launchers
+int init_conv_simt() {
+  cudaError_t e = cudaSuccess;
+  auto set = [&](auto kern) {
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WGRAD3X3_MAX_SMEM);
+  };
+  set(conv_wgrad3x3_kernel<1, 1>); set(conv_wgrad3x3_kernel<1, 2>); set(conv_wgrad3x3_kernel<2, 1>); set(conv_wgrad3x3_kernel<2, 2>);
+  if (e != cudaSuccess) { set_error("init_conv_simt: %s", cudaGetErrorString(e)); return SE_ERR_CUDA; }
+  return SE_OK;
+}
+
 template <int BM, int BN, int TM, int TN>
 static int launch_fwd(const ConvP& p, const float* x, const float* w, const float* bias, const float* residual,
                       float* y, int relu, double* stats, cudaStream_t st) {
@@ -512,13 +525,10 @@ static int launch_wgrad3x3(const ConvP& p, const float* x, const float* dy, floa
   int cy = p.Cin / CIT, cz = p.Cout / COT;
   int gx = min(num_tiles, max(1, (2 * sm_count()) / (cy * cz)));
   auto kern = conv_wgrad3x3_kernel<CI_T, CO_T>;
-  if (smem > 48 * 1024) {
-    if (smem > 200 * 1024) return SE_ERR_UNSUPPORTED;
-    static int configured = 0;   // per instantiation; set once, outside any later graph capture
-    if (configured < (int)smem) {
-      cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      configured = (int)smem;
-    }
+  if (smem > WGRAD3X3_MAX_SMEM) return SE_ERR_UNSUPPORTED;
+  if (smem > 48 * 1024) {   // attribute normally raised by se_init(); direct C-ABI callers get it lazily
+    static bool inited = false;
+    if (!inited) { int rc = init_conv_simt(); if (rc) return rc; inited = true; }
   }
   kern<<<dim3(gx, cy, cz), 256, smem, st>>>(p, x, dy, dw, dbias, TH, tiles_per_img, num_tiles);
   return check_launch("conv_wgrad3x3_kernel");

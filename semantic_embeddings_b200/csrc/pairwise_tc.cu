@@ -1,8 +1,304 @@
+// All-pairs distance (evaluate_retrieval.py:56-63) on the 5th-gen tensor cores -- SE_MODE_TF32 path.
+//
+// Arithmetic: "split-fp16 x3".  After a global power-of-two scaling that brings max|f| <= 1, every fp32
+// feature value f is split into h = fp16(f) and l = fp16(f - h) (11 + 11 significand bits, the low part
+// may be subnormal: absolute error <= 2^-25).  The fp32 product sum is recovered from three fp16 tensor-core
+// products accumulated in ONE fp32 TMEM accumulator:  F F^T ~= Fh Fh^T + Fh Fl^T + Fl Fh^T  (missing l*l term
+// <= 2^-24).  kind::f16 moves 2 bytes per element and runs at twice the TF32 rate, which is what keeps the
+// contraction hidden behind the fp32 output stream (4 bytes per pair -- the HBM roofline of this kernel).
+//
+// Structure (one persistent CTA per SM, 256 threads, warp-specialised):
+//   warp 0 : TMA producer -- A row block (128 rows, h and l, all K) stays RESIDENT while the CTA sweeps the
+//            column tiles; B tiles (256 rows) stream through a 2-stage ring, one 64-wide K block per stage
+//   warp 1 : single-thread tcgen05.mma issuer, M=128 N=256 K=16, accumulators double-buffered in TMEM (2 x 256 cols)
+//   warp 2 : TMEM allocator
+//   warps 4-11: epilogue -- warp w owns TMEM lanes 32*(w%4).. and one half of the 256 columns; per 32x32 block:
+//            tcgen05.ld, apply norms / sign, write a private swizzled 4 KB staging buffer, TMA store it
+//            (coalesced 128-byte rows; out-of-range rows/columns clipped by the tensor map).  No cross-warp barriers.
+#include <cuda_fp16.h>
+
 #include "common.cuh"
+#include "tc.cuh"
+
 namespace se {
-long long pairwise_tc_workspace_floats(int N, int D) { return 0; }
-int pairwise_tc(const float*, int, int, int, int, int, int, int, float*, long long, float*, cudaStream_t) {
-  set_error("pairwise tensor-core path not built");
-  return SE_ERR_UNSUPPORTED;
+
+using namespace tc;
+
+constexpr int PW_BM = 128, PW_BN = 256, PW_KB = 64;     // K block = 64 halfs = 128 bytes (SWIZZLE_128B row)
+constexpr int PW_MAXKB = 2;                              // resident A: at most 2 K blocks (D <= 128)
+constexpr int PW_STAGES = 2;
+constexpr int PW_A_BYTES = PW_BM * 128;                  // one K block of A (h or l): 16 KB
+constexpr int PW_B_BYTES = PW_BN * 128;                  // one K block of B (h or l): 32 KB
+constexpr int PW_EPI_WARPS = 8;
+constexpr int PW_OUT_BYTES = 32 * 128;                   // per-warp staging: 32 rows x 32 fp32 = 4 KB
+constexpr int PW_SMEM = 2 * PW_MAXKB * PW_A_BYTES + PW_STAGES * 2 * PW_B_BYTES + PW_EPI_WARPS * PW_OUT_BYTES + 1024 /*align*/ + 256;
+
+struct PwParams {
+  int N, row0, rows, pmode, tiles_m, tiles_n, kblocks, ksteps_total;
+  const float* sq;       // squared norms of the (normalised) rows, [N]
+  const float* scal;     // scal[1] = 4^e: undoes the power-of-two input scaling
+};
+
+// ---- prep: fp32 features -> scaled fp16 (h, l) matrices with row pitch KW
+__global__ void __launch_bounds__(256)
+pairwise_absmax_kernel(const float* __restrict__ F, int ldF, int N, int D, const float* __restrict__ norms,
+                       unsigned* __restrict__ absmax_bits) {
+  float m = 0.f;
+  const long long total = (long long)N * D;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    int r = (int)(e / D), k = (int)(e % D);
+    m = fmaxf(m, fabsf(F[(long long)r * ldF + k] / norms[r]));
+  }
+  m = warp_max(m);
+  if ((threadIdx.x & 31) == 0 && m > 0.f && m < 3.0e38f) atomicMax(absmax_bits, __float_as_uint(m));
 }
+
+__global__ void __launch_bounds__(256)
+pairwise_split_kernel(const float* __restrict__ F, int ldF, int N, int D, int KW, const float* __restrict__ norms,
+                      float* __restrict__ scal, __half* __restrict__ Fh, __half* __restrict__ Fl) {
+  // scal[0] holds the bit pattern of max|f| (0 if the matrix is all zero)
+  float amax = __uint_as_float(reinterpret_cast<const unsigned*>(scal)[0]);
+  int e = 0;
+  if (amax > 0.f) frexpf(amax, &e);            // amax = m * 2^e, m in [0.5, 1)  =>  amax * 2^-e < 1
+  const float s = ldexpf(1.f, -e);
+  if (blockIdx.x == 0 && threadIdx.x == 0) scal[1] = ldexpf(1.f, 2 * e);
+  const long long total = (long long)N * KW;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    int r = (int)(idx / KW), k = (int)(idx % KW);
+    float v = 0.f;
+    if (k < D) v = (F[(long long)r * ldF + k] / norms[r]) * s;
+    __half h = __float2half_rn(v);
+    __half l = __float2half_rn(v - __half2float(h));
+    Fh[idx] = h;
+    Fl[idx] = l;
+  }
+}
+
+// ---- main kernel
+__global__ void __launch_bounds__(128 + 32 * PW_EPI_WARPS, 1)
+pairwise_tc_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_constant__ CUtensorMap map_l,
+                   const __grid_constant__ CUtensorMap map_out, PwParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* sA = smem;                                            // [h|l][kb] x 16 KB
+  uint8_t* sB = sA + 2 * PW_MAXKB * PW_A_BYTES;                  // [stage][h|l] x 32 KB
+  uint8_t* sOut = sB + PW_STAGES * 2 * PW_B_BYTES;               // [PW_EPI_WARPS] x 4 KB
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sOut + PW_EPI_WARPS * PW_OUT_BYTES);
+  uint64_t* full = bars;                 // [PW_STAGES]
+  uint64_t* empty = bars + PW_STAGES;    // [PW_STAGES]
+  uint64_t* a_full = bars + 2 * PW_STAGES;
+  uint64_t* a_empty = a_full + 1;
+  uint64_t* t_full = a_empty + 1;        // [2]
+  uint64_t* t_empty = t_full + 2;        // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int total_tiles = p.tiles_m * p.tiles_n;
+  const int per_cta = (total_tiles + gridDim.x - 1) / gridDim.x;
+  const int t_begin = blockIdx.x * per_cta;
+  const int t_end = min(total_tiles, t_begin + per_cta);
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&map_h); prefetch_tmap(&map_l); prefetch_tmap(&map_out);
+    for (int s = 0; s < PW_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    mbar_init(a_full, 1); mbar_init(a_empty, 1);
+    for (int a = 0; a < 2; ++a) { mbar_init(&t_full[a], 1); mbar_init(&t_empty[a], 32 * PW_EPI_WARPS); }
+    fence_barrier_init();
+    fence_proxy_async();
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, 512);
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0 && lane == 0) {
+    // ===================== TMA producer
+    int stage = 0, phase = 0, cur_tm = -1, a_phase = 0;
+    for (int t = t_begin; t < t_end; ++t) {
+      const int tm = t / p.tiles_n, tn = t % p.tiles_n;
+      if (tm != cur_tm) {
+        if (cur_tm >= 0) { mbar_wait(a_empty, a_phase); a_phase ^= 1; }   // MMAs reading the old A have retired
+        mbar_expect_tx(a_full, 2 * p.kblocks * PW_A_BYTES);
+        for (int kb = 0; kb < p.kblocks; ++kb) {
+          tma_load_2d(sA + (0 * PW_MAXKB + kb) * PW_A_BYTES, &map_h, a_full, kb * PW_KB, p.row0 + tm * PW_BM);
+          tma_load_2d(sA + (1 * PW_MAXKB + kb) * PW_A_BYTES, &map_l, a_full, kb * PW_KB, p.row0 + tm * PW_BM);
+        }
+        cur_tm = tm;
+      }
+      for (int kb = 0; kb < p.kblocks; ++kb) {
+        mbar_wait(&empty[stage], phase ^ 1);
+        mbar_expect_tx(&full[stage], 2 * PW_B_BYTES);
+        uint8_t* bh = sB + (stage * 2 + 0) * PW_B_BYTES;
+        uint8_t* bl = sB + (stage * 2 + 1) * PW_B_BYTES;
+        tma_load_2d(bh, &map_h, &full[stage], kb * PW_KB, tn * PW_BN);
+        tma_load_2d(bh + PW_A_BYTES, &map_h, &full[stage], kb * PW_KB, tn * PW_BN + 128);
+        tma_load_2d(bl, &map_l, &full[stage], kb * PW_KB, tn * PW_BN);
+        tma_load_2d(bl + PW_A_BYTES, &map_l, &full[stage], kb * PW_KB, tn * PW_BN + 128);
+        if (++stage == PW_STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ===================== MMA issuer (one thread)
+    constexpr uint32_t idesc = umma_idesc(0 /*f16*/, PW_BM, PW_BN);
+    int stage = 0, phase = 0, cur_tm = -1, a_phase = 0, acc = 0, acc_phase = 0;
+    for (int t = t_begin; t < t_end; ++t) {
+      const int tm = t / p.tiles_n;
+      if (tm != cur_tm) { mbar_wait(a_full, a_phase); a_phase ^= 1; cur_tm = tm; }
+      mbar_wait(&t_empty[acc], acc_phase ^ 1);          // epilogue has drained this accumulator
+      fence_after_sync();
+      const uint32_t d_tmem = tmem_base + acc * PW_BN;
+      int ks_done = 0;
+      for (int kb = 0; kb < p.kblocks; ++kb) {
+        mbar_wait(&full[stage], phase);
+        fence_after_sync();
+        const uint32_t ah = smem_u32(sA + (0 * PW_MAXKB + kb) * PW_A_BYTES);
+        const uint32_t al = smem_u32(sA + (1 * PW_MAXKB + kb) * PW_A_BYTES);
+        const uint32_t bh = smem_u32(sB + (stage * 2 + 0) * PW_B_BYTES);
+        const uint32_t bl = smem_u32(sB + (stage * 2 + 1) * PW_B_BYTES);
+        const int nks = min(PW_KB / 16, p.ksteps_total - ks_done);
+        for (int ks = 0; ks < nks; ++ks) {
+          const uint32_t off = ks * 32;                 // 16 halfs = 32 bytes inside the 128-byte swizzled row
+          const uint64_t dah = umma_desc_kmajor(ah + off, 1024, 128), dal = umma_desc_kmajor(al + off, 1024, 128);
+          const uint64_t dbh = umma_desc_kmajor(bh + off, 1024, 128), dbl = umma_desc_kmajor(bl + off, 1024, 128);
+          mma_f16(d_tmem, dah, dbh, idesc, (ks_done + ks) > 0 ? 1u : 0u);
+          mma_f16(d_tmem, dah, dbl, idesc, 1u);
+          mma_f16(d_tmem, dal, dbh, idesc, 1u);
+        }
+        ks_done += nks;
+        mma_commit(&empty[stage]);                      // frees the B stage once these MMAs retire
+        if (++stage == PW_STAGES) { stage = 0; phase ^= 1; }
+      }
+      mma_commit(&t_full[acc]);                         // accumulator complete -> epilogue
+      const bool last_of_row = (t + 1 == t_end) || ((t + 1) / p.tiles_n != tm);
+      if (last_of_row) mma_commit(a_empty);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue (8 warps)
+    const int q4 = warp & 3;                            // TMEM lane quarter this warp may read
+    const int half = (warp - 4) >> 2;                   // which 128-column half of the tile
+    uint8_t* ob = sOut + (warp - 4) * PW_OUT_BYTES;
+    const float s2 = p.scal[1];
+    constexpr int CHUNKS = PW_BN / 2 / 32;              // 4 blocks of 32 columns per warp and tile
+    int acc = 0, acc_phase = 0;
+    for (int t = t_begin; t < t_end; ++t) {
+      const int tm = t / p.tiles_n, tn = t % p.tiles_n;
+      const int r_local = q4 * 32 + lane;               // row inside the tile == TMEM lane
+      const int gi = p.row0 + tm * PW_BM + r_local;
+      const float a_sq = p.sq[gi];                      // (rows past N read workspace padding; clipped at the store)
+      mbar_wait(&t_full[acc], acc_phase);
+      fence_after_sync();
+      for (int c = 0; c < CHUNKS; ++c) {
+        const int col = half * (PW_BN / 2) + c * 32;
+        uint32_t v[32];
+        tmem_ld_32x32(tmem_base + ((uint32_t)(q4 * 32) << 16) + acc * PW_BN + col, v);
+        tmem_ld_wait();
+        if (c == CHUNKS - 1) {                          // this warp is done with the accumulator
+          fence_before_sync();
+          mbar_arrive(&t_empty[acc]);
+        }
+        if (lane == 0) tma_store_wait_read<0>();        // the previous store of this warp has read the buffer
+        __syncwarp();
+        const int j0 = tn * PW_BN + col;
+        const float4* sqj = reinterpret_cast<const float4*>(p.sq + j0);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          float4 b = __ldg(sqj + q);
+          float4 o;
+          float c0 = __uint_as_float(v[4 * q + 0]) * s2, c1 = __uint_as_float(v[4 * q + 1]) * s2;
+          float c2 = __uint_as_float(v[4 * q + 2]) * s2, c3 = __uint_as_float(v[4 * q + 3]) * s2;
+          if (p.pmode == SE_PDIST_NEGDOT) {
+            o = make_float4(-c0, -c1, -c2, -c3);
+          } else {
+            o = make_float4((a_sq + b.x) - 2.f * c0, (a_sq + b.y) - 2.f * c1, (a_sq + b.z) - 2.f * c2, (a_sq + b.w) - 2.f * c3);
+          }
+          // SWIZZLE_128B staging: 16-byte chunk q of row r lives at chunk (q ^ (r & 7))
+          *reinterpret_cast<float4*>(ob + lane * 128 + ((q ^ (lane & 7)) << 4)) = o;
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_2d(&map_out, ob, j0, tm * PW_BM + q4 * 32);
+          tma_store_commit();
+        }
+      }
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+    if (lane == 0) tma_store_wait_all<0>();
+  }
+
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, 512);
+}
+
+// ---- host side
+int init_pairwise_tc() {
+  static bool configured = false;
+  if (!configured) {
+    if (cudaFuncSetAttribute(pairwise_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PW_SMEM) != cudaSuccess) {
+      set_error("pairwise_tc: cannot reserve %d bytes of shared memory", PW_SMEM);
+      return SE_ERR_CUDA;
+    }
+    configured = true;
+  }
+  return SE_OK;
+}
+
+long long pairwise_tc_workspace_floats(int N, int D) {
+  const long long KW = ceil_div(D, 16) * 16;
+  // [pad to 64 floats] scalars (64) + Fh + Fl (halfs, N x KW each, + one spare tile of rows for clipped reads)
+  return 64 + 64 + (long long)N * KW + 1024;
+}
+
+int pairwise_tc(const float* F, int ldF, int N, int D, int row0, int rows, int pmode, int normalize, float* out,
+                long long ldout, float* ws, cudaStream_t st) {
+  const int KW = ceil_div(D, 16) * 16;
+  const int kblocks = ceil_div(KW, PW_KB);
+  if (kblocks > PW_MAXKB) return SE_ERR_UNSUPPORTED;                       // D > 128: fp32 tiles
+  if ((ldout % 4) != 0 || (reinterpret_cast<uintptr_t>(out) & 15) != 0) return SE_ERR_UNSUPPORTED;  // TMA store alignment
+  float* sq = ws;
+  float* norms = ws + N;
+  uintptr_t base = (reinterpret_cast<uintptr_t>(ws + 2LL * N) + 255) & ~(uintptr_t)255;
+  float* scal = reinterpret_cast<float*>(base);
+  __half* Fh = reinterpret_cast<__half*>(base + 256);
+  __half* Fl = Fh + (long long)N * KW;
+  if (cudaMemsetAsync(scal, 0, 256, st) != cudaSuccess) { set_error("pairwise_tc: memset failed"); return SE_ERR_CUDA; }
+  long long w1 = ceil_div<long long>((long long)N * D, 256), cap = (long long)sm_count() * 8;
+  int g1 = (int)(w1 < cap ? w1 : cap);
+  pairwise_absmax_kernel<<<g1, 256, 0, st>>>(F, ldF, N, D, norms, reinterpret_cast<unsigned*>(scal));
+  int rc = check_launch("pairwise_absmax_kernel");
+  if (rc) return rc;
+  long long w2 = ceil_div<long long>((long long)N * KW, 256);
+  int g2 = (int)(w2 < cap ? w2 : cap);
+  pairwise_split_kernel<<<g2, 256, 0, st>>>(F, ldF, N, D, KW, norms, scal, Fh, Fl);
+  rc = check_launch("pairwise_split_kernel");
+  if (rc) return rc;
+
+  CUtensorMap mh, ml, mo;
+  {
+    uint64_t dims[2] = {(uint64_t)KW, (uint64_t)N};
+    uint64_t strides[1] = {(uint64_t)KW * 2};
+    uint32_t box[2] = {PW_KB, 128};
+    if (!make_tmap(&mh, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, Fh, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B) ||
+        !make_tmap(&ml, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, Fl, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B))
+      return SE_ERR_CUDA;
+    uint64_t odims[2] = {(uint64_t)N, (uint64_t)rows};
+    uint64_t ostrides[1] = {(uint64_t)ldout * 4};
+    uint32_t obox[2] = {32, 32};
+    if (!make_tmap(&mo, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, out, odims, ostrides, obox, CU_TENSOR_MAP_SWIZZLE_128B))
+      return SE_ERR_CUDA;
+  }
+  PwParams p;
+  p.N = N; p.row0 = row0; p.rows = rows; p.pmode = pmode;
+  p.tiles_m = ceil_div(rows, PW_BM); p.tiles_n = ceil_div(N, PW_BN);
+  p.kblocks = kblocks; p.ksteps_total = KW / 16;
+  p.sq = sq; p.scal = scal;
+  int rc0 = init_pairwise_tc();
+  if (rc0) return rc0;
+  int grid = min(sm_count(), p.tiles_m * p.tiles_n);
+  pairwise_tc_kernel<<<grid, 128 + 32 * PW_EPI_WARPS, PW_SMEM, st>>>(mh, ml, mo, p);
+  return check_launch("pairwise_tc_kernel");
+}
+
 }  // namespace se

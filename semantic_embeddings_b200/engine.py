@@ -39,7 +39,8 @@ class Engine:
         self.dev = torch.device(device)
         if self.dev.type == 'cuda':
             torch.cuda.set_device(self.dev)     # (device='cpu' only builds the plans: used by the CPU-side tests)
-        self.lib.se_device_sm_count()
+        if self.dev.type == 'cuda':
+            _lib.check(self.lib.se_init(), 'se_init')
         self.g = graph
         self.B = int(batch)
         self.mode = mode
@@ -183,6 +184,12 @@ class Engine:
     def get_grads(self):
         torch.cuda.synchronize(self.dev)
         return OrderedDict((n, self._pview(n, self.G).detach().cpu().numpy().copy()) for n in self.offsets)
+
+    def set_velocity(self, vel):
+        """Optimizer momentum buffers by weight name (resuming a snapshot; tests)."""
+        for name, a in vel.items():
+            v = self._pview(name, self.V)
+            v.copy_(torch.from_numpy(np.ascontiguousarray(np.asarray(a, dtype=np.float32))))
 
     def get_velocity(self):
         torch.cuda.synchronize(self.dev)
@@ -440,8 +447,8 @@ class Engine:
             return
         cg = self._graphs.get(which)
         if cg is None:
-            # warm-up run outside capture (lazy attribute setup inside the library), then capture
-            _lib.check(self.lib.se_run_ops(arr, len(arr), self.mode, _lib.stream_ptr()), 'se_run_ops(%s)' % which)
+            # capture only (no warm-up run: a plan has side effects -- optimizer step, moving statistics);
+            # se_init() has already done every lazy per-kernel attribute setup the library needs
             torch.cuda.synchronize(self.dev)
             cg = torch.cuda.CUDAGraph()
             with torch.cuda.graph(cg):

@@ -106,9 +106,31 @@ STEP_CASES = [
 ]
 
 
+def _grad_errors(eg, grads, norm):
+    num = den = 0.0
+    worst, worst_name = 0.0, ''
+    for name, gr in grads.items():
+        a = np.asarray(eg[name], np.float64)
+        b = gr.numpy().astype(np.float64)
+        num += float(((a - b) ** 2).sum())
+        den += float((b ** 2).sum())
+        r = rel_l2(a, b) if np.linalg.norm(b) > 1e-3 * norm else 0.0     # skip mathematically-zero grads (bias before BN)
+        if r > worst:
+            worst, worst_name = r, name
+    return float(np.sqrt(num / den)), worst, worst_name
+
+
 @pytest.mark.parametrize('case', STEP_CASES, ids=lambda c: c[0])
 def test_two_training_steps_match_oracle(case):
-    """Two consecutive optimizer steps (so that momentum and BN moving statistics are exercised)."""
+    """Two optimizer steps against the float64 oracle.  Before each step the engine is given the oracle's
+    weights / momentum / moving statistics (rounded to fp32 on both sides), so every step is a comparison on
+    IDENTICAL inputs -- the north-star criterion -- while step 2 still exercises momentum and BN state.
+
+    Embeddings, loss, regulariser, gradient norm: <= 1e-4 relative.  Gradients: ReLU networks are
+    discontinuous in their pre-activations, so fp32 arithmetic legitimately flips a few masks relative to
+    float64; the tolerance is therefore tied to the measured noise floor of the SAME step computed by the
+    oracle in float32 (max(2e-3, 5 x floor))."""
+    import copy
     from oracle import models as omodels
     from oracle import train as otrain
     from semantic_embeddings_b200 import utils
@@ -122,61 +144,60 @@ def test_two_training_steps_match_oracle(case):
     if cls_weight > 0:
         cls = otrain.ClsHead(D, C, seed=23)
         omodels.randomize(cls.params, seed=24)
-    to_f32_exact(om, cls)
     graph = utils.build_network(D, arch, input_channels=3)
     eng = Engine(graph, B, emb, loss=loss, cls_weight=cls_weight, num_classes=C, nesterov=nesterov, clipnorm=10.0,
                  use_cuda_graph=(tag == 'resnet-110-fc'))
-    eng.set_weights(oracle_weights_np(om, cls))
     vel = otrain.make_velocity(om, cls if cls_weight > 0 else None)
     emb_t = torch.as_tensor(emb.astype(np.float32)).double()
     g = torch.Generator().manual_seed(31)
     lr = 0.05
     errs = {}
     for step in range(2):
+        to_f32_exact(om, cls)
+        for v in vel.values():
+            v.copy_(v.float().double())
+        eng.set_weights(oracle_weights_np(om, cls))
+        eng.set_velocity({k: v.numpy() for k, v in vel.items()})
         x = torch.randn(B, 32, 32, 3, generator=g, dtype=torch.float64).float()
         y = torch.randint(0, C, (B,), generator=g)
+        # noise floor: the same step by the oracle in float32
+        om32, cls32 = copy.deepcopy(om), copy.deepcopy(cls)
+        otrain.cast_model(om32, torch.float32, cls32)
+        vel32 = {k: v.float() for k, v in vel.items()}
+        _, grads32, _ = otrain.train_step(om32, x, y, emb_t.float(), vel32, lr, loss, cls32, cls_weight, nesterov, 10.0)
         obj, grads, norm = otrain.train_step(om, x.double(), y, emb_t, vel, lr, loss, cls, cls_weight, nesterov, 10.0)
+        floor, _, _ = _grad_errors({k: v.numpy() for k, v in grads32.items()}, grads, norm)
         eng.train_step(x, y, lr=lr)
         m = eng.metrics()
         gn, reg = eng.grad_norm_and_reg()
         e = {
-            'loss': abs(m['loss'] - float(obj['embed_loss'])) / max(1.0, abs(float(obj['embed_loss']))),
+            'loss': abs(m['loss'] - float(obj['embed_loss'].detach())) / max(1.0, abs(float(obj['embed_loss'].detach()))),
             'emb': rel_max(eng.act['head_out'].cpu().numpy(), obj['emb'].detach().numpy()),
             'acc': abs(m['acc'] - float(obj['acc'].mean())),
             'gnorm': abs(gn - norm) / norm,
-            'reg': abs(reg - float(obj['reg'])) / max(float(obj['reg']), 1e-12),
+            'reg': abs(reg - float(obj['reg'].detach())) / max(float(obj['reg'].detach()), 1e-12),
+            'grad_floor_f32_oracle': floor,
         }
         if cls_weight > 0:
-            e['cls_loss'] = abs(m['cls_loss'] - float(obj['cls_loss'])) / max(1.0, abs(float(obj['cls_loss'])))
-        # gradients (the engine's G holds grad + 2*lambda*W after the optimizer's first pass)
-        eg = eng.get_grads()
-        worst_g, worst_name = 0.0, ''
+            e['cls_loss'] = abs(m['cls_loss'] - float(obj['cls_loss'].detach())) / max(1.0, abs(float(obj['cls_loss'].detach())))
+        e['grad_global'], e['grad_worst'], worst_name = _grad_errors(eng.get_grads(), grads, norm)
         allp = dict(om.params)
         if cls is not None:
             allp.update(cls.params)
-        gl2 = dict(om.l2)
-        if cls is not None and cls_weight > 0:
-            gl2.update(cls.l2)
-        num = den = 0.0
-        for name, gr in grads.items():
-            a = eg[name].astype(np.float64)
-            b = gr.numpy()
-            num += float(((a - b) ** 2).sum())
-            den += float((b ** 2).sum())
-            r = rel_l2(a, b) if np.linalg.norm(b) > 1e-6 * norm else 0.0
-            if r > worst_g:
-                worst_g, worst_name = r, name
-        e['grad_global'] = float(np.sqrt(num / den))
-        e['grad_worst'] = worst_g
         ew = eng.get_weights()
         e['weights'] = max(rel_l2(ew[n], allp[n].numpy()) for n in allp)
+        ev = eng.get_velocity()
+        vtot = float(np.sqrt(sum(float(v.norm()) ** 2 for v in vel.values())))
+        e['velocity'] = max([rel_l2(ev[n], vel[n].numpy()) for n in vel if float(vel[n].norm()) > 1e-3 * vtot] or [0.0])
         errs[step] = e
         report('train_step', case=tag, step=step, worst_grad_tensor=worst_name, **e)
     for step, e in errs.items():
+        gtol = max(2e-3, 5 * e['grad_floor_f32_oracle'])
         assert e['loss'] < 1e-4 and e['emb'] < 1e-4, (step, e)
-        assert e['gnorm'] < 1e-3 and e['reg'] < 1e-5, (step, e)
-        assert e['grad_global'] < 2e-3, (step, e)
-        assert e['weights'] < 1e-4, (step, e)
+        assert e.get('cls_loss', 0.0) < 1e-4, (step, e)
+        assert e['gnorm'] < max(1e-4, gtol / 10) and e['reg'] < 1e-5, (step, e)
+        assert e['grad_global'] < gtol, (step, e)
+        assert e['velocity'] < gtol and e['weights'] < gtol * lr, (step, e)
         assert e['acc'] <= 1.0 / B + 1e-9, (step, e)
 
 

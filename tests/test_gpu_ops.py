@@ -70,7 +70,7 @@ def test_conv_fwd_dgrad_wgrad(case, mode):
     from semantic_embeddings_b200.graph import same_pad
     L = _lib()
     N, H, W, Cin, Cout, k, stride, padding, use_bias = case
-    g = torch.Generator().manual_seed(hash(case[:7]) % 1000)
+    g = torch.Generator().manual_seed(sum(int(v) for v in case[:7]))
     x = torch.randn(N, H, W, Cin, generator=g, dtype=torch.float64)
     w = torch.randn(k, k, Cin, Cout, generator=g, dtype=torch.float64) * (1.0 / np.sqrt(k * k * Cin))
     b = torch.randn(Cout, generator=g, dtype=torch.float64) if use_bias else None
@@ -282,7 +282,7 @@ def test_pools_and_elementwise():
     Ho, Wo = y.shape[1], y.shape[2]
     yd = torch.empty(N, Ho, Wo, C, device='cuda')
     L.call('se_maxpool_fwd', L.ptr(xd), L.ptr(yd), N, H, W, C, 3, 2, 0, 0, Ho, Wo, sptr())
-    assert relerr(yd.cpu(), y.detach()) == 0.0
+    assert relerr(yd.cpu(), y.detach().float()) == 0.0       # max-pooling selects: exact in fp32
     dxd = torch.empty(N, H, W, C, device='cuda')
     L.call('se_maxpool_bwd', L.ptr(xd), L.ptr(yd), L.ptr(dev(dy)), L.ptr(dxd), N, H, W, C, 3, 2, 0, 0, Ho, Wo, sptr())
     assert relerr(dxd.cpu(), gx) < 1e-6
@@ -483,7 +483,7 @@ def test_pairwise_ragged_sizes(mode):
     from oracle import retrieval as oret
     L = _lib()
     rng = np.random.RandomState(4)
-    for N, D in ((1, 5), (37, 3), (130, 64), (257, 100), (300, 129)):
+    for N, D in ((1, 5), (37, 3), (130, 64), (257, 100), (300, 129), (132, 64), (260, 100), (1000, 37), (4, 16), (516, 128)):
         feat = rng.randn(N, D).astype(np.float32)
         fd = dev(feat)
         ws = torch.zeros(int(L.load().se_pairwise_workspace_bytes(N, D, mode)), dtype=torch.uint8, device='cuda')
