@@ -75,6 +75,13 @@ typedef struct {
  * (float64, caller zeroes) -- the BatchNormalization statistics of the next layer. */
 int se_conv2d_fwd(const se_conv_desc* d, const float* x, const float* w, const float* bias,
                   const float* residual, float* y, int relu, double* stats, int mode, void* stream);
+/* same, with an optional transposed copy w_t = [kh][kw][Cout][Cin] of the kernel: the tcgen05 forward path
+ * (SE_MODE_TF32) consumes K-major operands; without w_t the call uses the fp32 kernels. */
+int se_conv2d_fwd_ex(const se_conv_desc* d, const float* x, const float* w, const float* w_t, const float* bias,
+                     const float* residual, float* y, int relu, double* stats, int mode, void* stream);
+/* PT[off + (tap, co, ci)] = P[off + (tap, ci, co)] for n kernels of a flat buffer, one launch.
+ * table: host array of n x {element offset, taps, Cin, Cout} (int64). */
+int se_transpose_filters(const float* P, float* PT, const int64_t* table, int n, void* stream);
 /* dx = beta*dx + conv^T(dy, w)   (gradient wrt the input; autodiff of the above) */
 int se_conv2d_dgrad(const se_conv_desc* d, const float* dy, const float* w, float* dx, float beta,
                     int mode, void* stream);

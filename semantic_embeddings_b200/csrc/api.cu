@@ -78,16 +78,28 @@ extern "C" int se_init(void) {
 namespace se { int tc_capabilities(); }
 extern "C" int se_tc_capabilities(void) { return se::tc_capabilities(); }
 
-extern "C" int se_conv2d_fwd(const se_conv_desc* d, const float* x, const float* w, const float* bias,
-                             const float* residual, float* y, int relu, double* stats, int mode, void* stream) {
+extern "C" int se_conv2d_fwd_ex(const se_conv_desc* d, const float* x, const float* w, const float* w_t,
+                                const float* bias, const float* residual, float* y, int relu, double* stats, int mode,
+                                void* stream) {
   int rc = check_desc(d);
   if (rc) return rc;
   SE_REQUIRE(x && w && y, "null pointer");
-  if (mode == SE_MODE_TF32) {
-    rc = conv_fwd_tc(d, x, w, bias, residual, y, relu, stats, as_stream(stream));
+  if (mode == SE_MODE_TF32 && w_t) {
+    rc = conv_fwd_tc(d, x, w_t, bias, residual, y, relu, stats, as_stream(stream));
     if (rc != SE_ERR_UNSUPPORTED) return rc;
   }
   return conv_fwd_simt(d, x, w, bias, residual, y, relu, stats, as_stream(stream));
+}
+
+extern "C" int se_conv2d_fwd(const se_conv_desc* d, const float* x, const float* w, const float* bias,
+                             const float* residual, float* y, int relu, double* stats, int mode, void* stream) {
+  return se_conv2d_fwd_ex(d, x, w, nullptr, bias, residual, y, relu, stats, mode, stream);
+}
+
+namespace se { int transpose_filters(const float* P, float* PT, const long long* table, int n, cudaStream_t st); }
+extern "C" int se_transpose_filters(const float* P, float* PT, const int64_t* table, int n, void* stream) {
+  SE_REQUIRE(P && PT && table && n >= 0, "bad arguments");
+  return se::transpose_filters(P, PT, reinterpret_cast<const long long*>(table), n, as_stream(stream));
 }
 
 extern "C" int se_conv2d_dgrad(const se_conv_desc* d, const float* dy, const float* w, float* dx, float beta, int mode,
@@ -159,8 +171,8 @@ extern "C" int se_run_ops(const se_op* ops, int n, int mode, void* stream) {
     switch (o.opcode) {
       case SE_OP_CONV_FWD: {
         se_conv_desc d = desc_from(i);
-        rc = se_conv2d_fwd(&d, (const float*)p[0], (const float*)p[1], (const float*)p[2], (const float*)p[3],
-                           (float*)p[4], i[12], (double*)p[5], i[13] >= 0 ? i[13] : mode, stream);
+        rc = se_conv2d_fwd_ex(&d, (const float*)p[0], (const float*)p[1], (const float*)p[6], (const float*)p[2],
+                              (const float*)p[3], (float*)p[4], i[12], (double*)p[5], i[13] >= 0 ? i[13] : mode, stream);
         break;
       }
       case SE_OP_CONV_DGRAD: {
@@ -238,6 +250,10 @@ extern "C" int se_run_ops(const se_op* ops, int n, int mode, void* stream) {
         if (e != cudaSuccess) { set_error("memset: %s", cudaGetErrorString(e)); rc = SE_ERR_CUDA; }
         break;
       }
+      case SE_OP_TRANSPOSE_FILTERS:
+        if (mode == SE_MODE_TF32)
+          rc = se_transpose_filters((const float*)p[0], (float*)p[1], (const int64_t*)p[2], i[0], stream);
+        break;
       case SE_OP_SGD_PREPARE:
         rc = se_sgd_prepare((const float*)p[0], (float*)p[1], (int64_t)(uintptr_t)p[2], (const se_l2_segment*)p[3], i[0],
                             (double*)p[4], stream);

@@ -1,11 +1,380 @@
-// tcgen05 (kind::tf32) implicit-GEMM convolution -- placeholder until the kernels land:
-// every entry reports SE_ERR_UNSUPPORTED so that the dispatcher uses the fp32 FFMA kernels.
+// tcgen05 (kind::tf32) implicit-GEMM convolution for 3x3 / stride 1 / 'same' layers -- the bulk of every
+// reference architecture (models/cifar_resnet.py:96-105, models/wide_residual_network.py:20-53,
+// models/plainnet.py:52,70) -- forward and data gradient.  fp32 NHWC activations are read as TF32 operands
+// straight from HBM/L2 (no conversion pass), fp32 accumulation in TMEM.
+//
+//   GEMM view   D[m, n] = sum_{tap, k} A_tap[m, k] * B_tap[n, k]
+//     m : 128 output pixels of one tile = a (Wb x Hb x Nb) box of the NHWC tensor
+//     A_tap : the same box shifted by the filter tap (r-1, s-1); TMA zero-fills the out-of-image halo,
+//             which IS the 'same' padding -- no im2col buffer, no index arithmetic in the kernel
+//     forward : k = input channel,  n = output channel, B = transposed kernel copy [tap][co][ci]
+//     dgrad   : k = output channel, n = input channel,  B = the HWIO kernel itself [8-tap][ci][co]
+//               (dX = conv(dY, W rotated by 180 degrees and transposed))
+//
+// Persistent, warp-specialised: warp 0 TMA producer (one tap x channel-block per pipeline stage), warp 1
+// single-thread MMA issuer (M=128, N=BN<=256, K=8 per instruction), warp 2 TMEM allocator, warps 4-7 epilogue
+// (tcgen05.ld -> bias / residual / ReLU / beta*old -> 128-bit global stores, BatchNorm sum and sum-of-squares of the
+// stored values reduced with a shuffle butterfly and accumulated in float64).  Accumulators are double-buffered
+// in TMEM so the epilogue of tile i overlaps the MMAs of tile i+1.
 #include "common.cuh"
+#include "tc.cuh"
+
 namespace se {
-int conv_fwd_tc(const se_conv_desc*, const float*, const float*, const float*, const float*, float*, int, double*, cudaStream_t) { return SE_ERR_UNSUPPORTED; }
-int conv_dgrad_tc(const se_conv_desc*, const float*, const float*, float*, float, cudaStream_t) { return SE_ERR_UNSUPPORTED; }
+
+using namespace tc;
+
+constexpr int CT_BM = 128;
+constexpr int CT_MAX_STAGES = 8;
+constexpr int CT_SMEM_BUDGET = 200 * 1024;
+
+struct ConvTcParams {
+  int N, H, W;              // image batch / size (input == output size)
+  int Kc, Nc;               // GEMM K channels (A tensor channels), GEMM N channels (output tensor channels)
+  int Wb, Hb, Nb;           // pixel box, Wb*Hb*Nb == 128
+  int tiles_m, tiles_n, BN;
+  int cblk, kblocks;        // channels per pipeline stage (16 or 32), Kc / cblk
+  int flip;                 // 1: dgrad (tap index reversed when addressing B)
+  int relu;
+  float beta;               // dgrad: out = beta*out + D
+  int stages, stage_bytes, a_bytes, acc_stride, tmem_cols;
+  const float* bias;
+  const float* residual;
+  float* out;
+  double* stats;
+};
+
+// column sums of a 32 x NC block held one row per lane (v[j] = column j of this lane's row):
+// after the butterfly lane L holds the total of column L (NC == 32) or L >> 1 (NC == 16).
+template <int NC>
+__device__ __forceinline__ float butterfly_colsum(float (&v)[32], int lane) {
+#pragma unroll
+  for (int off = 16, cnt = NC / 2; cnt >= 1; off >>= 1, cnt >>= 1) {
+    const bool up = (lane & off) != 0;
+#pragma unroll
+    for (int k = 0; k < cnt; ++k) {
+      float send = up ? v[k] : v[k + cnt];
+      float keep = up ? v[k + cnt] : v[k];
+      v[k] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+  if (NC == 16) v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
+  return v[0];
+}
+
+__global__ void __launch_bounds__(256, 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, ConvTcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* tiles = smem;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(tiles + (size_t)p.stages * p.stage_bytes);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + CT_MAX_STAGES;
+  uint64_t* t_full = bars + 2 * CT_MAX_STAGES;
+  uint64_t* t_empty = t_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + 2);
+  double* s_stats = reinterpret_cast<double*>(bars + 2 * CT_MAX_STAGES + 8);   // [2 * Nc] when stats are requested
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int total_tiles = p.tiles_m * p.tiles_n;
+  const int per_cta = (total_tiles + gridDim.x - 1) / gridDim.x;
+  const int t_begin = blockIdx.x * per_cta;
+  const int t_end = min(total_tiles, t_begin + per_cta);
+  const int row_bytes = p.cblk * 4;
+  const int tiles_per_img = (p.Nb == 1) ? (p.H / p.Hb) : 1;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&map_a); prefetch_tmap(&map_b);
+    for (int s = 0; s < p.stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&t_full[a], 1); mbar_init(&t_empty[a], 128); }
+    fence_barrier_init();
+    fence_proxy_async();
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, p.tmem_cols);
+  if (p.stats) for (int i = threadIdx.x; i < 2 * p.Nc; i += blockDim.x) s_stats[i] = 0.0;
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0 && lane == 0) {
+    // ===================== TMA producer
+    int stage = 0, phase = 0;
+    const uint32_t tx = p.a_bytes + p.BN * row_bytes;
+    for (int t = t_begin; t < t_end; ++t) {
+      const int tm = t / p.tiles_n, tn = t % p.tiles_n;
+      int n0, h0;
+      if (p.Nb == 1) { n0 = tm / tiles_per_img; h0 = (tm % tiles_per_img) * p.Hb; }
+      else { n0 = tm * p.Nb; h0 = 0; }
+      for (int tap = 0; tap < 9; ++tap) {
+        const int r = tap / 3, s = tap % 3;
+        const int btap = p.flip ? 8 - tap : tap;
+        for (int kb = 0; kb < p.kblocks; ++kb) {
+          mbar_wait(&empty[stage], phase ^ 1);
+          mbar_expect_tx(&full[stage], tx);
+          uint8_t* sa = tiles + (size_t)stage * p.stage_bytes;
+          tma_load_4d(sa, &map_a, &full[stage], kb * p.cblk, s - 1, h0 + r - 1, n0);
+          tma_load_2d(sa + p.a_bytes, &map_b, &full[stage], kb * p.cblk, btap * p.Nc + tn * p.BN);
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ===================== MMA issuer
+    const uint32_t idesc = umma_idesc(2 /*tf32*/, CT_BM, p.BN);
+    const uint32_t sbo = 8 * row_bytes;
+    int stage = 0, phase = 0, acc = 0, acc_phase = 0;
+    for (int t = t_begin; t < t_end; ++t) {
+      mbar_wait(&t_empty[acc], acc_phase ^ 1);
+      fence_after_sync();
+      const uint32_t d_tmem = tmem_base + acc * p.acc_stride;
+      uint32_t first = 1;
+      for (int it = 0; it < 9 * p.kblocks; ++it) {
+        mbar_wait(&full[stage], phase);
+        fence_after_sync();
+        const uint32_t a0 = smem_u32(tiles + (size_t)stage * p.stage_bytes);
+        const uint32_t b0 = a0 + p.a_bytes;
+        for (int ks = 0; ks < p.cblk / 8; ++ks) {
+          const uint64_t da = umma_desc_kmajor(a0 + ks * 32, sbo, row_bytes);
+          const uint64_t db = umma_desc_kmajor(b0 + ks * 32, sbo, row_bytes);
+          mma_tf32(d_tmem, da, db, idesc, first ? 0u : 1u);
+          first = 0;
+        }
+        mma_commit(&empty[stage]);
+        if (++stage == p.stages) { stage = 0; phase ^= 1; }
+      }
+      mma_commit(&t_full[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue (4 warps, one TMEM lane quarter each)
+    const int q4 = warp & 3;
+    int acc = 0, acc_phase = 0;
+    for (int t = t_begin; t < t_end; ++t) {
+      const int tm = t / p.tiles_n, tn = t % p.tiles_n;
+      const int m = q4 * 32 + lane;                 // row of the tile == TMEM lane
+      const int wb = m % p.Wb, hb = (m / p.Wb) % p.Hb, nb = m / (p.Wb * p.Hb);
+      int n, h;
+      if (p.Nb == 1) { n = tm / tiles_per_img; h = (tm % tiles_per_img) * p.Hb + hb; }
+      else { n = tm * p.Nb + nb; h = hb; }
+      const bool valid = (n < p.N) && (h < p.H) && (wb < p.W);
+      const long long pix = ((long long)n * p.H + h) * p.W + wb;
+      float* orow = p.out + pix * p.Nc + tn * p.BN;
+      const float* rrow = p.residual ? p.residual + pix * p.Nc + tn * p.BN : nullptr;
+      mbar_wait(&t_full[acc], acc_phase);
+      fence_after_sync();
+      const uint32_t t_addr = tmem_base + ((uint32_t)(q4 * 32) << 16) + acc * p.acc_stride;
+      for (int c0 = 0; c0 < p.BN; c0 += 32) {
+        const int nc = min(32, p.BN - c0);          // 32, or a final block of 16
+        uint32_t v[32];
+        if (nc == 32) {
+          tmem_ld_32x32(t_addr + c0, v);
+        } else {
+          asm volatile(
+              "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+              : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+                "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+              : "r"(t_addr + c0)
+              : "memory");
+#pragma unroll
+          for (int j = 16; j < 32; ++j) v[j] = 0u;
+        }
+        tmem_ld_wait();
+        if (c0 + 32 >= p.BN) {                      // last block of this accumulator: release it
+          fence_before_sync();
+          mbar_arrive(&t_empty[acc]);
+        }
+        float o[32], o2[32];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          float4 val = make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]), __uint_as_float(v[4 * q + 2]),
+                                   __uint_as_float(v[4 * q + 3]));
+          const bool live = valid && (4 * q < nc);
+          if (live) {
+            const int cg = tn * p.BN + c0 + 4 * q;
+            if (p.bias) {
+              float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + cg));
+              val.x += b.x; val.y += b.y; val.z += b.z; val.w += b.w;
+            }
+            if (rrow) {
+              float4 rr = *reinterpret_cast<const float4*>(rrow + c0 + 4 * q);
+              val.x += rr.x; val.y += rr.y; val.z += rr.z; val.w += rr.w;
+            }
+            if (p.beta != 0.f) {
+              float4 old = *reinterpret_cast<const float4*>(orow + c0 + 4 * q);
+              val.x += p.beta * old.x; val.y += p.beta * old.y; val.z += p.beta * old.z; val.w += p.beta * old.w;
+            }
+            if (p.relu) { val.x = fmaxf(val.x, 0.f); val.y = fmaxf(val.y, 0.f); val.z = fmaxf(val.z, 0.f); val.w = fmaxf(val.w, 0.f); }
+            *reinterpret_cast<float4*>(orow + c0 + 4 * q) = val;
+          } else {
+            val = make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+          o[4 * q] = val.x; o[4 * q + 1] = val.y; o[4 * q + 2] = val.z; o[4 * q + 3] = val.w;
+        }
+        if (p.stats) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) o2[j] = o[j] * o[j];
+          float cs, cq;
+          int col;
+          if (nc == 32) { cs = butterfly_colsum<32>(o, lane); cq = butterfly_colsum<32>(o2, lane); col = lane; }
+          else { cs = butterfly_colsum<16>(o, lane); cq = butterfly_colsum<16>(o2, lane); col = lane >> 1; }
+          if (nc == 32 || (lane & 1) == 0) {
+            atomicAdd(&s_stats[tn * p.BN + c0 + col], (double)cs);
+            atomicAdd(&s_stats[p.Nc + tn * p.BN + c0 + col], (double)cq);
+          }
+        }
+      }
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  __syncthreads();
+  if (p.stats) {
+    for (int i = threadIdx.x; i < 2 * p.Nc; i += blockDim.x) {
+      double v = s_stats[i];
+      if (v != 0.0) atomicAdd(&p.stats[i], v);
+    }
+  }
+  if (warp == 2) tmem_dealloc(tmem_base, p.tmem_cols);
+}
+
+// [tap][ci][co] (HWIO) -> [tap][co][ci] for every listed conv kernel of a flat parameter buffer, in one launch
+struct TrEntry { long long off; int taps, cin, cout; };
+constexpr int TR_MAX = 160;
+struct TrTable { TrEntry e[TR_MAX]; int n; };
+
+__global__ void __launch_bounds__(256)
+transpose_filters_kernel(const float* __restrict__ P, float* __restrict__ PT, const __grid_constant__ TrTable tab) {
+  for (int li = blockIdx.y; li < tab.n; li += gridDim.y) {
+    const TrEntry e = tab.e[li];
+    const long long total = (long long)e.taps * e.cin * e.cout;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+      // i indexes the destination [tap][co][ci]
+      int ci = (int)(i % e.cin);
+      long long t2 = i / e.cin;
+      int co = (int)(t2 % e.cout);
+      int tap = (int)(t2 / e.cout);
+      PT[e.off + i] = P[e.off + ((long long)tap * e.cin + ci) * e.cout + co];
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------- host side
+static bool tc_shape_ok(const se_conv_desc* d, int Kc, int Nc) {
+  if (d->kh != 3 || d->kw != 3 || d->stride != 1 || d->pad_t != 1 || d->pad_l != 1 || d->Ho != d->H || d->Wo != d->W)
+    return false;
+  if (Kc % 16 != 0 || Nc % 16 != 0) return false;
+  if (Kc > 16 && Kc % 32 != 0) return false;
+  const int W = d->W, H = d->H;
+  if (W > 128 || (W & (W - 1)) != 0 || W < 4) return false;        // W must divide 128
+  if (W * H >= 128) { if (H % (128 / W) != 0) return false; }
+  else { if ((128 % (W * H)) != 0) return false; }
+  return true;
+}
+
+static int pick_bn(int Nc) {
+  if (Nc <= 256) return Nc;
+  for (int bn = 256; bn >= 16; bn -= 16)
+    if (Nc % bn == 0) return bn;
+  return 16;
+}
+
+static int conv_tc_launch(const se_conv_desc* d, const float* a_tensor, int Kc, const float* bmat, int Nc, int flip,
+                          const float* bias, const float* residual, float* out, int relu, float beta, double* stats,
+                          cudaStream_t st) {
+  ConvTcParams p;
+  p.N = d->N; p.H = d->H; p.W = d->W; p.Kc = Kc; p.Nc = Nc;
+  p.Wb = d->W;
+  if (d->W * d->H >= 128) { p.Hb = 128 / d->W; p.Nb = 1; } else { p.Hb = d->H; p.Nb = 128 / (d->W * d->H); }
+  p.BN = pick_bn(Nc);
+  if (p.BN % 16 != 0 || Nc % p.BN != 0) return SE_ERR_UNSUPPORTED;
+  p.tiles_n = Nc / p.BN;
+  p.tiles_m = (p.Nb == 1) ? d->N * (d->H / p.Hb) : ceil_div(d->N, p.Nb);
+  p.cblk = Kc >= 32 ? 32 : 16;
+  p.kblocks = Kc / p.cblk;
+  p.flip = flip; p.relu = relu; p.beta = beta;
+  p.a_bytes = CT_BM * p.cblk * 4;
+  const int b_bytes = ceil_div(p.BN * p.cblk * 4, 1024) * 1024;
+  p.stage_bytes = p.a_bytes + b_bytes;
+  p.stages = min(CT_MAX_STAGES, CT_SMEM_BUDGET / p.stage_bytes);
+  if (p.stages < 2) return SE_ERR_UNSUPPORTED;
+  int cols = 32;
+  while (cols < 2 * p.BN) cols <<= 1;
+  if (cols > 512) return SE_ERR_UNSUPPORTED;
+  p.tmem_cols = cols; p.acc_stride = cols / 2;
+  p.bias = bias; p.residual = residual; p.out = out; p.stats = stats;
+  if (stats && (size_t)2 * Nc * sizeof(double) > 16 * 1024) return SE_ERR_UNSUPPORTED;
+
+  CUtensorMap ma, mb;
+  {
+    uint64_t dims[4] = {(uint64_t)Kc, (uint64_t)d->W, (uint64_t)d->H, (uint64_t)d->N};
+    uint64_t strides[3] = {(uint64_t)Kc * 4, (uint64_t)d->W * Kc * 4, (uint64_t)d->H * d->W * Kc * 4};
+    uint32_t box[4] = {(uint32_t)p.cblk, (uint32_t)p.Wb, (uint32_t)p.Hb, (uint32_t)p.Nb};
+    CUtensorMapSwizzle sw = p.cblk == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+    if (!make_tmap(&ma, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(a_tensor), dims, strides, box, sw)) return SE_ERR_CUDA;
+    uint64_t bdims[2] = {(uint64_t)Kc, (uint64_t)9 * Nc};
+    uint64_t bstrides[1] = {(uint64_t)Kc * 4};
+    uint32_t bbox[2] = {(uint32_t)p.cblk, (uint32_t)p.BN};
+    if (!make_tmap(&mb, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(bmat), bdims, bstrides, bbox, sw)) return SE_ERR_CUDA;
+  }
+  const size_t smem = (size_t)p.stages * p.stage_bytes + (2 * CT_MAX_STAGES + 8) * 8 + (stats ? 2 * Nc * 8 : 0) + 1024 + 64;
+  if (smem > 227 * 1024) return SE_ERR_UNSUPPORTED;
+  int grid = min(sm_count(), p.tiles_m * p.tiles_n);
+  conv_tc_kernel<<<grid, 256, smem, st>>>(ma, mb, p);
+  return check_launch("conv_tc_kernel");
+}
+
+int init_conv_tc() {
+  if (cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) {
+    set_error("init_conv_tc: cannot raise the shared-memory limit");
+    return SE_ERR_CUDA;
+  }
+  return SE_OK;
+}
+
+static bool g_tc_inited = false;
+static int ensure_init() {
+  if (!g_tc_inited) { int rc = init_conv_tc(); if (rc) return rc; g_tc_inited = true; }
+  return SE_OK;
+}
+
+// forward needs the transposed kernel copy w_t = [tap][co][ci]; without it the caller falls back to the fp32 kernels
+int conv_fwd_tc(const se_conv_desc* d, const float* x, const float* w_t, const float* bias, const float* residual, float* y,
+                int relu, double* stats, cudaStream_t st) {
+  if (!w_t || !tc_shape_ok(d, d->Cin, d->Cout)) return SE_ERR_UNSUPPORTED;
+  int rc = ensure_init();
+  if (rc) return rc;
+  return conv_tc_launch(d, x, d->Cin, w_t, d->Cout, 0, bias, residual, y, relu, 0.f, stats, st);
+}
+
+int conv_dgrad_tc(const se_conv_desc* d, const float* dy, const float* w, float* dx, float beta, cudaStream_t st) {
+  if (!tc_shape_ok(d, d->Cout, d->Cin)) return SE_ERR_UNSUPPORTED;
+  int rc = ensure_init();
+  if (rc) return rc;
+  return conv_tc_launch(d, dy, d->Cout, w, d->Cin, 1, nullptr, nullptr, dx, 0, beta, nullptr, st);
+}
+
 int conv_wgrad_tc(const se_conv_desc*, const float*, const float*, float*, float*, cudaStream_t) { return SE_ERR_UNSUPPORTED; }
+
+int transpose_filters(const float* P, float* PT, const long long* table, int n, cudaStream_t st) {
+  for (int base = 0; base < n; base += TR_MAX) {
+    TrTable tab;
+    tab.n = min(TR_MAX, n - base);
+    long long maxtot = 1;
+    for (int i = 0; i < tab.n; ++i) {
+      const long long* e = table + 4 * (base + i);
+      tab.e[i].off = e[0]; tab.e[i].taps = (int)e[1]; tab.e[i].cin = (int)e[2]; tab.e[i].cout = (int)e[3];
+      maxtot = max(maxtot, e[1] * e[2] * e[3]);
+    }
+    long long gx = ceil_div<long long>(maxtot, 256);
+    dim3 grid((unsigned)(gx < 64 ? gx : 64), (unsigned)tab.n);
+    transpose_filters_kernel<<<grid, 256, 0, st>>>(P, PT, tab);
+    int rc = check_launch("transpose_filters_kernel");
+    if (rc) return rc;
+  }
+  return SE_OK;
+}
+
 // bit 0 conv fwd, bit 1 conv dgrad, bit 2 conv wgrad, bit 3 pairwise: which tcgen05 kernels are compiled in
-int tc_capabilities() { return 8; }
-int init_conv_tc() { return SE_OK; }
+int tc_capabilities() { return 1 | 2 | 8; }
+
 }  // namespace se

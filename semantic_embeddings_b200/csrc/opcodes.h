@@ -23,4 +23,5 @@ enum {
   SE_OP_MEMSET = 19,
   SE_OP_SGD_PREPARE = 20,
   SE_OP_SGD_APPLY = 21,
+  SE_OP_TRANSPOSE_FILTERS = 22,
 };

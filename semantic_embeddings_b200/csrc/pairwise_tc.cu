@@ -187,6 +187,9 @@ pairwise_tc_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_const
       const int r_local = q4 * 32 + lane;               // row inside the tile == TMEM lane
       const int gi = p.row0 + tm * PW_BM + r_local;
       const float a_sq = p.sq[gi];                      // (rows past N read workspace padding; clipped at the store)
+      // squared norms of this warp's 128 columns: lane i keeps columns 4i..4i+3, handed out by shuffles below
+      // (issued before the accumulator wait so that the L2 latency is off the critical path)
+      const float4 sqv = __ldg(reinterpret_cast<const float4*>(p.sq + tn * PW_BN + half * (PW_BN / 2)) + lane);
       mbar_wait(&t_full[acc], acc_phase);
       fence_after_sync();
       for (int c = 0; c < CHUNKS; ++c) {
@@ -198,24 +201,27 @@ pairwise_tc_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_const
           fence_before_sync();
           mbar_arrive(&t_empty[acc]);
         }
-        if (lane == 0) tma_store_wait_read<0>();        // the previous store of this warp has read the buffer
-        __syncwarp();
         const int j0 = tn * PW_BN + col;
-        const float4* sqj = reinterpret_cast<const float4*>(p.sq + j0);
+        float4 o[8];
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
-          float4 b = __ldg(sqj + q);
-          float4 o;
+          const int src = c * 8 + q;
+          const float bx = __shfl_sync(0xffffffffu, sqv.x, src), by = __shfl_sync(0xffffffffu, sqv.y, src);
+          const float bz = __shfl_sync(0xffffffffu, sqv.z, src), bw = __shfl_sync(0xffffffffu, sqv.w, src);
           float c0 = __uint_as_float(v[4 * q + 0]) * s2, c1 = __uint_as_float(v[4 * q + 1]) * s2;
           float c2 = __uint_as_float(v[4 * q + 2]) * s2, c3 = __uint_as_float(v[4 * q + 3]) * s2;
           if (p.pmode == SE_PDIST_NEGDOT) {
-            o = make_float4(-c0, -c1, -c2, -c3);
+            o[q] = make_float4(-c0, -c1, -c2, -c3);
           } else {
-            o = make_float4((a_sq + b.x) - 2.f * c0, (a_sq + b.y) - 2.f * c1, (a_sq + b.z) - 2.f * c2, (a_sq + b.w) - 2.f * c3);
+            o[q] = make_float4((a_sq + bx) - 2.f * c0, (a_sq + by) - 2.f * c1, (a_sq + bz) - 2.f * c2, (a_sq + bw) - 2.f * c3);
           }
-          // SWIZZLE_128B staging: 16-byte chunk q of row r lives at chunk (q ^ (r & 7))
-          *reinterpret_cast<float4*>(ob + lane * 128 + ((q ^ (lane & 7)) << 4)) = o;
         }
+        if (lane == 0) tma_store_wait_read<0>();        // the previous store of this warp has read the buffer
+        __syncwarp();
+        // SWIZZLE_128B staging: 16-byte chunk q of row r lives at chunk (q ^ (r & 7))
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+          *reinterpret_cast<float4*>(ob + lane * 128 + ((q ^ (lane & 7)) << 4)) = o[q];
         fence_proxy_async();
         __syncwarp();
         if (lane == 0) {

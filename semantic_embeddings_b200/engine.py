@@ -115,6 +115,14 @@ class Engine:
         self.P = torch.zeros(off, **f32)
         self.G = torch.zeros(off, **f32)
         self.V = torch.zeros(off, **f32)
+        # K-major ([tap][co][ci]) copies of the conv kernels for the tcgen05 forward path, refreshed once per step
+        self.PT = torch.zeros(off, **f32) if self.mode == _lib.SE_MODE_TF32 else None
+        convs = [n for n in self.nodes if n.op == 'conv']
+        self.tr_table = (ctypes.c_int64 * (4 * max(1, len(convs))))()
+        for k, n in enumerate(convs):
+            o, shape = self.offsets[n.name + '/kernel']
+            self.tr_table[4 * k:4 * k + 4] = [o, shape[0] * shape[1], shape[2], shape[3]]
+        self.n_tr = len(convs)
         state = [p for p in self.pspecs.values() if not p.trainable]
         self.soffsets, soff = OrderedDict(), 0
         for p in state:
@@ -234,6 +242,10 @@ class Engine:
         A, Gd = self.act, self.grad
         nbytes = lambda t: t.numel() * t.element_size()
         fwd.append(self._op(_lib.OP_MEMSET, p=[self.stats, nbytes(self.stats)]))
+        if self.PT is not None and self.n_tr:
+            tr = self._op(_lib.OP_TRANSPOSE_FILTERS, [self.n_tr], p=[self.P, self.PT, ctypes.addressof(self.tr_table)])
+            fwd.append(tr)
+            inf.append(tr)
         scale = 1.0 / (self.B * self.world)
         stats_by_conv = {}
         for n in self.nodes:
@@ -257,8 +269,9 @@ class Engine:
                 if n.name in stats_by_conv:
                     off, c = self.bn_slot[stats_by_conv[n.name].name]
                     st = self.stats[off:off + 2 * c]
-                fwd.append(self._op(_lib.OP_CONV_FWD, d + [relu], p=[A[n.inputs[0].name], W, b, res, out, st]))
-                inf.append(self._op(_lib.OP_CONV_FWD, d + [relu], p=[A[n.inputs[0].name], W, b, res, out, None]))
+                Wt = self._pview(n.name + '/kernel', self.PT) if (self.PT is not None and n.op == 'conv') else None
+                fwd.append(self._op(_lib.OP_CONV_FWD, d + [relu], p=[A[n.inputs[0].name], W, b, res, out, st, Wt]))
+                inf.append(self._op(_lib.OP_CONV_FWD, d + [relu], p=[A[n.inputs[0].name], W, b, res, out, None, Wt]))
             elif n.op == 'bn':
                 x = n.inputs[0]
                 c = x.shape[-1]

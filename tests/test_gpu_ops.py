@@ -60,6 +60,12 @@ CONV_CASES = [
     (5, 1, 1, 64, 100, 1, 1, 'valid', True),     # dense 64 -> 100
     (3, 1, 1, 20, 555, 1, 1, 'valid', True),     # dense -> 555 (not a multiple of 4)
     (2, 12, 12, 32, 64, 3, 1, 'same', True),     # wgrad <2,2> register tile
+    (5, 16, 16, 32, 64, 3, 1, 'same', True),     # tcgen05: 128-byte rows, 8-row box
+    (6, 8, 8, 64, 64, 3, 1, 'same', True),       # tcgen05: two images per 128-pixel tile, 2 K blocks
+    (3, 8, 8, 64, 160, 3, 1, 'same', False),     # tcgen05: N = 160 (WRN widths), odd image count
+    (2, 32, 32, 32, 16, 3, 1, 'same', True),
+    (2, 4, 4, 32, 32, 3, 1, 'same', True),       # tcgen05: 4x4 maps, 8 images per tile (batch 2 < 8)
+    (1, 32, 32, 64, 320, 3, 1, 'same', False),   # tcgen05: two N tiles of 160
 ]
 
 
@@ -93,7 +99,12 @@ def test_conv_fwd_dgrad_wgrad(case, mode):
     bd = dev(b.detach()) if b is not None else None
     yd = torch.empty(N, Ho, Wo, Cout, device='cuda')
     stats = torch.zeros(2 * Cout, dtype=torch.float64, device='cuda')
-    L.call('se_conv2d_fwd', d, L.ptr(xd), L.ptr(wd), L.ptr(bd), None, L.ptr(yd), 0, L.ptr(stats), mode, sptr())
+    wtd = torch.empty_like(wd)
+    import ctypes
+    tab = (ctypes.c_int64 * 4)(0, k * k, Cin, Cout)
+    L.call('se_transpose_filters', L.ptr(wd), L.ptr(wtd), tab, 1, sptr())
+    assert torch.equal(wtd.view(k * k, Cout, Cin), wd.view(k * k, Cin, Cout).transpose(1, 2))
+    L.call('se_conv2d_fwd_ex', d, L.ptr(xd), L.ptr(wd), L.ptr(wtd), L.ptr(bd), None, L.ptr(yd), 0, L.ptr(stats), mode, sptr())
     tol = 2e-5 if mode == 0 else 4e-3       # tf32 inputs: 10-bit mantissa
     e_y = relerr(yd.cpu(), y.detach())
     ys = y.detach().reshape(-1, Cout)
