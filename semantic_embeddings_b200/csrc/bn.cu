@@ -40,10 +40,22 @@ bn_stats_kernel(const float* __restrict__ x, long long rows, int C, double* __re
         }
         ds[0] += s.x; ds[1] += s.y; ds[2] += s.z; ds[3] += s.w;
         dq[0] += q.x; dq[1] += q.y; dq[2] += q.z; dq[3] += q.w;
+        // lanes of a warp that share this channel quad (lanes apart by `lanes`, when lanes divides 32) combine first
+        const bool pow2 = (lanes & (lanes - 1)) == 0 && lanes < 32 && (C4 <= lanes);
+        if (pow2) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          atomicAdd(&sred[4 * cq + j], ds[j]);
-          atomicAdd(&sred[C + 4 * cq + j], dq[j]);
+          for (int j = 0; j < 4; ++j)
+            for (int o = lanes; o < 32; o <<= 1) {
+              ds[j] += __shfl_xor_sync(0xffffffffu, ds[j], o);
+              dq[j] += __shfl_xor_sync(0xffffffffu, dq[j], o);
+            }
+        }
+        if (!pow2 || (tid & 31) < lanes) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            atomicAdd(&sred[4 * cq + j], ds[j]);
+            atomicAdd(&sred[C + 4 * cq + j], dq[j]);
+          }
         }
       }
     }
@@ -192,10 +204,22 @@ bn_bwd_reduce_kernel(const float* __restrict__ x, const float* __restrict__ y, c
           }
         }
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          ds[j] += s[j]; dq[j] += q[j];
-          atomicAdd(&sred[4 * cq + j], ds[j]);
-          atomicAdd(&sred[C + 4 * cq + j], dq[j]);
+        for (int j = 0; j < 4; ++j) { ds[j] += s[j]; dq[j] += q[j]; }
+        const bool pow2 = (lanes & (lanes - 1)) == 0 && lanes < 32 && (C4 <= lanes);
+        if (pow2) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            for (int o = lanes; o < 32; o <<= 1) {
+              ds[j] += __shfl_xor_sync(0xffffffffu, ds[j], o);
+              dq[j] += __shfl_xor_sync(0xffffffffu, dq[j], o);
+            }
+        }
+        if (!pow2 || (tid & 31) < lanes) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            atomicAdd(&sred[4 * cq + j], ds[j]);
+            atomicAdd(&sred[C + 4 * cq + j], dq[j]);
+          }
         }
       }
     }

@@ -3,19 +3,25 @@
 // models/plainnet.py:52,70) -- forward and data gradient.  fp32 NHWC activations are read as TF32 operands
 // straight from HBM/L2 (no conversion pass), fp32 accumulation in TMEM.
 //
-//   GEMM view   D[m, n] = sum_{tap, k} A_tap[m, k] * B_tap[n, k]
-//     m : 128 output pixels of one tile = a (Wb x Hb x Nb) box of the NHWC tensor
-//     A_tap : the same box shifted by the filter tap (r-1, s-1); TMA zero-fills the out-of-image halo,
-//             which IS the 'same' padding -- no im2col buffer, no index arithmetic in the kernel
+//   GEMM view   P[m, (s, n)] = sum_{r, k} A_r[m, k] * B_r[(s, n), k]      y[h, w, n] = sum_s P[(h, w + s - 1), (s, n)]
+//     m : 128 output pixels of one tile = a (W x Hb x Nb) box of the NHWC tensor
+//     A_r : the same box shifted VERTICALLY by the filter row (r-1); TMA zero-fills the rows above / below the
+//           image, which is the 'same' padding -- no im2col buffer, no index arithmetic in the kernel
+//     the three horizontal taps s are stacked along N (N_mma = 3 * BNc) so that the input tile is fetched 3x
+//     instead of 9x; the horizontal shift is applied to the OUTPUT in the epilogue: a thread owns pixel w of
+//     a row and takes P[., s=0] from lane-1 and P[., s=2] from lane+1 (zero at the image border) -- possible
+//     because a warp's 32 TMEM lanes are 32 consecutive pixels of whole image rows (W divides 32)
 //     forward : k = input channel,  n = output channel, B = transposed kernel copy [tap][co][ci]
 //     dgrad   : k = output channel, n = input channel,  B = the HWIO kernel itself [8-tap][ci][co]
 //               (dX = conv(dY, W rotated by 180 degrees and transposed))
 //
 // Persistent, warp-specialised: warp 0 TMA producer (one tap x channel-block per pipeline stage), warp 1
-// single-thread MMA issuer (M=128, N=BN<=256, K=8 per instruction), warp 2 TMEM allocator, warps 4-7 epilogue
+// single-thread MMA issuer (M=128, N=3*BNc<=240, K=8 per instruction), warp 2 TMEM allocator, warps 4-7 epilogue
 // (tcgen05.ld -> bias / residual / ReLU / beta*old -> 128-bit global stores, BatchNorm sum and sum-of-squares of the
 // stored values reduced with a shuffle butterfly and accumulated in float64).  Accumulators are double-buffered
 // in TMEM so the epilogue of tile i overlaps the MMAs of tile i+1.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "tc.cuh"
 
@@ -25,6 +31,7 @@ using namespace tc;
 
 constexpr int CT_BM = 128;
 constexpr int CT_MAX_STAGES = 8;
+constexpr int CT_MAX_ACC = 8;
 constexpr int CT_SMEM_BUDGET = 200 * 1024;
 
 struct ConvTcParams {
@@ -36,7 +43,9 @@ struct ConvTcParams {
   int flip;                 // 1: dgrad (tap index reversed when addressing B)
   int relu;
   float beta;               // dgrad: out = beta*out + D
-  int stages, stage_bytes, a_bytes, acc_stride, tmem_cols;
+  int stages, stage_bytes, a_bytes, acc_stride, tmem_cols, nacc, b_merged;
+  long long* trace;         // debug: per-role clock64 timeline of CTA 0 (SE_CT_TRACE_PTR)
+  int debug;                // bit 0: no tiles (fixed overhead only), bit 1: skip A loads, bit 2: skip epilogue stores/stats
   const float* bias;
   const float* residual;
   float* out;
@@ -61,6 +70,24 @@ __device__ __forceinline__ float butterfly_colsum(float (&v)[32], int lane) {
   return v[0];
 }
 
+__device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
+
+#define CT_TRACE(role, ev)                                                                 \
+  do {                                                                                     \
+    if (p.trace && blockIdx.x == 0 && tr_n < 250) {                                        \
+      p.trace[(role) * 512 + 2 * tr_n] = (ev);                                             \
+      p.trace[(role) * 512 + 2 * tr_n + 1] = clock64();                                    \
+      ++tr_n;                                                                              \
+    }                                                                                      \
+  } while (0)
+
 __global__ void __launch_bounds__(256, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, ConvTcParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -70,27 +97,27 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   uint64_t* full = bars;
   uint64_t* empty = bars + CT_MAX_STAGES;
   uint64_t* t_full = bars + 2 * CT_MAX_STAGES;
-  uint64_t* t_empty = t_full + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + 2);
-  double* s_stats = reinterpret_cast<double*>(bars + 2 * CT_MAX_STAGES + 8);   // [2 * Nc] when stats are requested
+  uint64_t* t_empty = t_full + CT_MAX_ACC;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + CT_MAX_ACC);
+  float* s_stats = reinterpret_cast<float*>(bars + 2 * CT_MAX_STAGES + 2 * CT_MAX_ACC + 2);   // [4 warps][2 * Nc] when stats are requested
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int total_tiles = p.tiles_m * p.tiles_n;
   const int per_cta = (total_tiles + gridDim.x - 1) / gridDim.x;
   const int t_begin = blockIdx.x * per_cta;
-  const int t_end = min(total_tiles, t_begin + per_cta);
+  const int t_end = (p.debug & 1) ? t_begin : min(total_tiles, t_begin + per_cta);
   const int row_bytes = p.cblk * 4;
   const int tiles_per_img = (p.Nb == 1) ? (p.H / p.Hb) : 1;
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&map_a); prefetch_tmap(&map_b);
     for (int s = 0; s < p.stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(&t_full[a], 1); mbar_init(&t_empty[a], 128); }
+    for (int a = 0; a < p.nacc; ++a) { mbar_init(&t_full[a], 1); mbar_init(&t_empty[a], 128); }
     fence_barrier_init();
     fence_proxy_async();
   }
   if (warp == 2) tmem_alloc(tmem_slot, p.tmem_cols);
-  if (p.stats) for (int i = threadIdx.x; i < 2 * p.Nc; i += blockDim.x) s_stats[i] = 0.0;
+  if (p.stats) for (int i = threadIdx.x; i < 8 * p.Nc; i += blockDim.x) s_stats[i] = 0.f;
   fence_before_sync();
   __syncthreads();
   fence_after_sync();
@@ -98,38 +125,53 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 
   if (warp == 0 && lane == 0) {
     // ===================== TMA producer
-    int stage = 0, phase = 0;
-    const uint32_t tx = p.a_bytes + p.BN * row_bytes;
+    int stage = 0, phase = 0, tr_n = 0;
+    CT_TRACE(0, 0);
+    const uint32_t tx = p.a_bytes + 3 * p.BN * row_bytes;
     for (int t = t_begin; t < t_end; ++t) {
       const int tm = t / p.tiles_n, tn = t % p.tiles_n;
       int n0, h0;
       if (p.Nb == 1) { n0 = tm / tiles_per_img; h0 = (tm % tiles_per_img) * p.Hb; }
       else { n0 = tm * p.Nb; h0 = 0; }
-      for (int tap = 0; tap < 9; ++tap) {
-        const int r = tap / 3, s = tap % 3;
-        const int btap = p.flip ? 8 - tap : tap;
+      for (int r = 0; r < 3; ++r) {
         for (int kb = 0; kb < p.kblocks; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1);
-          mbar_expect_tx(&full[stage], tx);
+          CT_TRACE(0, 1);
+          mbar_expect_tx(&full[stage], (p.debug & 2) ? tx - p.a_bytes : tx);
           uint8_t* sa = tiles + (size_t)stage * p.stage_bytes;
-          tma_load_4d(sa, &map_a, &full[stage], kb * p.cblk, s - 1, h0 + r - 1, n0);
-          tma_load_2d(sa + p.a_bytes, &map_b, &full[stage], kb * p.cblk, btap * p.Nc + tn * p.BN);
+          if (!(p.debug & 2)) tma_load_4d(sa, &map_a, &full[stage], kb * p.cblk, 0, h0 + r - 1, n0);
+          if (p.b_merged) {
+            // one box of 3*BN rows: taps (r,0),(r,1),(r,2) are consecutive row blocks of B.  For dgrad the tap index
+            // is reversed, so the box starts at tap 8-(3r+2) and holds the s-blocks in the order 2,1,0.
+            const int tap0 = p.flip ? 8 - (r * 3 + 2) : r * 3;
+            tma_load_2d(sa + p.a_bytes, &map_b, &full[stage], kb * p.cblk, tap0 * p.Nc);
+          } else {
+            for (int s = 0; s < 3; ++s) {
+              const int tap = r * 3 + s;
+              const int btap = p.flip ? 8 - tap : tap;
+              tma_load_2d(sa + p.a_bytes + s * p.BN * row_bytes, &map_b, &full[stage], kb * p.cblk, btap * p.Nc + tn * p.BN);
+            }
+          }
+          CT_TRACE(0, 2);
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1 && lane == 0) {
     // ===================== MMA issuer
-    const uint32_t idesc = umma_idesc(2 /*tf32*/, CT_BM, p.BN);
+    const uint32_t idesc = umma_idesc(2 /*tf32*/, CT_BM, 3 * p.BN);
     const uint32_t sbo = 8 * row_bytes;
-    int stage = 0, phase = 0, acc = 0, acc_phase = 0;
+    int stage = 0, phase = 0, acc = 0, acc_phase = 0, tr_n = 0;
+    CT_TRACE(1, 0);
     for (int t = t_begin; t < t_end; ++t) {
       mbar_wait(&t_empty[acc], acc_phase ^ 1);
+      CT_TRACE(1, 1);
       fence_after_sync();
       const uint32_t d_tmem = tmem_base + acc * p.acc_stride;
       uint32_t first = 1;
-      for (int it = 0; it < 9 * p.kblocks; ++it) {
+      for (int it = 0; it < 3 * p.kblocks; ++it) {
         mbar_wait(&full[stage], phase);
+        CT_TRACE(1, 2);
         fence_after_sync();
         const uint32_t a0 = smem_u32(tiles + (size_t)stage * p.stage_bytes);
         const uint32_t b0 = a0 + p.a_bytes;
@@ -140,15 +182,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           first = 0;
         }
         mma_commit(&empty[stage]);
+        CT_TRACE(1, 3);
         if (++stage == p.stages) { stage = 0; phase ^= 1; }
       }
       mma_commit(&t_full[acc]);
-      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      if (++acc == p.nacc) { acc = 0; acc_phase ^= 1; }
     }
   } else if (warp >= 4) {
     // ===================== epilogue (4 warps, one TMEM lane quarter each)
     const int q4 = warp & 3;
-    int acc = 0, acc_phase = 0;
+    int acc = 0, acc_phase = 0, tr_n = (warp == 4 && lane == 0) ? 0 : 1000;
+    CT_TRACE(2, 0);
     for (int t = t_begin; t < t_end; ++t) {
       const int tm = t / p.tiles_n, tn = t % p.tiles_n;
       const int m = q4 * 32 + lane;                 // row of the tile == TMEM lane
@@ -161,34 +205,47 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       float* orow = p.out + pix * p.Nc + tn * p.BN;
       const float* rrow = p.residual ? p.residual + pix * p.Nc + tn * p.BN : nullptr;
       mbar_wait(&t_full[acc], acc_phase);
+      CT_TRACE(2, 1);
       fence_after_sync();
       const uint32_t t_addr = tmem_base + ((uint32_t)(q4 * 32) << 16) + acc * p.acc_stride;
+      const bool has_left = wb > 0, has_right = wb < p.W - 1;
       for (int c0 = 0; c0 < p.BN; c0 += 32) {
         const int nc = min(32, p.BN - c0);          // 32, or a final block of 16
-        uint32_t v[32];
+        uint32_t v[32], vl[32], vr[32];             // centre (s=1), left (s=0) and right (s=2) partial sums
+        const int lblk = (p.b_merged && p.flip) ? 2 : 0;   // column block holding the s=0 partial sums
         if (nc == 32) {
-          tmem_ld_32x32(t_addr + c0, v);
+          tmem_ld_32x32(t_addr + lblk * p.BN + c0, vl);
+          tmem_ld_32x32(t_addr + p.BN + c0, v);
+          tmem_ld_32x32(t_addr + (2 - lblk) * p.BN + c0, vr);
         } else {
-          asm volatile(
-              "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-              : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-                "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-              : "r"(t_addr + c0)
-              : "memory");
+          tmem_ld_32x16(t_addr + lblk * p.BN + c0, vl);
+          tmem_ld_32x16(t_addr + p.BN + c0, v);
+          tmem_ld_32x16(t_addr + (2 - lblk) * p.BN + c0, vr);
 #pragma unroll
-          for (int j = 16; j < 32; ++j) v[j] = 0u;
+          for (int j = 16; j < 32; ++j) { v[j] = 0u; vl[j] = 0u; vr[j] = 0u; }
         }
         tmem_ld_wait();
+        CT_TRACE(2, 2);
         if (c0 + 32 >= p.BN) {                      // last block of this accumulator: release it
           fence_before_sync();
           mbar_arrive(&t_empty[acc]);
+        }
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          // y[w] = P0[w-1] + P1[w] + P2[w+1]: the neighbours' partial sums come from the adjacent lanes
+          float l = __shfl_up_sync(0xffffffffu, __uint_as_float(vl[j]), 1);
+          float r = __shfl_down_sync(0xffffffffu, __uint_as_float(vr[j]), 1);
+          float c = __uint_as_float(v[j]);
+          if (has_left) c += l;
+          if (has_right) c += r;
+          v[j] = __float_as_uint(c);
         }
         float o[32], o2[32];
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
           float4 val = make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]), __uint_as_float(v[4 * q + 2]),
                                    __uint_as_float(v[4 * q + 3]));
-          const bool live = valid && (4 * q < nc);
+          const bool live = valid && (4 * q < nc) && !(p.debug & 4);
           if (live) {
             const int cg = tn * p.BN + c0 + 4 * q;
             if (p.bias) {
@@ -210,7 +267,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           }
           o[4 * q] = val.x; o[4 * q + 1] = val.y; o[4 * q + 2] = val.z; o[4 * q + 3] = val.w;
         }
-        if (p.stats) {
+        if (p.stats && !(p.debug & 4)) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) o2[j] = o[j] * o[j];
           float cs, cq;
@@ -218,19 +275,22 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           if (nc == 32) { cs = butterfly_colsum<32>(o, lane); cq = butterfly_colsum<32>(o2, lane); col = lane; }
           else { cs = butterfly_colsum<16>(o, lane); cq = butterfly_colsum<16>(o2, lane); col = lane >> 1; }
           if (nc == 32 || (lane & 1) == 0) {
-            atomicAdd(&s_stats[tn * p.BN + c0 + col], (double)cs);
-            atomicAdd(&s_stats[p.Nc + tn * p.BN + c0 + col], (double)cq);
+            // each (warp, channel) slot is owned by exactly one lane: plain read-modify-write, no atomics
+            float* sw = s_stats + q4 * 2 * p.Nc;
+            sw[tn * p.BN + c0 + col] += cs;
+            sw[p.Nc + tn * p.BN + c0 + col] += cq;
           }
         }
       }
-      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      CT_TRACE(2, 3);
+      if (++acc == p.nacc) { acc = 0; acc_phase ^= 1; }
     }
   }
 
   __syncthreads();
   if (p.stats) {
     for (int i = threadIdx.x; i < 2 * p.Nc; i += blockDim.x) {
-      double v = s_stats[i];
+      double v = (double)s_stats[i] + (double)s_stats[2 * p.Nc + i] + (double)s_stats[4 * p.Nc + i] + (double)s_stats[6 * p.Nc + i];
       if (v != 0.0) atomicAdd(&p.stats[i], v);
     }
   }
@@ -265,15 +325,16 @@ static bool tc_shape_ok(const se_conv_desc* d, int Kc, int Nc) {
   if (Kc % 16 != 0 || Nc % 16 != 0) return false;
   if (Kc > 16 && Kc % 32 != 0) return false;
   const int W = d->W, H = d->H;
-  if (W > 128 || (W & (W - 1)) != 0 || W < 4) return false;        // W must divide 128
+  if (W > 32 || (W & (W - 1)) != 0 || W < 4) return false;         // whole image rows per warp: W divides 32
   if (W * H >= 128) { if (H % (128 / W) != 0) return false; }
   else { if ((128 % (W * H)) != 0) return false; }
   return true;
 }
 
+// output channels per N tile: the MMA N is 3*BNc (<= 240) and two accumulators must fit the 512 TMEM columns
 static int pick_bn(int Nc) {
-  if (Nc <= 256) return Nc;
-  for (int bn = 256; bn >= 16; bn -= 16)
+  if (Nc <= 80) return Nc;
+  for (int bn = 80; bn >= 16; bn -= 16)
     if (Nc % bn == 0) return bn;
   return 16;
 }
@@ -293,16 +354,23 @@ static int conv_tc_launch(const se_conv_desc* d, const float* a_tensor, int Kc, 
   p.kblocks = Kc / p.cblk;
   p.flip = flip; p.relu = relu; p.beta = beta;
   p.a_bytes = CT_BM * p.cblk * 4;
-  const int b_bytes = ceil_div(p.BN * p.cblk * 4, 1024) * 1024;
+  const int b_bytes = ceil_div(3 * p.BN * p.cblk * 4, 1024) * 1024;
   p.stage_bytes = p.a_bytes + b_bytes;
   p.stages = min(CT_MAX_STAGES, CT_SMEM_BUDGET / p.stage_bytes);
   if (p.stages < 2) return SE_ERR_UNSUPPORTED;
-  int cols = 32;
-  while (cols < 2 * p.BN) cols <<= 1;
-  if (cols > 512) return SE_ERR_UNSUPPORTED;
-  p.tmem_cols = cols; p.acc_stride = cols / 2;
+  static const char* dbg_stages = getenv("SE_CT_STAGES");         // tuning knobs for scripts/bench_conv.py
+  static const char* dbg_mode = getenv("SE_CT_DEBUG");
+  if (dbg_stages) p.stages = max(1, min(p.stages, atoi(dbg_stages)));
+  p.debug = dbg_mode ? atoi(dbg_mode) : 0;
+  static const char* dbg_trace = getenv("SE_CT_TRACE_PTR");
+  p.trace = dbg_trace ? reinterpret_cast<long long*>(strtoull(dbg_trace, nullptr, 0)) : nullptr;
+  int stride = 32;
+  while (stride < 3 * p.BN) stride <<= 1;
+  if (2 * stride > 512) return SE_ERR_UNSUPPORTED;
+  p.tmem_cols = 512; p.acc_stride = stride; p.nacc = min(CT_MAX_ACC, 512 / stride);
+  p.b_merged = (p.tiles_n == 1) ? 1 : 0;
   p.bias = bias; p.residual = residual; p.out = out; p.stats = stats;
-  if (stats && (size_t)2 * Nc * sizeof(double) > 16 * 1024) return SE_ERR_UNSUPPORTED;
+  if (stats && (size_t)8 * Nc * sizeof(float) > 24 * 1024) return SE_ERR_UNSUPPORTED;
 
   CUtensorMap ma, mb;
   {
@@ -313,10 +381,10 @@ static int conv_tc_launch(const se_conv_desc* d, const float* a_tensor, int Kc, 
     if (!make_tmap(&ma, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(a_tensor), dims, strides, box, sw)) return SE_ERR_CUDA;
     uint64_t bdims[2] = {(uint64_t)Kc, (uint64_t)9 * Nc};
     uint64_t bstrides[1] = {(uint64_t)Kc * 4};
-    uint32_t bbox[2] = {(uint32_t)p.cblk, (uint32_t)p.BN};
+    uint32_t bbox[2] = {(uint32_t)p.cblk, (uint32_t)(p.b_merged ? 3 * p.BN : p.BN)};
     if (!make_tmap(&mb, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(bmat), bdims, bstrides, bbox, sw)) return SE_ERR_CUDA;
   }
-  const size_t smem = (size_t)p.stages * p.stage_bytes + (2 * CT_MAX_STAGES + 8) * 8 + (stats ? 2 * Nc * 8 : 0) + 1024 + 64;
+  const size_t smem = (size_t)p.stages * p.stage_bytes + (2 * CT_MAX_STAGES + 2 * CT_MAX_ACC + 2) * 8 + (stats ? 8 * Nc * 4 : 0) + 1024 + 64;
   if (smem > 227 * 1024) return SE_ERR_UNSUPPORTED;
   int grid = min(sm_count(), p.tiles_m * p.tiles_n);
   conv_tc_kernel<<<grid, 256, smem, st>>>(ma, mb, p);
@@ -353,7 +421,6 @@ int conv_dgrad_tc(const se_conv_desc* d, const float* dy, const float* w, float*
   return conv_tc_launch(d, dy, d->Cout, w, d->Cin, 1, nullptr, nullptr, dx, 0, beta, nullptr, st);
 }
 
-int conv_wgrad_tc(const se_conv_desc*, const float*, const float*, float*, float*, cudaStream_t) { return SE_ERR_UNSUPPORTED; }
 
 int transpose_filters(const float* P, float* PT, const long long* table, int n, cudaStream_t st) {
   for (int base = 0; base < n; base += TR_MAX) {
@@ -375,6 +442,6 @@ int transpose_filters(const float* P, float* PT, const long long* table, int n, 
 }
 
 // bit 0 conv fwd, bit 1 conv dgrad, bit 2 conv wgrad, bit 3 pairwise: which tcgen05 kernels are compiled in
-int tc_capabilities() { return 1 | 2 | 8; }
+int tc_capabilities() { return 1 | 2 | 4 | 8; }
 
 }  // namespace se

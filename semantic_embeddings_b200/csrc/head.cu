@@ -99,15 +99,33 @@ embed_head_kernel(const float* __restrict__ z, int ldz, const int* __restrict__ 
   // ---- accuracy: nearest class over the whole class matrix (utils.py:73-93)
   if (acc) {
     float best = (loss_kind == SE_LOSS_MSE) ? FLT_MAX : -FLT_MAX;
-    for (int c = 0; c < C; ++c) {
-      const float* e = E + (long long)c * ldE;
-      float sim = warp_dot<VEC>(xs, e, D, lane);
-      if (loss_kind == SE_LOSS_MSE) {
-        float en = warp_dot<VEC>(e, e, D, lane);  // centroids_norm (utils.py:76)
-        float dist = xnorm2 + en - 2.f * sim;
-        best = fminf(best, dist);
-      } else {
-        best = fmaxf(best, sim);
+    // four classes per iteration: independent partial sums keep four rows of E in flight (the loop is latency-bound)
+    for (int c = 0; c < C; c += 4) {
+      float ps[4] = {0.f, 0.f, 0.f, 0.f}, pe[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int cc = min(c + u, C - 1);
+        const float* e = E + (long long)cc * ldE;
+        if (VEC) {
+          for (int i = lane; i < (D >> 2); i += 32) {
+            float4 b = *reinterpret_cast<const float4*>(e + 4 * i);
+            float4 a = *reinterpret_cast<const float4*>(xs + 4 * i);
+            ps[u] = fmaf(a.x, b.x, ps[u]); ps[u] = fmaf(a.y, b.y, ps[u]); ps[u] = fmaf(a.z, b.z, ps[u]); ps[u] = fmaf(a.w, b.w, ps[u]);
+            pe[u] = fmaf(b.x, b.x, pe[u]); pe[u] = fmaf(b.y, b.y, pe[u]); pe[u] = fmaf(b.z, b.z, pe[u]); pe[u] = fmaf(b.w, b.w, pe[u]);
+          }
+        } else {
+          for (int i = lane; i < D; i += 32) { float b = e[i]; ps[u] = fmaf(xs[i], b, ps[u]); pe[u] = fmaf(b, b, pe[u]); }
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        float sim = warp_sum(ps[u]);
+        if (loss_kind == SE_LOSS_MSE) {
+          float en = warp_sum(pe[u]);                   // centroids_norm (utils.py:76)
+          best = fminf(best, xnorm2 + en - 2.f * sim);
+        } else {
+          best = fmaxf(best, sim);
+        }
       }
     }
     float ref = (loss_kind == SE_LOSS_MSE) ? true_dist : true_sim;
