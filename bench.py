@@ -283,7 +283,10 @@ def run_native(args):
     resident = lambda s: eng.load_batch(xs_dev[s % pool], ys_dev[s % pool])
     from_host = lambda s: eng.load_batch(xs_host[s % pool], ys_host[s % pool])
 
-    launches_per_step = eng.launches_per_step() if rank == 0 or True else 0
+    launches_per_step = eng.launches_per_step()
+    if world > 1:
+        from semantic_embeddings_b200.parallel import broadcast_parameters
+        broadcast_parameters([eng.P, eng.S, eng.V])        # replicas start the timed region from identical weights
     timed(resident, args.warmup, False)                      # warm-up (also captures the CUDA graphs)
     sampler = ClockSampler(local)
     if rank == 0:

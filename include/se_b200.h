@@ -126,7 +126,8 @@ int se_bn_fwd_infer(const float* x, int64_t rows, int C, const float* gamma, con
  *   dgamma += sum g*xhat ; dbeta += sum g                 (accumulate: caller zeroes)
  *   dx = beta_dx*dx + gamma*invstd*(g - mean(g) - xhat*mean(g*xhat)) [* (x > 0) if relu_in]
  *   dres = beta_res*dres + g      (same-resolution residual only; NULL to skip)
- * scratch: float64 [2C], caller zeroes. relu_in: x itself is a relu output (plainnet.py:52-53). */
+ * scratch: float64 [2C + 1] (sums + the arrival counter of the fused single-launch path), caller zeroes.
+ * relu_in: x itself is a relu output (plainnet.py:52-53). */
 int se_bn_bwd(const float* x, const float* y, const float* dout, int64_t rows, int C, const float* gamma,
               const float* save_mean, const float* save_invstd, int relu, int relu_in, float* dx,
               float beta_dx, float* dres, float beta_res, float* dgamma, float* dbeta, double* scratch,

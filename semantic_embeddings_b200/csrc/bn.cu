@@ -3,6 +3,8 @@
 // models/plainnet.py:53,68,71; models/wide_residual_network.py:14-92; learn_image_embeddings.py:42-43).
 // HBM-bound elementwise + per-channel reductions: 128-bit coalesced accesses along the channel
 // axis, float64 cross-CTA accumulation of the statistics.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace se {
@@ -130,20 +132,37 @@ bn_fwd_kernel(const float* __restrict__ x, long long rows, int C, const double* 
   const long long total = rows * C;
   if ((C & 3) == 0) {
     const long long total4 = total >> 2;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (long long)gridDim.x * blockDim.x) {
-      long long e = i << 2;
-      int c = (int)(e % C);
-      long long row = e / C;
-      float4 v = *reinterpret_cast<const float4*>(x + e);
-      float o[4] = {v.x, v.y, v.z, v.w};
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const bool plain_res = res.ptr && res.pool == 1 && res.pad_lo == 0 && res.C == C;
+    for (long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x; i0 < total4; i0 += 4 * stride) {
+      float4 vq[4], rq[4];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        float t = o[j] * scale[c + j] + shift[c + j];
-        if (res.ptr) t += res_value(res, row, c + j);
-        if (relu) t = fmaxf(t, 0.f);
-        o[j] = t;
+      for (int u = 0; u < 4; ++u) {
+        const long long i = i0 + u * stride;
+        if (i < total4) {
+          vq[u] = *reinterpret_cast<const float4*>(x + (i << 2));
+          if (plain_res) rq[u] = *reinterpret_cast<const float4*>(res.ptr + (i << 2));
+        }
       }
-      *reinterpret_cast<float4*>(y + e) = make_float4(o[0], o[1], o[2], o[3]);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const long long i = i0 + u * stride;
+        if (i >= total4) continue;
+        const long long e = i << 2;
+        const int c = (int)(e % C);
+        const long long row = e / C;
+        float o[4] = {vq[u].x, vq[u].y, vq[u].z, vq[u].w};
+        const float r4[4] = {rq[u].x, rq[u].y, rq[u].z, rq[u].w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float t = o[j] * scale[c + j] + shift[c + j];
+          if (plain_res) t += r4[j];
+          else if (res.ptr) t += res_value(res, row, c + j);
+          if (relu) t = fmaxf(t, 0.f);
+          o[j] = t;
+        }
+        *reinterpret_cast<float4*>(y + e) = make_float4(o[0], o[1], o[2], o[3]);
+      }
     }
   } else {
     for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
@@ -318,6 +337,162 @@ bn_bwd_apply_kernel(const float* __restrict__ x, const float* __restrict__ y, co
   }
 }
 
+// Fused backward: ONE launch, every input read once.  Each CTA keeps its slab of x and g = dout*(y>0) in shared
+// memory, adds its partial sums into `scratch`, waits at a grid-wide barrier (all CTAs are co-resident: grid <= #SMs,
+// one CTA per SM), then finishes dx / dres from shared memory.  5 tensor passes instead of 8, one launch instead of two.
+// scratch: float64 [2C] sums + [1] arrival counter, caller zeroes.
+__global__ void __launch_bounds__(512, 1)
+bn_bwd_fused_kernel(const float* __restrict__ x, const float* __restrict__ y, const float* __restrict__ dout, long long rows,
+                    int C, const float* __restrict__ gamma, const float* __restrict__ save_mean,
+                    const float* __restrict__ save_invstd, int relu, int relu_in, float* __restrict__ dx, float beta_dx,
+                    float* __restrict__ dres, float beta_res, float* __restrict__ dgamma, float* __restrict__ dbeta,
+                    double* __restrict__ scratch, int rows_per_cta) {
+  extern __shared__ __align__(16) unsigned char fsm[];
+  const long long r0 = (long long)blockIdx.x * rows_per_cta;
+  const long long r1 = min(rows, r0 + rows_per_cta);
+  const int nrows = (int)max(0LL, r1 - r0);
+  const int n4 = nrows * C / 4;                       // C % 4 == 0 (checked by the launcher)
+  float4* sx = reinterpret_cast<float4*>(fsm);
+  float4* sg = sx + rows_per_cta * C / 4;
+  double* sred = reinterpret_cast<double*>(sg + rows_per_cta * C / 4);      // [2C]
+  float* coef = reinterpret_cast<float*>(sred + 2 * C);                    // a, b, k, mean: [4C]
+  const int tid = threadIdx.x, nt = blockDim.x;
+  for (int i = tid; i < 2 * C; i += nt) sred[i] = 0.0;
+  __syncthreads();
+
+  // ---- phase 1: load, mask, partial sums.  Thread t always touches channel quad (t*... ) % C4 == fixed when nt % C4 == 0
+  const int C4 = C >> 2;
+  const float4* gx = reinterpret_cast<const float4*>(x + r0 * C);
+  const float4* gd = reinterpret_cast<const float4*>(dout + r0 * C);
+  const float4* gy = reinterpret_cast<const float4*>(y + r0 * C);
+  const bool fixed_quad = (nt % C4) == 0;
+  float s[4] = {0, 0, 0, 0}, q[4] = {0, 0, 0, 0};
+  int cq_fixed = tid % C4;
+  float mu[4], is[4];
+  if (fixed_quad) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { mu[j] = save_mean[4 * cq_fixed + j]; is[j] = save_invstd[4 * cq_fixed + j]; }
+  }
+  for (int i0 = tid; i0 < n4; i0 += 4 * nt) {
+    // four independent rows in flight per thread (the slab loop is latency-bound otherwise)
+    float4 xq[4], gq[4], yq[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int i = i0 + u * nt;
+      if (i < n4) {
+        xq[u] = gx[i];
+        gq[u] = gd[i];
+        if (relu) yq[u] = gy[i];
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int i = i0 + u * nt;
+      if (i >= n4) continue;
+      float4 xv = xq[u], gv = gq[u];
+      if (relu) {
+        float4 yv = yq[u];
+        if (!(yv.x > 0.f)) gv.x = 0.f;
+        if (!(yv.y > 0.f)) gv.y = 0.f;
+        if (!(yv.z > 0.f)) gv.z = 0.f;
+        if (!(yv.w > 0.f)) gv.w = 0.f;
+      }
+      sx[i] = xv;
+      sg[i] = gv;
+      if (fixed_quad) {
+        s[0] += gv.x; s[1] += gv.y; s[2] += gv.z; s[3] += gv.w;
+        q[0] += gv.x * (xv.x - mu[0]) * is[0]; q[1] += gv.y * (xv.y - mu[1]) * is[1];
+        q[2] += gv.z * (xv.z - mu[2]) * is[2]; q[3] += gv.w * (xv.w - mu[3]) * is[3];
+      } else {
+        const int cq = i % C4;
+        const float g4[4] = {gv.x, gv.y, gv.z, gv.w}, x4[4] = {xv.x, xv.y, xv.z, xv.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float m = save_mean[4 * cq + j], iv = save_invstd[4 * cq + j];
+          atomicAdd(&sred[4 * cq + j], (double)g4[j]);
+          atomicAdd(&sred[C + 4 * cq + j], (double)(g4[j] * (x4[j] - m) * iv));
+        }
+      }
+    }
+  }
+  if (fixed_quad) {
+    // lanes that share the quad (when C4 divides 32) combine with shuffles; then one shared-memory atomic per warp
+    double ds[4], dq[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { ds[j] = s[j]; dq[j] = q[j]; }
+    const bool pow2 = (C4 & (C4 - 1)) == 0 && C4 < 32;
+    if (pow2) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        for (int o = C4; o < 32; o <<= 1) {
+          ds[j] += __shfl_xor_sync(0xffffffffu, ds[j], o);
+          dq[j] += __shfl_xor_sync(0xffffffffu, dq[j], o);
+        }
+    }
+    if (!pow2 || (tid & 31) < C4) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        atomicAdd(&sred[4 * cq_fixed + j], ds[j]);
+        atomicAdd(&sred[C + 4 * cq_fixed + j], dq[j]);
+      }
+    }
+  }
+  __syncthreads();
+  for (int i = tid; i < 2 * C; i += nt) atomicAdd(&scratch[i], sred[i]);
+
+  // ---- grid barrier (arrival counter in scratch[2C], zeroed by the caller once per step)
+  __threadfence();
+  __syncthreads();
+  unsigned long long* counter = reinterpret_cast<unsigned long long*>(scratch + 2 * C);
+  if (tid == 0) {
+    atomicAdd(counter, 1ULL);
+    while (*reinterpret_cast<volatile unsigned long long*>(counter) < (unsigned long long)gridDim.x) { __nanosleep(64); }
+    __threadfence();
+  }
+  __syncthreads();
+
+  // ---- phase 2: coefficients from the global sums, dx / dres from shared memory
+  for (int c = tid; c < C; c += nt) {
+    double sgm = __ldcg(&scratch[c]), sgx = __ldcg(&scratch[C + c]);
+    float invstd = save_invstd[c], g = gamma[c];
+    float a = g * invstd;
+    coef[c] = a;
+    coef[C + c] = (float)(-(double)a * sgm / (double)rows);
+    coef[2 * C + c] = (float)(-(double)a * sgx / (double)rows) * invstd;
+    coef[3 * C + c] = save_mean[c];
+    if (blockIdx.x == 0) {
+      if (dgamma) dgamma[c] += (float)sgx;
+      if (dbeta) dbeta[c] += (float)sgm;
+    }
+  }
+  __syncthreads();
+  float4* odx = reinterpret_cast<float4*>(dx + r0 * C);
+  float4* odr = dres ? reinterpret_cast<float4*>(dres + r0 * C) : nullptr;
+  for (int i = tid; i < n4; i += nt) {
+    const int c = (i % C4) * 4;
+    float4 xv = sx[i], gv = sg[i];
+    float xx[4] = {xv.x, xv.y, xv.z, xv.w}, gg[4] = {gv.x, gv.y, gv.z, gv.w}, o[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float d = coef[c + j] * gg[j] + coef[C + c + j] + coef[2 * C + c + j] * (xx[j] - coef[3 * C + c + j]);
+      if (relu_in && !(xx[j] > 0.f)) d = 0.f;
+      o[j] = d;
+    }
+    if (beta_dx != 0.f) {
+      float4 old = odx[i];
+      o[0] += beta_dx * old.x; o[1] += beta_dx * old.y; o[2] += beta_dx * old.z; o[3] += beta_dx * old.w;
+    }
+    odx[i] = make_float4(o[0], o[1], o[2], o[3]);
+    if (odr) {
+      if (beta_res != 0.f) {
+        float4 old = odr[i];
+        gv.x += beta_res * old.x; gv.y += beta_res * old.y; gv.z += beta_res * old.z; gv.w += beta_res * old.w;
+      }
+      odr[i] = gv;
+    }
+  }
+}
+
 // dsrc[n, 2h+i, 2w+j, c] = beta*dsrc + scale * g[n,h,w,c+pad_lo]   (pool==2: scale .25; pool==1: scale 1)
 __global__ void __launch_bounds__(256)
 shortcut_bwd_kernel(const float* __restrict__ dout, const float* __restrict__ y, int relu, int N, int H, int W, int C,
@@ -378,7 +553,7 @@ extern "C" int se_bn_fwd_train(const float* x, int64_t rows, int C, const double
   SE_REQUIRE(x && y && stats && gamma && beta && save_mean && save_invstd && rows > 0 && C > 0, "bad arguments");
   Res r = to_res(res);
   long long items = ((C & 3) == 0) ? rows * C / 4 : rows * C;
-  bn_fwd_kernel<true><<<ew_grid(items), 256, 2 * C * sizeof(float), as_stream(stream)>>>(
+  bn_fwd_kernel<true><<<ew_grid(ceil_div<long long>(items, 4)), 256, 2 * C * sizeof(float), as_stream(stream)>>>(
       x, rows, C, stats, gamma, beta, eps, momentum, moving_mean, moving_var, save_mean, save_invstd, r, relu, y);
   return check_launch("bn_fwd_kernel<train>");
 }
@@ -389,7 +564,7 @@ extern "C" int se_bn_fwd_infer(const float* x, int64_t rows, int C, const float*
   SE_REQUIRE(x && y && gamma && beta && moving_mean && moving_var && rows > 0 && C > 0, "bad arguments");
   Res r = to_res(res);
   long long items = ((C & 3) == 0) ? rows * C / 4 : rows * C;
-  bn_fwd_kernel<false><<<ew_grid(items), 256, 2 * C * sizeof(float), as_stream(stream)>>>(
+  bn_fwd_kernel<false><<<ew_grid(ceil_div<long long>(items, 4)), 256, 2 * C * sizeof(float), as_stream(stream)>>>(
       x, rows, C, nullptr, gamma, beta, eps, 0.f, const_cast<float*>(moving_mean), const_cast<float*>(moving_var),
       nullptr, nullptr, r, relu, y);
   return check_launch("bn_fwd_kernel<infer>");
@@ -401,6 +576,30 @@ extern "C" int se_bn_bwd(const float* x, const float* y, const float* dout, int6
                          void* stream) {
   SE_REQUIRE(x && dout && dx && gamma && save_mean && save_invstd && scratch && rows > 0 && C > 0, "bad arguments");
   SE_REQUIRE(!relu || y, "relu backward needs y");
+  if ((C & 3) == 0) {
+    // fused single-launch path when every CTA's slab of x and g fits in shared memory (one CTA per SM)
+    const int sms = sm_count();
+    long long per_l = ceil_div<long long>(rows, sms);
+    per_l = (per_l + 3) / 4 * 4;
+    const int gridf = (int)ceil_div<long long>(rows, per_l);
+    const size_t smem = (size_t)per_l * C * 8 + 2 * C * sizeof(double) + 4 * C * sizeof(float) + 16;
+    static const bool no_fuse = getenv("SE_BN_NO_FUSE") != nullptr;
+    if (!no_fuse && smem <= 200 * 1024 && gridf <= sms) {
+      static bool configured = false;
+      if (!configured) {
+        if (cudaFuncSetAttribute(bn_bwd_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) {
+          set_error("bn_bwd_fused: cannot raise the shared-memory limit");
+          return SE_ERR_CUDA;
+        }
+        configured = true;
+      }
+      // at least 116 KB per CTA would be needed to force one CTA per SM; co-residency only needs grid <= #SMs
+      bn_bwd_fused_kernel<<<gridf, 512, smem, as_stream(stream)>>>(x, y, dout, rows, C, gamma, save_mean, save_invstd, relu,
+                                                                    relu_in, dx, beta_dx, dres, beta_res, dgamma, dbeta,
+                                                                    scratch, (int)per_l);
+      return check_launch("bn_bwd_fused_kernel");
+    }
+  }
   int grid;
   int per = red_rows_per_cta(rows, &grid);
   bn_bwd_reduce_kernel<<<grid, 256, 2 * C * sizeof(double), as_stream(stream)>>>(x, y, dout, rows, C, save_mean,

@@ -40,22 +40,26 @@ struct ConvTcParams {
   int Wb, Hb, Nb;           // pixel box, Wb*Hb*Nb == 128
   int tiles_m, tiles_n, BN;
   int cblk, kblocks;        // channels per pipeline stage (16 or 32), Kc / cblk
+  int rg;                   // filter rows per pipeline stage (3 = the whole 3x3 window of one channel block, or 1)
   int flip;                 // 1: dgrad (tap index reversed when addressing B)
   int relu;
   float beta;               // dgrad: out = beta*out + D
   int stages, stage_bytes, a_bytes, acc_stride, tmem_cols, nacc, b_merged;
-  long long* trace;         // debug: per-role clock64 timeline of CTA 0 (SE_CT_TRACE_PTR)
-  int debug;                // bit 0: no tiles (fixed overhead only), bit 1: skip A loads, bit 2: skip epilogue stores/stats
+  int res, res_b_bytes, nt; // resident-weights mode: B loaded once per CTA, MMAs of `nt` tiles interleaved
   const float* bias;
   const float* residual;
   float* out;
   double* stats;
+  long long* trace;         // debug: per-role clock64 timeline of CTA 0 (SE_CT_TRACE_PTR)
+  int debug;                // bit 0: no tiles (fixed overhead only), bit 1: skip A loads, bit 2: skip epilogue stores/stats
 };
+
+constexpr int CT_THREADS = 384;   // warp 0 TMA, warp 1 MMA, warp 2 TMEM alloc, warps 4-7 / 8-11 two epilogue groups
 
 // column sums of a 32 x NC block held one row per lane (v[j] = column j of this lane's row):
 // after the butterfly lane L holds the total of column L (NC == 32) or L >> 1 (NC == 16).
 template <int NC>
-__device__ __forceinline__ float butterfly_colsum(float (&v)[32], int lane) {
+__device__ __forceinline__ float butterfly_colsum(float (&v)[NC], int lane) {
 #pragma unroll
   for (int off = 16, cnt = NC / 2; cnt >= 1; off >>= 1, cnt >>= 1) {
     const bool up = (lane & off) != 0;
@@ -70,7 +74,12 @@ __device__ __forceinline__ float butterfly_colsum(float (&v)[32], int lane) {
   return v[0];
 }
 
-__device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&v)[32]) {
+template <int NC>
+__device__ __forceinline__ void tmem_ld_cols(uint32_t taddr, uint32_t (&v)[NC]);
+template <>
+__device__ __forceinline__ void tmem_ld_cols<32>(uint32_t taddr, uint32_t (&v)[32]) { tmem_ld_32x32(taddr, v); }
+template <>
+__device__ __forceinline__ void tmem_ld_cols<16>(uint32_t taddr, uint32_t (&v)[16]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
       : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
@@ -88,18 +97,81 @@ __device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&v)[32])
     }                                                                                      \
   } while (0)
 
-__global__ void __launch_bounds__(256, 1)
+// One block of NC output channels of one pixel: combine the three horizontal partial sums, apply the epilogue
+// ops, store, and (optionally) fold the stored values into the BatchNorm statistics.
+template <int NC>
+__device__ __forceinline__ void conv_tc_epilogue_block(const ConvTcParams& p, uint32_t t_addr, int lblk, int c0, int tn,
+                                                       bool valid, bool has_left, bool has_right, float* orow,
+                                                       const float* rrow, float* sw, int lane) {
+  uint32_t v[NC], vl[NC], vr[NC];                 // centre (s=1), left (s=0) and right (s=2) partial sums
+  tmem_ld_cols<NC>(t_addr + lblk * p.BN + c0, vl);
+  tmem_ld_cols<NC>(t_addr + p.BN + c0, v);
+  tmem_ld_cols<NC>(t_addr + (2 - lblk) * p.BN + c0, vr);
+  tmem_ld_wait();
+  float o[NC];
+#pragma unroll
+  for (int j = 0; j < NC; ++j) {
+    // y[w] = P0[w-1] + P1[w] + P2[w+1]: the neighbours' partial sums come from the adjacent lanes
+    float l = __shfl_up_sync(0xffffffffu, __uint_as_float(vl[j]), 1);
+    float r = __shfl_down_sync(0xffffffffu, __uint_as_float(vr[j]), 1);
+    float c = __uint_as_float(v[j]);
+    if (has_left) c += l;
+    if (has_right) c += r;
+    o[j] = c;
+  }
+  const bool live = valid && !(p.debug & 4);
+#pragma unroll
+  for (int q = 0; q < NC / 4; ++q) {
+    float4 val = make_float4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
+    if (live) {
+      const int cg = tn * p.BN + c0 + 4 * q;
+      if (p.bias) {
+        float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + cg));
+        val.x += b.x; val.y += b.y; val.z += b.z; val.w += b.w;
+      }
+      if (rrow) {
+        float4 rr = *reinterpret_cast<const float4*>(rrow + c0 + 4 * q);
+        val.x += rr.x; val.y += rr.y; val.z += rr.z; val.w += rr.w;
+      }
+      if (p.beta != 0.f) {
+        float4 old = *reinterpret_cast<const float4*>(orow + c0 + 4 * q);
+        val.x += p.beta * old.x; val.y += p.beta * old.y; val.z += p.beta * old.z; val.w += p.beta * old.w;
+      }
+      if (p.relu) { val.x = fmaxf(val.x, 0.f); val.y = fmaxf(val.y, 0.f); val.z = fmaxf(val.z, 0.f); val.w = fmaxf(val.w, 0.f); }
+      *reinterpret_cast<float4*>(orow + c0 + 4 * q) = val;
+    } else {
+      val = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    o[4 * q] = val.x; o[4 * q + 1] = val.y; o[4 * q + 2] = val.z; o[4 * q + 3] = val.w;
+  }
+  if (sw && !(p.debug & 4)) {
+    float o2[NC];
+#pragma unroll
+    for (int j = 0; j < NC; ++j) o2[j] = o[j] * o[j];
+    const float cs = butterfly_colsum<NC>(o, lane), cq = butterfly_colsum<NC>(o2, lane);
+    const int col = (NC == 32) ? lane : (lane >> 1);
+    if (NC == 32 || (lane & 1) == 0) {
+      // each (warp, channel) slot is owned by exactly one lane: plain read-modify-write, no atomics
+      sw[tn * p.BN + c0 + col] += cs;
+      sw[p.Nc + tn * p.BN + c0 + col] += cq;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(CT_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, ConvTcParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint8_t* tiles = smem;
+  uint8_t* res_b = smem;                                   // resident weights (res mode), else empty
+  uint8_t* tiles = smem + p.res_b_bytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(tiles + (size_t)p.stages * p.stage_bytes);
   uint64_t* full = bars;
   uint64_t* empty = bars + CT_MAX_STAGES;
   uint64_t* t_full = bars + 2 * CT_MAX_STAGES;
   uint64_t* t_empty = t_full + CT_MAX_ACC;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + CT_MAX_ACC);
-  float* s_stats = reinterpret_cast<float*>(bars + 2 * CT_MAX_STAGES + 2 * CT_MAX_ACC + 2);   // [4 warps][2 * Nc] when stats are requested
+  uint64_t* b_full = t_empty + CT_MAX_ACC;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(b_full + 1);
+  float* s_stats = reinterpret_cast<float*>(bars + 2 * CT_MAX_STAGES + 2 * CT_MAX_ACC + 4);   // [8 warps][2 * Nc]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int total_tiles = p.tiles_m * p.tiles_n;
@@ -108,16 +180,18 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   const int t_end = (p.debug & 1) ? t_begin : min(total_tiles, t_begin + per_cta);
   const int row_bytes = p.cblk * 4;
   const int tiles_per_img = (p.Nb == 1) ? (p.H / p.Hb) : 1;
+  const int b_rows = 3 * p.BN;                              // B rows of one filter row: (s, n)
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&map_a); prefetch_tmap(&map_b);
     for (int s = 0; s < p.stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
     for (int a = 0; a < p.nacc; ++a) { mbar_init(&t_full[a], 1); mbar_init(&t_empty[a], 128); }
+    mbar_init(b_full, 1);
     fence_barrier_init();
     fence_proxy_async();
   }
   if (warp == 2) tmem_alloc(tmem_slot, p.tmem_cols);
-  if (p.stats) for (int i = threadIdx.x; i < 8 * p.Nc; i += blockDim.x) s_stats[i] = 0.f;
+  if (p.stats) for (int i = threadIdx.x; i < 16 * p.Nc; i += blockDim.x) s_stats[i] = 0.f;
   fence_before_sync();
   __syncthreads();
   fence_after_sync();
@@ -127,29 +201,56 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     // ===================== TMA producer
     int stage = 0, phase = 0, tr_n = 0;
     CT_TRACE(0, 0);
-    const uint32_t tx = p.a_bytes + 3 * p.BN * row_bytes;
-    for (int t = t_begin; t < t_end; ++t) {
+    const uint32_t tx = p.rg * (p.a_bytes + b_rows * row_bytes);
+    if (p.res && t_begin < t_end) {
+      // weights once per CTA: three boxes of 3*BN rows (one per filter row; see the tap order note below)
+      mbar_expect_tx(b_full, 3 * b_rows * row_bytes);
+      for (int r = 0; r < 3; ++r) {
+        const int tap0 = p.flip ? 8 - (r * 3 + 2) : r * 3;
+        tma_load_2d(res_b + r * b_rows * row_bytes, &map_b, b_full, 0, tap0 * p.Nc);
+      }
+    }
+    for (int t = t_begin; p.res && t < t_end; ++t) {
+      // one stage per tile: the three vertically shifted input boxes
+      const int tm = t;
+      int n0, h0;
+      if (p.Nb == 1) { n0 = tm / tiles_per_img; h0 = (tm % tiles_per_img) * p.Hb; }
+      else { n0 = tm * p.Nb; h0 = 0; }
+      mbar_wait(&empty[stage], phase ^ 1);
+      CT_TRACE(0, 1);
+      mbar_expect_tx(&full[stage], 3 * p.a_bytes);
+      uint8_t* sa = tiles + (size_t)stage * p.stage_bytes;
+      for (int r = 0; r < 3; ++r) tma_load_4d(sa + r * p.a_bytes, &map_a, &full[stage], 0, 0, h0 + r - 1, n0);
+      CT_TRACE(0, 2);
+      if (++stage == p.stages) { stage = 0; phase ^= 1; }
+    }
+    for (int t = t_begin; !p.res && t < t_end; ++t) {
       const int tm = t / p.tiles_n, tn = t % p.tiles_n;
       int n0, h0;
       if (p.Nb == 1) { n0 = tm / tiles_per_img; h0 = (tm % tiles_per_img) * p.Hb; }
       else { n0 = tm * p.Nb; h0 = 0; }
-      for (int r = 0; r < 3; ++r) {
+      for (int rb = 0; rb < 3; rb += p.rg) {
         for (int kb = 0; kb < p.kblocks; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1);
           CT_TRACE(0, 1);
-          mbar_expect_tx(&full[stage], (p.debug & 2) ? tx - p.a_bytes : tx);
+          mbar_expect_tx(&full[stage], (p.debug & 2) ? tx - p.rg * p.a_bytes : tx);
           uint8_t* sa = tiles + (size_t)stage * p.stage_bytes;
-          if (!(p.debug & 2)) tma_load_4d(sa, &map_a, &full[stage], kb * p.cblk, 0, h0 + r - 1, n0);
-          if (p.b_merged) {
-            // one box of 3*BN rows: taps (r,0),(r,1),(r,2) are consecutive row blocks of B.  For dgrad the tap index
-            // is reversed, so the box starts at tap 8-(3r+2) and holds the s-blocks in the order 2,1,0.
-            const int tap0 = p.flip ? 8 - (r * 3 + 2) : r * 3;
-            tma_load_2d(sa + p.a_bytes, &map_b, &full[stage], kb * p.cblk, tap0 * p.Nc);
-          } else {
-            for (int s = 0; s < 3; ++s) {
-              const int tap = r * 3 + s;
-              const int btap = p.flip ? 8 - tap : tap;
-              tma_load_2d(sa + p.a_bytes + s * p.BN * row_bytes, &map_b, &full[stage], kb * p.cblk, btap * p.Nc + tn * p.BN);
+          uint8_t* sb = sa + p.rg * p.a_bytes;
+          for (int rr = 0; rr < p.rg; ++rr) {
+            const int r = rb + rr;
+            if (!(p.debug & 2)) tma_load_4d(sa + rr * p.a_bytes, &map_a, &full[stage], kb * p.cblk, 0, h0 + r - 1, n0);
+            uint8_t* sbr = sb + rr * b_rows * row_bytes;
+            if (p.b_merged) {
+              // one box of 3*BN rows: taps (r,0),(r,1),(r,2) are consecutive row blocks of B.  For dgrad the tap
+              // index is reversed, so the box starts at tap 8-(3r+2) and holds the s-blocks in the order 2,1,0.
+              const int tap0 = p.flip ? 8 - (r * 3 + 2) : r * 3;
+              tma_load_2d(sbr, &map_b, &full[stage], kb * p.cblk, tap0 * p.Nc);
+            } else {
+              for (int s = 0; s < 3; ++s) {
+                const int tap = r * 3 + s;
+                const int btap = p.flip ? 8 - tap : tap;
+                tma_load_2d(sbr + s * p.BN * row_bytes, &map_b, &full[stage], kb * p.cblk, btap * p.Nc + tn * p.BN);
+              }
             }
           }
           CT_TRACE(0, 2);
@@ -161,39 +262,98 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     // ===================== MMA issuer
     const uint32_t idesc = umma_idesc(2 /*tf32*/, CT_BM, 3 * p.BN);
     const uint32_t sbo = 8 * row_bytes;
-    int stage = 0, phase = 0, acc = 0, acc_phase = 0, tr_n = 0;
+    int stage = 0, phase = 0, tr_n = 0;
     CT_TRACE(1, 0);
-    for (int t = t_begin; t < t_end; ++t) {
+    if (p.res && t_begin < t_end) {
+      // Small layers are bound by the instruction stream of this single issuing thread: everything that does
+      // not change inside a group of tiles is hoisted, descriptors are (constant high word | address), and the
+      // MMAs of up to four tiles are interleaved (independent accumulators back to back).
+      mbar_wait(b_full, 0);
+      const uint32_t dhi = umma_desc_hi_kmajor(sbo, row_bytes);
+      const uint32_t bres = smem_u32(res_b);
+      const uint32_t tiles_u32 = smem_u32(tiles);
+      const int kst = p.cblk / 8;
+      int s_idx = 0, s_ph = 0, a_idx = 0, a_ph = 0;
+      for (int g0 = t_begin; g0 < t_end; g0 += p.nt) {
+        const int nj = min(p.nt, t_end - g0);
+        uint32_t a_addr[4], d_addr[4];
+        uint64_t* e_bar[4];
+        uint64_t* f_bar[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (j < nj) {
+            mbar_wait(&t_empty[a_idx], a_ph ^ 1);
+            mbar_wait(&full[s_idx], s_ph);
+            a_addr[j] = tiles_u32 + s_idx * p.stage_bytes;
+            d_addr[j] = tmem_base + a_idx * p.acc_stride;
+            e_bar[j] = &empty[s_idx];
+            f_bar[j] = &t_full[a_idx];
+            if (++s_idx == p.stages) { s_idx = 0; s_ph ^= 1; }
+            if (++a_idx == p.nacc) { a_idx = 0; a_ph ^= 1; }
+          }
+        }
+        CT_TRACE(1, 2);
+        fence_after_sync();
+        for (int r = 0; r < 3; ++r) {
+          for (int ks = 0; ks < kst; ++ks) {
+            const uint64_t db = umma_desc_join(dhi, bres + r * b_rows * row_bytes + ks * 32);
+            const uint32_t aoff = r * p.a_bytes + ks * 32;
+            if ((r | ks) == 0) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+                if (j < nj) mma_tf32_c<false>(d_addr[j], umma_desc_join(dhi, a_addr[j] + aoff), db, idesc);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+                if (j < nj) mma_tf32_c<true>(d_addr[j], umma_desc_join(dhi, a_addr[j] + aoff), db, idesc);
+            }
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (j < nj) { mma_commit(e_bar[j]); mma_commit(f_bar[j]); }
+        }
+        CT_TRACE(1, 3);
+      }
+    }
+    for (int t = t_begin; !p.res && t < t_end; ++t) {
+      const int i = t - t_begin, acc = i % p.nacc, acc_phase = (i / p.nacc) & 1;
       mbar_wait(&t_empty[acc], acc_phase ^ 1);
       CT_TRACE(1, 1);
       fence_after_sync();
       const uint32_t d_tmem = tmem_base + acc * p.acc_stride;
       uint32_t first = 1;
-      for (int it = 0; it < 3 * p.kblocks; ++it) {
+      for (int it = 0; it < (3 / p.rg) * p.kblocks; ++it) {
         mbar_wait(&full[stage], phase);
         CT_TRACE(1, 2);
         fence_after_sync();
         const uint32_t a0 = smem_u32(tiles + (size_t)stage * p.stage_bytes);
-        const uint32_t b0 = a0 + p.a_bytes;
-        for (int ks = 0; ks < p.cblk / 8; ++ks) {
-          const uint64_t da = umma_desc_kmajor(a0 + ks * 32, sbo, row_bytes);
-          const uint64_t db = umma_desc_kmajor(b0 + ks * 32, sbo, row_bytes);
-          mma_tf32(d_tmem, da, db, idesc, first ? 0u : 1u);
-          first = 0;
+        const uint32_t b0 = a0 + p.rg * p.a_bytes;
+        const uint32_t dhi = umma_desc_hi_kmajor(sbo, row_bytes);
+        for (int rr = 0; rr < p.rg; ++rr) {
+          for (int ks = 0; ks < p.cblk / 8; ++ks) {
+            const uint64_t da = umma_desc_join(dhi, a0 + rr * p.a_bytes + ks * 32);
+            const uint64_t db = umma_desc_join(dhi, b0 + rr * b_rows * row_bytes + ks * 32);
+            if (first) mma_tf32_c<false>(d_tmem, da, db, idesc);
+            else mma_tf32_c<true>(d_tmem, da, db, idesc);
+            first = 0;
+          }
         }
         mma_commit(&empty[stage]);
         CT_TRACE(1, 3);
         if (++stage == p.stages) { stage = 0; phase ^= 1; }
       }
       mma_commit(&t_full[acc]);
-      if (++acc == p.nacc) { acc = 0; acc_phase ^= 1; }
     }
   } else if (warp >= 4) {
-    // ===================== epilogue (4 warps, one TMEM lane quarter each)
-    const int q4 = warp & 3;
-    int acc = 0, acc_phase = 0, tr_n = (warp == 4 && lane == 0) ? 0 : 1000;
+    // ===================== epilogue: two groups of 4 warps take alternate tiles; a warp owns one TMEM lane quarter
+    const int q4 = warp & 3, grp = (warp - 4) >> 2;
+    int tr_n = (warp == 4 && lane == 0) ? 0 : 1000;
     CT_TRACE(2, 0);
-    for (int t = t_begin; t < t_end; ++t) {
+    float* sw = p.stats ? s_stats + (warp - 4) * 2 * p.Nc : nullptr;
+    const int lblk = (p.b_merged && p.flip) ? 2 : 0;   // column block holding the s=0 partial sums
+    for (int t = t_begin + grp; t < t_end; t += 2) {
+      const int i = t - t_begin, acc = i % p.nacc, acc_phase = (i / p.nacc) & 1;
       const int tm = t / p.tiles_n, tn = t % p.tiles_n;
       const int m = q4 * 32 + lane;                 // row of the tile == TMEM lane
       const int wb = m % p.Wb, hb = (m / p.Wb) % p.Hb, nb = m / (p.Wb * p.Hb);
@@ -204,93 +364,29 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       const long long pix = ((long long)n * p.H + h) * p.W + wb;
       float* orow = p.out + pix * p.Nc + tn * p.BN;
       const float* rrow = p.residual ? p.residual + pix * p.Nc + tn * p.BN : nullptr;
+      const bool has_left = wb > 0, has_right = wb < p.W - 1;
       mbar_wait(&t_full[acc], acc_phase);
       CT_TRACE(2, 1);
       fence_after_sync();
       const uint32_t t_addr = tmem_base + ((uint32_t)(q4 * 32) << 16) + acc * p.acc_stride;
-      const bool has_left = wb > 0, has_right = wb < p.W - 1;
-      for (int c0 = 0; c0 < p.BN; c0 += 32) {
-        const int nc = min(32, p.BN - c0);          // 32, or a final block of 16
-        uint32_t v[32], vl[32], vr[32];             // centre (s=1), left (s=0) and right (s=2) partial sums
-        const int lblk = (p.b_merged && p.flip) ? 2 : 0;   // column block holding the s=0 partial sums
-        if (nc == 32) {
-          tmem_ld_32x32(t_addr + lblk * p.BN + c0, vl);
-          tmem_ld_32x32(t_addr + p.BN + c0, v);
-          tmem_ld_32x32(t_addr + (2 - lblk) * p.BN + c0, vr);
-        } else {
-          tmem_ld_32x16(t_addr + lblk * p.BN + c0, vl);
-          tmem_ld_32x16(t_addr + p.BN + c0, v);
-          tmem_ld_32x16(t_addr + (2 - lblk) * p.BN + c0, vr);
-#pragma unroll
-          for (int j = 16; j < 32; ++j) { v[j] = 0u; vl[j] = 0u; vr[j] = 0u; }
-        }
-        tmem_ld_wait();
-        CT_TRACE(2, 2);
-        if (c0 + 32 >= p.BN) {                      // last block of this accumulator: release it
-          fence_before_sync();
-          mbar_arrive(&t_empty[acc]);
-        }
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          // y[w] = P0[w-1] + P1[w] + P2[w+1]: the neighbours' partial sums come from the adjacent lanes
-          float l = __shfl_up_sync(0xffffffffu, __uint_as_float(vl[j]), 1);
-          float r = __shfl_down_sync(0xffffffffu, __uint_as_float(vr[j]), 1);
-          float c = __uint_as_float(v[j]);
-          if (has_left) c += l;
-          if (has_right) c += r;
-          v[j] = __float_as_uint(c);
-        }
-        float o[32], o2[32];
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          float4 val = make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]), __uint_as_float(v[4 * q + 2]),
-                                   __uint_as_float(v[4 * q + 3]));
-          const bool live = valid && (4 * q < nc) && !(p.debug & 4);
-          if (live) {
-            const int cg = tn * p.BN + c0 + 4 * q;
-            if (p.bias) {
-              float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + cg));
-              val.x += b.x; val.y += b.y; val.z += b.z; val.w += b.w;
-            }
-            if (rrow) {
-              float4 rr = *reinterpret_cast<const float4*>(rrow + c0 + 4 * q);
-              val.x += rr.x; val.y += rr.y; val.z += rr.z; val.w += rr.w;
-            }
-            if (p.beta != 0.f) {
-              float4 old = *reinterpret_cast<const float4*>(orow + c0 + 4 * q);
-              val.x += p.beta * old.x; val.y += p.beta * old.y; val.z += p.beta * old.z; val.w += p.beta * old.w;
-            }
-            if (p.relu) { val.x = fmaxf(val.x, 0.f); val.y = fmaxf(val.y, 0.f); val.z = fmaxf(val.z, 0.f); val.w = fmaxf(val.w, 0.f); }
-            *reinterpret_cast<float4*>(orow + c0 + 4 * q) = val;
-          } else {
-            val = make_float4(0.f, 0.f, 0.f, 0.f);
-          }
-          o[4 * q] = val.x; o[4 * q + 1] = val.y; o[4 * q + 2] = val.z; o[4 * q + 3] = val.w;
-        }
-        if (p.stats && !(p.debug & 4)) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) o2[j] = o[j] * o[j];
-          float cs, cq;
-          int col;
-          if (nc == 32) { cs = butterfly_colsum<32>(o, lane); cq = butterfly_colsum<32>(o2, lane); col = lane; }
-          else { cs = butterfly_colsum<16>(o, lane); cq = butterfly_colsum<16>(o2, lane); col = lane >> 1; }
-          if (nc == 32 || (lane & 1) == 0) {
-            // each (warp, channel) slot is owned by exactly one lane: plain read-modify-write, no atomics
-            float* sw = s_stats + q4 * 2 * p.Nc;
-            sw[tn * p.BN + c0 + col] += cs;
-            sw[p.Nc + tn * p.BN + c0 + col] += cq;
-          }
-        }
-      }
+      int c0 = 0;
+      for (; c0 + 32 <= p.BN; c0 += 32)
+        conv_tc_epilogue_block<32>(p, t_addr, lblk, c0, tn, valid, has_left, has_right, orow, rrow, sw, lane);
+      if (c0 < p.BN)
+        conv_tc_epilogue_block<16>(p, t_addr, lblk, c0, tn, valid, has_left, has_right, orow, rrow, sw, lane);
+      CT_TRACE(2, 2);
+      fence_before_sync();                          // all TMEM reads of this accumulator are complete
+      mbar_arrive(&t_empty[acc]);
       CT_TRACE(2, 3);
-      if (++acc == p.nacc) { acc = 0; acc_phase ^= 1; }
     }
   }
 
   __syncthreads();
   if (p.stats) {
     for (int i = threadIdx.x; i < 2 * p.Nc; i += blockDim.x) {
-      double v = (double)s_stats[i] + (double)s_stats[2 * p.Nc + i] + (double)s_stats[4 * p.Nc + i] + (double)s_stats[6 * p.Nc + i];
+      double v = 0.0;
+#pragma unroll
+      for (int wv = 0; wv < 8; ++wv) v += (double)s_stats[wv * 2 * p.Nc + i];
       if (v != 0.0) atomicAdd(&p.stats[i], v);
     }
   }
@@ -354,10 +450,28 @@ static int conv_tc_launch(const se_conv_desc* d, const float* a_tensor, int Kc, 
   p.kblocks = Kc / p.cblk;
   p.flip = flip; p.relu = relu; p.beta = beta;
   p.a_bytes = CT_BM * p.cblk * 4;
-  const int b_bytes = ceil_div(3 * p.BN * p.cblk * 4, 1024) * 1024;
-  p.stage_bytes = p.a_bytes + b_bytes;
+  // the whole 3x3 window of a channel block in one pipeline stage when two such stages fit (fewer barrier
+  // round trips per tile: small layers are bound by the single MMA-issuing thread, not by bandwidth)
+  p.rg = 3;
+  p.stage_bytes = 3 * p.a_bytes + ceil_div(9 * p.BN * p.cblk * 4, 1024) * 1024;
+  if (2 * p.stage_bytes > CT_SMEM_BUDGET) {
+    p.rg = 1;
+    p.stage_bytes = p.a_bytes + ceil_div(3 * p.BN * p.cblk * 4, 1024) * 1024;
+  }
   p.stages = min(CT_MAX_STAGES, CT_SMEM_BUDGET / p.stage_bytes);
   if (p.stages < 2) return SE_ERR_UNSUPPORTED;
+  // resident-weights mode: every tile of the CTA uses the same 9*BN x Kc weight block
+  p.res = 0; p.res_b_bytes = 0; p.nt = 1;
+  static const char* dbg_nores = getenv("SE_CT_NORES");
+  const int wbytes = ceil_div(9 * p.BN * Kc * 4, 1024) * 1024;
+  if (!dbg_nores && p.tiles_n == 1 && p.kblocks == 1 && wbytes <= 40 * 1024) {
+    p.res = 1; p.res_b_bytes = wbytes; p.rg = 3;
+    p.stage_bytes = 3 * p.a_bytes;
+    p.stages = min(CT_MAX_STAGES, (CT_SMEM_BUDGET - wbytes) / p.stage_bytes);
+    static const char* dbg_nt = getenv("SE_CT_NT");
+    p.nt = dbg_nt ? atoi(dbg_nt) : 4;
+    p.nt = max(1, min(min(p.nt, 4), p.stages - 1));
+  }
   static const char* dbg_stages = getenv("SE_CT_STAGES");         // tuning knobs for scripts/bench_conv.py
   static const char* dbg_mode = getenv("SE_CT_DEBUG");
   if (dbg_stages) p.stages = max(1, min(p.stages, atoi(dbg_stages)));
@@ -368,9 +482,10 @@ static int conv_tc_launch(const se_conv_desc* d, const float* a_tensor, int Kc, 
   while (stride < 3 * p.BN) stride <<= 1;
   if (2 * stride > 512) return SE_ERR_UNSUPPORTED;
   p.tmem_cols = 512; p.acc_stride = stride; p.nacc = min(CT_MAX_ACC, 512 / stride);
+  p.nt = max(1, min(p.nt, p.nacc));
   p.b_merged = (p.tiles_n == 1) ? 1 : 0;
   p.bias = bias; p.residual = residual; p.out = out; p.stats = stats;
-  if (stats && (size_t)8 * Nc * sizeof(float) > 24 * 1024) return SE_ERR_UNSUPPORTED;
+  if (stats && (size_t)16 * Nc * sizeof(float) > 24 * 1024) return SE_ERR_UNSUPPORTED;
 
   CUtensorMap ma, mb;
   {
@@ -384,10 +499,10 @@ static int conv_tc_launch(const se_conv_desc* d, const float* a_tensor, int Kc, 
     uint32_t bbox[2] = {(uint32_t)p.cblk, (uint32_t)(p.b_merged ? 3 * p.BN : p.BN)};
     if (!make_tmap(&mb, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(bmat), bdims, bstrides, bbox, sw)) return SE_ERR_CUDA;
   }
-  const size_t smem = (size_t)p.stages * p.stage_bytes + (2 * CT_MAX_STAGES + 2 * CT_MAX_ACC + 2) * 8 + (stats ? 8 * Nc * 4 : 0) + 1024 + 64;
+  const size_t smem = (size_t)p.res_b_bytes + (size_t)p.stages * p.stage_bytes + (2 * CT_MAX_STAGES + 2 * CT_MAX_ACC + 4) * 8 + (stats ? 16 * Nc * 4 : 0) + 1024 + 64;
   if (smem > 227 * 1024) return SE_ERR_UNSUPPORTED;
   int grid = min(sm_count(), p.tiles_m * p.tiles_n);
-  conv_tc_kernel<<<grid, 256, smem, st>>>(ma, mb, p);
+  conv_tc_kernel<<<grid, CT_THREADS, smem, st>>>(ma, mb, p);
   return check_launch("conv_tc_kernel");
 }
 

@@ -4,7 +4,11 @@
 //
 // The reduction dimension is the PIXEL axis, so both operands are "MN-major" for the tensor core (channels are
 // contiguous, pixels are strided): no transposition of activations is needed, the NHWC tiles that TMA drops into
-// shared memory are consumed as they are.
+// shared memory are consumed as they are.  For 32-bit (TF32) operands the tensor core accepts MN-major data only in
+// the SWIZZLE_128B_BASE32B layout (32-byte swizzle granules, atoms of 32 channels x 4 pixels), which TMA produces
+// with CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B.  Channel counts that are not multiples of 32 (the 16-channel stage of
+// ResNet-110) are handled by letting the TMA box be 32 channels wide: the out-of-range channels are zero-filled
+// by the hardware, so the tile still has 128-byte rows; the zero rows / columns of D are simply not written back.
 //
 //   GEMM per pixel tile:  D[(blk, ci), co] += A[(blk, ci), pix] * B[co, pix]
 //     A = the nine tap-shifted input tiles (4-D TMA boxes, zero-filled halo = 'same' padding) plus one all-ones
@@ -14,6 +18,8 @@
 //   Accumulators stay in TMEM across ALL pixel tiles of a CTA (split-K over CTAs); one epilogue at the end adds
 //   them into dW / dbias with vector atomics.
 // grid = (pixel-tile groups, ci chunks of 32, 1); persistent over its pixel tiles.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "tc.cuh"
 
@@ -37,11 +43,10 @@ struct WgTcParams {
   float* dbias;
 };
 
-// MN-major operand: `blocks` of (cb channels x 8 pixels) atoms; LBO = distance between channel blocks,
-// SBO = distance between 8-pixel groups (one instruction consumes exactly one group: K = 8).
-__device__ __forceinline__ uint64_t umma_desc_mnmajor(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes,
-                                                      uint32_t swizzle_bytes) {
-  uint64_t layout = swizzle_bytes == 128 ? 2ull : (swizzle_bytes == 64 ? 4ull : 6ull);
+// MN-major TF32 operand: atoms of 32 channels x 4 pixels (512 B); LBO = distance between 32-channel blocks,
+// SBO = distance between consecutive 4-pixel atoms (one instruction consumes two of them: K = 8).
+__device__ __forceinline__ uint64_t umma_desc_mnmajor(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  const uint64_t layout = 1ull;             // SWIZZLE_128B_BASE32B
   uint64_t d = 0;
   d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
   d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
@@ -119,11 +124,18 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
         fence_after_sync();
         const uint32_t sb = smem_u32(tiles + (size_t)stage * p.stage_bytes);
         const uint32_t dyb = sb + 10 * p.xa_bytes;
+        // descriptors = constant high word | (address, LBO) low word; accumulate flag resolved at compile time
+        const uint32_t hi = ((4 * n_row_bytes) >> 4) | (1u << 14) | (1u << 29);          // SBO, version 1, BASE32B
+        const uint32_t hia = ((4 * row_bytes) >> 4) | (1u << 14) | (1u << 29);
+        const uint32_t lbo_b = (((uint32_t)(p.PT * n_row_bytes) >> 4) & 0x3FFFu) << 16;
+        const uint32_t lbo_a = (((uint32_t)p.xa_bytes >> 4) & 0x3FFFu) << 16;
         for (int ks = 0; ks < p.PT / 8; ++ks) {
-          const uint64_t db = umma_desc_mnmajor(dyb + ks * 8 * n_row_bytes, p.PT * n_row_bytes, 8 * n_row_bytes, n_row_bytes);
+          const uint64_t db = ((uint64_t)hi << 32) | (uint64_t)((((dyb + ks * 8 * n_row_bytes) & 0x3FFFFu) >> 4) | lbo_b);
           for (int g = 0; g < p.G; ++g) {
-            const uint64_t da = umma_desc_mnmajor(sb + p.first[g] * p.xa_bytes + ks * 8 * row_bytes, p.xa_bytes, 8 * row_bytes, row_bytes);
-            mma_tf32(tmem_base + g * ncols, da, db, idesc, first ? 0u : 1u);
+            const uint32_t aaddr = sb + min(g * p.per, p.nblk - p.per) * p.xa_bytes + ks * 8 * row_bytes;
+            const uint64_t da = ((uint64_t)hia << 32) | (uint64_t)(((aaddr & 0x3FFFFu) >> 4) | lbo_a);
+            if (first) mma_tf32_c<false>(tmem_base + g * ncols, da, db, idesc);
+            else mma_tf32_c<true>(tmem_base + g * ncols, da, db, idesc);
           }
           first = 0;
         }
@@ -138,14 +150,16 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
       fence_after_sync();
       const int l = q4 * 32 + lane;
       for (int g = 0; g < p.G; ++g) {
-        const int blk = p.first[g] + l / p.cb;
+        const int fg = min(g * p.per, p.nblk - p.per), fprev = min((g - 1) * p.per, p.nblk - p.per);
+        const int blk = fg + l / p.cb;
         const int ci = ci0 + l % p.cb;
-        const bool fresh = (g == 0) || (blk >= p.first[g - 1] + p.per);      // not already covered by the previous MMA
+        const bool fresh = (g == 0) || (blk >= fprev + p.per);               // not already covered by the previous MMA
         const bool is_bias = (blk == 9);
         float* dst = nullptr;
         if (fresh && blk < 9 && ci < p.Cin) dst = p.dw + ((long long)blk * p.Cin + ci) * p.Cout;
         if (fresh && is_bias && (l % p.cb) == 0 && blockIdx.y == 0 && p.dbias) dst = p.dbias;
         for (int c0 = 0; c0 < ncols; c0 += 16) {
+          const bool col_ok = c0 < p.Cout;             // columns past Cout come from zero-filled channels
           uint32_t v[16];
           asm volatile(
               "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
@@ -154,7 +168,7 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
               : "r"(tmem_base + ((uint32_t)(q4 * 32) << 16) + g * ncols + c0)
               : "memory");
           tmem_ld_wait();
-          if (dst) {
+          if (dst && col_ok) {
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
               float4 val = make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]), __uint_as_float(v[4 * q + 2]),
@@ -183,8 +197,11 @@ int conv_wgrad_tc(const se_conv_desc* d, const float* x, const float* dy, float*
   if (d->kh != 3 || d->kw != 3 || d->stride != 1 || d->pad_t != 1 || d->pad_l != 1 || d->Ho != d->H || d->Wo != d->W)
     return SE_ERR_UNSUPPORTED;
   const int Cin = d->Cin, Cout = d->Cout, W = d->W, H = d->H;
-  if (Cin % 16 != 0 || Cout % 16 != 0 || (Cin > 16 && Cin % 32 != 0) || (Cout > 16 && Cout % 32 != 0) || Cout > 256)
-    return SE_ERR_UNSUPPORTED;
+  if (Cin % 16 != 0 || Cout % 16 != 0 || Cout > 256) return SE_ERR_UNSUPPORTED;
+  // 16-channel layers would run with half-empty (zero-filled) 32-wide blocks: measured slower (44 us) than the fp32
+  // FFMA kernel (32 us) on the ResNet-110 stage-1 shape because the single MMA-issuing thread is the limit there
+  static const char* force16 = getenv("SE_WG_TC16");
+  if ((Cin < 32 || Cout < 32) && !force16) return SE_ERR_UNSUPPORTED;
   if (W > 64 || (W & (W - 1)) != 0 || W < 4) return SE_ERR_UNSUPPORTED;
   if ((reinterpret_cast<uintptr_t>(dw) & 15) != 0 || (dbias && (reinterpret_cast<uintptr_t>(dbias) & 15) != 0))
     return SE_ERR_UNSUPPORTED;
@@ -193,11 +210,11 @@ int conv_wgrad_tc(const se_conv_desc* d, const float* x, const float* dy, float*
 
   WgTcParams p;
   p.N = d->N; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout;
-  p.cb = Cin >= 32 ? 32 : 16;
-  p.ci_chunk = p.cb;
-  p.cbn = Cout >= 32 ? 32 : 16;
-  p.nnb = Cout / p.cbn;
-  p.PT = (p.cb == 16 && p.nnb <= 1) ? 128 : 64;
+  p.cb = 32;
+  p.ci_chunk = 32;
+  p.cbn = 32;
+  p.nnb = ceil_div(Cout, 32);
+  p.PT = 64;
   p.Wb = W;
   if (W * H >= p.PT) { if (H % (p.PT / W) != 0) return SE_ERR_UNSUPPORTED; p.Hb = p.PT / W; p.Nb = 1; }
   else { if (p.PT % (W * H) != 0) return SE_ERR_UNSUPPORTED; p.Hb = H; p.Nb = p.PT / (W * H); }
@@ -206,9 +223,9 @@ int conv_wgrad_tc(const se_conv_desc* d, const float* x, const float* dy, float*
   p.G = ceil_div(p.nblk, p.per);
   for (int g = 0; g < 4; ++g) p.first[g] = 0;
   for (int g = 0; g < p.G; ++g) p.first[g] = min(g * p.per, p.nblk - p.per);
-  if (p.G * Cout > 512) return SE_ERR_UNSUPPORTED;
+  if (p.G * p.cbn * p.nnb > 512) return SE_ERR_UNSUPPORTED;
   p.xa_bytes = p.PT * p.cb * 4;
-  p.dy_bytes = p.PT * Cout * 4;
+  p.dy_bytes = p.PT * p.cbn * p.nnb * 4;
   p.stage_bytes = ceil_div(10 * p.xa_bytes + p.dy_bytes, 1024) * 1024;
   p.stages = min(4, (200 * 1024) / p.stage_bytes);
   if (p.stages < 1) return SE_ERR_UNSUPPORTED;
@@ -221,16 +238,16 @@ int conv_wgrad_tc(const se_conv_desc* d, const float* x, const float* dy, float*
     uint64_t strides[3] = {(uint64_t)Cin * 4, (uint64_t)W * Cin * 4, (uint64_t)H * W * Cin * 4};
     uint32_t box[4] = {(uint32_t)p.cb, (uint32_t)p.Wb, (uint32_t)p.Hb, (uint32_t)p.Nb};
     if (!make_tmap(&mx, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(x), dims, strides, box,
-                   p.cb == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B))
+                   CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B))
       return SE_ERR_CUDA;
     uint64_t ydims[4] = {(uint64_t)Cout, (uint64_t)W, (uint64_t)H, (uint64_t)d->N};
     uint64_t ystrides[3] = {(uint64_t)Cout * 4, (uint64_t)W * Cout * 4, (uint64_t)H * W * Cout * 4};
     uint32_t ybox[4] = {(uint32_t)p.cbn, (uint32_t)p.Wb, (uint32_t)p.Hb, (uint32_t)p.Nb};
     if (!make_tmap(&mdy, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(dy), ydims, ystrides, ybox,
-                   p.cbn == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B))
+                   CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B))
       return SE_ERR_CUDA;
   }
-  const int gy = Cin / p.ci_chunk;
+  const int gy = ceil_div(Cin, p.ci_chunk);
   const int gx = max(1, min(p.tiles_m, sm_count() / gy));
   const size_t smem = (size_t)p.stages * p.stage_bytes + 16 * 8 + 1024 + 64;
   conv_wgrad_tc_kernel<<<dim3(gx, gy, 1), 192, smem, st>>>(mx, mdy, p);

@@ -103,6 +103,25 @@ __device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64
       ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// same with the accumulate flag fixed at compile time: no runtime predicate (which costs a divergence-safe
+// uniform-predicate sequence per instruction) -- use these in latency-critical issue loops
+template <bool ACC>
+__device__ __forceinline__ void mma_tf32_c(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc) {
+  if (ACC)
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.eq.u32 p, 1, 1;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc) : "memory");
+  else
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.eq.u32 p, 1, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc) : "memory");
+}
+// shared-memory descriptor split into its constant high word and the low word (start address + LBO field)
+__device__ __forceinline__ uint32_t umma_desc_hi_kmajor(uint32_t sbo_bytes, uint32_t swizzle_bytes) {
+  uint32_t layout = swizzle_bytes == 128 ? 2u : (swizzle_bytes == 64 ? 4u : (swizzle_bytes == 32 ? 6u : 0u));
+  return ((sbo_bytes >> 4) & 0x3FFFu) | (1u << 14) | (layout << 29);
+}
+__device__ __forceinline__ uint64_t umma_desc_join(uint32_t hi, uint32_t addr_bytes) {
+  return ((uint64_t)hi << 32) | (uint64_t)(((addr_bytes & 0x3FFFFu) >> 4) | (1u << 16));
+}
 // arrive on an mbarrier when every previously issued tcgen05.mma of this thread has completed
 __device__ __forceinline__ void mma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");

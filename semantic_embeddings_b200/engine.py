@@ -153,9 +153,9 @@ class Engine:
             if n.op == 'bn':
                 c = n.output.shape[-1]
                 self.bn_slot[n.name] = (tot, c)
-                tot += 4 * c
+                tot += 4 * c + 2                              # fwd sums 2C | bwd sums 2C | grid-barrier counter
         self.stats = torch.zeros(max(tot, 4), dtype=torch.float64, device=dev)
-        self.saved = torch.zeros(max(tot // 2, 4), **f32)
+        self.saved = torch.zeros(max(tot // 2 + 4, 4), **f32)
         self.sgd_out = torch.zeros(2, dtype=torch.float64, device=dev)
         self.lr_dev = torch.zeros(1, **f32)
         self.set_weights(self._initial_weights(seed))
@@ -380,7 +380,7 @@ class Engine:
                 c = x.shape[-1]
                 rows = self._rows(x)
                 off, _ = self.bn_slot[n.name]
-                scratch = self.stats[off + 2 * c:off + 4 * c]
+                scratch = self.stats[off + 2 * c:off + 4 * c + 2]
                 sm = self.saved[off // 2:off // 2 + c]
                 si = self.saved[off // 2 + c:off // 2 + 2 * c]
                 a = n.attrs

@@ -230,7 +230,7 @@ def test_bn_train_forward_backward(case):
     dxd = torch.full((N, H, W, C), 3.0, device='cuda')
     dgd = torch.zeros(C, device='cuda')
     dbd = torch.zeros(C, device='cuda')
-    scratch = torch.zeros(2 * C, dtype=torch.float64, device='cuda')
+    scratch = torch.zeros(2 * C + 1, dtype=torch.float64, device='cuda')
     dresd = None
     if reskind == 'same':
         dresd = torch.full((N, H, W, C), 5.0, device='cuda')
