@@ -95,6 +95,8 @@ def cpu_reference_arm(steps, warmup, sample_batch=None, budget_s=150.0):
     from oracle import models as omodels
     from oracle import train as otrain
     emb = np.load(os.path.join(ROOT, 'tests', 'golden', 'class_matrices.npz'))['cifar100_embedding']
+    # torch.distributed.run exports OMP_NUM_THREADS=1: give the CPU arm every host core explicitly
+    torch.set_num_threads(max(1, os.cpu_count() or 1))
     cores = torch.get_num_threads()
     om = omodels.build_network(100, ARCH, input_channels=3, seed=0)
     otrain.cast_model(om, torch.float32)
@@ -234,6 +236,8 @@ def run_native(args):
     dev = torch.device('cuda', local)
     if world > 1:
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        if os.environ.get('NCCL_DEBUG', 'VERSION').upper() == 'VERSION':
+            os.environ['NCCL_DEBUG'] = 'WARN'         # keep stdout to the single JSON line (NCCL prints its version there)
         dist.init_process_group('nccl', device_id=dev)
     L.load()
     pk = peaks()

@@ -356,20 +356,25 @@ conv_wgrad_kernel(ConvP p, const float* __restrict__ x, const float* __restrict_
 }
 
 // ---------------------------------------------------------------------------------------- wgrad 3x3 stride 1 'same'
-// One CTA walks over (image, row-band) tiles with the 9 x CI_T x CO_T partial sums of its
-// (ci, co) pairs in registers: per pixel it reads 3 new x values per ci and 1 dy value per co
-// from shared memory for 9 FMAs per pair (sliding 3x3 window), then adds the result into dW once.
-template <int CI_T, int CO_T>
+// One CTA walks over (image, row-band) tiles with the 9 x 2 x 2 partial sums of its (ci, co) pairs in registers:
+// per pixel a thread reads 3x2 new x values and 2 dy values from shared memory for 36 FMAs (sliding 3x3 window,
+// 2x2 register block).  NCI x NCO threads cover the channel tile; when that is fewer than 256 (16-channel layers)
+// the remaining threads form RG "row groups" that take alternate rows of the band and are reduced through shared
+// memory at the end, so that all 256 threads have work.  The result is added into dW once per CTA.
+template <int NCI, int NCO>
 __global__ void __launch_bounds__(256)
 conv_wgrad3x3_kernel(ConvP p, const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ dw,
                      float* __restrict__ dbias, int TH, int tiles_per_img, int num_tiles) {
-  constexpr int CIT = 16 * CI_T, COT = 16 * CO_T;
+  constexpr int CI_T = 2, CO_T = 2;
+  constexpr int CIT = NCI * CI_T, COT = NCO * CO_T;
+  constexpr int PAIRS = NCI * NCO, RG = 256 / PAIRS;
   extern __shared__ __align__(16) float smem[];
   const int W = p.W, H = p.H;
   float* xs = smem;                                   // [(TH+2)][(W+2)][CIT]
   float* ds = smem + (TH + 2) * (W + 2) * CIT;        // [TH][W][COT]
   const int tid = threadIdx.x;
-  const int tco = tid & 15, tci = tid >> 4;
+  const int pair = tid % PAIRS, rg = tid / PAIRS;
+  const int tco = pair % NCO, tci = pair / NCO;
   const int ci0 = blockIdx.y * CIT, co0 = blockIdx.z * COT;
 
   float acc[3][3][CI_T][CO_T];
@@ -410,19 +415,19 @@ conv_wgrad3x3_kernel(ConvP p, const float* __restrict__ x, const float* __restri
       *reinterpret_cast<float4*>(ds + t * COT + 4 * q) = v;
     }
     __syncthreads();
-    for (int h = 0; h < th; ++h) {
+    for (int h = rg; h < th; h += RG) {
       float win[3][2][CI_T];  // previous two columns of the three halo rows
 #pragma unroll
       for (int r = 0; r < 3; ++r)
 #pragma unroll
         for (int a = 0; a < CI_T; ++a) {
-          win[r][0][a] = xs[((h + r) * (W + 2) + 0) * CIT + tci + 16 * a];
-          win[r][1][a] = xs[((h + r) * (W + 2) + 1) * CIT + tci + 16 * a];
+          win[r][0][a] = xs[((h + r) * (W + 2) + 0) * CIT + tci + NCI * a];
+          win[r][1][a] = xs[((h + r) * (W + 2) + 1) * CIT + tci + NCI * a];
         }
       for (int wcol = 0; wcol < W; ++wcol) {
         float d[CO_T];
 #pragma unroll
-        for (int b = 0; b < CO_T; ++b) d[b] = ds[(h * W + wcol) * COT + tco + 16 * b];
+        for (int b = 0; b < CO_T; ++b) d[b] = ds[(h * W + wcol) * COT + tco + NCO * b];
         if (tci == 0) {
 #pragma unroll
           for (int b = 0; b < CO_T; ++b) bacc[b] += d[b];
@@ -431,7 +436,7 @@ conv_wgrad3x3_kernel(ConvP p, const float* __restrict__ x, const float* __restri
         for (int r = 0; r < 3; ++r) {
           float xc[CI_T];
 #pragma unroll
-          for (int a = 0; a < CI_T; ++a) xc[a] = xs[((h + r) * (W + 2) + wcol + 2) * CIT + tci + 16 * a];
+          for (int a = 0; a < CI_T; ++a) xc[a] = xs[((h + r) * (W + 2) + wcol + 2) * CIT + tci + NCI * a];
 #pragma unroll
           for (int a = 0; a < CI_T; ++a)
 #pragma unroll
@@ -446,20 +451,66 @@ conv_wgrad3x3_kernel(ConvP p, const float* __restrict__ x, const float* __restri
       }
     }
   }
+  if (RG > 1) {
+    // combine the row groups: red[rg][(r,s,a,b)][pair] in shared memory (reuses the tile buffers)
+    __syncthreads();
+    float* red = smem;
 #pragma unroll
-  for (int r = 0; r < 3; ++r)
+    for (int r = 0; r < 3; ++r)
 #pragma unroll
-    for (int s = 0; s < 3; ++s)
+      for (int s = 0; s < 3; ++s)
 #pragma unroll
-      for (int a = 0; a < CI_T; ++a)
+        for (int a = 0; a < CI_T; ++a)
+#pragma unroll
+          for (int b = 0; b < CO_T; ++b)
+            red[(rg * 36 + ((r * 3 + s) * CI_T + a) * CO_T + b) * PAIRS + pair] = acc[r][s][a][b];
+    float* redb = smem + RG * 36 * PAIRS;
+    if (tci == 0) {
+#pragma unroll
+      for (int b = 0; b < CO_T; ++b) redb[(rg * CO_T + b) * NCO + tco] = bacc[b];
+    }
+    __syncthreads();
+    if (rg == 0) {
+#pragma unroll
+      for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int s = 0; s < 3; ++s)
+#pragma unroll
+          for (int a = 0; a < CI_T; ++a)
+#pragma unroll
+            for (int b = 0; b < CO_T; ++b) {
+              float v = 0.f;
+#pragma unroll
+              for (int g = 0; g < RG; ++g) v += red[(g * 36 + ((r * 3 + s) * CI_T + a) * CO_T + b) * PAIRS + pair];
+              acc[r][s][a][b] = v;
+            }
+      if (tci == 0) {
 #pragma unroll
         for (int b = 0; b < CO_T; ++b) {
-          int ci = ci0 + tci + 16 * a, co = co0 + tco + 16 * b;
-          atomicAdd(&dw[((long long)(r * 3 + s) * p.Cin + ci) * p.Cout + co], acc[r][s][a][b]);
-        }
-  if (dbias != nullptr && tci == 0 && blockIdx.y == 0) {
+          float v = 0.f;
 #pragma unroll
-    for (int b = 0; b < CO_T; ++b) atomicAdd(&dbias[co0 + tco + 16 * b], bacc[b]);
+          for (int g = 0; g < RG; ++g) v += redb[(g * CO_T + b) * NCO + tco];
+          bacc[b] = v;
+        }
+      }
+    }
+  }
+  if (rg == 0) {
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+      for (int s = 0; s < 3; ++s)
+#pragma unroll
+        for (int a = 0; a < CI_T; ++a)
+#pragma unroll
+          for (int b = 0; b < CO_T; ++b) {
+            int ci = ci0 + tci + NCI * a, co = co0 + tco + NCO * b;
+            atomicAdd(&dw[((long long)(r * 3 + s) * p.Cin + ci) * p.Cout + co], acc[r][s][a][b]);
+          }
+    if (dbias != nullptr && tci == 0 && blockIdx.y == 0) {
+#pragma unroll
+      for (int b = 0; b < CO_T; ++b) atomicAdd(&dbias[co0 + tco + NCO * b], bacc[b]);
+    }
   }
 }
 
@@ -469,7 +520,7 @@ int init_conv_simt() {
   auto set = [&](auto kern) {
     if (e == cudaSuccess) e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WGRAD3X3_MAX_SMEM);
   };
-  set(conv_wgrad3x3_kernel<1, 1>); set(conv_wgrad3x3_kernel<1, 2>); set(conv_wgrad3x3_kernel<2, 1>); set(conv_wgrad3x3_kernel<2, 2>);
+  set(conv_wgrad3x3_kernel<16, 16>); set(conv_wgrad3x3_kernel<8, 16>); set(conv_wgrad3x3_kernel<16, 8>); set(conv_wgrad3x3_kernel<8, 8>);
   if (e != cudaSuccess) { set_error("init_conv_simt: %s", cudaGetErrorString(e)); return SE_ERR_CUDA; }
   return SE_OK;
 }
@@ -514,17 +565,19 @@ int conv_dgrad_simt(const se_conv_desc* d, const float* dy, const float* w, floa
   return launch_dgrad<64, 64, 4, 4>(p, dy, w, dx, beta, st);
 }
 
-template <int CI_T, int CO_T>
+template <int NCI, int NCO>
 static int launch_wgrad3x3(const ConvP& p, const float* x, const float* dy, float* dw, float* dbias, cudaStream_t st) {
-  constexpr int CIT = 16 * CI_T, COT = 16 * CO_T;
+  constexpr int CIT = 2 * NCI, COT = 2 * NCO, RG = 256 / (NCI * NCO);
   int TH = max(1, 128 / p.W);
   if (TH > p.H) TH = p.H;
-  size_t smem = ((size_t)(TH + 2) * (p.W + 2) * CIT + (size_t)TH * p.W * COT) * sizeof(float);
+  size_t tile_bytes = ((size_t)(TH + 2) * (p.W + 2) * CIT + (size_t)TH * p.W * COT) * sizeof(float);
+  size_t red_bytes = RG > 1 ? ((size_t)RG * 36 * NCI * NCO + (size_t)RG * 2 * NCO) * sizeof(float) : 0;
+  size_t smem = max(tile_bytes, red_bytes);
   int tiles_per_img = ceil_div(p.H, TH);
   int num_tiles = p.N * tiles_per_img;
   int cy = p.Cin / CIT, cz = p.Cout / COT;
   int gx = min(num_tiles, max(1, (2 * sm_count()) / (cy * cz)));
-  auto kern = conv_wgrad3x3_kernel<CI_T, CO_T>;
+  auto kern = conv_wgrad3x3_kernel<NCI, NCO>;
   if (smem > WGRAD3X3_MAX_SMEM) return SE_ERR_UNSUPPORTED;
   if (smem > 48 * 1024) {   // attribute normally raised by se_init(); direct C-ABI callers get it lazily
     static bool inited = false;
@@ -540,10 +593,10 @@ int conv_wgrad_simt(const se_conv_desc* d, const float* x, const float* dy, floa
                        p.Wo == p.W && (p.Cin % 16 == 0) && (p.Cout % 16 == 0);
   if (same3x3) {
     int rc;
-    if (p.Cin % 32 == 0 && p.Cout % 32 == 0) rc = launch_wgrad3x3<2, 2>(p, x, dy, dw, dbias, st);
-    else if (p.Cout % 32 == 0) rc = launch_wgrad3x3<1, 2>(p, x, dy, dw, dbias, st);
-    else if (p.Cin % 32 == 0) rc = launch_wgrad3x3<2, 1>(p, x, dy, dw, dbias, st);
-    else rc = launch_wgrad3x3<1, 1>(p, x, dy, dw, dbias, st);
+    if (p.Cin % 32 == 0 && p.Cout % 32 == 0) rc = launch_wgrad3x3<16, 16>(p, x, dy, dw, dbias, st);
+    else if (p.Cout % 32 == 0) rc = launch_wgrad3x3<8, 16>(p, x, dy, dw, dbias, st);
+    else if (p.Cin % 32 == 0) rc = launch_wgrad3x3<16, 8>(p, x, dy, dw, dbias, st);
+    else rc = launch_wgrad3x3<8, 8>(p, x, dy, dw, dbias, st);
     if (rc != SE_ERR_UNSUPPORTED) return rc;
   }
   constexpr int BM = 64, BN = 64, TM = 4, TN = 4;
