@@ -247,3 +247,59 @@ def test_fast_mode_error_is_reported_not_hidden():
     e_loss = abs(eng.metrics()['loss'] - float(obj['embed_loss']))
     report('fast_mode', emb=e_emb, loss=e_loss)
     assert e_emb < 5e-2 and e_loss < 5e-2
+
+
+def test_resnet50_step_matches_oracle():
+    """Config 4 architecture (keras.applications ResNet50 v1 + GAP + Dense 'embedding', utils.py:228-243) on a small
+    64x64 input: 7x7/2 stem with explicit padding, 3x3/2 max-pool, bottleneck blocks with projection shortcuts, NAB-sized
+    (555-d) head.  The backbone itself is third-party and unpinned; this checks engine vs oracle."""
+    from oracle import models as omodels
+    from oracle import train as otrain
+    from semantic_embeddings_b200.models import resnet50
+    from semantic_embeddings_b200.engine import Engine
+    emb = class_matrix('nab')
+    C, D = emb.shape
+    B = 2
+    om = omodels.build_resnet50(D, 3, seed=51)
+    omodels.randomize(om, seed=52)
+    to_f32_exact(om)
+    graph = resnet50.ResNet50(D, input_shape=(64, 64, 3))
+    eng = Engine(graph, B, emb, use_cuda_graph=False)
+    eng.set_weights(oracle_weights_np(om))
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(B, 64, 64, 3, generator=g, dtype=torch.float64).float()
+    y = torch.randint(0, C, (B,), generator=g)
+    vel = otrain.make_velocity(om)
+    emb_t = torch.as_tensor(emb.astype(np.float32)).double()
+    obj, grads, norm = otrain.train_step(om, x.double(), y, emb_t, vel, 0.05)
+    eng.train_step(x, y, lr=0.05)
+    m = eng.metrics()
+    e_loss = abs(m['loss'] - float(obj['embed_loss'].detach()))
+    e_emb = rel_max(eng.act['head_out'].cpu().numpy(), obj['emb'].detach().numpy())
+    gg, gw, name = _grad_errors(eng.get_grads(), grads, norm)
+    report('resnet50_step', loss=e_loss, emb=e_emb, grad_global=gg, worst=name)
+    assert e_loss < 1e-4 and e_emb < 1e-4, (e_loss, e_emb)
+    assert gg < 5e-2, gg          # batch of 2 with 2x2 final maps: BN backward is ill-conditioned in fp32
+
+
+def test_pairwise_retrieval_api_matches_reference_fixture():
+    """The drop-in function (same call as evaluate_retrieval.pairwise_retrieval, evaluate_retrieval.py:22) on the
+    dict-of-features form against the rankings the reference's own code produced (make_golden.py)."""
+    from semantic_embeddings_b200.evaluate_retrieval import pairwise_retrieval
+    d = np.load(os.path.join(G, 'retrieval_ref.npz'))
+    fd = {int(i): f.copy() for i, f in zip(d['ids'], d['feat'])}
+    r = pairwise_retrieval({'feat': fd}, normalize=False, return_generator=False)
+    assert list(r.keys()) == d['rank_dict_keys'].tolist()
+    got = np.array(list(r.values()))
+    ref = d['rank_dict_vals']
+    assert got.shape == ref.shape
+    assert (got != ref).mean() < 2e-3          # only fp32-level near-ties may swap
+    assert (got[:, 0] == ref[:, 0]).all()       # every query retrieves itself first
+    # generator form + normalize=True side effect on a caller-supplied array (evaluate_retrieval.py:58)
+    f = d['feat'].copy()
+    gen = pairwise_retrieval(f, normalize=True)
+    first = next(gen)
+    assert first[0] == 0 and first[1][0] == 0
+    np.testing.assert_allclose(np.linalg.norm(f, axis=1), 1.0, atol=1e-5)
+    with pytest.raises(ValueError):
+        pairwise_retrieval({0: np.zeros((2, 3), np.float32), 1: np.zeros((2, 3), np.float32)})
