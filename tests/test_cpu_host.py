@@ -201,7 +201,7 @@ t = torch.zeros(1001); t[r0:r0 + rows] = 1
 dist.all_reduce(t)
 assert torch.equal(t, torch.ones(1001))
 dist.destroy_process_group()
-print('rank', rank, 'ok')
+open(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'rank' + str(rank) + '.ok'), 'w').write('ok')
 '''
 
 
@@ -213,4 +213,4 @@ def test_data_parallel_plumbing_gloo_world2(tmp_path):
                           '--master-addr', '127.0.0.1', '--master-port', '29533', str(script)],
                          capture_output=True, text=True, timeout=300, env=env)
     assert out.returncode == 0, out.stdout + out.stderr
-    assert 'rank 0 ok' in out.stdout and 'rank 1 ok' in out.stdout
+    assert (tmp_path / 'rank0.ok').exists() and (tmp_path / 'rank1.ok').exists(), out.stdout + out.stderr
