@@ -1,6 +1,7 @@
 // C-ABI glue: error state, launch counter, conv/dense dispatch between the arithmetic modes,
 // and the plan runner (se_run_ops) that issues a whole training step without returning to Python.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <atomic>
@@ -19,6 +20,10 @@ void set_error(const char* fmt, ...) {
   va_start(ap, fmt);
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
+}
+bool pdl_enabled() {
+  static const bool on = getenv("SE_NO_PDL") == nullptr;
+  return on;
 }
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 int sm_count() {

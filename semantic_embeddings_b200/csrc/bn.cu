@@ -14,6 +14,7 @@ namespace se {
 // along channels, the rest of the block strides over rows.
 __global__ void __launch_bounds__(256)
 bn_stats_kernel(const float* __restrict__ x, long long rows, int C, double* __restrict__ stats, int rows_per_cta) {
+  pdl_grid_sync();
   extern __shared__ double sred[];  // [2*C]
   const int tid = threadIdx.x;
   for (int i = tid; i < 2 * C; i += blockDim.x) sred[i] = 0.0;
@@ -99,6 +100,7 @@ bn_fwd_kernel(const float* __restrict__ x, long long rows, int C, const double* 
               const float* __restrict__ gamma, const float* __restrict__ beta, float eps, float momentum,
               float* __restrict__ moving_mean, float* __restrict__ moving_var, float* __restrict__ save_mean,
               float* __restrict__ save_invstd, Res res, int relu, float* __restrict__ y) {
+  pdl_grid_sync();
   extern __shared__ float sc[];  // scale[C], shift[C]
   float* scale = sc;
   float* shift = sc + C;
@@ -182,6 +184,7 @@ __global__ void __launch_bounds__(256)
 bn_bwd_reduce_kernel(const float* __restrict__ x, const float* __restrict__ y, const float* __restrict__ dout,
                      long long rows, int C, const float* __restrict__ save_mean, const float* __restrict__ save_invstd,
                      int relu, double* __restrict__ scratch, int rows_per_cta) {
+  pdl_grid_sync();
   extern __shared__ double sred[];
   const int tid = threadIdx.x;
   for (int i = tid; i < 2 * C; i += blockDim.x) sred[i] = 0.0;
@@ -265,6 +268,7 @@ bn_bwd_apply_kernel(const float* __restrict__ x, const float* __restrict__ y, co
                     const float* __restrict__ save_invstd, int relu, int relu_in, float* __restrict__ dx, float beta_dx,
                     float* __restrict__ dres, float beta_res, float* __restrict__ dgamma, float* __restrict__ dbeta,
                     const double* __restrict__ scratch) {
+  pdl_grid_sync();
   extern __shared__ float sc[];  // a[C], b[C], m[C], k[C]:  dx = a*g + b + k*x   (k = -a*... folded)
   float* ca = sc;
   float* cb = sc + C;
@@ -347,6 +351,7 @@ bn_bwd_fused_kernel(const float* __restrict__ x, const float* __restrict__ y, co
                     const float* __restrict__ save_invstd, int relu, int relu_in, float* __restrict__ dx, float beta_dx,
                     float* __restrict__ dres, float beta_res, float* __restrict__ dgamma, float* __restrict__ dbeta,
                     double* __restrict__ scratch, int rows_per_cta) {
+  pdl_grid_sync();
   extern __shared__ __align__(16) unsigned char fsm[];
   const long long r0 = (long long)blockIdx.x * rows_per_cta;
   const long long r1 = min(rows, r0 + rows_per_cta);
@@ -497,6 +502,7 @@ bn_bwd_fused_kernel(const float* __restrict__ x, const float* __restrict__ y, co
 __global__ void __launch_bounds__(256)
 shortcut_bwd_kernel(const float* __restrict__ dout, const float* __restrict__ y, int relu, int N, int H, int W, int C,
                     Res res, float* __restrict__ dsrc, float beta) {
+  pdl_grid_sync();
   const int SH = H * res.pool, SW = W * res.pool;
   const long long total = (long long)N * SH * SW * res.C;
   for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
@@ -542,7 +548,7 @@ extern "C" int se_bn_stats(const float* x, int64_t rows, int C, double* stats, v
   SE_REQUIRE(x && stats && rows > 0 && C > 0, "bad arguments");
   int grid;
   int per = red_rows_per_cta(rows, &grid);
-  bn_stats_kernel<<<grid, 256, 2 * C * sizeof(double), as_stream(stream)>>>(x, rows, C, stats, per);
+  launch(bn_stats_kernel, dim3(grid), dim3(256), 2 * C * sizeof(double), as_stream(stream), x, rows, C, stats, per);
   return check_launch("bn_stats_kernel");
 }
 
@@ -553,7 +559,7 @@ extern "C" int se_bn_fwd_train(const float* x, int64_t rows, int C, const double
   SE_REQUIRE(x && y && stats && gamma && beta && save_mean && save_invstd && rows > 0 && C > 0, "bad arguments");
   Res r = to_res(res);
   long long items = ((C & 3) == 0) ? rows * C / 4 : rows * C;
-  bn_fwd_kernel<true><<<ew_grid(ceil_div<long long>(items, 4)), 256, 2 * C * sizeof(float), as_stream(stream)>>>(
+  launch(bn_fwd_kernel<true>, dim3(ew_grid(ceil_div<long long>(items, 4))), dim3(256), 2 * C * sizeof(float), as_stream(stream), 
       x, rows, C, stats, gamma, beta, eps, momentum, moving_mean, moving_var, save_mean, save_invstd, r, relu, y);
   return check_launch("bn_fwd_kernel<train>");
 }
@@ -564,7 +570,7 @@ extern "C" int se_bn_fwd_infer(const float* x, int64_t rows, int C, const float*
   SE_REQUIRE(x && y && gamma && beta && moving_mean && moving_var && rows > 0 && C > 0, "bad arguments");
   Res r = to_res(res);
   long long items = ((C & 3) == 0) ? rows * C / 4 : rows * C;
-  bn_fwd_kernel<false><<<ew_grid(ceil_div<long long>(items, 4)), 256, 2 * C * sizeof(float), as_stream(stream)>>>(
+  launch(bn_fwd_kernel<false>, dim3(ew_grid(ceil_div<long long>(items, 4))), dim3(256), 2 * C * sizeof(float), as_stream(stream), 
       x, rows, C, nullptr, gamma, beta, eps, 0.f, const_cast<float*>(moving_mean), const_cast<float*>(moving_var),
       nullptr, nullptr, r, relu, y);
   return check_launch("bn_fwd_kernel<infer>");
@@ -594,7 +600,7 @@ extern "C" int se_bn_bwd(const float* x, const float* y, const float* dout, int6
         configured = true;
       }
       // at least 116 KB per CTA would be needed to force one CTA per SM; co-residency only needs grid <= #SMs
-      bn_bwd_fused_kernel<<<gridf, 512, smem, as_stream(stream)>>>(x, y, dout, rows, C, gamma, save_mean, save_invstd, relu,
+      launch(bn_bwd_fused_kernel, dim3(gridf), dim3(512), smem, as_stream(stream), x, y, dout, rows, C, gamma, save_mean, save_invstd, relu,
                                                                     relu_in, dx, beta_dx, dres, beta_res, dgamma, dbeta,
                                                                     scratch, (int)per_l);
       return check_launch("bn_bwd_fused_kernel");
@@ -602,12 +608,12 @@ extern "C" int se_bn_bwd(const float* x, const float* y, const float* dout, int6
   }
   int grid;
   int per = red_rows_per_cta(rows, &grid);
-  bn_bwd_reduce_kernel<<<grid, 256, 2 * C * sizeof(double), as_stream(stream)>>>(x, y, dout, rows, C, save_mean,
+  launch(bn_bwd_reduce_kernel, dim3(grid), dim3(256), 2 * C * sizeof(double), as_stream(stream), x, y, dout, rows, C, save_mean,
                                                                                    save_invstd, relu, scratch, per);
   int rc = check_launch("bn_bwd_reduce_kernel");
   if (rc) return rc;
   long long items = ((C & 3) == 0) ? rows * C / 4 : rows * C;
-  bn_bwd_apply_kernel<<<ew_grid(items), 256, 4 * C * sizeof(float), as_stream(stream)>>>(
+  launch(bn_bwd_apply_kernel, dim3(ew_grid(items)), dim3(256), 4 * C * sizeof(float), as_stream(stream), 
       x, y, dout, rows, C, gamma, save_mean, save_invstd, relu, relu_in, dx, beta_dx, dres, beta_res, dgamma, dbeta,
       scratch);
   return check_launch("bn_bwd_apply_kernel");
@@ -620,6 +626,6 @@ extern "C" int se_shortcut_bwd(const float* dout, const float* y, int relu, int 
   Res r = to_res(res);
   r.ptr = dsrc;  // only the geometry is used
   long long total = (long long)N * H * r.pool * W * r.pool * r.C;
-  shortcut_bwd_kernel<<<ew_grid(total), 256, 0, as_stream(stream)>>>(dout, y, relu, N, H, W, C, r, dsrc, beta);
+  launch(shortcut_bwd_kernel, dim3(ew_grid(total)), dim3(256), 0, as_stream(stream), dout, y, relu, N, H, W, C, r, dsrc, beta);
   return check_launch("shortcut_bwd_kernel");
 }

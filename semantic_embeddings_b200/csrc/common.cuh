@@ -4,6 +4,8 @@
 #include <stdint.h>
 #include <stdio.h>
 
+#include <utility>
+
 #include "../../include/se_b200.h"
 
 namespace se {
@@ -29,6 +31,32 @@ inline int check_launch(const char* what) {
       return SE_ERR_ARG;                                     \
     }                                                        \
   } while (0)
+
+// Programmatic dependent launch (PDL).  Every kernel of this library is launched with the
+// programmatic-stream-serialization attribute and starts with pdl_grid_sync(): the dependent grid may become resident
+// (barrier init, TMEM allocation, descriptor prefetch) while the preceding grid drains, and it blocks in
+// griddepcontrol.wait -- which returns only when ALL prerequisite grids have completed and flushed their writes --
+// before it touches global memory.  Invariant that keeps this safe at any chain depth: no kernel reads or writes
+// global memory before its griddepcontrol.wait.  SE_NO_PDL=1 turns the attribute off (kernels then serialise fully).
+bool pdl_enabled();
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_grid_sync() { pdl_trigger(); pdl_wait(); }
+
+template <typename... KArgs, typename... Args>
+inline void launch(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr;
+  attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr.val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = &attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);   // errors surface through check_launch()
+}
 
 inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 

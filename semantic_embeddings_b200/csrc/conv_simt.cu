@@ -33,6 +33,7 @@ __global__ void __launch_bounds__((BM / TM) * (BN / TN))
 conv_fwd_kernel(ConvP p, const float* __restrict__ x, const float* __restrict__ w,
                 const float* __restrict__ bias, const float* __restrict__ residual, float* __restrict__ y,
                 int relu, double* __restrict__ stats) {
+  pdl_grid_sync();
   constexpr int NT = (BM / TM) * (BN / TN);
   constexpr int CG = BN / TN;  // threads along the channel dimension
   __shared__ __align__(16) float As[BK][BM + 4];
@@ -165,6 +166,7 @@ template <int BM, int BN, int TM, int TN, bool VEC>
 __global__ void __launch_bounds__((BM / TM) * (BN / TN))
 conv_dgrad_kernel(ConvP p, const float* __restrict__ dy, const float* __restrict__ w, float* __restrict__ dx,
                   float beta) {
+  pdl_grid_sync();
   constexpr int NT = (BM / TM) * (BN / TN);
   constexpr int CG = BN / TN;
   __shared__ __align__(16) float As[BK][BM + 4];
@@ -269,6 +271,7 @@ template <int BM, int BN, int TM, int TN>
 __global__ void __launch_bounds__((BM / TM) * (BN / TN))
 conv_wgrad_kernel(ConvP p, const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ dw,
                   float* __restrict__ dbias, long long pix_per_split) {
+  pdl_grid_sync();
   constexpr int NT = (BM / TM) * (BN / TN);
   constexpr int CG = BN / TN;
   __shared__ __align__(16) float As[BK][BM + 4];
@@ -365,6 +368,7 @@ template <int NCI, int NCO>
 __global__ void __launch_bounds__(256)
 conv_wgrad3x3_kernel(ConvP p, const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ dw,
                      float* __restrict__ dbias, int TH, int tiles_per_img, int num_tiles) {
+  pdl_grid_sync();
   constexpr int CI_T = 2, CO_T = 2;
   constexpr int CIT = NCI * CI_T, COT = NCO * CO_T;
   constexpr int PAIRS = NCI * NCO, RG = 256 / PAIRS;
@@ -532,9 +536,9 @@ static int launch_fwd(const ConvP& p, const float* x, const float* w, const floa
   dim3 grid((unsigned)ceil_div<long long>(M, BM), (unsigned)ceil_div(p.Cout, BN));
   bool vec = (p.Cin % 4 == 0) && (p.Cout % 4 == 0);
   if (vec)
-    conv_fwd_kernel<BM, BN, TM, TN, true><<<grid, (BM / TM) * (BN / TN), 0, st>>>(p, x, w, bias, residual, y, relu, stats);
+    launch(conv_fwd_kernel<BM, BN, TM, TN, true>, dim3(grid), dim3((BM / TM) * (BN / TN)), 0, st, p, x, w, bias, residual, y, relu, stats);
   else
-    conv_fwd_kernel<BM, BN, TM, TN, false><<<grid, (BM / TM) * (BN / TN), 0, st>>>(p, x, w, bias, residual, y, relu, stats);
+    launch(conv_fwd_kernel<BM, BN, TM, TN, false>, dim3(grid), dim3((BM / TM) * (BN / TN)), 0, st, p, x, w, bias, residual, y, relu, stats);
   return check_launch("conv_fwd_kernel");
 }
 
@@ -552,9 +556,9 @@ static int launch_dgrad(const ConvP& p, const float* dy, const float* w, float* 
   dim3 grid((unsigned)ceil_div<long long>(M, BM), (unsigned)ceil_div(p.Cin, BN));
   bool vec = (p.Cout % 4 == 0);
   if (vec)
-    conv_dgrad_kernel<BM, BN, TM, TN, true><<<grid, (BM / TM) * (BN / TN), 0, st>>>(p, dy, w, dx, beta);
+    launch(conv_dgrad_kernel<BM, BN, TM, TN, true>, dim3(grid), dim3((BM / TM) * (BN / TN)), 0, st, p, dy, w, dx, beta);
   else
-    conv_dgrad_kernel<BM, BN, TM, TN, false><<<grid, (BM / TM) * (BN / TN), 0, st>>>(p, dy, w, dx, beta);
+    launch(conv_dgrad_kernel<BM, BN, TM, TN, false>, dim3(grid), dim3((BM / TM) * (BN / TN)), 0, st, p, dy, w, dx, beta);
   return check_launch("conv_dgrad_kernel");
 }
 
@@ -583,7 +587,7 @@ static int launch_wgrad3x3(const ConvP& p, const float* x, const float* dy, floa
     static bool inited = false;
     if (!inited) { int rc = init_conv_simt(); if (rc) return rc; inited = true; }
   }
-  kern<<<dim3(gx, cy, cz), 256, smem, st>>>(p, x, dy, dw, dbias, TH, tiles_per_img, num_tiles);
+  launch(kern, dim3(gx, cy, cz), dim3(256), smem, st, p, x, dy, dw, dbias, TH, tiles_per_img, num_tiles);
   return check_launch("conv_wgrad3x3_kernel");
 }
 
@@ -608,7 +612,7 @@ int conv_wgrad_simt(const se_conv_desc* d, const float* x, const float* dy, floa
   long long splits = min(want, ceil_div<long long>(P, 4 * BK));
   long long per = ceil_div<long long>(ceil_div<long long>(P, splits), BK) * BK;
   splits = ceil_div<long long>(P, per);
-  conv_wgrad_kernel<BM, BN, TM, TN><<<dim3(gx, gy, (unsigned)splits), (BM / TM) * (BN / TN), 0, st>>>(p, x, dy, dw, dbias, per);
+  launch(conv_wgrad_kernel<BM, BN, TM, TN>, dim3(gx, gy, (unsigned)splits), dim3((BM / TM) * (BN / TN)), 0, st, p, x, dy, dw, dbias, per);
   return check_launch("conv_wgrad_kernel");
 }
 

@@ -160,6 +160,7 @@ __device__ __forceinline__ void conv_tc_epilogue_block(const ConvTcParams& p, ui
 
 __global__ void __launch_bounds__(CT_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, ConvTcParams p) {
+  pdl_trigger();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* res_b = smem;                                   // resident weights (res mode), else empty
@@ -173,7 +174,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(b_full + 1);
   float* s_stats = reinterpret_cast<float*>(bars + 2 * CT_MAX_STAGES + 2 * CT_MAX_ACC + 4);   // [8 warps][2 * Nc]
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
   const int total_tiles = p.tiles_m * p.tiles_n;
   const int per_cta = (total_tiles + gridDim.x - 1) / gridDim.x;
   const int t_begin = blockIdx.x * per_cta;
@@ -195,9 +196,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   fence_before_sync();
   __syncthreads();
   fence_after_sync();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);   // provably warp-uniform (see tc.cuh elect_one)
+  pdl_wait();                               // nothing above touches global memory (see common.cuh)
 
-  if (warp == 0 && lane == 0) {
+  if (warp == 0 && elect_one()) {
     // ===================== TMA producer
     int stage = 0, phase = 0, tr_n = 0;
     CT_TRACE(0, 0);
@@ -258,7 +260,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         }
       }
     }
-  } else if (warp == 1 && lane == 0) {
+  } else if (warp == 1 && elect_one()) {
     // ===================== MMA issuer
     const uint32_t idesc = umma_idesc(2 /*tf32*/, CT_BM, 3 * p.BN);
     const uint32_t sbo = 8 * row_bytes;
@@ -400,6 +402,7 @@ struct TrTable { TrEntry e[TR_MAX]; int n; };
 
 __global__ void __launch_bounds__(256)
 transpose_filters_kernel(const float* __restrict__ P, float* __restrict__ PT, const __grid_constant__ TrTable tab) {
+  pdl_grid_sync();
   for (int li = blockIdx.y; li < tab.n; li += gridDim.y) {
     const TrEntry e = tab.e[li];
     const long long total = (long long)e.taps * e.cin * e.cout;
@@ -502,7 +505,7 @@ static int conv_tc_launch(const se_conv_desc* d, const float* a_tensor, int Kc, 
   const size_t smem = (size_t)p.res_b_bytes + (size_t)p.stages * p.stage_bytes + (2 * CT_MAX_STAGES + 2 * CT_MAX_ACC + 4) * 8 + (stats ? 16 * Nc * 4 : 0) + 1024 + 64;
   if (smem > 227 * 1024) return SE_ERR_UNSUPPORTED;
   int grid = min(sm_count(), p.tiles_m * p.tiles_n);
-  conv_tc_kernel<<<grid, CT_THREADS, smem, st>>>(ma, mb, p);
+  launch(conv_tc_kernel, dim3(grid), dim3(CT_THREADS), smem, st, ma, mb, p);
   return check_launch("conv_tc_kernel");
 }
 
@@ -549,7 +552,7 @@ int transpose_filters(const float* P, float* PT, const long long* table, int n, 
     }
     long long gx = ceil_div<long long>(maxtot, 256);
     dim3 grid((unsigned)(gx < 64 ? gx : 64), (unsigned)tab.n);
-    transpose_filters_kernel<<<grid, 256, 0, st>>>(P, PT, tab);
+    launch(transpose_filters_kernel, dim3(grid), dim3(256), 0, st, P, PT, tab);
     int rc = check_launch("transpose_filters_kernel");
     if (rc) return rc;
   }

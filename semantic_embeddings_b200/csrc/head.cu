@@ -40,6 +40,7 @@ __global__ void __launch_bounds__(HEAD_WARPS * 32)
 embed_head_kernel(const float* __restrict__ z, int ldz, const int* __restrict__ labels, const float* __restrict__ E,
                   int ldE, int B, int D, int C, int loss_kind, float loss_scale, const float* __restrict__ extra_dx,
                   float* __restrict__ x_out, float* __restrict__ loss, float* __restrict__ acc, float* __restrict__ dz) {
+  pdl_grid_sync();
   extern __shared__ __align__(16) float smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int Dp = (D + 3) & ~3;
@@ -162,6 +163,7 @@ __global__ void __launch_bounds__(HEAD_WARPS * 32)
 softmax_xent_kernel(const float* __restrict__ logits, int ld, const int* __restrict__ labels, int B, int C, float scale,
                     float* __restrict__ prob, float* __restrict__ loss, float* __restrict__ acc,
                     float* __restrict__ dlogits) {
+  pdl_grid_sync();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int row = blockIdx.x * HEAD_WARPS + warp;
   if (row >= B) return;
@@ -213,10 +215,10 @@ extern "C" int se_embed_head_fwd_bwd(const float* z, int ldz, const int32_t* lab
   bool vec = (D % 4 == 0) && (ldz % 4 == 0) && (ldE % 4 == 0) && al16(z) && al16(E) && (!x_out || al16(x_out));
   int grid = ceil_div(B, HEAD_WARPS);
   if (vec)
-    embed_head_kernel<true><<<grid, HEAD_WARPS * 32, smem, as_stream(stream)>>>(z, ldz, labels, E, ldE, B, D, C, loss_kind,
+    launch(embed_head_kernel<true>, dim3(grid), dim3(HEAD_WARPS * 32), smem, as_stream(stream), z, ldz, labels, E, ldE, B, D, C, loss_kind,
                                                                                 loss_scale, extra_dx, x_out, loss, acc, dz);
   else
-    embed_head_kernel<false><<<grid, HEAD_WARPS * 32, smem, as_stream(stream)>>>(z, ldz, labels, E, ldE, B, D, C, loss_kind,
+    launch(embed_head_kernel<false>, dim3(grid), dim3(HEAD_WARPS * 32), smem, as_stream(stream), z, ldz, labels, E, ldE, B, D, C, loss_kind,
                                                                                  loss_scale, extra_dx, x_out, loss, acc, dz);
   return check_launch("embed_head_kernel");
 }
@@ -224,7 +226,7 @@ extern "C" int se_embed_head_fwd_bwd(const float* z, int ldz, const int32_t* lab
 extern "C" int se_softmax_xent_fwd_bwd(const float* logits, int ld, const int32_t* labels, int B, int C, float scale,
                                        float* prob, float* loss, float* acc, float* dlogits, void* stream) {
   SE_REQUIRE(logits && labels && B > 0 && C > 0 && ld >= C, "bad arguments");
-  softmax_xent_kernel<<<ceil_div(B, HEAD_WARPS), HEAD_WARPS * 32, 0, as_stream(stream)>>>(logits, ld, labels, B, C, scale,
+  launch(softmax_xent_kernel, dim3(ceil_div(B, HEAD_WARPS)), dim3(HEAD_WARPS * 32), 0, as_stream(stream), logits, ld, labels, B, C, scale,
                                                                                          prob, loss, acc, dlogits);
   return check_launch("softmax_xent_kernel");
 }

@@ -15,6 +15,7 @@ namespace se {
 __global__ void __launch_bounds__(256)
 pairwise_prep_kernel(const float* __restrict__ F, int ldF, int N, int D, int normalize, float* __restrict__ sq,
                      float* __restrict__ invn) {
+  pdl_grid_sync();
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (warp >= N) return;
   const float* r = F + (long long)warp * ldF;
@@ -36,6 +37,7 @@ __global__ void __launch_bounds__((BM / TM) * (BN / TN))
 pairwise_f32_kernel(const float* __restrict__ F, int ldF, int N, int D, int row0, int rows, int pmode,
                     const float* __restrict__ sq, const float* __restrict__ invn, float* __restrict__ out,
                     long long ldout) {
+  pdl_grid_sync();
   constexpr int NT = (BM / TM) * (BN / TN);
   constexpr int CG = BN / TN;
   __shared__ __align__(16) float As[BK][BM + 4];
@@ -108,7 +110,7 @@ extern "C" int se_pairwise_dist(const float* F, int ldF, int N, int D, int row0,
   float* ws = reinterpret_cast<float*>(workspace);
   float* sq = ws;
   float* invn = ws + N;
-  pairwise_prep_kernel<<<ceil_div(N, 8), 256, 0, st>>>(F, ldF, N, D, normalize, sq, invn);
+  launch(pairwise_prep_kernel, dim3(ceil_div(N, 8)), dim3(256), 0, st, F, ldF, N, D, normalize, sq, invn);
   int rc = check_launch("pairwise_prep_kernel");
   if (rc) return rc;
   if (mode == SE_MODE_TF32) {
@@ -117,6 +119,6 @@ extern "C" int se_pairwise_dist(const float* F, int ldF, int N, int D, int row0,
   }
   constexpr int BM = 64, BN = 64;
   dim3 grid(ceil_div(N, BN), ceil_div(rows, BM));
-  pairwise_f32_kernel<BM, BN, 4, 4><<<grid, 256, 0, st>>>(F, ldF, N, D, row0, rows, pdist_mode, sq, invn, out, ldout);
+  launch(pairwise_f32_kernel<BM, BN, 4, 4>, dim3(grid), dim3(256), 0, st, F, ldF, N, D, row0, rows, pdist_mode, sq, invn, out, ldout);
   return check_launch("pairwise_f32_kernel");
 }

@@ -43,6 +43,7 @@ struct PwParams {
 __global__ void __launch_bounds__(256)
 pairwise_absmax_kernel(const float* __restrict__ F, int ldF, int N, int D, const float* __restrict__ norms,
                        unsigned* __restrict__ absmax_bits) {
+  pdl_grid_sync();
   float m = 0.f;
   const long long total = (long long)N * D;
   for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
@@ -56,6 +57,7 @@ pairwise_absmax_kernel(const float* __restrict__ F, int ldF, int N, int D, const
 __global__ void __launch_bounds__(256)
 pairwise_split_kernel(const float* __restrict__ F, int ldF, int N, int D, int KW, const float* __restrict__ norms,
                       float* __restrict__ scal, __half* __restrict__ Fh, __half* __restrict__ Fl) {
+  pdl_grid_sync();
   // scal[0] holds the bit pattern of max|f| (0 if the matrix is all zero)
   float amax = __uint_as_float(reinterpret_cast<const unsigned*>(scal)[0]);
   int e = 0;
@@ -78,6 +80,7 @@ pairwise_split_kernel(const float* __restrict__ F, int ldF, int N, int D, int KW
 __global__ void __launch_bounds__(128 + 32 * PW_EPI_WARPS, 1)
 pairwise_tc_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_constant__ CUtensorMap map_l,
                    const __grid_constant__ CUtensorMap map_out, PwParams p) {
+  pdl_trigger();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* sA = smem;                                            // [h|l][kb] x 16 KB
@@ -92,7 +95,7 @@ pairwise_tc_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_const
   uint64_t* t_empty = t_full + 2;        // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + 2);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
   const int total_tiles = p.tiles_m * p.tiles_n;
   const int per_cta = (total_tiles + gridDim.x - 1) / gridDim.x;
   const int t_begin = blockIdx.x * per_cta;
@@ -110,9 +113,10 @@ pairwise_tc_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_const
   fence_before_sync();
   __syncthreads();
   fence_after_sync();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);   // provably warp-uniform (see tc.cuh elect_one)
+  pdl_wait();                               // nothing above touches global memory (see common.cuh)
 
-  if (warp == 0 && lane == 0) {
+  if (warp == 0 && elect_one()) {
     // ===================== TMA producer
     int stage = 0, phase = 0, cur_tm = -1, a_phase = 0;
     for (int t = t_begin; t < t_end; ++t) {
@@ -138,7 +142,7 @@ pairwise_tc_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_const
         if (++stage == PW_STAGES) { stage = 0; phase ^= 1; }
       }
     }
-  } else if (warp == 1 && lane == 0) {
+  } else if (warp == 1 && elect_one()) {
     // ===================== MMA issuer (one thread)
     constexpr uint32_t idesc = umma_idesc(0 /*f16*/, PW_BM, PW_BN);
     int stage = 0, phase = 0, cur_tm = -1, a_phase = 0, acc = 0, acc_phase = 0;
@@ -272,12 +276,12 @@ int pairwise_tc(const float* F, int ldF, int N, int D, int row0, int rows, int p
   if (cudaMemsetAsync(scal, 0, 256, st) != cudaSuccess) { set_error("pairwise_tc: memset failed"); return SE_ERR_CUDA; }
   long long w1 = ceil_div<long long>((long long)N * D, 256), cap = (long long)sm_count() * 8;
   int g1 = (int)(w1 < cap ? w1 : cap);
-  pairwise_absmax_kernel<<<g1, 256, 0, st>>>(F, ldF, N, D, norms, reinterpret_cast<unsigned*>(scal));
+  launch(pairwise_absmax_kernel, dim3(g1), dim3(256), 0, st, F, ldF, N, D, norms, reinterpret_cast<unsigned*>(scal));
   int rc = check_launch("pairwise_absmax_kernel");
   if (rc) return rc;
   long long w2 = ceil_div<long long>((long long)N * KW, 256);
   int g2 = (int)(w2 < cap ? w2 : cap);
-  pairwise_split_kernel<<<g2, 256, 0, st>>>(F, ldF, N, D, KW, norms, scal, Fh, Fl);
+  launch(pairwise_split_kernel, dim3(g2), dim3(256), 0, st, F, ldF, N, D, KW, norms, scal, Fh, Fl);
   rc = check_launch("pairwise_split_kernel");
   if (rc) return rc;
 
@@ -303,7 +307,7 @@ int pairwise_tc(const float* F, int ldF, int N, int D, int row0, int rows, int p
   int rc0 = init_pairwise_tc();
   if (rc0) return rc0;
   int grid = min(sm_count(), p.tiles_m * p.tiles_n);
-  pairwise_tc_kernel<<<grid, 128 + 32 * PW_EPI_WARPS, PW_SMEM, st>>>(mh, ml, mo, p);
+  launch(pairwise_tc_kernel, dim3(grid), dim3(128 + 32 * PW_EPI_WARPS), PW_SMEM, st, mh, ml, mo, p);
   return check_launch("pairwise_tc_kernel");
 }
 

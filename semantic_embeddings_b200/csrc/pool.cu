@@ -15,6 +15,7 @@ static int ew_grid2(long long n) {
 }
 
 __global__ void avgpool2_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, int N, int H, int W, int C) {
+  pdl_grid_sync();
   const int Ho = H / 2, Wo = W / 2;
   const long long total = (long long)N * Ho * Wo * C;
   for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
@@ -30,6 +31,7 @@ __global__ void avgpool2_fwd_kernel(const float* __restrict__ x, float* __restri
 }
 
 __global__ void avgpool2_bwd_kernel(const float* __restrict__ dy, float* __restrict__ dx, float beta, int N, int H, int W, int C) {
+  pdl_grid_sync();
   const int Ho = H / 2, Wo = W / 2;
   const long long total = (long long)N * H * W * C;
   for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
@@ -46,6 +48,7 @@ __global__ void avgpool2_bwd_kernel(const float* __restrict__ dy, float* __restr
 
 __global__ void maxpool_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, int N, int H, int W, int C, int k,
                                    int stride, int pad_t, int pad_l, int Ho, int Wo) {
+  pdl_grid_sync();
   const long long total = (long long)N * Ho * Wo * C;
   for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
     int c = (int)(e % C);
@@ -68,6 +71,7 @@ __global__ void maxpool_fwd_kernel(const float* __restrict__ x, float* __restric
 __global__ void maxpool_bwd_kernel(const float* __restrict__ x, const float* __restrict__ y, const float* __restrict__ dy,
                                    float* __restrict__ dx, int N, int H, int W, int C, int k, int stride, int pad_t,
                                    int pad_l, int Ho, int Wo) {
+  pdl_grid_sync();
   const long long total = (long long)N * Ho * Wo * C;
   for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
     int c = (int)(e % C);
@@ -90,6 +94,7 @@ __global__ void maxpool_bwd_kernel(const float* __restrict__ x, const float* __r
 
 // one warp per (n, 32-channel group): lanes along channels, loop over HW
 __global__ void gap_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, int N, int HW, int C) {
+  pdl_grid_sync();
   const long long total = (long long)N * C;
   for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
     int c = (int)(e % C);
@@ -102,6 +107,7 @@ __global__ void gap_fwd_kernel(const float* __restrict__ x, float* __restrict__ 
 }
 
 __global__ void gap_bwd_kernel(const float* __restrict__ dy, float* __restrict__ dx, float beta, int N, int HW, int C) {
+  pdl_grid_sync();
   const long long total = (long long)N * HW * C;
   const float inv = 1.f / (float)HW;
   for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
@@ -112,6 +118,7 @@ __global__ void gap_bwd_kernel(const float* __restrict__ dy, float* __restrict__
 }
 
 __global__ void add_fwd_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ y, long long n, int relu) {
+  pdl_grid_sync();
   for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
     float v = a[e] + (b ? b[e] : 0.f);
     y[e] = relu ? fmaxf(v, 0.f) : v;
@@ -120,6 +127,7 @@ __global__ void add_fwd_kernel(const float* __restrict__ a, const float* __restr
 
 __global__ void add_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ y, int relu, float* __restrict__ da,
                                float beta_a, float* __restrict__ db, float beta_b, long long n) {
+  pdl_grid_sync();
   for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
     float g = dy[e];
     if (relu && !(y[e] > 0.f)) g = 0.f;
@@ -135,18 +143,18 @@ using namespace se;
 extern "C" int se_avgpool2_fwd(const float* x, float* y, int N, int H, int W, int C, void* stream) {
   SE_REQUIRE(x && y, "null pointer");
   long long total = (long long)N * (H / 2) * (W / 2) * C;
-  avgpool2_fwd_kernel<<<ew_grid2(total), 256, 0, as_stream(stream)>>>(x, y, N, H, W, C);
+  launch(avgpool2_fwd_kernel, dim3(ew_grid2(total)), dim3(256), 0, as_stream(stream), x, y, N, H, W, C);
   return check_launch("avgpool2_fwd_kernel");
 }
 extern "C" int se_avgpool2_bwd(const float* dy, float* dx, float beta, int N, int H, int W, int C, void* stream) {
   SE_REQUIRE(dy && dx, "null pointer");
-  avgpool2_bwd_kernel<<<ew_grid2((long long)N * H * W * C), 256, 0, as_stream(stream)>>>(dy, dx, beta, N, H, W, C);
+  launch(avgpool2_bwd_kernel, dim3(ew_grid2((long long)N * H * W * C)), dim3(256), 0, as_stream(stream), dy, dx, beta, N, H, W, C);
   return check_launch("avgpool2_bwd_kernel");
 }
 extern "C" int se_maxpool_fwd(const float* x, float* y, int N, int H, int W, int C, int k, int stride, int pad_t,
                               int pad_l, int Ho, int Wo, void* stream) {
   SE_REQUIRE(x && y, "null pointer");
-  maxpool_fwd_kernel<<<ew_grid2((long long)N * Ho * Wo * C), 256, 0, as_stream(stream)>>>(x, y, N, H, W, C, k, stride,
+  launch(maxpool_fwd_kernel, dim3(ew_grid2((long long)N * Ho * Wo * C)), dim3(256), 0, as_stream(stream), x, y, N, H, W, C, k, stride,
                                                                                            pad_t, pad_l, Ho, Wo);
   return check_launch("maxpool_fwd_kernel");
 }
@@ -155,29 +163,29 @@ extern "C" int se_maxpool_bwd(const float* x, const float* y, const float* dy, f
   SE_REQUIRE(x && y && dy && dx, "null pointer");
   cudaError_t e = cudaMemsetAsync(dx, 0, sizeof(float) * (size_t)N * H * W * C, as_stream(stream));
   if (e != cudaSuccess) { set_error("memset: %s", cudaGetErrorString(e)); return SE_ERR_CUDA; }
-  maxpool_bwd_kernel<<<ew_grid2((long long)N * Ho * Wo * C), 256, 0, as_stream(stream)>>>(x, y, dy, dx, N, H, W, C, k,
+  launch(maxpool_bwd_kernel, dim3(ew_grid2((long long)N * Ho * Wo * C)), dim3(256), 0, as_stream(stream), x, y, dy, dx, N, H, W, C, k,
                                                                                            stride, pad_t, pad_l, Ho, Wo);
   return check_launch("maxpool_bwd_kernel");
 }
 extern "C" int se_gap_fwd(const float* x, float* y, int N, int HW, int C, void* stream) {
   SE_REQUIRE(x && y, "null pointer");
-  gap_fwd_kernel<<<ew_grid2((long long)N * C), 256, 0, as_stream(stream)>>>(x, y, N, HW, C);
+  launch(gap_fwd_kernel, dim3(ew_grid2((long long)N * C)), dim3(256), 0, as_stream(stream), x, y, N, HW, C);
   return check_launch("gap_fwd_kernel");
 }
 extern "C" int se_gap_bwd(const float* dy, float* dx, float beta, int N, int HW, int C, void* stream) {
   SE_REQUIRE(dy && dx, "null pointer");
-  gap_bwd_kernel<<<ew_grid2((long long)N * HW * C), 256, 0, as_stream(stream)>>>(dy, dx, beta, N, HW, C);
+  launch(gap_bwd_kernel, dim3(ew_grid2((long long)N * HW * C)), dim3(256), 0, as_stream(stream), dy, dx, beta, N, HW, C);
   return check_launch("gap_bwd_kernel");
 }
 extern "C" int se_add_fwd(const float* a, const float* b, float* y, int64_t n, int relu, void* stream) {
   SE_REQUIRE(a && y, "null pointer");
-  add_fwd_kernel<<<ew_grid2(n), 256, 0, as_stream(stream)>>>(a, b, y, n, relu);
+  launch(add_fwd_kernel, dim3(ew_grid2(n)), dim3(256), 0, as_stream(stream), a, b, y, n, relu);
   return check_launch("add_fwd_kernel");
 }
 extern "C" int se_add_bwd(const float* dy, const float* y, int relu, float* da, float beta_a, float* db, float beta_b,
                           int64_t n, void* stream) {
   SE_REQUIRE(dy && (!relu || y), "null pointer");
-  add_bwd_kernel<<<ew_grid2(n), 256, 0, as_stream(stream)>>>(dy, y, relu, da, beta_a, db, beta_b, n);
+  launch(add_bwd_kernel, dim3(ew_grid2(n)), dim3(256), 0, as_stream(stream), dy, y, relu, da, beta_a, db, beta_b, n);
   return check_launch("add_bwd_kernel");
 }
 extern "C" int se_relu_fwd(const float* x, float* y, int64_t n, void* stream) {

@@ -24,6 +24,7 @@ __device__ __forceinline__ float seg_l2(const Segs& s, long long i) {
 // g += 2*lambda*p ; out[0] += sum g^2 ; out[1] += sum lambda*p^2
 __global__ void __launch_bounds__(256)
 sgd_prepare_kernel(const float* __restrict__ p, float* __restrict__ g, long long n, Segs segs, double* __restrict__ out) {
+  pdl_grid_sync();
   double sq = 0.0, reg = 0.0;
   const long long n4 = n >> 2;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
@@ -71,6 +72,7 @@ __global__ void __launch_bounds__(256)
 sgd_apply_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ v, long long n, float lr,
                  const float* __restrict__ lr_dev, float momentum, int nesterov, float clipnorm,
                  const double* __restrict__ out) {
+  pdl_grid_sync();
   if (lr_dev) lr = *lr_dev;   // graph-captured steps read the schedule's learning rate from device memory
   float scale = 1.f;
   if (clipnorm > 0.f) {
@@ -120,21 +122,21 @@ extern "C" int se_sgd_prepare(const float* p, float* g, int64_t n, const se_l2_s
     s.end[k] = k < nsegs ? segs[k].end : 0;
     s.l2[k] = k < nsegs ? segs[k].l2 : 0.f;
   }
-  sgd_prepare_kernel<<<flat_grid(n), 256, 0, as_stream(stream)>>>(p, g, n, s, out);
+  launch(sgd_prepare_kernel, dim3(flat_grid(n)), dim3(256), 0, as_stream(stream), p, g, n, s, out);
   return check_launch("sgd_prepare_kernel");
 }
 
 extern "C" int se_sgd_apply(float* p, const float* g, float* v, int64_t n, float lr, float momentum, int nesterov,
                             float clipnorm, const double* out, void* stream) {
   SE_REQUIRE(p && g && v && out && n > 0, "bad arguments");
-  sgd_apply_kernel<<<flat_grid(n), 256, 0, as_stream(stream)>>>(p, g, v, n, lr, nullptr, momentum, nesterov, clipnorm, out);
+  launch(sgd_apply_kernel, dim3(flat_grid(n)), dim3(256), 0, as_stream(stream), p, g, v, n, lr, nullptr, momentum, nesterov, clipnorm, out);
   return check_launch("sgd_apply_kernel");
 }
 
 extern "C" int se_sgd_apply_devlr(float* p, const float* g, float* v, int64_t n, const float* lr_dev, float momentum,
                                   int nesterov, float clipnorm, const double* out, void* stream) {
   SE_REQUIRE(p && g && v && out && lr_dev && n > 0, "bad arguments");
-  sgd_apply_kernel<<<flat_grid(n), 256, 0, as_stream(stream)>>>(p, g, v, n, 0.f, lr_dev, momentum, nesterov, clipnorm, out);
+  launch(sgd_apply_kernel, dim3(flat_grid(n)), dim3(256), 0, as_stream(stream), p, g, v, n, 0.f, lr_dev, momentum, nesterov, clipnorm, out);
   return check_launch("sgd_apply_kernel");
 }
 

@@ -114,6 +114,19 @@ __device__ __forceinline__ void mma_tf32_c(uint32_t tmem_d, uint64_t adesc, uint
     asm volatile("{\n\t.reg .pred p;\n\tsetp.eq.u32 p, 1, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
                  ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc) : "memory");
 }
+// One lane of a CONVERGENT warp.  Issue loops are written as "whole warp runs the loop, elect_one() guards the
+// instruction": loop counters, descriptors and addresses then live in uniform registers.  Running the loop inside
+// `if (lane == 0)` instead makes the compiler wrap every tcgen05.mma / TMA in a divergence-safe ELECT + R2UR +
+// BRA.U.ANY waterfall (~200 cycles per instruction, measured).  The elected lane is the same on every call with the
+// same mask, so tcgen05.commit sees the MMAs of "its" thread.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+// warp index the compiler can prove warp-uniform (a shuffle from lane 0), so `if (warp == k)` is a uniform branch
+__device__ __forceinline__ int uniform_warp_idx() { return __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0); }
+
 // shared-memory descriptor split into its constant high word and the low word (start address + LBO field)
 __device__ __forceinline__ uint32_t umma_desc_hi_kmajor(uint32_t sbo_bytes, uint32_t swizzle_bytes) {
   uint32_t layout = swizzle_bytes == 128 ? 2u : (swizzle_bytes == 64 ? 4u : (swizzle_bytes == 32 ? 6u : 0u));

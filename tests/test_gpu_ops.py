@@ -66,6 +66,8 @@ CONV_CASES = [
     (2, 32, 32, 32, 16, 3, 1, 'same', True),
     (2, 4, 4, 32, 32, 3, 1, 'same', True),       # tcgen05: 4x4 maps, 8 images per tile (batch 2 < 8)
     (1, 32, 32, 64, 320, 3, 1, 'same', False),   # tcgen05: two N tiles of 160
+    (5, 4, 8, 32, 48, 3, 1, 'same', True),       # tcgen05 wgrad: two 4x8 images per pixel tile (halo rows between them)
+    (3, 64, 64, 16, 16, 3, 1, 'same', False),    # tcgen05 wgrad: 64-pixel rows, 16-channel boxes zero-filled to 32
 ]
 
 
