@@ -166,8 +166,45 @@ static se_conv_desc desc_from(const int32_t* i) {
 extern "C" int se_sgd_apply_devlr(float* p, const float* g, float* v, int64_t n, const float* lr_dev, float momentum,
                                   int nesterov, float clipnorm, const double* out, void* stream);
 
+// Weight gradients are off the critical path of the backward pass (nothing reads dW before the optimizer), so a
+// multi-op plan issues them on a second, lowest-priority stream: fork after the op that produced dY, join at the end of
+// the plan.  Inside a CUDA-graph capture this becomes a parallel branch.  The backward-data / BatchNorm-backward
+// chain and the wgrad kernels are sized to be co-resident on an SM (shared memory, TMEM columns, registers; see
+// conv_tc.cu / conv_wgrad_tc.cu), so the side branch fills the latency bubbles of the main chain.  SE_NO_SIDE_STREAM=1
+// keeps everything on one stream.
+static cudaStream_t g_side = nullptr;
+static cudaEvent_t g_ev_fork = nullptr, g_ev_join = nullptr;
+static bool side_stream_ready() {
+  static const bool off = getenv("SE_NO_SIDE_STREAM") != nullptr;
+  if (off) return false;
+  if (!g_side) {
+    int lo = 0, hi = 0;
+    if (cudaDeviceGetStreamPriorityRange(&lo, &hi) != cudaSuccess) return false;
+    if (cudaStreamCreateWithPriority(&g_side, cudaStreamNonBlocking, lo) != cudaSuccess) { g_side = nullptr; return false; }
+    if (cudaEventCreateWithFlags(&g_ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&g_ev_join, cudaEventDisableTiming) != cudaSuccess) {
+      g_side = nullptr;
+      return false;
+    }
+  }
+  return true;
+}
+
+static int run_ops_impl(const se_op* ops, int n, int mode, void* stream, bool* forked);
+
 extern "C" int se_run_ops(const se_op* ops, int n, int mode, void* stream) {
   SE_REQUIRE(ops && n >= 0, "bad arguments");
+  bool forked = false;
+  int rc = run_ops_impl(ops, n, mode, stream, &forked);
+  if (forked) {   // join on every path (an unjoined fork would invalidate an ongoing capture)
+    cudaEventRecord(g_ev_join, g_side);
+    cudaStreamWaitEvent(as_stream(stream), g_ev_join, 0);
+  }
+  return rc;
+}
+
+static int run_ops_impl(const se_op* ops, int n, int mode, void* stream, bool* forked) {
+  const bool use_side = n > 1 && side_stream_ready();
   for (int k = 0; k < n; ++k) {
     const se_op& o = ops[k];
     const int32_t* i = o.i;
@@ -188,7 +225,14 @@ extern "C" int se_run_ops(const se_op* ops, int n, int mode, void* stream) {
       }
       case SE_OP_CONV_WGRAD: {
         se_conv_desc d = desc_from(i);
-        rc = se_conv2d_wgrad(&d, (const float*)p[0], (const float*)p[1], (float*)p[2], (float*)p[3], i[13] >= 0 ? i[13] : mode, stream);
+        void* ws = stream;
+        if (use_side) {
+          cudaEventRecord(g_ev_fork, as_stream(stream));
+          cudaStreamWaitEvent(g_side, g_ev_fork, 0);
+          ws = g_side;
+          *forked = true;
+        }
+        rc = se_conv2d_wgrad(&d, (const float*)p[0], (const float*)p[1], (float*)p[2], (float*)p[3], i[13] >= 0 ? i[13] : mode, ws);
         break;
       }
       case SE_OP_BN_STATS:
@@ -261,10 +305,20 @@ extern "C" int se_run_ops(const se_op* ops, int n, int mode, void* stream) {
           rc = se_transpose_filters((const float*)p[0], (float*)p[1], (const int64_t*)p[2], i[0], stream);
         break;
       case SE_OP_SGD_PREPARE:
+        if (*forked) {   // the optimizer reads every gradient: the side branch joins here
+          cudaEventRecord(g_ev_join, g_side);
+          cudaStreamWaitEvent(as_stream(stream), g_ev_join, 0);
+          *forked = false;
+        }
         rc = se_sgd_prepare((const float*)p[0], (float*)p[1], (int64_t)(uintptr_t)p[2], (const se_l2_segment*)p[3], i[0],
                             (double*)p[4], stream);
         break;
       case SE_OP_SGD_APPLY:
+        if (*forked) {
+          cudaEventRecord(g_ev_join, g_side);
+          cudaStreamWaitEvent(as_stream(stream), g_ev_join, 0);
+          *forked = false;
+        }
         rc = se_sgd_apply_devlr((float*)p[0], (const float*)p[1], (float*)p[5], (int64_t)(uintptr_t)p[2], (const float*)p[3],
                                 f[0], i[0], f[1], (const double*)p[4], stream);
         break;

@@ -438,6 +438,9 @@ static int pick_bn(int Nc) {
   return 16;
 }
 
+size_t conv_wgrad_tc_smem(const se_conv_desc* d, int* tmem_cols);   // conv_wgrad_tc.cu
+constexpr int WG_COOP_SMEM_MAX = 116 * 1024;
+
 static int conv_tc_launch(const se_conv_desc* d, const float* a_tensor, int Kc, const float* bmat, int Nc, int flip,
                           const float* bias, const float* residual, float* out, int relu, float beta, double* stats,
                           cudaStream_t st) {
@@ -455,14 +458,32 @@ static int conv_tc_launch(const se_conv_desc* d, const float* a_tensor, int Kc, 
   p.a_bytes = CT_BM * p.cblk * 4;
   // the whole 3x3 window of a channel block in one pipeline stage when two such stages fit (fewer barrier
   // round trips per tile: small layers are bound by the single MMA-issuing thread, not by bandwidth)
+  // Backward-data launches leave room for the weight-gradient kernel of the same layer (it runs concurrently on the
+  // side stream of se_run_ops): shared memory = what that kernel leaves, TMEM <= 256 columns -- unless that would
+  // cost this kernel its pipeline, in which case it takes the whole SM as the forward launches do.
+  int budget = CT_SMEM_BUDGET, tmem_budget = 512;
+  static const bool no_coop = getenv("SE_NO_SIDE_STREAM") != nullptr;
+  if (flip && !no_coop) {
+    int wg_cols = 0;
+    const size_t wg = conv_wgrad_tc_smem(d, &wg_cols);
+    if (wg > 0 && wg <= (size_t)WG_COOP_SMEM_MAX && wg_cols <= 256) {
+      budget = 225 * 1024 - (int)wg - 2048;
+      tmem_budget = 256;
+    }
+  }
+  const int full_budget = CT_SMEM_BUDGET;
+ retry:
   p.rg = 3;
   p.stage_bytes = 3 * p.a_bytes + ceil_div(9 * p.BN * p.cblk * 4, 1024) * 1024;
-  if (2 * p.stage_bytes > CT_SMEM_BUDGET) {
+  if (2 * p.stage_bytes > budget) {
     p.rg = 1;
     p.stage_bytes = p.a_bytes + ceil_div(3 * p.BN * p.cblk * 4, 1024) * 1024;
   }
-  p.stages = min(CT_MAX_STAGES, CT_SMEM_BUDGET / p.stage_bytes);
-  if (p.stages < 2) return SE_ERR_UNSUPPORTED;
+  p.stages = min(CT_MAX_STAGES, budget / p.stage_bytes);
+  if (p.stages < 2) {
+    if (budget != full_budget) { budget = full_budget; tmem_budget = 512; goto retry; }
+    return SE_ERR_UNSUPPORTED;
+  }
   // resident-weights mode: every tile of the CTA uses the same 9*BN x Kc weight block
   p.res = 0; p.res_b_bytes = 0; p.nt = 1;
   static const char* dbg_nores = getenv("SE_CT_NORES");
@@ -470,7 +491,8 @@ static int conv_tc_launch(const se_conv_desc* d, const float* a_tensor, int Kc, 
   if (!dbg_nores && p.tiles_n == 1 && p.kblocks == 1 && wbytes <= 40 * 1024) {
     p.res = 1; p.res_b_bytes = wbytes; p.rg = 3;
     p.stage_bytes = 3 * p.a_bytes;
-    p.stages = min(CT_MAX_STAGES, (CT_SMEM_BUDGET - wbytes) / p.stage_bytes);
+    p.stages = min(CT_MAX_STAGES, (budget - wbytes) / p.stage_bytes);
+    if (p.stages < 2 && budget != full_budget) { budget = full_budget; tmem_budget = 512; goto retry; }
     static const char* dbg_nt = getenv("SE_CT_NT");
     p.nt = dbg_nt ? atoi(dbg_nt) : 4;
     p.nt = max(1, min(min(p.nt, 4), p.stages - 1));
@@ -484,7 +506,14 @@ static int conv_tc_launch(const se_conv_desc* d, const float* a_tensor, int Kc, 
   int stride = 32;
   while (stride < 3 * p.BN) stride <<= 1;
   if (2 * stride > 512) return SE_ERR_UNSUPPORTED;
-  p.tmem_cols = 512; p.acc_stride = stride; p.nacc = min(CT_MAX_ACC, 512 / stride);
+  if (tmem_budget < 512) {
+    // one accumulator is enough only when a CTA has a single tile; otherwise keep the MMA / epilogue overlap
+    const int tiles_per_cta = ceil_div(p.tiles_m * p.tiles_n, min(sm_count(), p.tiles_m * p.tiles_n));
+    if (tmem_budget / stride < min(2, tiles_per_cta)) tmem_budget = 512;
+  }
+  p.acc_stride = stride; p.nacc = min(CT_MAX_ACC, tmem_budget / stride);
+  p.tmem_cols = 32;
+  while (p.tmem_cols < p.nacc * stride) p.tmem_cols <<= 1;
   p.nt = max(1, min(p.nt, p.nacc));
   p.b_merged = (p.tiles_n == 1) ? 1 : 0;
   p.bias = bias; p.residual = residual; p.out = out; p.stats = stats;

@@ -50,8 +50,8 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* tiles = smem;
-  uint8_t* ones = tiles + (size_t)p.stages * p.stage_bytes;               // PT pixels x 32 channels of 1.0f (G == 4)
-  uint64_t* bars = reinterpret_cast<uint64_t*>(ones + (p.G == 4 ? p.PT * 128 : 0));
+  uint8_t* ones = tiles + (size_t)p.stages * p.stage_bytes;               // 8 pixels x 32 channels of 1.0f (G == 4)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ones + (p.G == 4 ? 1024 : 0));
   uint64_t* full = bars;
   uint64_t* empty = bars + 4;
   uint64_t* done = bars + 8;
@@ -69,7 +69,7 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
 
   if (p.G == 4) {
     float4* o = reinterpret_cast<float4*>(ones);
-    for (int i = threadIdx.x; i < p.PT * 8; i += blockDim.x) o[i] = make_float4(1.f, 1.f, 1.f, 1.f);
+    for (int i = threadIdx.x; i < 64; i += blockDim.x) o[i] = make_float4(1.f, 1.f, 1.f, 1.f);
   }
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&map_x); prefetch_tmap(&map_dy);
@@ -114,7 +114,7 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
       const uint32_t hi = (512u >> 4) | (1u << 14) | (1u << 29);
       const uint32_t lbo_a = (((uint32_t)(p.W * 128) >> 4) & 0x3FFFu) << 16;      // next vertical tap = next image row
       const uint32_t lbo_b = (((uint32_t)(p.PT * 128) >> 4) & 0x3FFFu) << 16;     // next 32-channel block of dY
-      const uint32_t ones_lo = (smem_u32(ones) & 0x3FFFFu) >> 4;                  // LBO 0: all four blocks are ones
+      const uint32_t ones_lo = (smem_u32(ones) & 0x3FFFFu) >> 4;                  // LBO 0, the same 8 pixels for every k-step
       const uint32_t tiles_u32 = smem_u32(tiles);
       const int ksteps = (p.debug & 4) ? 0 : p.PT / 8;
       int stage = 0, phase = 0;
@@ -134,7 +134,7 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
               const uint64_t da = ((uint64_t)hi << 32) | (uint64_t)((((a0 + s * p.xbuf_bytes) & 0x3FFFFu) >> 4) | lbo_a);
               mma_tf32(tmem_base + s * p.ncols, da, db, idesc, acc);
             }
-            if (p.G == 4) mma_tf32(tmem_base + 3 * p.ncols, ((uint64_t)hi << 32) | (uint64_t)(ones_lo + ks * 64), db, idesc, acc);
+            if (p.G == 4) mma_tf32(tmem_base + 3 * p.ncols, ((uint64_t)hi << 32) | (uint64_t)ones_lo, db, idesc, acc);
           }
           __syncwarp();
           acc = 1;
@@ -198,19 +198,20 @@ int init_conv_wgrad_tc() {
   return SE_OK;
 }
 
-int conv_wgrad_tc(const se_conv_desc* d, const float* x, const float* dy, float* dw, float* dbias, cudaStream_t st) {
+// Geometry + shared-memory plan; SE_OK when the tcgen05 path can run this layer.  `with_bias` adds the ones tile.
+// Co-residency with the backward-data kernel of the same layer (se_run_ops issues wgrad on a side stream): when two
+// pipeline stages fit in ~half of the SM's shared memory the kernel takes only those, and conv_tc.cu sizes the
+// dgrad kernel to the rest (conv_wgrad_tc_smem() is what it asks).
+constexpr int WG_COOP_SMEM = 116 * 1024;
+
+static int plan_wgrad(const se_conv_desc* d, bool with_bias, WgTcParams* pp, size_t* smem_out) {
   if (d->kh != 3 || d->kw != 3 || d->stride != 1 || d->pad_t != 1 || d->pad_l != 1 || d->Ho != d->H || d->Wo != d->W)
     return SE_ERR_UNSUPPORTED;
   const int Cin = d->Cin, Cout = d->Cout, W = d->W, H = d->H;
   if (Cin % 16 != 0 || Cout % 16 != 0) return SE_ERR_UNSUPPORTED;
   // vertical taps are address offsets of r*W pixels: whole 1024-byte swizzle periods need W % 8 == 0
   if (W > 64 || (W & (W - 1)) != 0 || W < 8) return SE_ERR_UNSUPPORTED;
-  if ((reinterpret_cast<uintptr_t>(dw) & 15) != 0 || (dbias && (reinterpret_cast<uintptr_t>(dbias) & 15) != 0))
-    return SE_ERR_UNSUPPORTED;
-  static bool inited = false;
-  if (!inited) { int rc = init_conv_wgrad_tc(); if (rc) return rc; inited = true; }
-
-  WgTcParams p;
+  WgTcParams& p = *pp;
   p.N = d->N; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout;
   p.PT = max(64, 2 * W);
   if (W * H >= p.PT) { if (H % (p.PT / W) != 0) return SE_ERR_UNSUPPORTED; p.Hb = p.PT / W; p.Nb = 1; }
@@ -218,16 +219,44 @@ int conv_wgrad_tc(const se_conv_desc* d, const float* x, const float* dy, float*
   p.img_px = p.Hb * W;
   p.img_stride = (p.Hb + 2) * W * 128;
   p.xbuf_bytes = p.Nb * p.img_stride;
-  p.G = dbias ? 4 : 3;
+  p.G = with_bias ? 4 : 3;
   // output channels per CTA: at most 128 (4 accumulators x 128 columns = the 512 TMEM columns), in 32-channel blocks
   const int gz = ceil_div(Cout, 128);
   p.nnb = ceil_div(ceil_div(Cout, gz), 32);
   p.ncols = 32 * p.nnb;
   p.dy_bytes = p.PT * 128 * p.nnb;
   p.stage_bytes = ceil_div(3 * p.xbuf_bytes + p.dy_bytes, 1024) * 1024;
-  p.stages = min(4, (200 * 1024) / p.stage_bytes);
+  const int fixed = (with_bias ? 1024 : 0) + 16 * 8 + 1024 + 64;
+  if (2 * p.stage_bytes + fixed <= WG_COOP_SMEM) p.stages = 2;
+  else p.stages = min(4, (200 * 1024) / p.stage_bytes);
   if (p.stages < 1) return SE_ERR_UNSUPPORTED;
   p.tiles_m = (p.Nb == 1) ? d->N * (H / p.Hb) : ceil_div(d->N, p.Nb);
+  *smem_out = (size_t)p.stages * p.stage_bytes + fixed;
+  return SE_OK;
+}
+
+// dynamic shared memory the wgrad kernel of this layer will take, and its TMEM columns (0 when it cannot run)
+size_t conv_wgrad_tc_smem(const se_conv_desc* d, int* tmem_cols) {
+  WgTcParams p;
+  size_t smem = 0;
+  if (plan_wgrad(d, true, &p, &smem) != SE_OK) return 0;
+  int cols = 32;
+  while (cols < p.G * p.ncols) cols <<= 1;
+  if (tmem_cols) *tmem_cols = cols;
+  return smem;
+}
+
+int conv_wgrad_tc(const se_conv_desc* d, const float* x, const float* dy, float* dw, float* dbias, cudaStream_t st) {
+  if ((reinterpret_cast<uintptr_t>(dw) & 15) != 0 || (dbias && (reinterpret_cast<uintptr_t>(dbias) & 15) != 0))
+    return SE_ERR_UNSUPPORTED;
+  WgTcParams p;
+  size_t smem = 0;
+  int rc = plan_wgrad(d, dbias != nullptr, &p, &smem);
+  if (rc != SE_OK) return rc;
+  static bool inited = false;
+  if (!inited) { rc = init_conv_wgrad_tc(); if (rc) return rc; inited = true; }
+  const int Cin = d->Cin, Cout = d->Cout, W = d->W, H = d->H;
+  const int gz = ceil_div(Cout, 128);
   p.dw = dw; p.dbias = dbias;
   static const char* dbg = getenv("SE_WG_DEBUG");
   p.debug = dbg ? atoi(dbg) : 0;
@@ -249,7 +278,6 @@ int conv_wgrad_tc(const se_conv_desc* d, const float* x, const float* dy, float*
   }
   const int gy = ceil_div(Cin, 32);
   const int gx = max(1, min(p.tiles_m, sm_count() / (gy * gz)));
-  const size_t smem = (size_t)p.stages * p.stage_bytes + (p.G == 4 ? p.PT * 128 : 0) + 16 * 8 + 1024 + 64;
   launch(conv_wgrad_tc_kernel, dim3(gx, gy, gz), dim3(192), smem, st, mx, mdy, p);
   return check_launch("conv_wgrad_tc_kernel");
 }
