@@ -171,7 +171,8 @@ def run_reference(args):
 # ----------------------------------------------------------------------------------------------- GPU arm
 def op_category(op, L):
     i = op.i
-    names = {L.OP_CONV_FWD: 'conv_fwd', L.OP_CONV_DGRAD: 'conv_dgrad', L.OP_CONV_WGRAD: 'conv_wgrad'}
+    names = {L.OP_CONV_FWD: 'conv_fwd', L.OP_CONV_DGRAD: 'conv_dgrad', L.OP_CONV_WGRAD: 'conv_wgrad',
+             L.OP_CONV_BN_FWD: 'conv_bn_fwd'}
     if op.opcode in names:
         key = '%s %dx%d s%d %d->%d @%dx%d' % (names[op.opcode], i[5], i[6], i[7], i[3], i[4], i[1], i[2])
         flops = 2.0 * i[0] * i[10] * i[11] * i[4] * i[5] * i[6] * i[3]

@@ -18,7 +18,8 @@ SE_PDIST_SQEUCLID, SE_PDIST_NEGDOT = 0, 1
 # opcodes of se_run_ops (csrc/opcodes.h)
 OP_CONV_FWD, OP_CONV_DGRAD, OP_CONV_WGRAD, OP_BN_STATS, OP_BN_FWD_TRAIN, OP_BN_FWD_INFER, OP_BN_BWD, \
     OP_SHORTCUT_BWD, OP_AVGPOOL_FWD, OP_AVGPOOL_BWD, OP_MAXPOOL_FWD, OP_MAXPOOL_BWD, OP_GAP_FWD, OP_GAP_BWD, \
-    OP_ADD_FWD, OP_ADD_BWD, OP_HEAD, OP_XENT, OP_MEMSET, OP_SGD_PREPARE, OP_SGD_APPLY, OP_TRANSPOSE_FILTERS = range(1, 23)
+    OP_ADD_FWD, OP_ADD_BWD, OP_HEAD, OP_XENT, OP_MEMSET, OP_SGD_PREPARE, OP_SGD_APPLY, OP_TRANSPOSE_FILTERS, \
+    OP_CONV_BN_FWD = range(1, 24)
 
 
 class SeError(RuntimeError):
@@ -51,6 +52,8 @@ _SIGS = {
     'se_tc_capabilities': (c_int, []),
     'se_conv2d_fwd': (c_int, [POINTER(ConvDesc), _P, _P, _P, _P, _P, c_int, _P, c_int, _P]),
     'se_conv2d_fwd_ex': (c_int, [POINTER(ConvDesc), _P, _P, _P, _P, _P, _P, c_int, _P, c_int, _P]),
+    'se_conv_bn_fwd': (c_int, [POINTER(ConvDesc), _P, _P, _P, _P, _P, c_int, _P, _P, _P, c_float, c_float, _P, _P, _P, _P, _P,
+                               c_int, _P, _P, c_int, _P]),
     'se_transpose_filters': (c_int, [_P, _P, POINTER(c_int64), c_int, _P]),
     'se_conv2d_dgrad': (c_int, [POINTER(ConvDesc), _P, _P, _P, c_float, c_int, _P]),
     'se_conv2d_wgrad': (c_int, [POINTER(ConvDesc), _P, _P, _P, _P, c_int, _P]),

@@ -45,6 +45,10 @@ int conv_wgrad_simt(const se_conv_desc*, const float*, const float*, float*, flo
 // conv_tc.cu (tcgen05 kind::tf32); each returns SE_ERR_UNSUPPORTED for shapes it does not cover
 int conv_fwd_tc(const se_conv_desc*, const float*, const float*, const float*, const float*, float*, int, double*, cudaStream_t);
 int conv_dgrad_tc(const se_conv_desc*, const float*, const float*, float*, float, cudaStream_t);
+int conv_bn_fwd_tc(const se_conv_desc* d, const float* x, const float* w_t, const float* bias, float* y, int relu, double* stats,
+                   const float* gamma, const float* beta, float eps, float momentum, float* moving_mean, float* moving_var,
+                   float* save_mean, float* save_invstd, const float* bn_res, int bn_relu, float* bn_out,
+                   unsigned long long* counter, cudaStream_t st);
 int conv_wgrad_tc(const se_conv_desc*, const float*, const float*, float*, float*, cudaStream_t);
 
 static int check_desc(const se_conv_desc* d) {
@@ -95,6 +99,26 @@ extern "C" int se_conv2d_fwd_ex(const se_conv_desc* d, const float* x, const flo
     if (rc != SE_ERR_UNSUPPORTED) return rc;
   }
   return conv_fwd_simt(d, x, w, bias, residual, y, relu, stats, as_stream(stream));
+}
+
+extern "C" int se_conv_bn_fwd(const se_conv_desc* d, const float* x, const float* w, const float* w_t, const float* bias,
+                              float* y, int relu, double* stats, const float* gamma, const float* beta, float eps,
+                              float momentum, float* moving_mean, float* moving_var, float* save_mean, float* save_invstd,
+                              const float* res, int bn_relu, float* bn_out, void* counter, int mode, void* stream) {
+  int rc = check_desc(d);
+  if (rc) return rc;
+  SE_REQUIRE(x && w && y && stats && gamma && beta && save_mean && save_invstd && bn_out, "null pointer");
+  if (mode == SE_MODE_TF32 && w_t && counter) {
+    rc = conv_bn_fwd_tc(d, x, w_t, bias, y, relu, stats, gamma, beta, eps, momentum, moving_mean, moving_var, save_mean,
+                        save_invstd, res, bn_relu, bn_out, reinterpret_cast<unsigned long long*>(counter), as_stream(stream));
+    if (rc != SE_ERR_UNSUPPORTED) return rc;
+  }
+  rc = se_conv2d_fwd_ex(d, x, w, w_t, bias, nullptr, y, relu, stats, mode, stream);
+  if (rc) return rc;
+  se_residual r;
+  r.ptr = res; r.C = d->Cout; r.pad_lo = 0; r.pool = 1; r.H = d->Ho; r.W = d->Wo;
+  return se_bn_fwd_train(y, (int64_t)d->N * d->Ho * d->Wo, d->Cout, stats, gamma, beta, eps, momentum, moving_mean, moving_var,
+                         save_mean, save_invstd, res ? &r : nullptr, bn_relu, bn_out, stream);
 }
 
 extern "C" int se_conv2d_fwd(const se_conv_desc* d, const float* x, const float* w, const float* bias,
@@ -216,6 +240,16 @@ static int run_ops_impl(const se_op* ops, int n, int mode, void* stream, bool* f
         se_conv_desc d = desc_from(i);
         rc = se_conv2d_fwd_ex(&d, (const float*)p[0], (const float*)p[1], (const float*)p[6], (const float*)p[2],
                               (const float*)p[3], (float*)p[4], i[12], (double*)p[5], i[13] >= 0 ? i[13] : mode, stream);
+        break;
+      }
+      case SE_OP_CONV_BN_FWD: {
+        // p: 0 x, 1 w, 2 bias, 3 y, 4 stats, 5 w_t, 6 gamma, 7 beta, 8 moving_mean, 9 moving_var, 10 save_mean,
+        //    11 save_invstd, 12 residual, 13 bn_out, 14 counter;  i[12] conv relu, i[14] bn relu;  f: eps, momentum
+        se_conv_desc d = desc_from(i);
+        rc = se_conv_bn_fwd(&d, (const float*)p[0], (const float*)p[1], (const float*)p[5], (const float*)p[2], (float*)p[3],
+                            i[12], (double*)p[4], (const float*)p[6], (const float*)p[7], f[0], f[1], (float*)p[8],
+                            (float*)p[9], (float*)p[10], (float*)p[11], (const float*)p[12], i[14], (float*)p[13], p[14],
+                            i[13] >= 0 ? i[13] : mode, stream);
         break;
       }
       case SE_OP_CONV_DGRAD: {

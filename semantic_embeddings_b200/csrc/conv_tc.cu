@@ -50,6 +50,20 @@ struct ConvTcParams {
   const float* residual;
   float* out;
   double* stats;
+  // fused training-mode BatchNorm of the convolution output (forward only; every tile of the CTA keeps its own
+  // accumulator, so after a grid-wide barrier on the batch statistics a second epilogue pass re-reads TMEM and
+  // writes act(scale * conv + shift [+ residual]) -- no separate BatchNorm launch, no re-read of the conv output)
+  int bn, bn_relu;
+  float bn_eps, bn_momentum;
+  const float* bn_gamma;
+  const float* bn_beta;
+  float* bn_moving_mean;
+  float* bn_moving_var;
+  float* bn_save_mean;
+  float* bn_save_invstd;
+  const float* bn_res;      // same shape as the output, or null
+  float* bn_out;
+  unsigned long long* bn_counter;   // grid barrier arrival counter (zeroed by the caller once per step)
   long long* trace;         // debug: per-role clock64 timeline of CTA 0 (SE_CT_TRACE_PTR)
   int debug;                // bit 0: no tiles (fixed overhead only), bit 1: skip A loads, bit 2: skip epilogue stores/stats
 };
@@ -100,15 +114,13 @@ __device__ __forceinline__ void tmem_ld_cols<16>(uint32_t taddr, uint32_t (&v)[1
 // One block of NC output channels of one pixel: combine the three horizontal partial sums, apply the epilogue
 // ops, store, and (optionally) fold the stored values into the BatchNorm statistics.
 template <int NC>
-__device__ __forceinline__ void conv_tc_epilogue_block(const ConvTcParams& p, uint32_t t_addr, int lblk, int c0, int tn,
-                                                       bool valid, bool has_left, bool has_right, float* orow,
-                                                       const float* rrow, float* sw, int lane) {
+__device__ __forceinline__ void conv_tc_load_combine(const ConvTcParams& p, uint32_t t_addr, int lblk, int c0, bool has_left,
+                                                     bool has_right, float (&o)[NC]) {
   uint32_t v[NC], vl[NC], vr[NC];                 // centre (s=1), left (s=0) and right (s=2) partial sums
   tmem_ld_cols<NC>(t_addr + lblk * p.BN + c0, vl);
   tmem_ld_cols<NC>(t_addr + p.BN + c0, v);
   tmem_ld_cols<NC>(t_addr + (2 - lblk) * p.BN + c0, vr);
   tmem_ld_wait();
-  float o[NC];
 #pragma unroll
   for (int j = 0; j < NC; ++j) {
     // y[w] = P0[w-1] + P1[w] + P2[w+1]: the neighbours' partial sums come from the adjacent lanes
@@ -119,23 +131,45 @@ __device__ __forceinline__ void conv_tc_epilogue_block(const ConvTcParams& p, ui
     if (has_right) c += r;
     o[j] = c;
   }
+}
+
+// 16 columns of this warp's 32 TMEM lanes <- 16 registers per lane (the fused BatchNorm keeps the finished
+// convolution values where the second epilogue pass can fetch them with one load and no neighbour shuffles)
+__device__ __forceinline__ void tmem_st_16(uint32_t taddr, const float* o) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
+      ::"r"(taddr), "f"(o[0]), "f"(o[1]), "f"(o[2]), "f"(o[3]), "f"(o[4]), "f"(o[5]), "f"(o[6]), "f"(o[7]), "f"(o[8]),
+        "f"(o[9]), "f"(o[10]), "f"(o[11]), "f"(o[12]), "f"(o[13]), "f"(o[14]), "f"(o[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+template <int NC>
+__device__ __forceinline__ void conv_tc_epilogue_block(const ConvTcParams& p, uint32_t t_addr, int lblk, int c0, int tn,
+                                                       bool valid, bool has_left, bool has_right, float* orow,
+                                                       const float* exrow, float exs, const float* s_bias, float* sw, int lane,
+                                                       long long* dbg = nullptr) {
+  // exrow / exs: the one extra per-pixel term of the epilogue -- the residual (forward, exs = 1) or the previous
+  // contents of the output (dgrad accumulate, exs = beta).  Loaded in full before the first store (see conv_tc_bn_block).
   const bool live = valid && !(p.debug & 4);
+  float4 ex[NC / 4];
+  if (dbg) dbg[0] = clock64();
+  if (exrow && live) {
+#pragma unroll
+    for (int q = 0; q < NC / 4; ++q) ex[q] = *reinterpret_cast<const float4*>(exrow + c0 + 4 * q);
+  }
+  float o[NC];
+  conv_tc_load_combine<NC>(p, t_addr, lblk, c0, has_left, has_right, o);
+  if (dbg) dbg[1] = clock64();
 #pragma unroll
   for (int q = 0; q < NC / 4; ++q) {
     float4 val = make_float4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
     if (live) {
-      const int cg = tn * p.BN + c0 + 4 * q;
-      if (p.bias) {
-        float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + cg));
-        val.x += b.x; val.y += b.y; val.z += b.z; val.w += b.w;
-      }
-      if (rrow) {
-        float4 rr = *reinterpret_cast<const float4*>(rrow + c0 + 4 * q);
-        val.x += rr.x; val.y += rr.y; val.z += rr.z; val.w += rr.w;
-      }
-      if (p.beta != 0.f) {
-        float4 old = *reinterpret_cast<const float4*>(orow + c0 + 4 * q);
-        val.x += p.beta * old.x; val.y += p.beta * old.y; val.z += p.beta * old.z; val.w += p.beta * old.w;
+      const float4 b = *reinterpret_cast<const float4*>(s_bias + tn * p.BN + c0 + 4 * q);
+      val.x += b.x; val.y += b.y; val.z += b.z; val.w += b.w;
+      if (exrow) {
+        val.x = fmaf(exs, ex[q].x, val.x); val.y = fmaf(exs, ex[q].y, val.y);
+        val.z = fmaf(exs, ex[q].z, val.z); val.w = fmaf(exs, ex[q].w, val.w);
       }
       if (p.relu) { val.x = fmaxf(val.x, 0.f); val.y = fmaxf(val.y, 0.f); val.z = fmaxf(val.z, 0.f); val.w = fmaxf(val.w, 0.f); }
       *reinterpret_cast<float4*>(orow + c0 + 4 * q) = val;
@@ -144,6 +178,11 @@ __device__ __forceinline__ void conv_tc_epilogue_block(const ConvTcParams& p, ui
     }
     o[4 * q] = val.x; o[4 * q + 1] = val.y; o[4 * q + 2] = val.z; o[4 * q + 3] = val.w;
   }
+  if (p.bn) {
+#pragma unroll
+    for (int h = 0; h < NC / 16; ++h) tmem_st_16(t_addr + p.BN + c0 + 16 * h, o + 16 * h);
+  }
+  if (dbg) dbg[2] = clock64();
   if (sw && !(p.debug & 4)) {
     float o2[NC];
 #pragma unroll
@@ -156,9 +195,10 @@ __device__ __forceinline__ void conv_tc_epilogue_block(const ConvTcParams& p, ui
       sw[p.Nc + tn * p.BN + c0 + col] += cq;
     }
   }
+  if (dbg) dbg[3] = clock64();
 }
 
-__global__ void __launch_bounds__(CT_THREADS, 1)
+__global__ void __maxnreg__(128)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, ConvTcParams p) {
   pdl_trigger();
   extern __shared__ uint8_t smem_raw[];
@@ -172,7 +212,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   uint64_t* t_empty = t_full + CT_MAX_ACC;
   uint64_t* b_full = t_empty + CT_MAX_ACC;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(b_full + 1);
-  float* s_stats = reinterpret_cast<float*>(bars + 2 * CT_MAX_STAGES + 2 * CT_MAX_ACC + 4);   // [8 warps][2 * Nc]
+  float* s_bias = reinterpret_cast<float*>(bars + 2 * CT_MAX_STAGES + 2 * CT_MAX_ACC + 4);    // [Nc] (zeros without a bias)
+  float* s_stats = s_bias + p.Nc;                                                              // [8 warps][2 * Nc]
 
   const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
   const int total_tiles = p.tiles_m * p.tiles_n;
@@ -353,6 +394,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     int tr_n = (warp == 4 && lane == 0) ? 0 : 1000;
     CT_TRACE(2, 0);
     float* sw = p.stats ? s_stats + (warp - 4) * 2 * p.Nc : nullptr;
+    for (int i = threadIdx.x - 128; i < p.Nc; i += 256) s_bias[i] = p.bias ? p.bias[i] : 0.f;
+    named_bar_sync(1, 256);
+    const float* exbase = p.residual ? p.residual : (p.beta != 0.f ? p.out : nullptr);
+    const float exs = p.residual ? 1.f : p.beta;
     const int lblk = (p.b_merged && p.flip) ? 2 : 0;   // column block holding the s=0 partial sums
     for (int t = t_begin + grp; t < t_end; t += 2) {
       const int i = t - t_begin, acc = i % p.nacc, acc_phase = (i / p.nacc) & 1;
@@ -365,26 +410,136 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       const bool valid = (n < p.N) && (h < p.H) && (wb < p.W);
       const long long pix = ((long long)n * p.H + h) * p.W + wb;
       float* orow = p.out + pix * p.Nc + tn * p.BN;
-      const float* rrow = p.residual ? p.residual + pix * p.Nc + tn * p.BN : nullptr;
+      const float* rrow = exbase ? exbase + pix * p.Nc + tn * p.BN : nullptr;
       const bool has_left = wb > 0, has_right = wb < p.W - 1;
       mbar_wait(&t_full[acc], acc_phase);
       CT_TRACE(2, 1);
       fence_after_sync();
       const uint32_t t_addr = tmem_base + ((uint32_t)(q4 * 32) << 16) + acc * p.acc_stride;
       int c0 = 0;
+      long long* dbg = (p.trace && blockIdx.x == 0 && warp == 4 && lane == 0 && t == t_begin) ? p.trace + 2 * 512 + 400 : nullptr;
       for (; c0 + 32 <= p.BN; c0 += 32)
-        conv_tc_epilogue_block<32>(p, t_addr, lblk, c0, tn, valid, has_left, has_right, orow, rrow, sw, lane);
+        conv_tc_epilogue_block<32>(p, t_addr, lblk, c0, tn, valid, has_left, has_right, orow, rrow, exs, s_bias, sw, lane, c0 == 0 ? dbg : nullptr);
       if (c0 < p.BN)
-        conv_tc_epilogue_block<16>(p, t_addr, lblk, c0, tn, valid, has_left, has_right, orow, rrow, sw, lane);
+        conv_tc_epilogue_block<16>(p, t_addr, lblk, c0, tn, valid, has_left, has_right, orow, rrow, exs, s_bias, sw, lane, c0 == 0 ? dbg : nullptr);
       CT_TRACE(2, 2);
       fence_before_sync();                          // all TMEM reads of this accumulator are complete
       mbar_arrive(&t_empty[acc]);
       CT_TRACE(2, 3);
     }
+    if (p.bn) {
+      // ---- batch statistics: CTA partial sums -> global, grid barrier, per-channel scale / shift
+      const int et = threadIdx.x - 128;             // 0..255 over the eight epilogue warps
+      float* coef = s_stats + 16 * p.Nc;            // [scale Nc | shift Nc]
+      tmem_st_wait();                               // pass-1 write-backs of this thread have landed in TMEM
+      fence_before_sync();
+      named_bar_sync(1, 256);
+      CT_TRACE(2, 4);
+      for (int i = et; i < 2 * p.Nc; i += 256) {
+        double v = 0.0;
+#pragma unroll
+        for (int wv = 0; wv < 8; ++wv) v += (double)s_stats[wv * 2 * p.Nc + i];
+        atomicAdd(&p.stats[i], v);
+      }
+      __threadfence();
+      named_bar_sync(1, 256);
+      CT_TRACE(2, 5);
+      if (et == 0) {
+        atomicAdd(p.bn_counter, 1ULL);
+        while (*reinterpret_cast<volatile unsigned long long*>(p.bn_counter) < (unsigned long long)gridDim.x) { }
+        __threadfence();
+      }
+      named_bar_sync(1, 256);
+      CT_TRACE(2, 6);
+      const double rows = (double)p.N * p.H * p.W;
+      for (int c = et; c < p.Nc; c += 256) {
+        // identical arithmetic to bn_fwd_kernel<true> (bn.cu): float64 moments, float32 scale / shift
+        double m = __ldcg(&p.stats[c]) / rows;
+        double var = __ldcg(&p.stats[p.Nc + c]) / rows - m * m;
+        if (var < 0) var = 0;
+        const float mean = (float)m;
+        const float invstd = (float)(1.0 / sqrt(var + (double)p.bn_eps));
+        const float g = p.bn_gamma[c];
+        coef[c] = g * invstd;
+        coef[p.Nc + c] = p.bn_beta[c] - mean * g * invstd;
+      }
+      named_bar_sync(1, 256);
+      fence_after_sync();
+      CT_TRACE(2, 7);
+      // ---- pass 2: items = (tile, 16-column block), dealt round-robin to the two epilogue groups; the TMEM loads of
+      // up to four items are in flight together, then each item is normalised and stored
+      const int m = q4 * 32 + lane;
+      const int wb = m % p.Wb, hb = (m / p.Wb) % p.Hb, nb = m / (p.Wb * p.Hb);
+      const int nb16 = p.BN / 16;
+      const int nitems = max(0, t_end - t_begin) * nb16;
+      const uint32_t lane_addr = tmem_base + ((uint32_t)(q4 * 32) << 16) + p.BN;
+      for (int base = grp; base < nitems; base += 8) {
+        uint32_t v[4][16];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int idx = base + 2 * u;
+          if (idx < nitems) {
+            const int i = idx / nb16, blk = idx - i * nb16;
+            tmem_ld_cols<16>(lane_addr + (i % p.nacc) * p.acc_stride + 16 * blk, v[u]);
+          }
+        }
+        tmem_ld_wait();
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int idx = base + 2 * u;
+          if (idx >= nitems) continue;
+          const int i = idx / nb16, blk = idx - i * nb16;
+          const int t = t_begin + i;
+          const int tm = t / p.tiles_n, tn = t - tm * p.tiles_n;
+          int n, h;
+          if (p.Nb == 1) { n = tm / tiles_per_img; h = (tm - n * tiles_per_img) * p.Hb + hb; }
+          else { n = tm * p.Nb + nb; h = hb; }
+          if (!((n < p.N) && (h < p.H) && (wb < p.W))) continue;
+          const long long off = (((long long)n * p.H + h) * p.W + wb) * p.Nc + tn * p.BN + 16 * blk;
+          const int cg = tn * p.BN + 16 * blk;
+          float4 ex[4];
+          if (p.bn_res) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) ex[q] = __ldg(reinterpret_cast<const float4*>(p.bn_res + off) + q);
+          }
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float4 sc = *reinterpret_cast<const float4*>(coef + cg + 4 * q);
+            const float4 sh = *reinterpret_cast<const float4*>(coef + p.Nc + cg + 4 * q);
+            float4 val;
+            val.x = __uint_as_float(v[u][4 * q]) * sc.x + sh.x;
+            val.y = __uint_as_float(v[u][4 * q + 1]) * sc.y + sh.y;
+            val.z = __uint_as_float(v[u][4 * q + 2]) * sc.z + sh.z;
+            val.w = __uint_as_float(v[u][4 * q + 3]) * sc.w + sh.w;
+            if (p.bn_res) { val.x += ex[q].x; val.y += ex[q].y; val.z += ex[q].z; val.w += ex[q].w; }
+            if (p.bn_relu) { val.x = fmaxf(val.x, 0.f); val.y = fmaxf(val.y, 0.f); val.z = fmaxf(val.z, 0.f); val.w = fmaxf(val.w, 0.f); }
+            *(reinterpret_cast<float4*>(p.bn_out + off) + q) = val;
+          }
+        }
+      }
+      CT_TRACE(2, 8);
+      // saved statistics and moving averages (CTA 0; off the critical path of the other CTAs' stores)
+      if (blockIdx.x == 0) {
+        for (int c = et; c < p.Nc; c += 256) {
+          double mm = __ldcg(&p.stats[c]) / rows;
+          double var = __ldcg(&p.stats[p.Nc + c]) / rows - mm * mm;
+          if (var < 0) var = 0;
+          const float mean = (float)mm;
+          p.bn_save_mean[c] = mean;
+          p.bn_save_invstd[c] = (float)(1.0 / sqrt(var + (double)p.bn_eps));
+          if (p.bn_moving_mean) {
+            double uvar = var * (rows / (rows - (1.0 + (double)p.bn_eps)));
+            p.bn_moving_mean[c] = p.bn_moving_mean[c] * p.bn_momentum + mean * (1.f - p.bn_momentum);
+            p.bn_moving_var[c] = p.bn_moving_var[c] * p.bn_momentum + (float)uvar * (1.f - p.bn_momentum);
+          }
+        }
+      }
+      fence_before_sync();
+    }
   }
 
   __syncthreads();
-  if (p.stats) {
+  if (p.stats && !p.bn) {
     for (int i = threadIdx.x; i < 2 * p.Nc; i += blockDim.x) {
       double v = 0.0;
 #pragma unroll
@@ -441,10 +596,19 @@ static int pick_bn(int Nc) {
 size_t conv_wgrad_tc_smem(const se_conv_desc* d, int* tmem_cols);   // conv_wgrad_tc.cu
 constexpr int WG_COOP_SMEM_MAX = 116 * 1024;
 
+struct ConvTcBn {            // fused BatchNorm arguments of conv_tc_launch (null = plain convolution)
+  const float* gamma; const float* beta; float eps, momentum; float* moving_mean; float* moving_var;
+  float* save_mean; float* save_invstd; const float* res; int relu; float* out; unsigned long long* counter;
+};
+
 static int conv_tc_launch(const se_conv_desc* d, const float* a_tensor, int Kc, const float* bmat, int Nc, int flip,
                           const float* bias, const float* residual, float* out, int relu, float beta, double* stats,
-                          cudaStream_t st) {
+                          cudaStream_t st, const ConvTcBn* bn = nullptr) {
   ConvTcParams p;
+  p.bn = 0; p.bn_relu = 0; p.bn_eps = 0.f; p.bn_momentum = 0.f;
+  p.bn_gamma = p.bn_beta = p.bn_res = nullptr;
+  p.bn_moving_mean = p.bn_moving_var = p.bn_save_mean = p.bn_save_invstd = p.bn_out = nullptr;
+  p.bn_counter = nullptr;
   p.N = d->N; p.H = d->H; p.W = d->W; p.Kc = Kc; p.Nc = Nc;
   p.Wb = d->W;
   if (d->W * d->H >= 128) { p.Hb = 128 / d->W; p.Nb = 1; } else { p.Hb = d->H; p.Nb = 128 / (d->W * d->H); }
@@ -512,12 +676,23 @@ static int conv_tc_launch(const se_conv_desc* d, const float* a_tensor, int Kc, 
     if (tmem_budget / stride < min(2, tiles_per_cta)) tmem_budget = 512;
   }
   p.acc_stride = stride; p.nacc = min(CT_MAX_ACC, tmem_budget / stride);
+  if (bn) {
+    // every tile of a CTA needs its own accumulator until the second epilogue pass
+    const int total = p.tiles_m * p.tiles_n;
+    const int per_cta = ceil_div(total, min(sm_count(), total));
+    if (!stats || residual || beta != 0.f || per_cta > p.nacc) return SE_ERR_UNSUPPORTED;
+    p.bn = 1; p.bn_relu = bn->relu; p.bn_eps = bn->eps; p.bn_momentum = bn->momentum;
+    p.bn_gamma = bn->gamma; p.bn_beta = bn->beta; p.bn_moving_mean = bn->moving_mean; p.bn_moving_var = bn->moving_var;
+    p.bn_save_mean = bn->save_mean; p.bn_save_invstd = bn->save_invstd; p.bn_res = bn->res; p.bn_out = bn->out;
+    p.bn_counter = bn->counter;
+  }
   p.tmem_cols = 32;
   while (p.tmem_cols < p.nacc * stride) p.tmem_cols <<= 1;
   p.nt = max(1, min(p.nt, p.nacc));
   p.b_merged = (p.tiles_n == 1) ? 1 : 0;
   p.bias = bias; p.residual = residual; p.out = out; p.stats = stats;
   if (stats && (size_t)16 * Nc * sizeof(float) > 24 * 1024) return SE_ERR_UNSUPPORTED;
+  if (residual && beta != 0.f) return SE_ERR_UNSUPPORTED;      // one extra per-pixel epilogue term at a time
 
   CUtensorMap ma, mb;
   {
@@ -531,7 +706,7 @@ static int conv_tc_launch(const se_conv_desc* d, const float* a_tensor, int Kc, 
     uint32_t bbox[2] = {(uint32_t)p.cblk, (uint32_t)(p.b_merged ? 3 * p.BN : p.BN)};
     if (!make_tmap(&mb, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(bmat), bdims, bstrides, bbox, sw)) return SE_ERR_CUDA;
   }
-  const size_t smem = (size_t)p.res_b_bytes + (size_t)p.stages * p.stage_bytes + (2 * CT_MAX_STAGES + 2 * CT_MAX_ACC + 4) * 8 + (stats ? 16 * Nc * 4 : 0) + 1024 + 64;
+  const size_t smem = (size_t)p.res_b_bytes + (size_t)p.stages * p.stage_bytes + (2 * CT_MAX_STAGES + 2 * CT_MAX_ACC + 4) * 8 + Nc * 4 + (stats ? 16 * Nc * 4 : 0) + (bn ? 2 * Nc * 4 : 0) + 1024 + 64;
   if (smem > 227 * 1024) return SE_ERR_UNSUPPORTED;
   int grid = min(sm_count(), p.tiles_m * p.tiles_n);
   launch(conv_tc_kernel, dim3(grid), dim3(CT_THREADS), smem, st, ma, mb, p);
@@ -559,6 +734,22 @@ int conv_fwd_tc(const se_conv_desc* d, const float* x, const float* w_t, const f
   int rc = ensure_init();
   if (rc) return rc;
   return conv_tc_launch(d, x, d->Cin, w_t, d->Cout, 0, bias, residual, y, relu, 0.f, stats, st);
+}
+
+// convolution + training-mode BatchNorm (+ same-shape residual, + ReLU) in one launch; y receives the convolution
+// output (BatchNorm backward needs it), bn_out the normalised activation.  stats: float64 [2*Cout] zeroed by the
+// caller, counter: one zeroed 64-bit word.  SE_ERR_UNSUPPORTED -> the caller runs the two kernels separately.
+int conv_bn_fwd_tc(const se_conv_desc* d, const float* x, const float* w_t, const float* bias, float* y, int relu, double* stats,
+                   const float* gamma, const float* beta, float eps, float momentum, float* moving_mean, float* moving_var,
+                   float* save_mean, float* save_invstd, const float* bn_res, int bn_relu, float* bn_out,
+                   unsigned long long* counter, cudaStream_t st) {
+  if (!w_t || !tc_shape_ok(d, d->Cin, d->Cout)) return SE_ERR_UNSUPPORTED;
+  static const bool off = getenv("SE_NO_CONV_BN_FUSION") != nullptr;
+  if (off) return SE_ERR_UNSUPPORTED;
+  int rc = ensure_init();
+  if (rc) return rc;
+  ConvTcBn bn = {gamma, beta, eps, momentum, moving_mean, moving_var, save_mean, save_invstd, bn_res, bn_relu, bn_out, counter};
+  return conv_tc_launch(d, x, d->Cin, w_t, d->Cout, 0, bias, nullptr, y, relu, 0.f, stats, st, &bn);
 }
 
 int conv_dgrad_tc(const se_conv_desc* d, const float* dy, const float* w, float* dx, float beta, cudaStream_t st) {

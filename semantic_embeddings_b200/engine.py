@@ -32,7 +32,7 @@ def _vp(x):
 class Engine:
     def __init__(self, graph, batch, embedding, loss='inv_corr', cls_weight=0.0, num_classes=None,
                  mode=_lib.SE_MODE_F32, device='cuda:0', momentum=0.9, nesterov=False, clipnorm=10.0,
-                 world_size=1, fuse_stats=True, use_cuda_graph=True, seed=0):
+                 world_size=1, fuse_stats=True, use_cuda_graph=True, seed=0, fuse_conv_bn=False):
         if loss not in LOSS_KINDS:
             raise ValueError('loss %r is not supported by the fused head (softmax_corr is not on the hot path)' % loss)
         self.lib = _lib.load()
@@ -49,6 +49,7 @@ class Engine:
         self.momentum, self.nesterov, self.clipnorm = float(momentum), bool(nesterov), float(clipnorm or 0.0)
         self.world = int(world_size)
         self.fuse_stats = fuse_stats
+        self.fuse_conv_bn = fuse_conv_bn and fuse_stats
         self.use_cuda_graph = use_cuda_graph
         emb = np.asarray(embedding, dtype=np.float32)
         self.C, self.D = emb.shape
@@ -254,6 +255,7 @@ class Engine:
                 if self.fuse_stats and prod is not None and prod.op in ('conv', 'dense'):
                     stats_by_conv[prod.name] = n
         # ---------------- forward
+        fused_bn = set()
         for n in self.nodes:
             out = A[n.output.name]
             if n.op in ('conv', 'dense'):
@@ -270,7 +272,23 @@ class Engine:
                     off, c = self.bn_slot[stats_by_conv[n.name].name]
                     st = self.stats[off:off + 2 * c]
                 Wt = self._pview(n.name + '/kernel', self.PT) if (self.PT is not None and n.op == 'conv') else None
-                fwd.append(self._op(_lib.OP_CONV_FWD, d + [relu], p=[A[n.inputs[0].name], W, b, res, out, st, Wt]))
+                m = stats_by_conv.get(n.name)
+                if (m is not None and Wt is not None and res is None and self.fuse_conv_bn
+                        and (not m.attrs['residual'] or (m.attrs['res_pool'] == 1 and m.attrs['res_pad_lo'] == 0
+                                                         and m.inputs[1].shape == m.inputs[0].shape))):
+                    # conv + training BatchNorm (+ same-shape residual, ReLU) as one op: se_conv_bn_fwd
+                    off, c = self.bn_slot[m.name]
+                    ma = m.attrs
+                    fwd.append(self._op(
+                        _lib.OP_CONV_BN_FWD, d + [relu, -1, 1 if ma['relu'] else 0], [ma['eps'], ma['momentum']],
+                        [A[n.inputs[0].name], W, b, out, st, Wt, self._pview(m.name + '/gamma'), self._pview(m.name + '/beta'),
+                         self._pview(m.name + '/moving_mean'), self._pview(m.name + '/moving_variance'),
+                         self.saved[off // 2:off // 2 + c], self.saved[off // 2 + c:off // 2 + 2 * c],
+                         A[m.inputs[1].name] if ma['residual'] else None, A[m.output.name],
+                         self.stats[off + 4 * c + 1:off + 4 * c + 2]]))
+                    fused_bn.add(m.name)
+                else:
+                    fwd.append(self._op(_lib.OP_CONV_FWD, d + [relu], p=[A[n.inputs[0].name], W, b, res, out, st, Wt]))
                 inf.append(self._op(_lib.OP_CONV_FWD, d + [relu], p=[A[n.inputs[0].name], W, b, res, out, None, Wt]))
             elif n.op == 'bn':
                 x = n.inputs[0]
@@ -293,7 +311,8 @@ class Engine:
                 ii = [c, rows, 1 if a['relu'] else 0, rc, pad, pool, hh, ww]
                 pp = [A[x.name], st, self._pview(n.name + '/gamma'), self._pview(n.name + '/beta'),
                       self._pview(n.name + '/moving_mean'), self._pview(n.name + '/moving_variance'), sm, si, rp, out]
-                fwd.append(self._op(_lib.OP_BN_FWD_TRAIN, ii, [a['eps'], a['momentum']], pp))
+                if n.name not in fused_bn:
+                    fwd.append(self._op(_lib.OP_BN_FWD_TRAIN, ii, [a['eps'], a['momentum']], pp))
                 inf.append(self._op(_lib.OP_BN_FWD_INFER, ii, [a['eps'], a['momentum']], pp))
             elif n.op == 'avgpool2':
                 h, w, c = n.inputs[0].shape

@@ -157,6 +157,86 @@ def test_conv_rejects_bad_descriptor():
     assert rc == -1 and b'inconsistent' in L.load().se_last_error()
 
 
+CONV_BN_CASES = [
+    # N, H, W, Cin, Cout, bias, conv relu, residual, bn relu, one launch expected (tcgen05 fused path)
+    (128, 32, 32, 16, 16, True, False, True, True, True),     # ResNet-110 stage 1: 7 tiles per CTA, all in TMEM
+    (32, 16, 16, 32, 32, True, False, False, True, True),
+    (16, 8, 8, 64, 64, False, True, False, False, True),      # plainnet: conv + relu -> BN
+    (3, 8, 8, 64, 160, False, False, True, True, True),       # WRN width, ragged last tile (3 images, 2 per tile)
+    (4, 32, 32, 3, 16, True, False, False, True, False),      # stem: not a tcgen05 shape -> two kernels, same result
+]
+
+
+@pytest.mark.parametrize('case', CONV_BN_CASES, ids=lambda c: 'x'.join(str(int(v)) for v in c))
+def test_conv_bn_fused_matches_oracle_and_unfused(case):
+    """se_conv_bn_fwd (conv + training BatchNorm [+ residual] [+ relu]; models/cifar_resnet.py:96-107) against the
+    float64 oracle and against the two separate calls it replaces."""
+    import ctypes
+    from oracle import nn as onn
+    L = _lib()
+    N, H, W, Cin, Cout, use_bias, crelu, use_res, brelu, one_launch = case
+    g = torch.Generator().manual_seed(97 + Cin + Cout)
+    x = torch.randn(N, H, W, Cin, generator=g, dtype=torch.float64)
+    w = torch.randn(3, 3, Cin, Cout, generator=g, dtype=torch.float64) / np.sqrt(9 * Cin)
+    b = torch.randn(Cout, generator=g, dtype=torch.float64) if use_bias else None
+    gamma = torch.rand(Cout, generator=g, dtype=torch.float64) + 0.5
+    beta = torch.randn(Cout, generator=g, dtype=torch.float64) * 0.1
+    res = torch.randn(N, H, W, Cout, generator=g, dtype=torch.float64) if use_res else None
+    eps, momentum = 1e-3, 0.99
+    y = onn.conv2d(x, w, b, 1, 'same')
+    if crelu:
+        y = torch.relu(y)
+    z, mean, var = onn.batchnorm_train(y, gamma, beta, eps)
+    if res is not None:
+        z = z + res
+    if brelu:
+        z = torch.relu(z)
+    rows = N * H * W
+    d = L.ConvDesc(N, H, W, Cin, Cout, 3, 3, 1, 1, 1, H, W)
+    xd, wd = dev(x), dev(w)
+    wtd = torch.empty_like(wd)
+    tab = (ctypes.c_int64 * 4)(0, 9, Cin, Cout)
+    L.call('se_transpose_filters', L.ptr(wd), L.ptr(wtd), tab, 1, sptr())
+    bd = dev(b) if b is not None else None
+    gd, btd = dev(gamma), dev(beta)
+    resd = dev(res) if res is not None else None
+
+    def buffers():
+        return dict(y=torch.empty(N, H, W, Cout, device='cuda'), z=torch.empty(N, H, W, Cout, device='cuda'),
+                    stats=torch.zeros(2 * Cout, dtype=torch.float64, device='cuda'), mm=torch.zeros(Cout, device='cuda'),
+                    mv=torch.ones(Cout, device='cuda'), sm=torch.empty(Cout, device='cuda'), si=torch.empty(Cout, device='cuda'),
+                    counter=torch.zeros(1, dtype=torch.int64, device='cuda'))
+    f = buffers()
+    torch.cuda.synchronize()
+    before = L.launch_count()
+    L.call('se_conv_bn_fwd', d, L.ptr(xd), L.ptr(wd), L.ptr(wtd), L.ptr(bd), L.ptr(f['y']), int(crelu), L.ptr(f['stats']),
+           L.ptr(gd), L.ptr(btd), eps, momentum, L.ptr(f['mm']), L.ptr(f['mv']), L.ptr(f['sm']), L.ptr(f['si']), L.ptr(resd),
+           int(brelu), L.ptr(f['z']), L.ptr(f['counter']), 1, sptr())
+    torch.cuda.synchronize()
+    launches = L.launch_count() - before
+    assert launches == (1 if one_launch else 2), launches
+    u = buffers()
+    L.call('se_conv2d_fwd_ex', d, L.ptr(xd), L.ptr(wd), L.ptr(wtd), L.ptr(bd), None, L.ptr(u['y']), int(crelu), L.ptr(u['stats']),
+           1, sptr())
+    r = L.Residual(L.ptr(resd), Cout, 0, 1, H, W)
+    L.call('se_bn_fwd_train', L.ptr(u['y']), rows, Cout, L.ptr(u['stats']), L.ptr(gd), L.ptr(btd), eps, momentum, L.ptr(u['mm']),
+           L.ptr(u['mv']), L.ptr(u['sm']), L.ptr(u['si']), r if res is not None else None, int(brelu), L.ptr(u['z']), sptr())
+    torch.cuda.synchronize()
+    # fused == unfused (same tensor-core convolution, same BatchNorm arithmetic; only the order of the float64
+    # statistics atomics differs)
+    assert torch.equal(f['y'], u['y'])
+    for k in ('z', 'sm', 'si', 'mm', 'mv'):
+        assert relerr(f[k].cpu(), u[k].cpu().double()) < 2e-6, k
+    # vs the float64 oracle (TF32 operands: 10-bit mantissa)
+    e = dict(y=relerr(f['y'].cpu(), y), z=relerr(f['z'].cpu(), z), mean=relerr(f['sm'].cpu(), mean),
+             invstd=relerr(f['si'].cpu(), torch.rsqrt(var + eps)),
+             mm=relerr(f['mm'].cpu(), onn.moving_update(torch.zeros(Cout, dtype=torch.float64), mean, momentum)),
+             mv=relerr(f['mv'].cpu(), onn.moving_update(torch.ones(Cout, dtype=torch.float64), onn.unbiased_var(var, rows, eps),
+                                                         momentum)))
+    report('conv_bn_fused', case=str(case), launches=launches, **e)
+    assert max(e.values()) < 6e-3, e
+
+
 BN_CASES = [
     # rows-shape (N,H,W,C), relu, residual kind, relu_in
     ((4, 8, 8, 16), True, None, False),
