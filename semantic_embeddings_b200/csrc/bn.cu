@@ -136,6 +136,11 @@ bn_fwd_kernel(const float* __restrict__ x, long long rows, int C, const double* 
     const long long total4 = total >> 2;
     const long long stride = (long long)gridDim.x * blockDim.x;
     const bool plain_res = res.ptr && res.pool == 1 && res.pad_lo == 0 && res.C == C;
+    // channel quad of this thread: fixed when the grid stride is a multiple of C/4 (every power-of-two width), so the
+    // per-element 64-bit modulo / division -- which made this kernel instruction-bound -- is done once, in 32 bits
+    const int C4 = C >> 2;
+    const bool fixed_c = (stride % C4) == 0;
+    const int c_fixed = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) % C4) * 4;
     for (long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x; i0 < total4; i0 += 4 * stride) {
       float4 vq[4], rq[4];
 #pragma unroll
@@ -151,15 +156,14 @@ bn_fwd_kernel(const float* __restrict__ x, long long rows, int C, const double* 
         const long long i = i0 + u * stride;
         if (i >= total4) continue;
         const long long e = i << 2;
-        const int c = (int)(e % C);
-        const long long row = e / C;
+        const int c = fixed_c ? c_fixed : (int)(e % C);
         float o[4] = {vq[u].x, vq[u].y, vq[u].z, vq[u].w};
         const float r4[4] = {rq[u].x, rq[u].y, rq[u].z, rq[u].w};
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           float t = o[j] * scale[c + j] + shift[c + j];
           if (plain_res) t += r4[j];
-          else if (res.ptr) t += res_value(res, row, c + j);
+          else if (res.ptr) t += res_value(res, e / C, c + j);
           if (relu) t = fmaxf(t, 0.f);
           o[j] = t;
         }
@@ -474,7 +478,7 @@ bn_bwd_fused_kernel(const float* __restrict__ x, const float* __restrict__ y, co
   float4* odx = reinterpret_cast<float4*>(dx + r0 * C);
   float4* odr = dres ? reinterpret_cast<float4*>(dres + r0 * C) : nullptr;
   for (int i = tid; i < n4; i += nt) {
-    const int c = (i % C4) * 4;
+    const int c = fixed_quad ? cq_fixed * 4 : (i % C4) * 4;
     float4 xv = sx[i], gv = sg[i];
     float xx[4] = {xv.x, xv.y, xv.z, xv.w}, gg[4] = {gv.x, gv.y, gv.z, gv.w}, o[4];
 #pragma unroll

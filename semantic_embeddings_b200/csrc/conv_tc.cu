@@ -32,7 +32,8 @@ using namespace tc;
 constexpr int CT_BM = 128;
 constexpr int CT_MAX_STAGES = 8;
 constexpr int CT_MAX_ACC = 8;
-constexpr int CT_SMEM_BUDGET = 200 * 1024;
+constexpr int CT_STAGE_OUT = 4096;          // per epilogue warp: two 32-pixel x 16-channel sub-buffers (2 KB each)
+constexpr int CT_SMEM_BUDGET = 200 * 1024 - 8 * CT_STAGE_OUT;
 
 struct ConvTcParams {
   int N, H, W;              // image batch / size (input == output size)
@@ -45,6 +46,7 @@ struct ConvTcParams {
   int relu;
   float beta;               // dgrad: out = beta*out + D
   int stages, stage_bytes, a_bytes, acc_stride, tmem_cols, nacc, b_merged;
+  int stage_out;            // output staging bytes per epilogue warp: 4096 (two sub-buffers) or 2048
   int res, res_b_bytes, nt; // resident-weights mode: B loaded once per CTA, MMAs of `nt` tiles interleaved
   const float* bias;
   const float* residual;
@@ -144,20 +146,23 @@ __device__ __forceinline__ void tmem_st_16(uint32_t taddr, const float* o) {
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
+// Output staging: a warp's 32 pixels x 16 channels sit in shared memory as 32 rows of 64 bytes in the TMA
+// SWIZZLE_64B layout (16-byte chunk c of row r at chunk c ^ ((r >> 1) & 3): the 8 lanes of a store phase hit 8
+// different bank groups), and leave with ONE bulk tensor store -- full 32-byte sectors, out-of-range rows clipped by
+// the hardware.  Direct 16-byte stores from the one-row-per-lane register layout cost one memory transaction per lane
+// and instruction and were what the epilogue spent most of its time on.
+__device__ __forceinline__ void stage_put(uint8_t* sub, int lane, int q, float4 val) {
+  *reinterpret_cast<float4*>(sub + lane * 64 + ((q ^ ((lane >> 1) & 3)) << 4)) = val;
+}
+
 template <int NC>
-__device__ __forceinline__ void conv_tc_epilogue_block(const ConvTcParams& p, uint32_t t_addr, int lblk, int c0, int tn,
-                                                       bool valid, bool has_left, bool has_right, float* orow,
-                                                       const float* exrow, float exs, const float* s_bias, float* sw, int lane,
-                                                       long long* dbg = nullptr) {
-  // exrow / exs: the one extra per-pixel term of the epilogue -- the residual (forward, exs = 1) or the previous
-  // contents of the output (dgrad accumulate, exs = beta).  Loaded in full before the first store (see conv_tc_bn_block).
+__device__ __forceinline__ void conv_tc_epilogue_block(const ConvTcParams& p, const CUtensorMap* map_o, uint32_t t_addr, int lblk,
+                                                       int c0, int tn, bool valid, bool has_left, bool has_right, int row0,
+                                                       uint8_t* stg, const float* exrow, const float* s_bias, float* sw,
+                                                       int lane, long long* dbg = nullptr) {
+  // exrow: residual row of this pixel (forward only)
   const bool live = valid && !(p.debug & 4);
-  float4 ex[NC / 4];
   if (dbg) dbg[0] = clock64();
-  if (exrow && live) {
-#pragma unroll
-    for (int q = 0; q < NC / 4; ++q) ex[q] = *reinterpret_cast<const float4*>(exrow + c0 + 4 * q);
-  }
   float o[NC];
   conv_tc_load_combine<NC>(p, t_addr, lblk, c0, has_left, has_right, o);
   if (dbg) dbg[1] = clock64();
@@ -167,16 +172,26 @@ __device__ __forceinline__ void conv_tc_epilogue_block(const ConvTcParams& p, ui
     if (live) {
       const float4 b = *reinterpret_cast<const float4*>(s_bias + tn * p.BN + c0 + 4 * q);
       val.x += b.x; val.y += b.y; val.z += b.z; val.w += b.w;
-      if (exrow) {
-        val.x = fmaf(exs, ex[q].x, val.x); val.y = fmaf(exs, ex[q].y, val.y);
-        val.z = fmaf(exs, ex[q].z, val.z); val.w = fmaf(exs, ex[q].w, val.w);
+      if (exrow) {   // read-only path load: free to be scheduled ahead of the shared-memory stores of this block
+        const float4 e = __ldg(reinterpret_cast<const float4*>(exrow + c0) + q);
+        val.x += e.x; val.y += e.y; val.z += e.z; val.w += e.w;
       }
       if (p.relu) { val.x = fmaxf(val.x, 0.f); val.y = fmaxf(val.y, 0.f); val.z = fmaxf(val.z, 0.f); val.w = fmaxf(val.w, 0.f); }
-      *reinterpret_cast<float4*>(orow + c0 + 4 * q) = val;
     } else {
       val = make_float4(0.f, 0.f, 0.f, 0.f);
     }
+    stage_put(stg + (q >> 2) * 2048, lane, q & 3, val);
     o[4 * q] = val.x; o[4 * q + 1] = val.y; o[4 * q + 2] = val.z; o[4 * q + 3] = val.w;
+  }
+  fence_proxy_async();                          // the staged values -> visible to the bulk-copy engine
+  __syncwarp();
+  if (lane == 0 && !(p.debug & 4)) {
+#pragma unroll
+    for (int h = 0; h < NC / 16; ++h) {
+      if (p.beta != 0.f) tma_reduce_add_2d(map_o, stg + h * 2048, tn * p.BN + c0 + 16 * h, row0);   // dgrad accumulate
+      else tma_store_2d(map_o, stg + h * 2048, tn * p.BN + c0 + 16 * h, row0);
+    }
+    tma_store_commit();
   }
   if (p.bn) {
 #pragma unroll
@@ -199,13 +214,15 @@ __device__ __forceinline__ void conv_tc_epilogue_block(const ConvTcParams& p, ui
 }
 
 __global__ void __maxnreg__(128)
-conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, ConvTcParams p) {
+conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+               const __grid_constant__ CUtensorMap map_o, const __grid_constant__ CUtensorMap map_z, ConvTcParams p) {
   pdl_trigger();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* res_b = smem;                                   // resident weights (res mode), else empty
   uint8_t* tiles = smem + p.res_b_bytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(tiles + (size_t)p.stages * p.stage_bytes);
+  uint8_t* stg_all = tiles + (size_t)p.stages * p.stage_bytes;          // output staging: [8 epilogue warps][4 KB]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(stg_all + 8 * p.stage_out);
   uint64_t* full = bars;
   uint64_t* empty = bars + CT_MAX_STAGES;
   uint64_t* t_full = bars + 2 * CT_MAX_STAGES;
@@ -225,7 +242,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   const int b_rows = 3 * p.BN;                              // B rows of one filter row: (s, n)
 
   if (warp == 0 && lane == 0) {
-    prefetch_tmap(&map_a); prefetch_tmap(&map_b);
+    prefetch_tmap(&map_a); prefetch_tmap(&map_b); prefetch_tmap(&map_o); prefetch_tmap(&map_z);
     for (int s = 0; s < p.stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
     for (int a = 0; a < p.nacc; ++a) { mbar_init(&t_full[a], 1); mbar_init(&t_empty[a], 128); }
     mbar_init(b_full, 1);
@@ -396,36 +413,53 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     float* sw = p.stats ? s_stats + (warp - 4) * 2 * p.Nc : nullptr;
     for (int i = threadIdx.x - 128; i < p.Nc; i += 256) s_bias[i] = p.bias ? p.bias[i] : 0.f;
     named_bar_sync(1, 256);
-    const float* exbase = p.residual ? p.residual : (p.beta != 0.f ? p.out : nullptr);
-    const float exs = p.residual ? 1.f : p.beta;
+    uint8_t* stg_w = stg_all + (warp - 4) * p.stage_out;
+    const bool two_sub = p.stage_out >= 4096 && p.BN == 16;
+    int sbuf = 0;                                      // 16-channel layers alternate the two sub-buffers
     const int lblk = (p.b_merged && p.flip) ? 2 : 0;   // column block holding the s=0 partial sums
+    // per-thread geometry, computed once: integer divisions by run-time values cost ~100 cycles each and used to
+    // make up a third of the per-tile epilogue time.  A tile is 128 consecutive pixels of the NHWC tensor, so the
+    // pixel index is tm*128 + m and only the column position inside the image row (wb) needs a division.
+    const int m = q4 * 32 + lane;                   // row of the tile == TMEM lane
+    const int wb = m % p.Wb;
+    const bool has_left = wb > 0, has_right = wb < p.W - 1;
+    const long long total_px = (long long)p.N * p.H * p.W;
+    int acc = grp, acc_phase = 0;                   // accumulator ring position of tile t_begin + grp (nacc >= 2 ... or 1)
+    if (p.nacc == 1) { acc = 0; acc_phase = grp & 1; }
     for (int t = t_begin + grp; t < t_end; t += 2) {
-      const int i = t - t_begin, acc = i % p.nacc, acc_phase = (i / p.nacc) & 1;
-      const int tm = t / p.tiles_n, tn = t % p.tiles_n;
-      const int m = q4 * 32 + lane;                 // row of the tile == TMEM lane
-      const int wb = m % p.Wb, hb = (m / p.Wb) % p.Hb, nb = m / (p.Wb * p.Hb);
-      int n, h;
-      if (p.Nb == 1) { n = tm / tiles_per_img; h = (tm % tiles_per_img) * p.Hb + hb; }
-      else { n = tm * p.Nb + nb; h = hb; }
-      const bool valid = (n < p.N) && (h < p.H) && (wb < p.W);
-      const long long pix = ((long long)n * p.H + h) * p.W + wb;
-      float* orow = p.out + pix * p.Nc + tn * p.BN;
-      const float* rrow = exbase ? exbase + pix * p.Nc + tn * p.BN : nullptr;
-      const bool has_left = wb > 0, has_right = wb < p.W - 1;
+      int tm = t, tn = 0;
+      if (p.tiles_n != 1) { tm = t / p.tiles_n; tn = t - tm * p.tiles_n; }
+      const long long pix = (long long)tm * CT_BM + m;
+      const bool valid = pix < total_px;
+      const float* rrow = p.residual ? p.residual + pix * p.Nc + tn * p.BN : nullptr;
+      const int row0 = tm * CT_BM + q4 * 32;          // first pixel of this warp's 32 rows
       mbar_wait(&t_full[acc], acc_phase);
       CT_TRACE(2, 1);
       fence_after_sync();
       const uint32_t t_addr = tmem_base + ((uint32_t)(q4 * 32) << 16) + acc * p.acc_stride;
       int c0 = 0;
       long long* dbg = (p.trace && blockIdx.x == 0 && warp == 4 && lane == 0 && t == t_begin) ? p.trace + 2 * 512 + 400 : nullptr;
-      for (; c0 + 32 <= p.BN; c0 += 32)
-        conv_tc_epilogue_block<32>(p, t_addr, lblk, c0, tn, valid, has_left, has_right, orow, rrow, exs, s_bias, sw, lane, c0 == 0 ? dbg : nullptr);
-      if (c0 < p.BN)
-        conv_tc_epilogue_block<16>(p, t_addr, lblk, c0, tn, valid, has_left, has_right, orow, rrow, exs, s_bias, sw, lane, c0 == 0 ? dbg : nullptr);
+      for (; c0 + 32 <= p.BN; c0 += 32) {
+        if (lane == 0) tma_store_wait_read<0>();      // the bulk stores that read this warp's staging have drained it
+        __syncwarp();
+        conv_tc_epilogue_block<32>(p, &map_o, t_addr, lblk, c0, tn, valid, has_left, has_right, row0, stg_w, rrow, s_bias, sw, lane,
+                                   c0 == 0 ? dbg : nullptr);
+        sbuf = 0;
+      }
+      if (c0 < p.BN) {
+        if (lane == 0) { if (two_sub) tma_store_wait_read<1>(); else tma_store_wait_read<0>(); }
+        __syncwarp();
+        conv_tc_epilogue_block<16>(p, &map_o, t_addr, lblk, c0, tn, valid, has_left, has_right, row0, stg_w + sbuf * 2048, rrow, s_bias,
+                                   sw, lane, c0 == 0 ? dbg : nullptr);
+        if (two_sub) sbuf ^= 1;
+      }
       CT_TRACE(2, 2);
       fence_before_sync();                          // all TMEM reads of this accumulator are complete
       mbar_arrive(&t_empty[acc]);
       CT_TRACE(2, 3);
+      // next tile of this group is two further along the accumulator ring
+      if (p.nacc == 1) acc_phase = (t + 2 - t_begin) & 1;
+      else { acc += 2; while (acc >= p.nacc) { acc -= p.nacc; acc_phase ^= 1; } }
     }
     if (p.bn) {
       // ---- batch statistics: CTA partial sums -> global, grid barrier, per-channel scale / shift
@@ -468,19 +502,21 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       CT_TRACE(2, 7);
       // ---- pass 2: items = (tile, 16-column block), dealt round-robin to the two epilogue groups; the TMEM loads of
       // up to four items are in flight together, then each item is normalised and stored
-      const int m = q4 * 32 + lane;
-      const int wb = m % p.Wb, hb = (m / p.Wb) % p.Hb, nb = m / (p.Wb * p.Hb);
       const int nb16 = p.BN / 16;
+      const int sh16 = (nb16 == 1) ? 0 : (nb16 == 2) ? 1 : (nb16 == 4) ? 2 : -1;     // items -> (tile, block) without a division
       const int nitems = max(0, t_end - t_begin) * nb16;
       const uint32_t lane_addr = tmem_base + ((uint32_t)(q4 * 32) << 16) + p.BN;
+      if (lane == 0) tma_store_wait_read<0>();
+      __syncwarp();
+      sbuf = 0;
       for (int base = grp; base < nitems; base += 8) {
         uint32_t v[4][16];
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
           const int idx = base + 2 * u;
           if (idx < nitems) {
-            const int i = idx / nb16, blk = idx - i * nb16;
-            tmem_ld_cols<16>(lane_addr + (i % p.nacc) * p.acc_stride + 16 * blk, v[u]);
+            const int i = sh16 >= 0 ? (idx >> sh16) : idx / nb16, blk = idx - i * nb16;
+            tmem_ld_cols<16>(lane_addr + (p.nacc > i ? i : i % p.nacc) * p.acc_stride + 16 * blk, v[u]);
           }
         }
         tmem_ld_wait();
@@ -488,17 +524,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         for (int u = 0; u < 4; ++u) {
           const int idx = base + 2 * u;
           if (idx >= nitems) continue;
-          const int i = idx / nb16, blk = idx - i * nb16;
+          const int i = sh16 >= 0 ? (idx >> sh16) : idx / nb16, blk = idx - i * nb16;
           const int t = t_begin + i;
-          const int tm = t / p.tiles_n, tn = t - tm * p.tiles_n;
-          int n, h;
-          if (p.Nb == 1) { n = tm / tiles_per_img; h = (tm - n * tiles_per_img) * p.Hb + hb; }
-          else { n = tm * p.Nb + nb; h = hb; }
-          if (!((n < p.N) && (h < p.H) && (wb < p.W))) continue;
-          const long long off = (((long long)n * p.H + h) * p.W + wb) * p.Nc + tn * p.BN + 16 * blk;
+          int tm = t, tn = 0;
+          if (p.tiles_n != 1) { tm = t / p.tiles_n; tn = t - tm * p.tiles_n; }
+          const long long pix = (long long)tm * CT_BM + m;
+          const bool valid = pix < total_px;
+          const long long off = pix * p.Nc + tn * p.BN + 16 * blk;
           const int cg = tn * p.BN + 16 * blk;
+          uint8_t* sub = stg_w + sbuf * 2048;
+          if (lane == 0) { if (p.stage_out >= 4096) tma_store_wait_read<1>(); else tma_store_wait_read<0>(); }
+          __syncwarp();
           float4 ex[4];
-          if (p.bn_res) {
+          if (p.bn_res && valid) {
 #pragma unroll
             for (int q = 0; q < 4; ++q) ex[q] = __ldg(reinterpret_cast<const float4*>(p.bn_res + off) + q);
           }
@@ -511,10 +549,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             val.y = __uint_as_float(v[u][4 * q + 1]) * sc.y + sh.y;
             val.z = __uint_as_float(v[u][4 * q + 2]) * sc.z + sh.z;
             val.w = __uint_as_float(v[u][4 * q + 3]) * sc.w + sh.w;
-            if (p.bn_res) { val.x += ex[q].x; val.y += ex[q].y; val.z += ex[q].z; val.w += ex[q].w; }
+            if (p.bn_res && valid) { val.x += ex[q].x; val.y += ex[q].y; val.z += ex[q].z; val.w += ex[q].w; }
             if (p.bn_relu) { val.x = fmaxf(val.x, 0.f); val.y = fmaxf(val.y, 0.f); val.z = fmaxf(val.z, 0.f); val.w = fmaxf(val.w, 0.f); }
-            *(reinterpret_cast<float4*>(p.bn_out + off) + q) = val;
+            stage_put(sub, lane, q, val);
           }
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) { tma_store_2d(&map_z, sub, cg, tm * CT_BM + q4 * 32); tma_store_commit(); }
+          if (p.stage_out >= 4096) sbuf ^= 1;
         }
       }
       CT_TRACE(2, 8);
@@ -538,6 +580,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     }
   }
 
+  if (warp >= 4 && lane == 0) tma_store_wait_all<0>();     // bulk stores read shared memory: drain before the CTA exits
   __syncthreads();
   if (p.stats && !p.bn) {
     for (int i = threadIdx.x; i < 2 * p.Nc; i += blockDim.x) {
@@ -625,13 +668,15 @@ static int conv_tc_launch(const se_conv_desc* d, const float* a_tensor, int Kc, 
   // Backward-data launches leave room for the weight-gradient kernel of the same layer (it runs concurrently on the
   // side stream of se_run_ops): shared memory = what that kernel leaves, TMEM <= 256 columns -- unless that would
   // cost this kernel its pipeline, in which case it takes the whole SM as the forward launches do.
+  p.stage_out = CT_STAGE_OUT;
   int budget = CT_SMEM_BUDGET, tmem_budget = 512;
   static const bool no_coop = getenv("SE_NO_SIDE_STREAM") != nullptr;
   if (flip && !no_coop) {
     int wg_cols = 0;
     const size_t wg = conv_wgrad_tc_smem(d, &wg_cols);
     if (wg > 0 && wg <= (size_t)WG_COOP_SMEM_MAX && wg_cols <= 256) {
-      budget = 225 * 1024 - (int)wg - 2048;
+      if (pick_bn(Nc) == 16) p.stage_out = 2048;          // one sub-buffer per warp buys the input pipeline a stage
+      budget = 225 * 1024 - (int)wg - 2048 - 8 * p.stage_out;
       tmem_budget = 256;
     }
   }
@@ -645,7 +690,7 @@ static int conv_tc_launch(const se_conv_desc* d, const float* a_tensor, int Kc, 
   }
   p.stages = min(CT_MAX_STAGES, budget / p.stage_bytes);
   if (p.stages < 2) {
-    if (budget != full_budget) { budget = full_budget; tmem_budget = 512; goto retry; }
+    if (budget != full_budget) { budget = full_budget; tmem_budget = 512; p.stage_out = CT_STAGE_OUT; goto retry; }
     return SE_ERR_UNSUPPORTED;
   }
   // resident-weights mode: every tile of the CTA uses the same 9*BN x Kc weight block
@@ -656,9 +701,9 @@ static int conv_tc_launch(const se_conv_desc* d, const float* a_tensor, int Kc, 
     p.res = 1; p.res_b_bytes = wbytes; p.rg = 3;
     p.stage_bytes = 3 * p.a_bytes;
     p.stages = min(CT_MAX_STAGES, (budget - wbytes) / p.stage_bytes);
-    if (p.stages < 2 && budget != full_budget) { budget = full_budget; tmem_budget = 512; goto retry; }
+    if (p.stages < 2 && budget != full_budget) { budget = full_budget; tmem_budget = 512; p.stage_out = CT_STAGE_OUT; goto retry; }
     static const char* dbg_nt = getenv("SE_CT_NT");
-    p.nt = dbg_nt ? atoi(dbg_nt) : 4;
+    p.nt = dbg_nt ? atoi(dbg_nt) : 2;   // measured: 2 beats 4 (first epilogue starts earlier) and 1 (MMA bubbles)
     p.nt = max(1, min(min(p.nt, 4), p.stages - 1));
   }
   static const char* dbg_stages = getenv("SE_CT_STAGES");         // tuning knobs for scripts/bench_conv.py
@@ -692,7 +737,7 @@ static int conv_tc_launch(const se_conv_desc* d, const float* a_tensor, int Kc, 
   p.b_merged = (p.tiles_n == 1) ? 1 : 0;
   p.bias = bias; p.residual = residual; p.out = out; p.stats = stats;
   if (stats && (size_t)16 * Nc * sizeof(float) > 24 * 1024) return SE_ERR_UNSUPPORTED;
-  if (residual && beta != 0.f) return SE_ERR_UNSUPPORTED;      // one extra per-pixel epilogue term at a time
+  if (beta != 0.f && (beta != 1.f || residual || relu)) return SE_ERR_UNSUPPORTED;   // accumulate = bulk reduce-add of the raw result
 
   CUtensorMap ma, mb;
   {
@@ -706,10 +751,21 @@ static int conv_tc_launch(const se_conv_desc* d, const float* a_tensor, int Kc, 
     uint32_t bbox[2] = {(uint32_t)p.cblk, (uint32_t)(p.b_merged ? 3 * p.BN : p.BN)};
     if (!make_tmap(&mb, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(bmat), bdims, bstrides, bbox, sw)) return SE_ERR_CUDA;
   }
-  const size_t smem = (size_t)p.res_b_bytes + (size_t)p.stages * p.stage_bytes + (2 * CT_MAX_STAGES + 2 * CT_MAX_ACC + 4) * 8 + Nc * 4 + (stats ? 16 * Nc * 4 : 0) + (bn ? 2 * Nc * 4 : 0) + 1024 + 64;
+  CUtensorMap mo, mz;
+  {
+    // output(s) as [pixels][channels]: 32-pixel x 16-channel boxes, SWIZZLE_64B staging (see stage_put)
+    uint64_t odims[2] = {(uint64_t)Nc, (uint64_t)d->N * d->H * d->W};
+    uint64_t ostrides[1] = {(uint64_t)Nc * 4};
+    uint32_t obox[2] = {16u, 32u};
+    if (!make_tmap(&mo, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, out, odims, ostrides, obox, CU_TENSOR_MAP_SWIZZLE_64B)) return SE_ERR_CUDA;
+    mz = mo;
+    if (bn && !make_tmap(&mz, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, bn->out, odims, ostrides, obox, CU_TENSOR_MAP_SWIZZLE_64B))
+      return SE_ERR_CUDA;
+  }
+  const size_t smem = (size_t)p.res_b_bytes + (size_t)p.stages * p.stage_bytes + 8 * p.stage_out + (2 * CT_MAX_STAGES + 2 * CT_MAX_ACC + 4) * 8 + Nc * 4 + (stats ? 16 * Nc * 4 : 0) + (bn ? 2 * Nc * 4 : 0) + 1024 + 64;
   if (smem > 227 * 1024) return SE_ERR_UNSUPPORTED;
   int grid = min(sm_count(), p.tiles_m * p.tiles_n);
-  launch(conv_tc_kernel, dim3(grid), dim3(CT_THREADS), smem, st, ma, mb, p);
+  launch(conv_tc_kernel, dim3(grid), dim3(CT_THREADS), smem, st, ma, mb, mo, mz, p);
   return check_launch("conv_tc_kernel");
 }
 
