@@ -345,6 +345,147 @@ bn_bwd_apply_kernel(const float* __restrict__ x, const float* __restrict__ y, co
   }
 }
 
+// Register-slab variant of the fused backward below: the CTA's slab of x and g = dout*(y>0) stays in REGISTERS
+// (up to BNR float4 of each per thread) between the reduction and the apply phase, so the kernel needs almost no shared
+// memory -- it can share an SM with the weight-gradient kernel that se_run_ops runs on its side stream -- and skips the
+// shared-memory round trip of the slab.  Requires blockDim % (C/4) == 0 (a thread always sees the same channel quad).
+// scratch: float64 [2C] sums + [1] arrival counter, caller zeroes.  grid <= #SMs (all CTAs co-resident).
+constexpr int BNR = 8;
+__global__ void __maxnreg__(112)
+bn_bwd_reg_kernel(const float* __restrict__ x, const float* __restrict__ y, const float* __restrict__ dout, long long rows,
+                  int C, const float* __restrict__ gamma, const float* __restrict__ save_mean,
+                  const float* __restrict__ save_invstd, int relu, int relu_in, float* __restrict__ dx, float beta_dx,
+                  float* __restrict__ dres, float beta_res, float* __restrict__ dgamma, float* __restrict__ dbeta,
+                  double* __restrict__ scratch, int rows_per_cta) {
+  pdl_grid_sync();
+  __shared__ double sred[2 * 512];                 // [2C], C <= 512
+  __shared__ float coef[3 * 512];                  // a, b, k per channel
+  const long long r0 = (long long)blockIdx.x * rows_per_cta;
+  const long long r1 = min(rows, r0 + rows_per_cta);
+  const int nrows = (int)max(0LL, r1 - r0);
+  const int n4 = nrows * C / 4;
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const int C4 = C >> 2;
+  const int cq = tid % C4;
+  for (int i = tid; i < 2 * C; i += nt) sred[i] = 0.0;
+  const float4* gx = reinterpret_cast<const float4*>(x + r0 * C);
+  const float4* gd = reinterpret_cast<const float4*>(dout + r0 * C);
+  const float4* gy = reinterpret_cast<const float4*>(y + r0 * C);
+  const float4 mu = make_float4(save_mean[4 * cq], save_mean[4 * cq + 1], save_mean[4 * cq + 2], save_mean[4 * cq + 3]);
+  const float4 is = make_float4(save_invstd[4 * cq], save_invstd[4 * cq + 1], save_invstd[4 * cq + 2], save_invstd[4 * cq + 3]);
+
+  // ---- phase 1: everything this thread will need, in flight at once
+  float4 xv[BNR], gv[BNR];
+#pragma unroll
+  for (int u = 0; u < BNR; ++u) {
+    const int i = tid + u * nt;
+    if (i < n4) { xv[u] = ldg_nc_f4(reinterpret_cast<const float*>(gx + i)); gv[u] = ldg_nc_f4(reinterpret_cast<const float*>(gd + i)); }
+  }
+  if (relu) {
+#pragma unroll
+    for (int u = 0; u < BNR; ++u) {
+      const int i = tid + u * nt;
+      if (i < n4) {
+        const float4 yv = ldg_nc_f4(reinterpret_cast<const float*>(gy + i));
+        if (!(yv.x > 0.f)) gv[u].x = 0.f;
+        if (!(yv.y > 0.f)) gv[u].y = 0.f;
+        if (!(yv.z > 0.f)) gv[u].z = 0.f;
+        if (!(yv.w > 0.f)) gv[u].w = 0.f;
+      }
+    }
+  }
+  float s[4] = {0, 0, 0, 0}, q[4] = {0, 0, 0, 0};
+#pragma unroll
+  for (int u = 0; u < BNR; ++u) {
+    const int i = tid + u * nt;
+    if (i < n4) {
+      s[0] += gv[u].x; s[1] += gv[u].y; s[2] += gv[u].z; s[3] += gv[u].w;
+      q[0] += gv[u].x * (xv[u].x - mu.x) * is.x; q[1] += gv[u].y * (xv[u].y - mu.y) * is.y;
+      q[2] += gv[u].z * (xv[u].z - mu.z) * is.z; q[3] += gv[u].w * (xv[u].w - mu.w) * is.w;
+    }
+  }
+  // lanes that share the quad (C4 divides 32) combine with shuffles, then one shared-memory atomic per warp and quad
+  const bool pow2 = (C4 & (C4 - 1)) == 0 && C4 < 32;
+  if (pow2) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      for (int o = C4; o < 32; o <<= 1) {
+        s[j] += __shfl_xor_sync(0xffffffffu, s[j], o);
+        q[j] += __shfl_xor_sync(0xffffffffu, q[j], o);
+      }
+  }
+  __syncthreads();                                  // sred zeroed
+  if (!pow2 || (tid & 31) < C4) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      atomicAdd(&sred[4 * cq + j], (double)s[j]);
+      atomicAdd(&sred[C + 4 * cq + j], (double)q[j]);
+    }
+  }
+  __syncthreads();
+  for (int i = tid; i < 2 * C; i += nt) atomicAdd(&scratch[i], sred[i]);
+
+  // ---- grid barrier (arrival counter in scratch[2C], zeroed by the caller once per step)
+  __threadfence();
+  __syncthreads();
+  unsigned long long* counter = reinterpret_cast<unsigned long long*>(scratch + 2 * C);
+  if (tid == 0) {
+    atomicAdd(counter, 1ULL);
+    while (*reinterpret_cast<volatile unsigned long long*>(counter) < (unsigned long long)gridDim.x) { }
+    __threadfence();
+  }
+  __syncthreads();
+
+  // ---- phase 2: coefficients from the global sums, dx / dres from the registers
+  for (int c = tid; c < C; c += nt) {
+    const double sgm = __ldcg(&scratch[c]), sgx = __ldcg(&scratch[C + c]);
+    const float invstd = save_invstd[c], g = gamma[c];
+    const float a = g * invstd;
+    coef[c] = a;
+    coef[C + c] = (float)(-(double)a * sgm / (double)rows);
+    coef[2 * C + c] = (float)(-(double)a * sgx / (double)rows) * invstd;
+    if (blockIdx.x == 0) {
+      if (dgamma) dgamma[c] += (float)sgx;
+      if (dbeta) dbeta[c] += (float)sgm;
+    }
+  }
+  __syncthreads();
+  const float4 ca = *reinterpret_cast<const float4*>(coef + 4 * cq);
+  const float4 cb = *reinterpret_cast<const float4*>(coef + C + 4 * cq);
+  const float4 ck = *reinterpret_cast<const float4*>(coef + 2 * C + 4 * cq);
+  float4* odx = reinterpret_cast<float4*>(dx + r0 * C);
+  float4* odr = dres ? reinterpret_cast<float4*>(dres + r0 * C) : nullptr;
+#pragma unroll
+  for (int u = 0; u < BNR; ++u) {
+    const int i = tid + u * nt;
+    if (i >= n4) continue;
+    float4 o;
+    o.x = ca.x * gv[u].x + cb.x + ck.x * (xv[u].x - mu.x);
+    o.y = ca.y * gv[u].y + cb.y + ck.y * (xv[u].y - mu.y);
+    o.z = ca.z * gv[u].z + cb.z + ck.z * (xv[u].z - mu.z);
+    o.w = ca.w * gv[u].w + cb.w + ck.w * (xv[u].w - mu.w);
+    if (relu_in) {
+      if (!(xv[u].x > 0.f)) o.x = 0.f;
+      if (!(xv[u].y > 0.f)) o.y = 0.f;
+      if (!(xv[u].z > 0.f)) o.z = 0.f;
+      if (!(xv[u].w > 0.f)) o.w = 0.f;
+    }
+    if (beta_dx != 0.f) {
+      const float4 old = odx[i];
+      o.x += beta_dx * old.x; o.y += beta_dx * old.y; o.z += beta_dx * old.z; o.w += beta_dx * old.w;
+    }
+    odx[i] = o;
+    if (odr) {
+      float4 r = gv[u];
+      if (beta_res != 0.f) {
+        const float4 old = odr[i];
+        r.x += beta_res * old.x; r.y += beta_res * old.y; r.z += beta_res * old.z; r.w += beta_res * old.w;
+      }
+      odr[i] = r;
+    }
+  }
+}
+
 // Fused backward: ONE launch, every input read once.  Each CTA keeps its slab of x and g = dout*(y>0) in shared
 // memory, adds its partial sums into `scratch`, waits at a grid-wide barrier (all CTAs are co-resident: grid <= #SMs,
 // one CTA per SM), then finishes dx / dres from shared memory.  5 tensor passes instead of 8, one launch instead of two.
@@ -594,6 +735,13 @@ extern "C" int se_bn_bwd(const float* x, const float* y, const float* dout, int6
     const int gridf = (int)ceil_div<long long>(rows, per_l);
     const size_t smem = (size_t)per_l * C * 8 + 2 * C * sizeof(double) + 4 * C * sizeof(float) + 16;
     static const bool no_fuse = getenv("SE_BN_NO_FUSE") != nullptr;
+    static const bool no_reg = getenv("SE_BN_NO_REG") != nullptr;
+    const int C4 = C >> 2;
+    if (!no_fuse && !no_reg && gridf <= sms && C <= 512 && (512 % C4) == 0 && per_l * C4 <= (long long)BNR * 512) {
+      launch(bn_bwd_reg_kernel, dim3(gridf), dim3(512), 0, as_stream(stream), x, y ? y : x, dout, rows, C, gamma, save_mean, save_invstd,
+             relu, relu_in, dx, beta_dx, dres, beta_res, dgamma, dbeta, scratch, (int)per_l);
+      return check_launch("bn_bwd_reg_kernel");
+    }
     if (!no_fuse && smem <= 200 * 1024 && gridf <= sms) {
       static bool configured = false;
       if (!configured) {
