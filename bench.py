@@ -263,8 +263,11 @@ def run_native(args):
     dev = torch.device('cuda', local)
     if world > 1:
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
-        if os.environ.get('NCCL_DEBUG', 'VERSION').upper() == 'VERSION':
-            os.environ['NCCL_DEBUG'] = 'WARN'         # keep stdout to the single JSON line (NCCL prints its version there)
+        # stdout carries the single JSON line: NCCL's own log (the version banner at any NCCL_DEBUG level, INFO lines)
+        # goes to stderr instead
+        if os.environ.get('NCCL_DEBUG', '').upper() in ('VERSION', 'WARN'):
+            os.environ.pop('NCCL_DEBUG')
+        os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')
         dist.init_process_group('nccl', device_id=dev)
     L.load()
     pk = peaks()

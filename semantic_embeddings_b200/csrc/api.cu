@@ -285,9 +285,9 @@ static int run_ops_impl(const se_op* ops, int n, int mode, void* stream, bool* f
         break;
       }
       case SE_OP_BN_BWD:
-        rc = se_bn_bwd((const float*)p[0], (const float*)p[1], (const float*)p[2], i[1], i[0], (const float*)p[3],
-                       (const float*)p[4], (const float*)p[5], i[2], i[3], (float*)p[6], f[0], (float*)p[7], f[1],
-                       (float*)p[8], (float*)p[9], (double*)p[10], stream);
+        rc = se::bn_bwd((const float*)p[0], (const float*)p[1], (const float*)p[2], i[1], i[0], (const float*)p[3],
+                        (const float*)p[4], (const float*)p[5], i[2], i[3], (float*)p[6], f[0], (float*)p[7], f[1],
+                        (float*)p[8], (float*)p[9], (double*)p[10], i[4], stream);
         break;
       case SE_OP_SHORTCUT_BWD: {
         se_residual r;

@@ -356,8 +356,12 @@ bn_bwd_reg_kernel(const float* __restrict__ x, const float* __restrict__ y, cons
                   int C, const float* __restrict__ gamma, const float* __restrict__ save_mean,
                   const float* __restrict__ save_invstd, int relu, int relu_in, float* __restrict__ dx, float beta_dx,
                   float* __restrict__ dres, float beta_res, float* __restrict__ dgamma, float* __restrict__ dbeta,
-                  double* __restrict__ scratch, int rows_per_cta) {
-  pdl_grid_sync();
+                  double* __restrict__ scratch, int rows_per_cta, int early) {
+  // early != 0: x, y and the saved statistics were written many launches ago (the forward pass), so they are fetched
+  // BEFORE the grid dependency resolves -- two thirds of this kernel's input traffic overlaps the tail of the kernel
+  // that produces dout.  (The engine sets it only when the producing launch is far enough back; common.cuh.)
+  pdl_trigger();
+  if (!early) pdl_wait();
   __shared__ double sred[2 * 512];                 // [2C], C <= 512
   __shared__ float coef[3 * 512];                  // a, b, k per channel
   const long long r0 = (long long)blockIdx.x * rows_per_cta;
@@ -376,23 +380,31 @@ bn_bwd_reg_kernel(const float* __restrict__ x, const float* __restrict__ y, cons
 
   // ---- phase 1: everything this thread will need, in flight at once
   float4 xv[BNR], gv[BNR];
+  unsigned keep[BNR];                               // ReLU mask of the four channels (bit j: y_j > 0)
 #pragma unroll
   for (int u = 0; u < BNR; ++u) {
     const int i = tid + u * nt;
-    if (i < n4) { xv[u] = ldg_nc_f4(reinterpret_cast<const float*>(gx + i)); gv[u] = ldg_nc_f4(reinterpret_cast<const float*>(gd + i)); }
-  }
-  if (relu) {
-#pragma unroll
-    for (int u = 0; u < BNR; ++u) {
-      const int i = tid + u * nt;
-      if (i < n4) {
+    keep[u] = 0xFu;
+    if (i < n4) {
+      xv[u] = ldg_nc_f4(reinterpret_cast<const float*>(gx + i));
+      if (relu) {
         const float4 yv = ldg_nc_f4(reinterpret_cast<const float*>(gy + i));
-        if (!(yv.x > 0.f)) gv[u].x = 0.f;
-        if (!(yv.y > 0.f)) gv[u].y = 0.f;
-        if (!(yv.z > 0.f)) gv[u].z = 0.f;
-        if (!(yv.w > 0.f)) gv[u].w = 0.f;
+        keep[u] = (yv.x > 0.f ? 1u : 0u) | (yv.y > 0.f ? 2u : 0u) | (yv.z > 0.f ? 4u : 0u) | (yv.w > 0.f ? 8u : 0u);
       }
     }
+  }
+  if (early) pdl_wait();                            // dout comes from the preceding launch
+#pragma unroll
+  for (int u = 0; u < BNR; ++u) {
+    const int i = tid + u * nt;
+    if (i < n4) gv[u] = ldg_nc_f4(reinterpret_cast<const float*>(gd + i));
+  }
+#pragma unroll
+  for (int u = 0; u < BNR; ++u) {
+    if (!(keep[u] & 1u)) gv[u].x = 0.f;
+    if (!(keep[u] & 2u)) gv[u].y = 0.f;
+    if (!(keep[u] & 4u)) gv[u].z = 0.f;
+    if (!(keep[u] & 8u)) gv[u].w = 0.f;
   }
   float s[4] = {0, 0, 0, 0}, q[4] = {0, 0, 0, 0};
 #pragma unroll
@@ -725,6 +737,15 @@ extern "C" int se_bn_bwd(const float* x, const float* y, const float* dout, int6
                          const float* save_mean, const float* save_invstd, int relu, int relu_in, float* dx,
                          float beta_dx, float* dres, float beta_res, float* dgamma, float* dbeta, double* scratch,
                          void* stream) {
+  return se::bn_bwd(x, y, dout, rows, C, gamma, save_mean, save_invstd, relu, relu_in, dx, beta_dx, dres, beta_res, dgamma, dbeta,
+                    scratch, 0, stream);
+}
+
+// `early`: plan-runner hint (se_run_ops): x / y / saved statistics date from the forward pass, prefetch them before the
+// programmatic grid dependency resolves.  The public entry point never sets it.
+int se::bn_bwd(const float* x, const float* y, const float* dout, int64_t rows, int C, const float* gamma,
+               const float* save_mean, const float* save_invstd, int relu, int relu_in, float* dx, float beta_dx, float* dres,
+               float beta_res, float* dgamma, float* dbeta, double* scratch, int early, void* stream) {
   SE_REQUIRE(x && dout && dx && gamma && save_mean && save_invstd && scratch && rows > 0 && C > 0, "bad arguments");
   SE_REQUIRE(!relu || y, "relu backward needs y");
   if ((C & 3) == 0) {
@@ -739,7 +760,7 @@ extern "C" int se_bn_bwd(const float* x, const float* y, const float* dout, int6
     const int C4 = C >> 2;
     if (!no_fuse && !no_reg && gridf <= sms && C <= 512 && (512 % C4) == 0 && per_l * C4 <= (long long)BNR * 512) {
       launch(bn_bwd_reg_kernel, dim3(gridf), dim3(512), 0, as_stream(stream), x, y ? y : x, dout, rows, C, gamma, save_mean, save_invstd,
-             relu, relu_in, dx, beta_dx, dres, beta_res, dgamma, dbeta, scratch, (int)per_l);
+             relu, relu_in, dx, beta_dx, dres, beta_res, dgamma, dbeta, scratch, (int)per_l, early && pdl_enabled() ? 1 : 0);
       return check_launch("bn_bwd_reg_kernel");
     }
     if (!no_fuse && smem <= 200 * 1024 && gridf <= sms) {

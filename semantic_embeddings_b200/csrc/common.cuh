@@ -11,6 +11,9 @@
 namespace se {
 
 void set_error(const char* fmt, ...);
+int bn_bwd(const float* x, const float* y, const float* dout, int64_t rows, int C, const float* gamma, const float* save_mean,
+           const float* save_invstd, int relu, int relu_in, float* dx, float beta_dx, float* dres, float beta_res, float* dgamma,
+           float* dbeta, double* scratch, int early, void* stream);
 void count_launch(int n = 1);
 int sm_count();
 

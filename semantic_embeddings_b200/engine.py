@@ -256,6 +256,7 @@ class Engine:
                     stats_by_conv[prod.name] = n
         # ---------------- forward
         fused_bn = set()
+        fwd_pos = {}                       # BatchNorm node -> index of its forward op (for the backward prefetch hint)
         for n in self.nodes:
             out = A[n.output.name]
             if n.op in ('conv', 'dense'):
@@ -311,6 +312,7 @@ class Engine:
                 ii = [c, rows, 1 if a['relu'] else 0, rc, pad, pool, hh, ww]
                 pp = [A[x.name], st, self._pview(n.name + '/gamma'), self._pview(n.name + '/beta'),
                       self._pview(n.name + '/moving_mean'), self._pview(n.name + '/moving_variance'), sm, si, rp, out]
+                fwd_pos[n.name] = len(fwd)
                 if n.name not in fused_bn:
                     fwd.append(self._op(_lib.OP_BN_FWD_TRAIN, ii, [a['eps'], a['momentum']], pp))
                 inf.append(self._op(_lib.OP_BN_FWD_INFER, ii, [a['eps'], a['momentum']], pp))
@@ -418,7 +420,10 @@ class Engine:
                         sc_op = self._op(_lib.OP_SHORTCUT_BWD,
                                          [self.B, hh, ww, c, relu, r.shape[-1], a['res_pad_lo'], a['res_pool']],
                                          [bsrc], [dY, A[n.output.name], dsrc])
-                bwd.append(self._op(_lib.OP_BN_BWD, [c, rows, relu, relu_in], [beta, bres],
+                # inputs saved by the forward pass >= 24 launches ago may be prefetched before the preceding launch has
+                # finished (csrc/bn.cu bn_bwd_reg_kernel); the last layers of the network are too close for that
+                early = 1 if (len(fwd) - fwd_pos[n.name]) + len(bwd) >= 24 else 0
+                bwd.append(self._op(_lib.OP_BN_BWD, [c, rows, relu, relu_in, early], [beta, bres],
                                     [A[x.name], A[n.output.name], dY, self._pview(n.name + '/gamma'), sm, si, dx, dres,
                                      self._pview(n.name + '/gamma', self.G), self._pview(n.name + '/beta', self.G), scratch]))
                 if sc_op is not None:
