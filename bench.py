@@ -176,7 +176,9 @@ def op_category(op, L):
     if op.opcode in names:
         key = '%s %dx%d s%d %d->%d @%dx%d' % (names[op.opcode], i[5], i[6], i[7], i[3], i[4], i[1], i[2])
         flops = 2.0 * i[0] * i[10] * i[11] * i[4] * i[5] * i[6] * i[3]
-        return key, flops, 0.0
+        # algorithmic bytes of one launch: the input tensor, the output tensor and the filter, each once (fp32)
+        byts = 4.0 * (i[0] * i[1] * i[2] * i[3] + i[0] * i[10] * i[11] * i[4] + i[5] * i[6] * i[3] * i[4])
+        return key, flops, byts
     bn = {L.OP_BN_STATS: ('bn_stats', 1), L.OP_BN_FWD_TRAIN: ('bn_fwd', 2), L.OP_BN_BWD: ('bn_bwd', 7)}
     if op.opcode in bn:
         nm, passes = bn[op.opcode]
@@ -205,18 +207,23 @@ def profile_step(eng, L, pk):
     top = sorted(cats.items(), key=lambda kv: -kv[1]['ms'])
     name, c = top[0]
     avg_s = c['ms'] / c['n'] / 1000.0
-    if c['flops'] > 0:
+    # a convolution is bounded by whichever takes longer at the measured peaks: its flops on the tensor cores (TF32 =
+    # half the dense bf16 rate) or its algorithmic bytes on HBM; the 16..64-channel layers of ResNet-110 (36 flop/byte
+    # and less) are on the HBM side of the machine balance (~100 flop/byte)
+    tf32_peak = pk['tflops_sustained'] / 2.0
+    if c['flops'] > 0 and c['flops'] / (tf32_peak * 1e12) > c['bytes'] / (pk['hbm_gbs'] * 1e9):
         achieved = c['flops'] / avg_s / 1e12
-        roof = {'bound': 'tensor', 'kernel': name, 'achieved': achieved, 'peak': pk['tflops_sustained'], 'unit': 'TFLOP/s',
-                'frac': achieved / pk['tflops_sustained'], 'traffic': None}
+        roof = {'bound': 'tensor', 'kernel': name, 'achieved': achieved, 'peak': tf32_peak, 'unit': 'TFLOP/s',
+                'frac': achieved / tf32_peak, 'traffic': None}
     else:
         achieved = c['bytes'] / avg_s / 1e9 if c['bytes'] else 0.0
         roof = {'bound': 'hbm', 'kernel': name, 'achieved': achieved, 'peak': pk['hbm_gbs'], 'unit': 'GB/s',
                 'frac': achieved / pk['hbm_gbs'], 'traffic': None}
     roof['traffic'] = traffic_lookup(name)
     roof.update({'avg_launch_us': 1e6 * avg_s, 'launches_per_step': c['n'], 'share_of_step': c['ms'] / total,
-                 'peak_source': pk['source'] + ', sustained bf16' if c['flops'] > 0 else pk['source']})
-    breakdown = [{'kernel': k, 'ms_per_step': v['ms'], 'launches': v['n'], 'share': v['ms'] / total} for k, v in top[:12]]
+                 'peak_source': pk['source'] + (', sustained bf16 / 2 (TF32)' if roof['bound'] == 'tensor' else ''),
+                 'algorithmic_bytes_per_launch': c['bytes'], 'algorithmic_flops_per_launch': c['flops']})
+    breakdown = [{'kernel': k, 'ms_per_step': v['ms'], 'launches': v['n'], 'share': v['ms'] / total} for k, v in top[:40]]
     conv_flops = sum(v['flops'] * v['n'] for v in cats.values())
     return roof, breakdown, total, conv_flops
 

@@ -165,7 +165,10 @@ conv_fwd_kernel(ConvP p, const float* __restrict__ x, const float* __restrict__ 
 template <int BM, int BN, int TM, int TN, bool VEC>
 __global__ void __launch_bounds__((BM / TM) * (BN / TN))
 conv_dgrad_kernel(ConvP p, const float* __restrict__ dy, const float* __restrict__ w, float* __restrict__ dx,
-                  float beta) {
+                  float beta, int par) {
+  // par != 0 (stride 2, even H and W): GEMM rows are ordered (parity class, n, h/2, w/2) so that a CTA only holds
+  // input pixels of one (h & 1, w & 1) class -- for which only the filter taps of matching parity contribute.  The
+  // other taps (3/4 of the 3x3 window on average) are skipped instead of being multiplied by zeros.
   pdl_grid_sync();
   constexpr int NT = (BM / TM) * (BN / TN);
   constexpr int CG = BN / TN;
@@ -179,13 +182,24 @@ conv_dgrad_kernel(ConvP p, const float* __restrict__ dy, const float* __restrict
   const long long m0 = (long long)blockIdx.x * BM;
   const int n0 = blockIdx.y * BN;  // input-channel tile
 
+  const long long Q = (long long)p.N * (p.H / 2) * (p.W / 2);      // pixels per parity class (par only)
+  const int cls = par ? (int)(m0 / Q) : 0;                        // uniform in the CTA: Q % BM == 0 (checked by the host)
   for (int r = tid; r < BM; r += NT) {
     long long m = m0 + r;
     if (m < M) {
-      row_w[r] = (int)(m % p.W);
-      long long t = m / p.W;
-      row_h[r] = (int)(t % p.H);
-      row_n[r] = (int)(t / p.H);
+      if (par) {
+        long long rem = m - (long long)cls * Q;
+        const int W2 = p.W / 2, H2 = p.H / 2;
+        row_w[r] = 2 * (int)(rem % W2) + (cls & 1);
+        long long t = rem / W2;
+        row_h[r] = 2 * (int)(t % H2) + (cls >> 1);
+        row_n[r] = (int)(t / H2);
+      } else {
+        row_w[r] = (int)(m % p.W);
+        long long t = m / p.W;
+        row_h[r] = (int)(t % p.H);
+        row_n[r] = (int)(t / p.H);
+      }
     } else {
       row_n[r] = -1; row_h[r] = 0; row_w[r] = 0;
     }
@@ -201,6 +215,7 @@ conv_dgrad_kernel(ConvP p, const float* __restrict__ dy, const float* __restrict
   const int taps = p.kh * p.kw;
   for (int tap = 0; tap < taps; ++tap) {
     const int fr = tap / p.kw, fs = tap % p.kw;
+    if (par && ((((cls >> 1) + p.pad_t - fr) & 1) || (((cls & 1) + p.pad_l - fs) & 1))) continue;   // tap of the other parity
     for (int co0 = 0; co0 < p.Cout; co0 += BK) {
       // A[m, k=co] = dy[n, (ih+pad_t-fr)/s, (iw+pad_l-fs)/s, co] when divisible and in range
       if (VEC) {
@@ -254,13 +269,15 @@ conv_dgrad_kernel(ConvP p, const float* __restrict__ dy, const float* __restrict
   for (int i = 0; i < TM; ++i) {
     long long m = m0 + tm * TM + i;
     if (m >= M) continue;
+    const int rr = tm * TM + i;
+    const long long pix = par ? ((long long)row_n[rr] * p.H + row_h[rr]) * p.W + row_w[rr] : m;
 #pragma unroll
     for (int j = 0; j < TN; ++j) {
       int ci = n0 + tn * TN + j;
       if (ci >= p.Cin) continue;
       float v = acc[i][j];
-      if (beta != 0.f) v += beta * dx[m * p.Cin + ci];
-      dx[m * p.Cin + ci] = v;
+      if (beta != 0.f) v += beta * dx[pix * p.Cin + ci];
+      dx[pix * p.Cin + ci] = v;
     }
   }
 }
@@ -555,10 +572,11 @@ static int launch_dgrad(const ConvP& p, const float* dy, const float* w, float* 
   long long M = (long long)p.N * p.H * p.W;
   dim3 grid((unsigned)ceil_div<long long>(M, BM), (unsigned)ceil_div(p.Cin, BN));
   bool vec = (p.Cout % 4 == 0);
+  const int par = (p.stride == 2 && p.H % 2 == 0 && p.W % 2 == 0 && (((long long)p.N * (p.H / 2) * (p.W / 2)) % BM) == 0) ? 1 : 0;
   if (vec)
-    launch(conv_dgrad_kernel<BM, BN, TM, TN, true>, dim3(grid), dim3((BM / TM) * (BN / TN)), 0, st, p, dy, w, dx, beta);
+    launch(conv_dgrad_kernel<BM, BN, TM, TN, true>, dim3(grid), dim3((BM / TM) * (BN / TN)), 0, st, p, dy, w, dx, beta, par);
   else
-    launch(conv_dgrad_kernel<BM, BN, TM, TN, false>, dim3(grid), dim3((BM / TM) * (BN / TN)), 0, st, p, dy, w, dx, beta);
+    launch(conv_dgrad_kernel<BM, BN, TM, TN, false>, dim3(grid), dim3((BM / TM) * (BN / TN)), 0, st, p, dy, w, dx, beta, par);
   return check_launch("conv_dgrad_kernel");
 }
 
@@ -591,8 +609,91 @@ static int launch_wgrad3x3(const ConvP& p, const float* x, const float* dy, floa
   return check_launch("conv_wgrad3x3_kernel");
 }
 
+// Weight gradient of a 3x3 / stride 1 / 'same' convolution with very few input channels (the RGB stem,
+// models/cifar_resnet.py:218 `conv0`): the 27 x Cout outputs are far too small for the tiled GEMM above (64x64 tiles
+// at 1/6 occupancy, 293-way split-K: 123 us).  Here one thread owns (k = (tap, ci) or the bias row, 4 output channels)
+// for one of PG pixel groups of a 8-row tile staged in shared memory: 2 shared loads per 4 FMAs, a shared-memory
+// combine of the pixel groups, then one atomic per output and CTA.  Persistent over the tiles.
+__global__ void __launch_bounds__(512)
+conv_wgrad_stem_kernel(ConvP p, const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ dw,
+                       float* __restrict__ dbias, int TH, int PG, int num_tiles) {
+  pdl_grid_sync();
+  extern __shared__ __align__(16) float ssm[];
+  const int Wp = p.W + 2;
+  const int KK = 9 * p.Cin;                       // rows of dW; row KK is the bias (x == 1)
+  const int CQ = p.Cout >> 2;
+  const int per_pg = (KK + 1) * CQ;               // threads of one pixel group
+  float* xs = ssm;                                // [(TH+2)][Wp][Cin], zero halo
+  float* dys = xs + (((TH + 2) * Wp * p.Cin + 3) & ~3);   // [TH*W][Cout]
+  float* red = dys + TH * p.W * p.Cout;           // [PG-1][per_pg][4]
+  const int tid = threadIdx.x;
+  const bool worker = tid < PG * per_pg;
+  const int pg = tid / per_pg, rem = tid - pg * per_pg;
+  const int k = rem / CQ, cq = rem - k * CQ;
+  int xoff = 0;                                   // offset of this thread's (tap, ci) inside the padded x tile
+  if (k < KK) { const int tap = k / p.Cin, ci = k - tap * p.Cin; xoff = ((tap / 3) * Wp + (tap % 3)) * p.Cin + ci; }
+  const int tiles_per_img = p.H / TH;
+  const int px = TH * p.W, px_pg = px / PG;
+  const int lw = 31 - __clz(p.W);
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+  for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+    const int n = t / tiles_per_img, h0 = (t - n * tiles_per_img) * TH;
+    __syncthreads();                              // previous tile fully consumed
+    for (int i = tid; i < (TH + 2) * Wp * p.Cin; i += blockDim.x) {
+      const int ci = i % p.Cin, q = i / p.Cin, w = q % Wp - 1, h = h0 + q / Wp - 1;
+      xs[i] = (h >= 0 && h < p.H && w >= 0 && w < p.W) ? x[(((long long)n * p.H + h) * p.W + w) * p.Cin + ci] : 0.f;
+    }
+    const float4* gsrc = reinterpret_cast<const float4*>(dy + ((long long)n * p.H + h0) * p.W * p.Cout);
+    for (int i = tid; i < px * p.Cout / 4; i += blockDim.x) reinterpret_cast<float4*>(dys)[i] = gsrc[i];
+    __syncthreads();
+    if (worker) {
+      const int p0 = pg * px_pg;
+#pragma unroll 4
+      for (int j = 0; j < px_pg; ++j) {
+        const int pp = p0 + j, h = pp >> lw, w = pp & (p.W - 1);          // W is a power of two
+        const float xv = (k < KK) ? xs[(h * Wp + w) * p.Cin + xoff] : 1.f;
+        const float4 g = *reinterpret_cast<const float4*>(dys + pp * p.Cout + 4 * cq);
+        a0 = fmaf(xv, g.x, a0); a1 = fmaf(xv, g.y, a1); a2 = fmaf(xv, g.z, a2); a3 = fmaf(xv, g.w, a3);
+      }
+    }
+  }
+  __syncthreads();
+  if (worker && pg > 0) *reinterpret_cast<float4*>(red + ((pg - 1) * per_pg + rem) * 4) = make_float4(a0, a1, a2, a3);
+  __syncthreads();
+  if (worker && pg == 0) {
+    for (int g = 1; g < PG; ++g) {
+      const float4 o = *reinterpret_cast<const float4*>(red + ((g - 1) * per_pg + rem) * 4);
+      a0 += o.x; a1 += o.y; a2 += o.z; a3 += o.w;
+    }
+    float* dst = (k < KK) ? dw + (long long)k * p.Cout + 4 * cq : (dbias ? dbias + 4 * cq : nullptr);
+    if (dst) { atomicAdd(dst, a0); atomicAdd(dst + 1, a1); atomicAdd(dst + 2, a2); atomicAdd(dst + 3, a3); }
+  }
+}
+
+static int launch_wgrad_stem(const ConvP& p, const float* x, const float* dy, float* dw, float* dbias, cudaStream_t st) {
+  if (p.Cin > 4 || (p.Cout & 3) != 0 || p.Cout > 64 || (p.W & (p.W - 1)) != 0 || p.W > 64) return SE_ERR_UNSUPPORTED;
+  if ((reinterpret_cast<uintptr_t>(dy) & 15) != 0) return SE_ERR_UNSUPPORTED;
+  const int TH = (p.H % 8 == 0) ? 8 : ((p.H % 4 == 0) ? 4 : 1);
+  const int per_pg = (9 * p.Cin + 1) * (p.Cout >> 2);
+  if (per_pg > 512) return SE_ERR_UNSUPPORTED;
+  int PG = 1;
+  while (2 * PG * per_pg <= 512 && (TH * p.W) % (2 * PG) == 0) PG *= 2;
+  const int threads = ceil_div(PG * per_pg, 32) * 32;
+  const size_t smem = ((size_t)(((TH + 2) * (p.W + 2) * p.Cin + 3) & ~3) + (size_t)TH * p.W * p.Cout +
+                       (size_t)max(PG - 1, 1) * per_pg * 4) * sizeof(float);
+  if (smem > 48 * 1024) return SE_ERR_UNSUPPORTED;
+  const int num_tiles = p.N * (p.H / TH);
+  const int grid = min(num_tiles, 2 * sm_count());
+  launch(conv_wgrad_stem_kernel, dim3(grid), dim3(threads), smem, st, p, x, dy, dw, dbias, TH, PG, num_tiles);
+  return check_launch("conv_wgrad_stem_kernel");
+}
+
 int conv_wgrad_simt(const se_conv_desc* d, const float* x, const float* dy, float* dw, float* dbias, cudaStream_t st) {
   ConvP p = to_p(d);
+  if (p.kh == 3 && p.kw == 3 && p.stride == 1 && p.pad_t == 1 && p.pad_l == 1 && p.Ho == p.H && p.Wo == p.W && p.Cin <= 4) {
+    int rc = launch_wgrad_stem(p, x, dy, dw, dbias, st);
+    if (rc != SE_ERR_UNSUPPORTED) return rc;
+  }
   const bool same3x3 = p.kh == 3 && p.kw == 3 && p.stride == 1 && p.pad_t == 1 && p.pad_l == 1 && p.Ho == p.H &&
                        p.Wo == p.W && (p.Cin % 16 == 0) && (p.Cout % 16 == 0);
   if (same3x3) {

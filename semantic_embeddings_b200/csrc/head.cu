@@ -39,12 +39,21 @@ template <bool VEC>
 __global__ void __launch_bounds__(HEAD_WARPS * 32)
 embed_head_kernel(const float* __restrict__ z, int ldz, const int* __restrict__ labels, const float* __restrict__ E,
                   int ldE, int B, int D, int C, int loss_kind, float loss_scale, const float* __restrict__ extra_dx,
-                  float* __restrict__ x_out, float* __restrict__ loss, float* __restrict__ acc, float* __restrict__ dz) {
+                  float* __restrict__ x_out, float* __restrict__ loss, float* __restrict__ acc, float* __restrict__ dz,
+                  int es_classes) {
   pdl_grid_sync();
   extern __shared__ __align__(16) float smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int Dp = (D + 3) & ~3;
   float* xs = smem + warp * Dp;  // this warp's row (wrapped output x)
+  // class matrix staged in shared memory (row pitch D+1: conflict-free when every lane walks its own class row);
+  // es_classes == 0 -> the matrix does not fit, the accuracy loop reads it from global memory
+  float* Es = smem + HEAD_WARPS * Dp;
+  if (es_classes > 0 && acc) {
+    for (int c = warp; c < C; c += HEAD_WARPS)
+      for (int i = lane; i < D; i += 32) Es[c * (D + 1) + i] = E[(long long)c * ldE + i];
+    __syncthreads();
+  }
   const int row = blockIdx.x * HEAD_WARPS + warp;
   if (row >= B) return;
   const float* zr = z + (long long)row * ldz;
@@ -98,7 +107,22 @@ embed_head_kernel(const float* __restrict__ z, int ldz, const int* __restrict__ 
   if (loss && lane == 0) loss[row] = l;
 
   // ---- accuracy: nearest class over the whole class matrix (utils.py:73-93)
-  if (acc) {
+  if (acc && es_classes > 0) {
+    // one class per lane and step: 2 shared loads per FMA, no shuffles inside the loop
+    float best = (loss_kind == SE_LOSS_MSE) ? FLT_MAX : -FLT_MAX;
+    float mine = -FLT_MAX;                          // this row's own class, from the same summation order as `best`
+    for (int c = lane; c < C; c += 32) {
+      const float* e = Es + c * (D + 1);
+      float sim = 0.f, en = 0.f;
+      for (int i = 0; i < D; ++i) { const float b = e[i]; sim = fmaf(xs[i], b, sim); en = fmaf(b, b, en); }
+      if (loss_kind == SE_LOSS_MSE) best = fminf(best, xnorm2 + en - 2.f * sim);
+      else { best = fmaxf(best, sim); if (c == lab) mine = sim; }
+    }
+    best = (loss_kind == SE_LOSS_MSE) ? -warp_max(-best) : warp_max(best);
+    mine = warp_max(mine);
+    const float ref = (loss_kind == SE_LOSS_MSE) ? true_dist : mine;
+    if (lane == 0) acc[row] = (fabsf(best - ref) < 1e-6f) ? 1.f : 0.f;
+  } else if (acc) {
     float best = (loss_kind == SE_LOSS_MSE) ? FLT_MAX : -FLT_MAX;
     // four classes per iteration: independent partial sums keep four rows of E in flight (the loop is latency-bound)
     for (int c = 0; c < C; c += 4) {
@@ -214,12 +238,15 @@ extern "C" int se_embed_head_fwd_bwd(const float* z, int ldz, const int32_t* lab
   auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
   bool vec = (D % 4 == 0) && (ldz % 4 == 0) && (ldE % 4 == 0) && al16(z) && al16(E) && (!x_out || al16(x_out));
   int grid = ceil_div(B, HEAD_WARPS);
+  int es_classes = 0;
+  const size_t es_bytes = (size_t)C * (D + 1) * sizeof(float);
+  if (acc && smem + es_bytes <= 48 * 1024) { es_classes = C; smem += es_bytes; }
   if (vec)
     launch(embed_head_kernel<true>, dim3(grid), dim3(HEAD_WARPS * 32), smem, as_stream(stream), z, ldz, labels, E, ldE, B, D, C, loss_kind,
-                                                                                loss_scale, extra_dx, x_out, loss, acc, dz);
+           loss_scale, extra_dx, x_out, loss, acc, dz, es_classes);
   else
     launch(embed_head_kernel<false>, dim3(grid), dim3(HEAD_WARPS * 32), smem, as_stream(stream), z, ldz, labels, E, ldE, B, D, C, loss_kind,
-                                                                                 loss_scale, extra_dx, x_out, loss, acc, dz);
+           loss_scale, extra_dx, x_out, loss, acc, dz, es_classes);
   return check_launch("embed_head_kernel");
 }
 
