@@ -103,10 +103,11 @@ def ncu_report(path, title):
 # bench.py op-category -> (ncu report, kernel-name substring, grid) for the `roofline.traffic` field
 TRAFFIC_MAP = {
     'pairwise_dist': ('pairwise_tc', 'pairwise_tc_kernel', None),
-    'conv_wgrad 3x3 s1 16->16 @32x32': ('train_kernels', 'conv_wgrad3x3_kernel<8, 8>', None),
+    'conv_wgrad 3x3 s1 16->16 @32x32': ('train_kernels', 'conv_wgrad_tc_kernel', '148'),
     'conv_fwd 3x3 s1 16->16 @32x32': ('train_kernels', 'conv_tc_kernel', '148'),
     'conv_dgrad 3x3 s1 16->16 @32x32': ('train_kernels', 'conv_tc_kernel', '148'),
-    'bn_bwd C=16 rows=131072': ('train_kernels', 'bn_bwd_fused_kernel', None),
+    'bn_bwd C=16 rows=131072': ('train_kernels', 'bn_bwd_reg_kernel', None),
+    'bn_fwd C=16 rows=131072': ('train_kernels', 'bn_fwd_kernel', None),
 }
 
 

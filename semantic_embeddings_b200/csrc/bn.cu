@@ -104,14 +104,35 @@ bn_fwd_kernel(const float* __restrict__ x, long long rows, int C, const double* 
   extern __shared__ float sc[];  // scale[C], shift[C]
   float* scale = sc;
   float* shift = sc + C;
+  const long long total = rows * C;
+  const bool vec4 = (C & 3) == 0;
+  const long long total4 = total >> 2;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const bool plain_res = res.ptr && res.pool == 1 && res.pad_lo == 0 && res.C == C;
+  // the first batch of loads is issued BEFORE the per-channel coefficients are derived: the float64 moment arithmetic
+  // and the block barrier below then overlap the memory latency instead of preceding it
+  float4 vq[4], rq[4];
+  const long long i_first = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (vec4) {
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const long long i = i_first + u * stride;
+      if (i < total4) {
+        vq[u] = *reinterpret_cast<const float4*>(x + (i << 2));
+        if (plain_res) rq[u] = *reinterpret_cast<const float4*>(res.ptr + (i << 2));
+      }
+    }
+  }
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     float mean, invstd;
     if (TRAIN) {
-      double m = stats[c] / (double)rows;
-      double var = stats[C + c] / (double)rows - m * m;
+      // float64 moments (the subtraction cancels), float32 from there on; 1/rows once instead of two divisions
+      const double inv_rows = 1.0 / (double)rows;
+      double m = stats[c] * inv_rows;
+      double var = stats[C + c] * inv_rows - m * m;
       if (var < 0) var = 0;
       mean = (float)m;
-      invstd = (float)(1.0 / sqrt(var + (double)eps));
+      invstd = 1.0f / sqrtf((float)(var + (double)eps));
       if (blockIdx.x == 0) {
         save_mean[c] = mean;
         save_invstd[c] = invstd;
@@ -131,24 +152,21 @@ bn_fwd_kernel(const float* __restrict__ x, long long rows, int C, const double* 
     shift[c] = beta[c] - mean * g * invstd;
   }
   __syncthreads();
-  const long long total = rows * C;
-  if ((C & 3) == 0) {
-    const long long total4 = total >> 2;
-    const long long stride = (long long)gridDim.x * blockDim.x;
-    const bool plain_res = res.ptr && res.pool == 1 && res.pad_lo == 0 && res.C == C;
+  if (vec4) {
     // channel quad of this thread: fixed when the grid stride is a multiple of C/4 (every power-of-two width), so the
     // per-element 64-bit modulo / division -- which made this kernel instruction-bound -- is done once, in 32 bits
     const int C4 = C >> 2;
     const bool fixed_c = (stride % C4) == 0;
-    const int c_fixed = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) % C4) * 4;
-    for (long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x; i0 < total4; i0 += 4 * stride) {
-      float4 vq[4], rq[4];
+    const int c_fixed = (int)(i_first % C4) * 4;
+    for (long long i0 = i_first; i0 < total4; i0 += 4 * stride) {
+      if (i0 != i_first) {
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const long long i = i0 + u * stride;
-        if (i < total4) {
-          vq[u] = *reinterpret_cast<const float4*>(x + (i << 2));
-          if (plain_res) rq[u] = *reinterpret_cast<const float4*>(res.ptr + (i << 2));
+        for (int u = 0; u < 4; ++u) {
+          const long long i = i0 + u * stride;
+          if (i < total4) {
+            vq[u] = *reinterpret_cast<const float4*>(x + (i << 2));
+            if (plain_res) rq[u] = *reinterpret_cast<const float4*>(res.ptr + (i << 2));
+          }
         }
       }
 #pragma unroll
@@ -454,8 +472,9 @@ bn_bwd_reg_kernel(const float* __restrict__ x, const float* __restrict__ y, cons
     const float invstd = save_invstd[c], g = gamma[c];
     const float a = g * invstd;
     coef[c] = a;
-    coef[C + c] = (float)(-(double)a * sgm / (double)rows);
-    coef[2 * C + c] = (float)(-(double)a * sgx / (double)rows) * invstd;
+    const double inv_rows = 1.0 / (double)rows;
+    coef[C + c] = (float)(-(double)a * sgm * inv_rows);
+    coef[2 * C + c] = (float)(-(double)a * sgx * inv_rows) * invstd;
     if (blockIdx.x == 0) {
       if (dgamma) dgamma[c] += (float)sgx;
       if (dbeta) dbeta[c] += (float)sgm;
@@ -619,8 +638,9 @@ bn_bwd_fused_kernel(const float* __restrict__ x, const float* __restrict__ y, co
     float invstd = save_invstd[c], g = gamma[c];
     float a = g * invstd;
     coef[c] = a;
-    coef[C + c] = (float)(-(double)a * sgm / (double)rows);
-    coef[2 * C + c] = (float)(-(double)a * sgx / (double)rows) * invstd;
+    const double inv_rows = 1.0 / (double)rows;
+    coef[C + c] = (float)(-(double)a * sgm * inv_rows);
+    coef[2 * C + c] = (float)(-(double)a * sgx * inv_rows) * invstd;
     coef[3 * C + c] = save_mean[c];
     if (blockIdx.x == 0) {
       if (dgamma) dgamma[c] += (float)sgx;

@@ -488,11 +488,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       const double rows = (double)p.N * p.H * p.W;
       for (int c = et; c < p.Nc; c += 256) {
         // identical arithmetic to bn_fwd_kernel<true> (bn.cu): float64 moments, float32 scale / shift
-        double m = __ldcg(&p.stats[c]) / rows;
-        double var = __ldcg(&p.stats[p.Nc + c]) / rows - m * m;
+        const double inv_rows = 1.0 / rows;
+        double m = __ldcg(&p.stats[c]) * inv_rows;
+        double var = __ldcg(&p.stats[p.Nc + c]) * inv_rows - m * m;
         if (var < 0) var = 0;
         const float mean = (float)m;
-        const float invstd = (float)(1.0 / sqrt(var + (double)p.bn_eps));
+        const float invstd = 1.0f / sqrtf((float)(var + (double)p.bn_eps));
         const float g = p.bn_gamma[c];
         coef[c] = g * invstd;
         coef[p.Nc + c] = p.bn_beta[c] - mean * g * invstd;
@@ -563,12 +564,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       // saved statistics and moving averages (CTA 0; off the critical path of the other CTAs' stores)
       if (blockIdx.x == 0) {
         for (int c = et; c < p.Nc; c += 256) {
-          double mm = __ldcg(&p.stats[c]) / rows;
-          double var = __ldcg(&p.stats[p.Nc + c]) / rows - mm * mm;
+          const double inv_rows = 1.0 / rows;
+          double mm = __ldcg(&p.stats[c]) * inv_rows;
+          double var = __ldcg(&p.stats[p.Nc + c]) * inv_rows - mm * mm;
           if (var < 0) var = 0;
           const float mean = (float)mm;
           p.bn_save_mean[c] = mean;
-          p.bn_save_invstd[c] = (float)(1.0 / sqrt(var + (double)p.bn_eps));
+          p.bn_save_invstd[c] = 1.0f / sqrtf((float)(var + (double)p.bn_eps));
           if (p.bn_moving_mean) {
             double uvar = var * (rows / (rows - (1.0 + (double)p.bn_eps)));
             p.bn_moving_mean[c] = p.bn_moving_mean[c] * p.bn_momentum + mean * (1.f - p.bn_momentum);
