@@ -305,12 +305,18 @@ def run_native(args):
         t0 = torch.cuda.Event(enable_timing=True)
         t1 = torch.cuda.Event(enable_timing=True)
         t0.record()
-        last = None
+        last, pending = None, None
         for s in range(steps):
             loader(s)
             eng.train_step()
             if read_loss:
-                last = eng.metrics()['loss']
+                # every step's loss / accuracy is read back (pinned D2H); the host consumes step s-1 while step s runs
+                h = eng.metrics_async()
+                if pending is not None:
+                    last = eng.metrics_result(pending)['loss']
+                pending = h
+        if pending is not None:
+            last = eng.metrics_result(pending)['loss']
         t1.record()
         torch.cuda.synchronize(dev)
         ms = t0.elapsed_time(t1)

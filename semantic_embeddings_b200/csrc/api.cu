@@ -77,12 +77,15 @@ extern "C" int se_device_sm_count(void) { return sm_count(); }
 namespace se { int init_conv_simt(); int init_pairwise_tc(); int init_conv_tc(); int init_conv_wgrad_tc(); }
 // One-time per-process setup that must not happen inside a CUDA-graph capture: device query and the
 // cudaFuncSetAttribute calls of every kernel that needs more than 48 KB of dynamic shared memory.
+static bool side_stream_ready();
+
 extern "C" int se_init(void) {
   sm_count();
   int rc = se::init_conv_simt();
   if (rc == SE_OK) rc = se::init_pairwise_tc();
   if (rc == SE_OK) rc = se::init_conv_tc();
   if (rc == SE_OK) rc = se::init_conv_wgrad_tc();
+  if (rc == SE_OK) side_stream_ready();      // side stream + fork/join events of se_run_ops exist before any graph capture
   return rc;
 }
 namespace se { int tc_capabilities(); }

@@ -126,13 +126,14 @@ bn_fwd_kernel(const float* __restrict__ x, long long rows, int C, const double* 
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     float mean, invstd;
     if (TRAIN) {
-      // float64 moments (the subtraction cancels), float32 from there on; 1/rows once instead of two divisions
+      // float64 moments and inverse standard deviation (a 1-ulp change of invstd flips ReLU masks of near-zero
+      // activations against the float64 oracle); 1/rows once instead of two divisions
       const double inv_rows = 1.0 / (double)rows;
       double m = stats[c] * inv_rows;
       double var = stats[C + c] * inv_rows - m * m;
       if (var < 0) var = 0;
       mean = (float)m;
-      invstd = 1.0f / sqrtf((float)(var + (double)eps));
+      invstd = (float)(1.0 / sqrt(var + (double)eps));
       if (blockIdx.x == 0) {
         save_mean[c] = mean;
         save_invstd[c] = invstd;

@@ -493,7 +493,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         double var = __ldcg(&p.stats[p.Nc + c]) * inv_rows - m * m;
         if (var < 0) var = 0;
         const float mean = (float)m;
-        const float invstd = 1.0f / sqrtf((float)(var + (double)p.bn_eps));
+        const float invstd = (float)(1.0 / sqrt(var + (double)p.bn_eps));
         const float g = p.bn_gamma[c];
         coef[c] = g * invstd;
         coef[p.Nc + c] = p.bn_beta[c] - mean * g * invstd;
@@ -570,7 +570,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           if (var < 0) var = 0;
           const float mean = (float)mm;
           p.bn_save_mean[c] = mean;
-          p.bn_save_invstd[c] = 1.0f / sqrtf((float)(var + (double)p.bn_eps));
+          p.bn_save_invstd[c] = (float)(1.0 / sqrt(var + (double)p.bn_eps));
           if (p.bn_moving_mean) {
             double uvar = var * (rows / (rows - (1.0 + (double)p.bn_eps)));
             p.bn_moving_mean[c] = p.bn_moving_mean[c] * p.bn_momentum + mean * (1.f - p.bn_momentum);

@@ -538,6 +538,35 @@ class Engine:
             out['cls_acc'] = float(self.cls_acc_buf.cpu().numpy().mean())
         return out
 
+    def metrics_async(self):
+        """Enqueue the D2H read of the step that was just launched and return a handle; `metrics_result(handle)` waits
+        for that copy only.  Lets a training loop read the PREVIOUS step's numbers while the next step runs (the
+        reference's Keras progress bar shows running means, learn_image_embeddings.py:238)."""
+        if not hasattr(self, '_mring'):
+            n = 4 if self.xent_node is not None else 2
+            self._mring = [torch.empty(n, self.B, dtype=torch.float32).pin_memory() for _ in range(4)]
+            self._mev = [torch.cuda.Event() for _ in range(4)]
+            self._mpos = 0
+        k = self._mpos
+        self._mpos = (k + 1) % 4
+        host = self._mring[k]
+        host[0].copy_(self.loss_buf, non_blocking=True)
+        host[1].copy_(self.acc_buf, non_blocking=True)
+        if self.xent_node is not None:
+            host[2].copy_(self.cls_loss_buf, non_blocking=True)
+            host[3].copy_(self.cls_acc_buf, non_blocking=True)
+        self._mev[k].record()
+        return k
+
+    def metrics_result(self, handle):
+        self._mev[handle].synchronize()
+        host = self._mring[handle]
+        out = {'loss': float(host[0].mean()), 'acc': float(host[1].mean())}
+        if self.xent_node is not None:
+            out['cls_loss'] = float(host[2].mean())
+            out['cls_acc'] = float(host[3].mean())
+        return out
+
     def grad_norm_and_reg(self):
         o = self.sgd_out.cpu().numpy()
         return float(np.sqrt(o[0])), float(o[1])
