@@ -559,9 +559,99 @@ static int launch_fwd(const ConvP& p, const float* x, const float* w, const floa
   return check_launch("conv_fwd_kernel");
 }
 
+// Forward of the RGB stem (3x3 / stride 1 / 'same', Cin <= 4, Cout == 16; models/cifar_resnet.py:218 `conv0`): one thread
+// per output pixel keeps all 16 output channels in registers; the 8-row input tile (with its zero halo), the filter
+// and the bias sit in shared memory.  The tiled-GEMM kernel above spends a 16-deep K step on K = 27 and measured
+// 54 us; this is bound by its 432 FMAs per pixel.  BatchNorm statistics: warp butterfly -> per-warp slots -> one
+// float64 atomic per channel and CTA.
+__global__ void __launch_bounds__(256)
+conv_fwd_stem_kernel(ConvP p, const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
+                     float* __restrict__ y, int relu, double* __restrict__ stats, int TH) {
+  pdl_grid_sync();
+  extern __shared__ __align__(16) float fsm[];
+  constexpr int CO = 16;
+  const int Wp = p.W + 2, KK = 9 * p.Cin;
+  float* ws = fsm;                                   // [KK][16]
+  float* bs = ws + KK * CO;                          // [16]
+  float* xs = bs + CO;                               // [(TH+2)][Wp][Cin]
+  float* sst = xs + (((TH + 2) * Wp * p.Cin + 3) & ~3);   // [8 warps][32]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tiles_per_img = p.H / TH;
+  const int n = blockIdx.x / tiles_per_img, h0 = (blockIdx.x - n * tiles_per_img) * TH;
+  for (int i = tid; i < KK * CO; i += blockDim.x) ws[i] = w[i];
+  if (tid < CO) bs[tid] = bias ? bias[tid] : 0.f;
+  for (int i = tid; i < (TH + 2) * Wp * p.Cin; i += blockDim.x) {
+    const int ci = i % p.Cin, q = i / p.Cin, ww = q % Wp - 1, hh = h0 + q / Wp - 1;
+    xs[i] = (hh >= 0 && hh < p.H && ww >= 0 && ww < p.W) ? x[(((long long)n * p.H + hh) * p.W + ww) * p.Cin + ci] : 0.f;
+  }
+  if (stats) for (int i = tid; i < 8 * 32; i += blockDim.x) sst[i] = 0.f;
+  __syncthreads();
+  const int npx = TH * p.W;
+  for (int px = tid; px < npx; px += blockDim.x) {   // npx is a multiple of 32: warps stay whole
+    const int hl = px / p.W, wl = px - hl * p.W;
+    float o[CO];
+#pragma unroll
+    for (int c = 0; c < CO; ++c) o[c] = bs[c];
+    for (int tap = 0; tap < 9; ++tap) {
+      const float* xp = xs + ((hl + tap / 3) * Wp + wl + tap % 3) * p.Cin;
+      for (int ci = 0; ci < p.Cin; ++ci) {
+        const float xv = xp[ci];
+        const float4* wr = reinterpret_cast<const float4*>(ws + (tap * p.Cin + ci) * CO);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float4 wv = wr[q];
+          o[4 * q] = fmaf(xv, wv.x, o[4 * q]); o[4 * q + 1] = fmaf(xv, wv.y, o[4 * q + 1]);
+          o[4 * q + 2] = fmaf(xv, wv.z, o[4 * q + 2]); o[4 * q + 3] = fmaf(xv, wv.w, o[4 * q + 3]);
+        }
+      }
+    }
+    if (relu) {
+#pragma unroll
+      for (int c = 0; c < CO; ++c) o[c] = fmaxf(o[c], 0.f);
+    }
+    float4* dst = reinterpret_cast<float4*>(y + (((long long)n * p.H + h0 + hl) * p.W + wl) * CO);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) dst[q] = make_float4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
+    if (stats) {
+      // column sums over the warp's 32 pixels: after 5 xor-shuffle rounds every lane holds the totals
+#pragma unroll
+      for (int c = 0; c < CO; ++c) {
+        float sv = o[c], qv = o[c] * o[c];
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) { sv += __shfl_xor_sync(0xffffffffu, sv, off); qv += __shfl_xor_sync(0xffffffffu, qv, off); }
+        if (lane == c) { sst[warp * 32 + c] += sv; sst[warp * 32 + CO + c] += qv; }
+      }
+    }
+  }
+  if (stats) {
+    __syncthreads();
+    if (tid < 2 * CO) {
+      double v = 0.0;
+      for (int wv = 0; wv < (int)(blockDim.x >> 5); ++wv) v += (double)sst[wv * 32 + tid];
+      atomicAdd(&stats[tid], v);
+    }
+  }
+}
+
+static int launch_fwd_stem(const ConvP& p, const float* x, const float* w, const float* bias, float* y, int relu, double* stats,
+                           cudaStream_t st) {
+  if (p.Cin > 4 || p.Cout != 16 || (p.W % 32) != 0 || p.W > 64) return SE_ERR_UNSUPPORTED;
+  if ((reinterpret_cast<uintptr_t>(y) & 15) != 0) return SE_ERR_UNSUPPORTED;
+  const int TH = (p.H % 8 == 0) ? 8 : ((p.H % 4 == 0) ? 4 : 1);
+  const size_t smem = ((size_t)9 * p.Cin * 16 + 16 + (((TH + 2) * (p.W + 2) * p.Cin + 3) & ~3) + 8 * 32) * sizeof(float);
+  if (smem > 48 * 1024) return SE_ERR_UNSUPPORTED;
+  launch(conv_fwd_stem_kernel, dim3(p.N * (p.H / TH)), dim3(256), smem, st, p, x, w, bias, y, relu, stats, TH);
+  return check_launch("conv_fwd_stem_kernel");
+}
+
 int conv_fwd_simt(const se_conv_desc* d, const float* x, const float* w, const float* bias, const float* residual,
                   float* y, int relu, double* stats, cudaStream_t st) {
   ConvP p = to_p(d);
+  if (p.kh == 3 && p.kw == 3 && p.stride == 1 && p.pad_t == 1 && p.pad_l == 1 && p.Ho == p.H && p.Wo == p.W && p.Cin <= 4 &&
+      !residual) {
+    int rc = launch_fwd_stem(p, x, w, bias, y, relu, stats, st);
+    if (rc != SE_ERR_UNSUPPORTED) return rc;
+  }
   if (p.Cout <= 16) return launch_fwd<128, 16, 4, 2>(p, x, w, bias, residual, y, relu, stats, st);
   if (p.Cout <= 32) return launch_fwd<128, 32, 4, 4>(p, x, w, bias, residual, y, relu, stats, st);
   return launch_fwd<64, 64, 4, 4>(p, x, w, bias, residual, y, relu, stats, st);

@@ -244,7 +244,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&map_a); prefetch_tmap(&map_b); prefetch_tmap(&map_o); prefetch_tmap(&map_z);
     for (int s = 0; s < p.stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-    for (int a = 0; a < p.nacc; ++a) { mbar_init(&t_full[a], 1); mbar_init(&t_empty[a], 128); }
+    for (int a = 0; a < p.nacc; ++a) { mbar_init(&t_full[a], 1); mbar_init(&t_empty[a], 128 * ((p.BN + 31) >> 5)); }
     mbar_init(b_full, 1);
     fence_barrier_init();
     fence_proxy_async();
@@ -406,7 +406,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       mma_commit(&t_full[acc]);
     }
   } else if (warp >= 4) {
-    // ===================== epilogue: two groups of 4 warps take alternate tiles; a warp owns one TMEM lane quarter
+    // ===================== epilogue: two groups of 4 warps; a warp owns one TMEM lane quarter
     const int q4 = warp & 3, grp = (warp - 4) >> 2;
     int tr_n = (warp == 4 && lane == 0) ? 0 : 1000;
     CT_TRACE(2, 0);
@@ -424,9 +424,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     const int wb = m % p.Wb;
     const bool has_left = wb > 0, has_right = wb < p.W - 1;
     const long long total_px = (long long)p.N * p.H * p.W;
-    int acc = grp, acc_phase = 0;                   // accumulator ring position of tile t_begin + grp (nacc >= 2 ... or 1)
-    if (p.nacc == 1) { acc = 0; acc_phase = grp & 1; }
-    for (int t = t_begin + grp; t < t_end; t += 2) {
+    // work items = (tile, 32-column block), dealt alternately to the two groups: with one tile per CTA and 64 output
+    // channels both groups work on that tile instead of one group doing its blocks back to back
+    const int nblk = (p.BN + 31) >> 5;
+    int it = 0, blk = grp;                          // tile index inside the CTA, block inside the tile
+    int acc = 0, acc_phase = 0;                     // accumulator ring position of tile `it`
+    while (blk >= nblk) { blk -= nblk; ++it; if (++acc == p.nacc) { acc = 0; acc_phase ^= 1; } }
+    while (t_begin + it < t_end) {
+      const int t = t_begin + it;
       int tm = t, tn = 0;
       if (p.tiles_n != 1) { tm = t / p.tiles_n; tn = t - tm * p.tiles_n; }
       const long long pix = (long long)tm * CT_BM + m;
@@ -437,29 +442,26 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       CT_TRACE(2, 1);
       fence_after_sync();
       const uint32_t t_addr = tmem_base + ((uint32_t)(q4 * 32) << 16) + acc * p.acc_stride;
-      int c0 = 0;
-      long long* dbg = (p.trace && blockIdx.x == 0 && warp == 4 && lane == 0 && t == t_begin) ? p.trace + 2 * 512 + 400 : nullptr;
-      for (; c0 + 32 <= p.BN; c0 += 32) {
+      const int c0 = blk * 32;
+      long long* dbg = (p.trace && blockIdx.x == 0 && warp == 4 && lane == 0 && t == t_begin && blk == 0) ? p.trace + 2 * 512 + 400 : nullptr;
+      if (c0 + 32 <= p.BN) {
         if (lane == 0) tma_store_wait_read<0>();      // the bulk stores that read this warp's staging have drained it
         __syncwarp();
-        conv_tc_epilogue_block<32>(p, &map_o, t_addr, lblk, c0, tn, valid, has_left, has_right, row0, stg_w, rrow, s_bias, sw, lane,
-                                   c0 == 0 ? dbg : nullptr);
+        conv_tc_epilogue_block<32>(p, &map_o, t_addr, lblk, c0, tn, valid, has_left, has_right, row0, stg_w, rrow, s_bias, sw, lane, dbg);
         sbuf = 0;
-      }
-      if (c0 < p.BN) {
+      } else {
         if (lane == 0) { if (two_sub) tma_store_wait_read<1>(); else tma_store_wait_read<0>(); }
         __syncwarp();
         conv_tc_epilogue_block<16>(p, &map_o, t_addr, lblk, c0, tn, valid, has_left, has_right, row0, stg_w + sbuf * 2048, rrow, s_bias,
-                                   sw, lane, c0 == 0 ? dbg : nullptr);
+                                   sw, lane, dbg);
         if (two_sub) sbuf ^= 1;
       }
       CT_TRACE(2, 2);
-      fence_before_sync();                          // all TMEM reads of this accumulator are complete
-      mbar_arrive(&t_empty[acc]);
+      fence_before_sync();                          // this item's TMEM reads are complete
+      mbar_arrive(&t_empty[acc]);                   // the barrier expects one arrival per item and thread (128 * nblk)
       CT_TRACE(2, 3);
-      // next tile of this group is two further along the accumulator ring
-      if (p.nacc == 1) acc_phase = (t + 2 - t_begin) & 1;
-      else { acc += 2; while (acc >= p.nacc) { acc -= p.nacc; acc_phase ^= 1; } }
+      blk += 2;
+      while (blk >= nblk) { blk -= nblk; ++it; if (++acc == p.nacc) { acc = 0; acc_phase ^= 1; } }
     }
     if (p.bn) {
       // ---- batch statistics: CTA partial sums -> global, grid barrier, per-channel scale / shift

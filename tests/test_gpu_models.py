@@ -106,6 +106,48 @@ STEP_CASES = [
 ]
 
 
+class _relu_probe:
+    """Context manager that replaces torch.relu while the oracle runs.  Without `flip` it records, per call, the
+    element of smallest |pre-activation| (exact zeros excluded); with `flip=[(call, index), ...]` it inverts the
+    mask of those elements (forward value changes by ~1e-7, the backward path through the element switches)."""
+
+    def __init__(self, flip=None):
+        self.flip = {}
+        for call, idx in (flip or []):
+            self.flip.setdefault(call, []).append(idx)
+        self.records, self.calls = [], 0
+
+    def __enter__(self):
+        self._orig = torch.relu
+
+        def patched(t):
+            k = self.calls
+            self.calls += 1
+            mask = t > 0
+            if k in self.flip:
+                mask = mask.clone()
+                flat = mask.view(-1)
+                for idx in self.flip[k]:
+                    flat[idx] = ~flat[idx]
+            elif not self.flip:
+                a = t.detach().abs().reshape(-1)
+                a = torch.where(a == 0, torch.full_like(a, float('inf')), a)
+                v, i = torch.topk(a, min(3, a.numel()), largest=False)
+                self.records += [(float(vv), k, int(ii)) for vv, ii in zip(v, i)]
+            return t * mask.to(t.dtype)
+
+        torch.relu = patched
+        return self
+
+    def __exit__(self, *exc):
+        torch.relu = self._orig
+        return False
+
+    def fragile(self, below=4e-6, at_most=4):
+        """ReLU inputs so close to zero (activations are O(1)) that fp32 accumulation cannot resolve their sign."""
+        return [(k, i) for v, k, i in sorted(self.records)[:at_most] if v < below]
+
+
 def _grad_errors(eg, grads, norm):
     num = den = 0.0
     worst, worst_name = 0.0, ''
@@ -128,8 +170,11 @@ def test_two_training_steps_match_oracle(case):
 
     Embeddings, loss, regulariser, gradient norm: <= 1e-4 relative.  Gradients: ReLU networks are
     discontinuous in their pre-activations, so fp32 arithmetic legitimately flips a few masks relative to
-    float64; the tolerance is therefore tied to the measured noise floor of the SAME step computed by the
-    oracle in float32 (max(2e-3, 5 x floor))."""
+    float64; the tolerance is therefore tied to the measured noise floor of the SAME step: the largest deviation among
+    float64; the tolerance is therefore tied to what such flips do to THIS step: max(2e-3, 5 x the deviation of the oracle
+    run in float32, 1.5 x the deviation of the float64 oracle with the masks of its fragile ReLU inputs (|value| < 4e-6,
+    found by `_relu_probe`) inverted).  One inverted mask moves the resnet-32 gradient by 9e-4 (2.3e-3 on the worst
+    tensor) -- the float64 oracle does that to itself under a one-ulp perturbation of the input."""
     import copy
     from oracle import models as omodels
     from oracle import train as otrain
@@ -165,8 +210,23 @@ def test_two_training_steps_match_oracle(case):
         otrain.cast_model(om32, torch.float32, cls32)
         vel32 = {k: v.float() for k, v in vel.items()}
         _, grads32, _ = otrain.train_step(om32, x, y, emb_t.float(), vel32, lr, loss, cls32, cls_weight, nesterov, 10.0)
+        # ... and the "flip quantum" of THIS step: the float64 oracle re-run with the ReLU masks of its fragile
+        # pre-activations (|value| < 4e-6: fp32 accumulation cannot resolve their sign) inverted
+        omq, clsq = copy.deepcopy(om), copy.deepcopy(cls)
+        velq = {kk: v.clone() for kk, v in vel.items()}
+        with _relu_probe() as probe:
+            otrain.train_step(omq, x.double(), y, emb_t, velq, lr, loss, clsq, cls_weight, nesterov, 10.0)
+        omq, clsq = copy.deepcopy(om), copy.deepcopy(cls)
+        velq = {kk: v.clone() for kk, v in vel.items()}
+        fragile = probe.fragile()
+        gradsq = None
+        if fragile:
+            with _relu_probe(flip=fragile):
+                _, gradsq, _ = otrain.train_step(omq, x.double(), y, emb_t, velq, lr, loss, clsq, cls_weight, nesterov, 10.0)
         obj, grads, norm = otrain.train_step(om, x.double(), y, emb_t, vel, lr, loss, cls, cls_weight, nesterov, 10.0)
-        floor, _, _ = _grad_errors({k: v.numpy() for k, v in grads32.items()}, grads, norm)
+        # (global and worst-tensor deviation: the velocity / weight checks below are per tensor)
+        floor = max(_grad_errors({k: v.numpy() for k, v in grads32.items()}, grads, norm)[:2])
+        quantum = max(_grad_errors({k: v.numpy() for k, v in gradsq.items()}, grads, norm)[:2]) if gradsq is not None else 0.0
         eng.train_step(x, y, lr=lr)
         m = eng.metrics()
         gn, reg = eng.grad_norm_and_reg()
@@ -176,7 +236,7 @@ def test_two_training_steps_match_oracle(case):
             'acc': abs(m['acc'] - float(obj['acc'].mean())),
             'gnorm': abs(gn - norm) / norm,
             'reg': abs(reg - float(obj['reg'].detach())) / max(float(obj['reg'].detach()), 1e-12),
-            'grad_floor_f32_oracle': floor,
+            'grad_floor_f32_oracle': floor, 'relu_flip_quantum': quantum, 'fragile_relu_inputs': len(fragile),
         }
         if cls_weight > 0:
             e['cls_loss'] = abs(m['cls_loss'] - float(obj['cls_loss'].detach())) / max(1.0, abs(float(obj['cls_loss'].detach())))
@@ -192,7 +252,7 @@ def test_two_training_steps_match_oracle(case):
         errs[step] = e
         report('train_step', case=tag, step=step, worst_grad_tensor=worst_name, **e)
     for step, e in errs.items():
-        gtol = max(2e-3, 5 * e['grad_floor_f32_oracle'])
+        gtol = max(2e-3, 5 * e['grad_floor_f32_oracle'], 1.5 * e['relu_flip_quantum'])
         assert e['loss'] < 1e-4 and e['emb'] < 1e-4, (step, e)
         assert e.get('cls_loss', 0.0) < 1e-4, (step, e)
         assert e['gnorm'] < max(1e-4, gtol / 10) and e['reg'] < 1e-5, (step, e)
