@@ -106,7 +106,7 @@ TRAFFIC_MAP = {
     'conv_wgrad 3x3 s1 16->16 @32x32': ('train_kernels', 'conv_wgrad_tc_kernel', '148'),
     'conv_fwd 3x3 s1 16->16 @32x32': ('train_kernels', 'conv_tc_kernel', '148'),
     'conv_dgrad 3x3 s1 16->16 @32x32': ('train_kernels', 'conv_tc_kernel', '148'),
-    'bn_bwd C=16 rows=131072': ('train_kernels', 'bn_bwd_reg_kernel', None),
+    'bn_bwd C=16 rows=131072': ('train_kernels', 'bn_bwd_reg_kernel', '148'),
     'bn_fwd C=16 rows=131072': ('train_kernels', 'bn_fwd_kernel', None),
 }
 
