@@ -1,4 +1,5 @@
 #!/bin/bash
+timeout 100 python scripts/trace_bn_bwd.py 128 32 16; timeout 100 python scripts/trace_bn_bwd.py 128 8 64
 timeout 900 python -m pytest tests/test_gpu_ops.py tests/test_gpu_models.py -m gpu -x -q --timeout=600 -k "bn or train or forward" 2>&1 | tail -n 5 | cut -c1-300
 timeout 600 python bench.py --steps 30 --warmup 5 --skip-cpu-baseline --skip-retrieval > gpurun_out/bench_bn0.json 2> gpurun_out/bench_bn0.err
 echo "exit $?"; python -c "

@@ -370,19 +370,23 @@ bn_bwd_apply_kernel(const float* __restrict__ x, const float* __restrict__ y, co
 // shared-memory round trip of the slab.  Requires blockDim % (C/4) == 0 (a thread always sees the same channel quad).
 // scratch: float64 [2C] sums + [1] arrival counter, caller zeroes.  grid <= #SMs (all CTAs co-resident).
 constexpr int BNR = 8;
+constexpr int BNR_MAXC = 128;   // channel limit of the register-slab kernel (16 warps x 2C floats of partial sums)
+// debug: SE_BN_TRACE_PTR = device address of 8 int64: clock64 stamps of CTA 0 / thread 0 at the phase boundaries
+#define BN_STAMP(k) do { if (trace && blockIdx.x == 0 && threadIdx.x == 0) trace[k] = clock64(); } while (0)
 __global__ void __maxnreg__(112)
 bn_bwd_reg_kernel(const float* __restrict__ x, const float* __restrict__ y, const float* __restrict__ dout, long long rows,
                   int C, const float* __restrict__ gamma, const float* __restrict__ save_mean,
                   const float* __restrict__ save_invstd, int relu, int relu_in, float* __restrict__ dx, float beta_dx,
                   float* __restrict__ dres, float beta_res, float* __restrict__ dgamma, float* __restrict__ dbeta,
-                  double* __restrict__ scratch, int rows_per_cta, int early) {
+                  double* __restrict__ scratch, int rows_per_cta, int early, long long* trace) {
+  BN_STAMP(0);
   // early != 0: x, y and the saved statistics were written many launches ago (the forward pass), so they are fetched
   // BEFORE the grid dependency resolves -- two thirds of this kernel's input traffic overlaps the tail of the kernel
   // that produces dout.  (The engine sets it only when the producing launch is far enough back; common.cuh.)
   pdl_trigger();
   if (!early) pdl_wait();
-  __shared__ double sred[2 * 512];                 // [2C], C <= 512
-  __shared__ float coef[3 * 512];                  // a, b, k per channel
+  __shared__ float part[16 * 2 * BNR_MAXC];        // [warp][2C] partial sums (plain stores: no shared-memory atomics)
+  const double inv_rows = 1.0 / (double)rows;      // the one float64 division, hidden behind the loads
   const long long r0 = (long long)blockIdx.x * rows_per_cta;
   const long long r1 = min(rows, r0 + rows_per_cta);
   const int nrows = (int)max(0LL, r1 - r0);
@@ -390,12 +394,12 @@ bn_bwd_reg_kernel(const float* __restrict__ x, const float* __restrict__ y, cons
   const int tid = threadIdx.x, nt = blockDim.x;
   const int C4 = C >> 2;
   const int cq = tid % C4;
-  for (int i = tid; i < 2 * C; i += nt) sred[i] = 0.0;
   const float4* gx = reinterpret_cast<const float4*>(x + r0 * C);
   const float4* gd = reinterpret_cast<const float4*>(dout + r0 * C);
   const float4* gy = reinterpret_cast<const float4*>(y + r0 * C);
   const float4 mu = make_float4(save_mean[4 * cq], save_mean[4 * cq + 1], save_mean[4 * cq + 2], save_mean[4 * cq + 3]);
   const float4 is = make_float4(save_invstd[4 * cq], save_invstd[4 * cq + 1], save_invstd[4 * cq + 2], save_invstd[4 * cq + 3]);
+  const float4 gm = make_float4(gamma[4 * cq], gamma[4 * cq + 1], gamma[4 * cq + 2], gamma[4 * cq + 3]);
 
   // ---- phase 1: everything this thread will need, in flight at once
   float4 xv[BNR], gv[BNR];
@@ -412,7 +416,9 @@ bn_bwd_reg_kernel(const float* __restrict__ x, const float* __restrict__ y, cons
       }
     }
   }
+  BN_STAMP(1);
   if (early) pdl_wait();                            // dout comes from the preceding launch
+  BN_STAMP(2);
 #pragma unroll
   for (int u = 0; u < BNR; ++u) {
     const int i = tid + u * nt;
@@ -435,9 +441,11 @@ bn_bwd_reg_kernel(const float* __restrict__ x, const float* __restrict__ y, cons
       q[2] += gv[u].z * (xv[u].z - mu.z) * is.z; q[3] += gv[u].w * (xv[u].w - mu.w) * is.w;
     }
   }
-  // lanes that share the quad (C4 divides 32) combine with shuffles, then one shared-memory atomic per warp and quad
-  const bool pow2 = (C4 & (C4 - 1)) == 0 && C4 < 32;
-  if (pow2) {
+  // lanes that share the quad (C4 divides 32) combine with shuffles; one lane per quad and warp then owns a slot of
+  // `part` (plain stores), and 2C threads add the 16 warp partials in float64 into the global sums.  (Shared-memory
+  // float64 atomics under 16-way contention were the longest phase of this kernel: 2.6-3.4 us.)
+  const int warp = tid >> 5, lane = tid & 31;
+  if (C4 < 32) {
 #pragma unroll
     for (int j = 0; j < 4; ++j)
       for (int o = C4; o < 32; o <<= 1) {
@@ -445,46 +453,67 @@ bn_bwd_reg_kernel(const float* __restrict__ x, const float* __restrict__ y, cons
         q[j] += __shfl_xor_sync(0xffffffffu, q[j], o);
       }
   }
-  __syncthreads();                                  // sred zeroed
-  if (!pow2 || (tid & 31) < C4) {
+  BN_STAMP(3);
+  // C4 <= 32: lanes 0..C4-1 hold the quad totals of the warp.  C4 > 32 (C = 256, 512): consecutive warps cover
+  // different quads (quad = tid % C4), each (warp, quad) pair still has exactly one writer; slots of quads a warp
+  // does not touch stay zero.
+  if (C4 > 32) for (int i = tid; i < 16 * 2 * C; i += nt) part[i] = 0.f;
+  if (C4 > 32) __syncthreads();
+  if (lane < C4 || C4 > 32) {
+    float* pw = part + warp * 2 * C;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      atomicAdd(&sred[4 * cq + j], (double)s[j]);
-      atomicAdd(&sred[C + 4 * cq + j], (double)q[j]);
-    }
+    for (int j = 0; j < 4; ++j) { pw[4 * cq + j] = s[j]; pw[C + 4 * cq + j] = q[j]; }
   }
   __syncthreads();
-  for (int i = tid; i < 2 * C; i += nt) atomicAdd(&scratch[i], sred[i]);
+  for (int i = tid; i < 2 * C; i += nt) {
+    double v = 0.0;
+#pragma unroll
+    for (int w = 0; w < 16; ++w) v += (double)part[w * 2 * C + i];
+    atomicAdd(&scratch[i], v);
+  }
 
-  // ---- grid barrier (arrival counter in scratch[2C], zeroed by the caller once per step)
-  __threadfence();
+  // ---- grid barrier (arrival counter in scratch[2C], zeroed by the caller once per step).  The block barrier orders
+  // the atomics of all threads before thread 0's fence (cumulativity), so one thread fences for the CTA.
   __syncthreads();
+  BN_STAMP(4);
   unsigned long long* counter = reinterpret_cast<unsigned long long*>(scratch + 2 * C);
   if (tid == 0) {
+    __threadfence();
     atomicAdd(counter, 1ULL);
     while (*reinterpret_cast<volatile unsigned long long*>(counter) < (unsigned long long)gridDim.x) { }
     __threadfence();
   }
   __syncthreads();
+  BN_STAMP(5);
 
-  // ---- phase 2: coefficients from the global sums, dx / dres from the registers
-  for (int c = tid; c < C; c += nt) {
-    const double sgm = __ldcg(&scratch[c]), sgx = __ldcg(&scratch[C + c]);
-    const float invstd = save_invstd[c], g = gamma[c];
-    const float a = g * invstd;
-    coef[c] = a;
-    const double inv_rows = 1.0 / (double)rows;
-    coef[C + c] = (float)(-(double)a * sgm * inv_rows);
-    coef[2 * C + c] = (float)(-(double)a * sgx * inv_rows) * invstd;
+  // ---- phase 2: the global sums come into shared memory with ONE L2 read per value and CTA; every thread then
+  // derives the coefficients of its four channels itself.  Parameter gradients: fire-and-forget reductions by CTA 0.
+  __shared__ double ssum[2 * BNR_MAXC];
+  for (int i = tid; i < 2 * C; i += nt) {
+    const double v = __ldcg(&scratch[i]);
+    ssum[i] = v;
     if (blockIdx.x == 0) {
-      if (dgamma) dgamma[c] += (float)sgx;
-      if (dbeta) dbeta[c] += (float)sgm;
+      if (i < C) { if (dbeta) atomicAdd(&dbeta[i], (float)v); }
+      else if (dgamma) atomicAdd(&dgamma[i - C], (float)v);
     }
   }
   __syncthreads();
-  const float4 ca = *reinterpret_cast<const float4*>(coef + 4 * cq);
-  const float4 cb = *reinterpret_cast<const float4*>(coef + C + 4 * cq);
-  const float4 ck = *reinterpret_cast<const float4*>(coef + 2 * C + 4 * cq);
+  float ca_[4], cb_[4], ck_[4];
+  {
+    const float gmv[4] = {gm.x, gm.y, gm.z, gm.w}, isv[4] = {is.x, is.y, is.z, is.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const double sgm = ssum[4 * cq + j], sgx = ssum[C + 4 * cq + j];
+      const float a = gmv[j] * isv[j];
+      ca_[j] = a;
+      cb_[j] = (float)(-(double)a * sgm * inv_rows);
+      ck_[j] = (float)(-(double)a * sgx * inv_rows) * isv[j];
+    }
+  }
+  BN_STAMP(6);
+  const float4 ca = make_float4(ca_[0], ca_[1], ca_[2], ca_[3]);
+  const float4 cb = make_float4(cb_[0], cb_[1], cb_[2], cb_[3]);
+  const float4 ck = make_float4(ck_[0], ck_[1], ck_[2], ck_[3]);
   float4* odx = reinterpret_cast<float4*>(dx + r0 * C);
   float4* odr = dres ? reinterpret_cast<float4*>(dres + r0 * C) : nullptr;
 #pragma unroll
@@ -516,6 +545,7 @@ bn_bwd_reg_kernel(const float* __restrict__ x, const float* __restrict__ y, cons
       odr[i] = r;
     }
   }
+  BN_STAMP(7);
 }
 
 // Fused backward: ONE launch, every input read once.  Each CTA keeps its slab of x and g = dout*(y>0) in shared
@@ -778,10 +808,12 @@ int se::bn_bwd(const float* x, const float* y, const float* dout, int64_t rows, 
     const size_t smem = (size_t)per_l * C * 8 + 2 * C * sizeof(double) + 4 * C * sizeof(float) + 16;
     static const bool no_fuse = getenv("SE_BN_NO_FUSE") != nullptr;
     static const bool no_reg = getenv("SE_BN_NO_REG") != nullptr;
+    static const char* bn_trace_env = getenv("SE_BN_TRACE_PTR");
+    long long* bn_trace = bn_trace_env ? reinterpret_cast<long long*>(strtoull(bn_trace_env, nullptr, 0)) : nullptr;
     const int C4 = C >> 2;
-    if (!no_fuse && !no_reg && gridf <= sms && C <= 512 && (512 % C4) == 0 && per_l * C4 <= (long long)BNR * 512) {
+    if (!no_fuse && !no_reg && gridf <= sms && C <= BNR_MAXC && (512 % C4) == 0 && per_l * C4 <= (long long)BNR * 512) {
       launch(bn_bwd_reg_kernel, dim3(gridf), dim3(512), 0, as_stream(stream), x, y ? y : x, dout, rows, C, gamma, save_mean, save_invstd,
-             relu, relu_in, dx, beta_dx, dres, beta_res, dgamma, dbeta, scratch, (int)per_l, early && pdl_enabled() ? 1 : 0);
+             relu, relu_in, dx, beta_dx, dres, beta_res, dgamma, dbeta, scratch, (int)per_l, early && pdl_enabled() ? 1 : 0, bn_trace);
       return check_launch("bn_bwd_reg_kernel");
     }
     if (!no_fuse && smem <= 200 * 1024 && gridf <= sms) {
