@@ -18,6 +18,6 @@ t0 = min(int(t[r, 0, 1]) for r in range(3) if t[r, 0, 1] > 0)
 names = {0: {0: 'start', 1: 'got-empty', 2: 'tma-issued'}, 1: {0: 'start', 1: 'got-tmem-empty', 2: 'got-full', 3: 'committed'},
          2: {0: 'start', 1: 'got-tmem-full', 2: 'tmem-ld-done', 3: 'tile-done'}}
 for r, role in enumerate(('producer', 'mma', 'epilogue')):
-    ev = [(int(e), int(c) - t0) for e, c in t[r] if c > 0]
+    ev = [(int(e), int(c) - t0) for e, c in t[r][:200] if c > 0]
     print(role, len(ev), 'events')
-    print('   ', ' '.join('%s@%d' % (names[r][e], c) for e, c in ev[:60]))
+    print('   ', ' '.join('%s@%d' % (names[r].get(e, str(e)), c) for e, c in ev[:60]))

@@ -27,7 +27,7 @@ names = {0: {0: 'start', 1: 'got-empty', 2: 'tma-issued'}, 1: {0: 'start', 1: 'g
          2: {0: 'start', 1: 'got-tmem-full', 2: 'tmem-ld-done', 3: 'tile-done', 4: 'pass1-all-warps', 5: 'stats-atomics-done',
              6: 'grid-barrier-passed', 7: 'coef-ready', 8: 'pass2-done'}}
 for r, role in enumerate(('producer', 'mma', 'epilogue')):
-    ev = [(int(e), int(c) - t0) for e, c in t[r] if c > 0]
+    ev = [(int(e), int(c) - t0) for e, c in t[r][:200] if c > 0]
     print(role, len(ev), 'events')
     print('   ', ' '.join('%s@%d' % (names[r].get(e, str(e)), c) for e, c in ev[:60]))
 print('first block of the first tile (cycles from entry): combine %d, stores %d, stats %d' % (

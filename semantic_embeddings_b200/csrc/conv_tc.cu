@@ -249,12 +249,20 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     fence_barrier_init();
     fence_proxy_async();
   }
-  if (warp == 2) tmem_alloc(tmem_slot, p.tmem_cols);
-  if (p.stats) for (int i = threadIdx.x; i < 16 * p.Nc; i += blockDim.x) s_stats[i] = 0.f;
-  fence_before_sync();
-  __syncthreads();
-  fence_after_sync();
-  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);   // provably warp-uniform (see tc.cuh elect_one)
+  // The producer warp only ARRIVES at the prologue barrier (its mbarrier initialisation is what the others need):
+  // its first TMA loads go out without waiting for the TMEM allocation and the statistics zeroing of the other warps.
+  uint32_t tmem_base = 0;
+  if (warp == 0) {
+    __syncwarp();
+    asm volatile("barrier.arrive 3, %0;" ::"r"(CT_THREADS) : "memory");   // named barrier 3: never shared with the final __syncthreads
+  } else {
+    if (warp == 2) tmem_alloc(tmem_slot, p.tmem_cols);
+    if (p.stats) for (int i = threadIdx.x - 32; i < 16 * p.Nc; i += CT_THREADS - 32) s_stats[i] = 0.f;
+    fence_before_sync();
+    asm volatile("barrier.sync 3, %0;" ::"r"(CT_THREADS) : "memory");
+    fence_after_sync();
+    tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);   // provably warp-uniform (see tc.cuh elect_one)
+  }
   pdl_wait();                               // nothing above touches global memory (see common.cuh)
 
   if (warp == 0 && elect_one()) {
@@ -663,6 +671,13 @@ static int conv_tc_launch(const se_conv_desc* d, const float* a_tensor, int Kc, 
   if (p.BN % 16 != 0 || Nc % p.BN != 0) return SE_ERR_UNSUPPORTED;
   p.tiles_n = Nc / p.BN;
   p.tiles_m = (p.Nb == 1) ? d->N * (d->H / p.Hb) : ceil_div(d->N, p.Nb);
+  // few pixel tiles (64 channels at 8x8: 64 tiles for 148 SMs): split the output channels over two CTAs per tile --
+  // each then streams half of the 9*Cin*Cout weights, the dominant traffic of such a layer, and half of the epilogue
+  static const bool no_nsplit = getenv("SE_CT_NO_NSPLIT") != nullptr;
+  if (!no_nsplit && !bn && 2 * p.tiles_m * p.tiles_n <= sm_count() && p.BN >= 64 && (p.BN / 2) % 16 == 0) {
+    p.BN /= 2;
+    p.tiles_n *= 2;
+  }
   p.cblk = Kc >= 32 ? 32 : 16;
   p.kblocks = Kc / p.cblk;
   p.flip = flip; p.relu = relu; p.beta = beta;

@@ -222,10 +222,9 @@ def test_conv_bn_fused_matches_oracle_and_unfused(case):
     L.call('se_bn_fwd_train', L.ptr(u['y']), rows, Cout, L.ptr(u['stats']), L.ptr(gd), L.ptr(btd), eps, momentum, L.ptr(u['mm']),
            L.ptr(u['mv']), L.ptr(u['sm']), L.ptr(u['si']), r if res is not None else None, int(brelu), L.ptr(u['z']), sptr())
     torch.cuda.synchronize()
-    # fused == unfused (same tensor-core convolution, same BatchNorm arithmetic; only the order of the float64
-    # statistics atomics differs)
-    assert torch.equal(f['y'], u['y'])
-    for k in ('z', 'sm', 'si', 'mm', 'mv'):
+    # fused == unfused up to fp32 summation order (same TF32 products and BatchNorm arithmetic; the two paths may tile
+    # the output channels / order the filter taps differently, and the float64 statistics atomics arrive in any order)
+    for k in ('y', 'z', 'sm', 'si', 'mm', 'mv'):
         assert relerr(f[k].cpu(), u[k].cpu().double()) < 2e-6, k
     # vs the float64 oracle (TF32 operands: 10-bit mantissa)
     e = dict(y=relerr(f['y'].cpu(), y), z=relerr(f['z'].cpu(), z), mean=relerr(f['sm'].cpu(), mean),
