@@ -367,7 +367,7 @@ def run_native(args):
                                   'unit': 'GB/s', 'frac': ach / pk['hbm_gbs'],
                                   'traffic': traffic_lookup('pairwise_dist') if (n == 50000 and world == 1) else None,
                                   'algorithmic_bytes_per_launch': per_gpu_bytes, 'peak_source': pk['source']},
-                     'arithmetic': 'tcgen05 3xTF32' if (mode == L.SE_MODE_TF32 and caps & 8) else 'fp32 FFMA'}
+                     'arithmetic': 'tcgen05 kind::f16, split-fp16 x3 (fp32-level accuracy)' if (mode == L.SE_MODE_TF32 and caps & 8) else 'fp32 FFMA'}
 
     cpu = None
     if rank == 0 and world == 1 and not args.skip_cpu_baseline:

@@ -232,6 +232,7 @@ extern "C" int se_run_ops(const se_op* ops, int n, int mode, void* stream) {
 
 static int run_ops_impl(const se_op* ops, int n, int mode, void* stream, bool* forked) {
   const bool use_side = n > 1 && side_stream_ready();
+  bool transposing = false;          // filter transposition in flight on the side stream
   for (int k = 0; k < n; ++k) {
     const se_op& o = ops[k];
     const int32_t* i = o.i;
@@ -241,6 +242,12 @@ static int run_ops_impl(const se_op* ops, int n, int mode, void* stream, bool* f
     switch (o.opcode) {
       case SE_OP_CONV_FWD: {
         se_conv_desc d = desc_from(i);
+        if (transposing && p[6]) {   // first consumer of the transposed filters: the side branch joins here
+          cudaEventRecord(g_ev_join, g_side);
+          cudaStreamWaitEvent(as_stream(stream), g_ev_join, 0);
+          transposing = false;
+          *forked = false;
+        }
         rc = se_conv2d_fwd_ex(&d, (const float*)p[0], (const float*)p[1], (const float*)p[6], (const float*)p[2],
                               (const float*)p[3], (float*)p[4], i[12], (double*)p[5], i[13] >= 0 ? i[13] : mode, stream);
         break;
@@ -249,6 +256,12 @@ static int run_ops_impl(const se_op* ops, int n, int mode, void* stream, bool* f
         // p: 0 x, 1 w, 2 bias, 3 y, 4 stats, 5 w_t, 6 gamma, 7 beta, 8 moving_mean, 9 moving_var, 10 save_mean,
         //    11 save_invstd, 12 residual, 13 bn_out, 14 counter;  i[12] conv relu, i[14] bn relu;  f: eps, momentum
         se_conv_desc d = desc_from(i);
+        if (transposing && p[5]) {
+          cudaEventRecord(g_ev_join, g_side);
+          cudaStreamWaitEvent(as_stream(stream), g_ev_join, 0);
+          transposing = false;
+          *forked = false;
+        }
         rc = se_conv_bn_fwd(&d, (const float*)p[0], (const float*)p[1], (const float*)p[5], (const float*)p[2], (float*)p[3],
                             i[12], (double*)p[4], (const float*)p[6], (const float*)p[7], f[0], f[1], (float*)p[8],
                             (float*)p[9], (float*)p[10], (float*)p[11], (const float*)p[12], i[14], (float*)p[13], p[14],
@@ -338,8 +351,19 @@ static int run_ops_impl(const se_op* ops, int n, int mode, void* stream, bool* f
         break;
       }
       case SE_OP_TRANSPOSE_FILTERS:
-        if (mode == SE_MODE_TF32)
-          rc = se_transpose_filters((const float*)p[0], (float*)p[1], (const int64_t*)p[2], i[0], stream);
+        if (mode == SE_MODE_TF32) {
+          // the transposed filter copies are first needed by the first tensor-core convolution: the transposition runs
+          // on the side stream beside the statistics memset, the stem convolution and its BatchNorm
+          void* ts = stream;
+          if (use_side && !*forked) {
+            cudaEventRecord(g_ev_fork, as_stream(stream));
+            cudaStreamWaitEvent(g_side, g_ev_fork, 0);
+            ts = g_side;
+            *forked = true;
+            transposing = true;
+          }
+          rc = se_transpose_filters((const float*)p[0], (float*)p[1], (const int64_t*)p[2], i[0], ts);
+        }
         break;
       case SE_OP_SGD_PREPARE:
         if (*forked) {   // the optimizer reads every gradient: the side branch joins here
