@@ -251,7 +251,21 @@ def bench_retrieval(L, rank, world, dev, n, d, reps, mode):
     torch.cuda.synchronize(dev)
     ms = float(np.mean([a.elapsed_time(b) for a, b in evs]))
     chk = float(out[0, :8].sum().item())
-    return ms, rows, chk
+    # ranking step (evaluate_retrieval.py:67 restricted to the clip_ahp+1 = 251 ranks the metrics read): se_row_topk
+    rank_ms = None
+    if rows > 0 and n <= 52000:
+        from semantic_embeddings_b200.evaluate_retrieval import row_topk
+        k = min(251, n)
+        for _ in range(2):
+            row_topk(out, k)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(3):
+            row_topk(out, k)
+        b.record()
+        torch.cuda.synchronize(dev)
+        rank_ms = a.elapsed_time(b) / 3.0
+    return ms, rows, chk, rank_ms
 
 
 def run_native(args):
@@ -353,7 +367,7 @@ def run_native(args):
     retrieval = None
     if not args.skip_retrieval:
         n, d = args.retrieval_n, 100
-        ms_r, rows, chk = bench_retrieval(L, rank, world, dev, n, d, 5, mode)
+        ms_r, rows, chk, rank_ms = bench_retrieval(L, rank, world, dev, n, d, 5, mode)
         if world > 1:
             t = torch.tensor([ms_r], device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -368,6 +382,11 @@ def run_native(args):
                                   'traffic': traffic_lookup('pairwise_dist') if (n == 50000 and world == 1) else None,
                                   'algorithmic_bytes_per_launch': per_gpu_bytes, 'peak_source': pk['source']},
                      'arithmetic': 'tcgen05 kind::f16, split-fp16 x3 (fp32-level accuracy)' if (mode == L.SE_MODE_TF32 and caps & 8) else 'fp32 FFMA'}
+        if rank_ms is not None:
+            # per-row top-251 of this rank's row block; bound: one read of the block (4 bytes per pair)
+            retrieval['ranking_top251'] = {'ms': rank_ms, 'gpairs_per_s': float(rows) * n / (rank_ms / 1000.0) / 1e9,
+                                           'hbm_frac': 4.0 * rows * n / (rank_ms / 1000.0) / 1e9 / pk['hbm_gbs'],
+                                           'kernel': 'row_topk_kernel (radix select + bitonic sort in shared memory)'}
 
     cpu = None
     if rank == 0 and world == 1 and not args.skip_cpu_baseline:

@@ -219,6 +219,14 @@ int64_t se_pairwise_workspace_bytes(int N, int D, int mode);
 int se_pairwise_dist(const float* F, int ldF, int N, int D, int row0, int rows, int pdist_mode,
                      int normalize, float* out, int64_t ldout, void* workspace, int mode, void* stream);
 
+/* Ranking step of evaluate_retrieval.py:67 (`np.argsort(pdist, axis=-1)`) restricted to what the metrics read
+ * (class_hierarchy.py:242-244,273,283: the first clip_ahp+1 ranks): for each of `rows` rows of dist [rows, ld] the k
+ * smallest of its n values in ascending order, ties by ascending index (a stable argsort's prefix; -0.0 == +0.0).
+ * out_idx [rows, ldo] int32 column indices, out_val [rows, ldo] the distances (may be NULL).  k <= 1024 and
+ * n <= ~52000 (a row is staged in shared memory), else SE_ERR_UNSUPPORTED. */
+int se_row_topk(const float* dist, int64_t ld, int rows, int n, int k, float* out_val, int32_t* out_idx, int ldo,
+                void* stream);
+
 /* ------------------------------------------------------------------ plan runner
  * Runs a host-built array of ops (one training step is ~900 launches) in one call so that
  * neither Python nor ctypes sits between launches.  Each op is an opcode plus the argument

@@ -71,9 +71,28 @@ def pairwise_ranking(features, normalize=False, block_rows=4096, mode=None, devi
     for r0 in range(0, N, block_rows):
         r = min(block_rows, N - r0)
         d = pairwise_distances(None, normalize, r0, r, mode, out=buf[:r], feat_dev=fd)
-        idx = torch.sort(d, dim=-1, stable=True).indices[:, :k]
+        if k <= TOPK_MAX and N <= TOPK_MAX_N:
+            # the ranks the metrics read (class_hierarchy.py clip_ahp): hand-written per-row radix-select kernel
+            idx = row_topk(d, k)[0]
+        else:
+            idx = torch.sort(d, dim=-1, stable=True).indices[:, :k]     # full-length rankings: library sort
         ranking[r0:r0 + r] = idx.cpu().numpy()
     return ranking
+
+
+TOPK_MAX, TOPK_MAX_N = 1024, 52000
+
+
+def row_topk(dist, k, want_values=False):
+    """k smallest entries of every row of a device matrix, ascending, ties by index (se_row_topk).
+    Returns (int32 indices [rows, k], float32 values [rows, k] or None) as device tensors."""
+    import torch
+    rows, n = dist.shape
+    assert dist.is_cuda and dist.dtype == torch.float32 and dist.stride(1) == 1
+    idx = torch.empty((rows, k), dtype=torch.int32, device=dist.device)
+    val = torch.empty((rows, k), dtype=torch.float32, device=dist.device) if want_values else None
+    _lib.call('se_row_topk', _lib.ptr(dist), dist.stride(0), rows, n, k, _lib.ptr(val), _lib.ptr(idx), k, _lib.stream_ptr())
+    return idx, val
 
 
 def pairwise_retrieval(features, normalize=False, return_generator=True):

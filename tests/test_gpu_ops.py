@@ -585,3 +585,40 @@ def test_pairwise_ragged_sizes(mode):
         got = out.cpu().numpy()
         assert np.isfinite(got).all()
         assert np.abs(got - ref).max() < 3e-6 * max(1.0, np.abs(ref).max()), (N, D)
+
+
+TOPK_CASES = [(37, 1000, 10), (5, 52000, 251), (64, 4096, 1024), (3, 7, 7), (9, 1001, 1), (2, 50000, 251)]
+
+
+@pytest.mark.parametrize('case', TOPK_CASES, ids=lambda c: 'x'.join(map(str, c)))
+def test_row_topk_is_the_prefix_of_a_stable_argsort(case):
+    """se_row_topk against torch.sort(stable=True) on the SAME device matrix (bit-identical input, so the ranking must
+    be identical, ties included): evaluate_retrieval.py:67 restricted to the first k ranks."""
+    from semantic_embeddings_b200.evaluate_retrieval import row_topk
+    rows, n, k = case
+    g = torch.Generator().manual_seed(rows * 7 + n)
+    d = torch.randn(rows, n, generator=g)
+    d[:, ::3] = torch.round(d[:, ::3] * 4) / 4          # heavy ties (quantised values), also exact +0.0 / -0.0
+    d[0, : min(n, 5)] = -0.0
+    d[-1] = 1.5                                          # a constant row: ranking = 0, 1, 2, ...
+    dd = d.cuda()
+    idx, val = row_topk(dd, k, want_values=True)
+    ref = torch.sort(dd, dim=-1, stable=True)
+    assert torch.equal(idx.long(), ref.indices[:, :k])
+    assert torch.equal(val, ref.values[:, :k])
+    # strided input (row pitch > n) and no value output
+    big = torch.full((rows, n + 5), 9e9, device='cuda')
+    big[:, :n] = dd
+    idx2, _ = row_topk(big[:, :n], k)
+    assert torch.equal(idx2, idx)
+
+
+def test_pairwise_ranking_topk_equals_full_ranking_prefix():
+    from semantic_embeddings_b200.evaluate_retrieval import pairwise_ranking
+    fx = np.load(os.path.join(G, 'retrieval_ref.npz'))
+    feats = fx['feat'].astype(np.float32)
+    for normalize in (False, True):
+        full = pairwise_ranking(feats.copy(), normalize)
+        top = pairwise_ranking(feats.copy(), normalize, topk=50)
+        assert top.shape == (feats.shape[0], 50)
+        assert np.array_equal(top, full[:, :50])
