@@ -95,13 +95,18 @@ def row_topk(dist, k, want_values=False):
     return idx, val
 
 
-def pairwise_retrieval(features, normalize=False, return_generator=True):
+def pairwise_retrieval(features, normalize=False, return_generator=True, topk=None):
     """Uses each image as query and retrieves its nearest neighbors (evaluate_retrieval.py:22-73).
 
     features: 2-d array | dict id -> vector | dict with key 'feat' | path to a pickle of one of those.
-    Returns a generator of (id, ranked id list) tuples, or a dict when return_generator is False."""
+    Returns a generator of (id, ranked id list) tuples, or a dict when return_generator is False.
+
+    topk (extension, default off): return only the first `topk` ranks of every query (se_row_topk instead of a full
+    sort).  `ClassHierarchy.hierarchical_precision(..., compute_ahp=K, all_ids=...)` reads ret[:K+1] and completes the
+    list from `all_ids` (class_hierarchy.py:259-262,273,283), so P@k and AHP@K are unchanged for topk >= K + 1; the
+    classical AP (`compute_ap=True`) and the unclipped AHP need the full ranking."""
     features, ind2id = _features_to_array(features)
-    ranking = pairwise_ranking(features, normalize)
+    ranking = pairwise_ranking(features, normalize, topk=topk)
     if normalize and isinstance(features, np.ndarray) and features.dtype.kind == 'f':
         # the reference normalises its argument in place (line 58); keep the caller-visible side effect
         features /= np.linalg.norm(features, axis=-1, keepdims=True)

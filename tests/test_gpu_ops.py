@@ -622,3 +622,9 @@ def test_pairwise_ranking_topk_equals_full_ranking_prefix():
         top = pairwise_ranking(feats.copy(), normalize, topk=50)
         assert top.shape == (feats.shape[0], 50)
         assert np.array_equal(top, full[:, :50])
+    from semantic_embeddings_b200.evaluate_retrieval import pairwise_retrieval
+    ids = [int(v) for v in fx['ids']]
+    as_dict = {i: f for i, f in zip(ids, feats)}
+    full_d = pairwise_retrieval(dict(as_dict), False, return_generator=False)
+    top_d = pairwise_retrieval(dict(as_dict), False, return_generator=False, topk=20)
+    assert all(top_d[q] == full_d[q][:20] for q in ids)
