@@ -160,6 +160,23 @@ def test_engine_builds_plans_without_a_gpu(built_lib):
         covered = sum(e - b for b, e, _ in eng.segments)
         assert reg <= covered <= reg + 4 * len(eng.pspecs)
         w = eng.get_weights() if False else None
+    # plan-runner hints and the fused conv+BatchNorm op (engine.py _build_plans)
+    g = utils.build_network(100, 'resnet-110-fc')
+    eng = Engine(g, 2, emb, device='cpu', use_cuda_graph=False)
+    fwd, bwd = eng.plans['fwd'], eng.plans['bwd']
+    bn_bwd = [o for o in bwd if o.opcode == L.OP_BN_BWD]
+    # i[4] = "inputs date from the forward pass, >= 24 launches ago" (prefetch before the grid dependency resolves):
+    # set everywhere except for the last layers of the network, whose backward follows their forward closely
+    assert bn_bwd[0].i[4] == 0 and bn_bwd[-1].i[4] == 1
+    assert sum(o.i[4] for o in bn_bwd) >= len(bn_bwd) - 8
+    first_early = next(k for k, o in enumerate(bn_bwd) if o.i[4])
+    assert all(o.i[4] == 1 for o in bn_bwd[first_early:])
+    assert not any(o.opcode == L.OP_CONV_BN_FWD for o in fwd)               # off by default (measured slower)
+    engf = Engine(g, 2, emb, device='cpu', use_cuda_graph=False, fuse_conv_bn=True, mode=L.SE_MODE_TF32)
+    nfused = sum(1 for o in engf.plans['fwd'] if o.opcode == L.OP_CONV_BN_FWD)
+    nbn = sum(1 for n in engf.nodes if n.op == 'bn')
+    assert nfused > 100 and nfused + sum(1 for o in engf.plans['fwd'] if o.opcode == L.OP_BN_FWD_TRAIN) == nbn
+    assert sum(1 for o in engf.plans['infer'] if o.opcode == L.OP_CONV_BN_FWD) == 0   # inference: moving statistics
     # weight I/O round trip keeps Keras names and layouts
     g = utils.build_network(100, 'resnet-32')
     eng = Engine(g, 2, np.eye(64), device='cpu', use_cuda_graph=False)
