@@ -2,7 +2,9 @@
 // shortcut that follows it in the reference graphs (models/cifar_resnet.py:100-124,220;
 // models/plainnet.py:53,68,71; models/wide_residual_network.py:14-92; learn_image_embeddings.py:42-43).
 // HBM-bound elementwise + per-channel reductions: 128-bit coalesced accesses along the channel
-// axis, float64 cross-CTA accumulation of the statistics.
+// axis, float64 cross-CTA accumulation of the statistics.  Backward is ONE launch when a CTA's slab fits in registers
+// (bn_bwd_reg_kernel: grid barrier on the two sums, prefetch of the forward-pass inputs before the programmatic grid
+// dependency resolves) or in shared memory (bn_bwd_fused_kernel), else reduce + apply kernels.
 #include <stdlib.h>
 
 #include "common.cuh"

@@ -15,11 +15,18 @@
 //     dgrad   : k = output channel, n = input channel,  B = the HWIO kernel itself [8-tap][ci][co]
 //               (dX = conv(dY, W rotated by 180 degrees and transposed))
 //
-// Persistent, warp-specialised: warp 0 TMA producer (one tap x channel-block per pipeline stage), warp 1
-// single-thread MMA issuer (M=128, N=3*BNc<=240, K=8 per instruction), warp 2 TMEM allocator, warps 4-7 epilogue
-// (tcgen05.ld -> bias / residual / ReLU / beta*old -> 128-bit global stores, BatchNorm sum and sum-of-squares of the
-// stored values reduced with a shuffle butterfly and accumulated in float64).  Accumulators are double-buffered
-// in TMEM so the epilogue of tile i overlaps the MMAs of tile i+1.
+// Persistent, warp-specialised (384 threads): warp 0 TMA producer (weights resident in shared memory when they fit,
+// else one filter row x channel block per pipeline stage; it only ARRIVES at the prologue barrier so its first loads do
+// not wait for the TMEM allocation), warp 1 MMA issuer (elect.sync inside a provably uniform branch: descriptors stay
+// in uniform registers, no R2UR waterfalls; M=128, N=3*BNc<=240, K=8 per instruction, two tiles interleaved), warp 2
+// TMEM allocator, warps 4-11 two epilogue groups that share the (tile, 32-column block) work items: tcgen05.ld ->
+// combine taps -> bias (from shared memory) / residual / ReLU -> 32x16 blocks staged in shared memory in the TMA
+// SWIZZLE_64B layout -> ONE bulk tensor store per block (cp.reduce add for the accumulating dgrad); BatchNorm sum and
+// sum-of-squares of the stored values via a shuffle butterfly into per-warp slots, float64 across CTAs.  Optional
+// second epilogue pass = fused training BatchNorm (grid barrier on the statistics; see conv_tc_launch / DESIGN.md 4.1).
+// Backward-data launches are sized (shared memory, TMEM columns, 128 registers) to share the SM with the weight-
+// gradient kernel that se_run_ops runs on its side stream; layers with few pixel tiles split the output channels over
+// two CTAs.  No integer division per tile in the epilogue (pixel index = tile * 128 + lane).
 #include <stdlib.h>
 
 #include "common.cuh"
