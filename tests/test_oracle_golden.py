@@ -128,3 +128,24 @@ def test_sgd_clip_and_momentum():
     otrain.sgd_step(p, g, v, lr=0.1, clipnorm=10.0, nesterov=True)
     np.testing.assert_allclose(v['w'].numpy(), [-1.14, -1.52])
     np.testing.assert_allclose(p['w'].numpy(), [0.4 + 0.9 * -1.14 - 0.6, 1.2 + 0.9 * -1.52 - 0.8])
+
+
+def test_hierarchical_precision_oracle_matches_reference_metrics():
+    """oracle/hierarchy.py (the oracle of SURVEY.md section 8(f) rank 2) against ClassHierarchy.hierarchical_precision
+    of the reference itself (class_hierarchy.py:211-316), run by tests/golden/make_golden.py on the reference's own
+    rankings of the 256-item fixture: every metric of every query, clipped (compute_ahp=250) and unclipped + AP."""
+    from oracle import hierarchy as ohier
+    d = np.load(os.path.join(G, 'retrieval_ref.npz'))
+    rank, labels = d['rank_sq_unit'].astype(np.int64), d['labels']
+    avg, per = ohier.hierarchical_precision(rank, labels, d['wup_lut'], d['lcs_height_lut'], compute_ahp=True, compute_ap=True)
+    for k, name in enumerate(d['prec_names']):
+        np.testing.assert_allclose(per[str(name)], d['prec_per_query'][k], rtol=0, atol=1e-12, err_msg=str(name))
+        assert abs(avg[str(name)] - d['prec_avg'][k]) < 1e-12
+    avg, per = ohier.hierarchical_precision(rank, labels, d['wup_lut'], d['lcs_height_lut'], compute_ahp=250)
+    assert sorted(per.keys()) == [str(n) for n in d['prec250_names']]
+    for k, name in enumerate(d['prec250_names']):
+        np.testing.assert_allclose(per[str(name)], d['prec250_per_query'][k], rtol=0, atol=1e-12, err_msg=str(name))
+        assert abs(avg[str(name)] - d['prec250_avg'][k]) < 1e-12
+    # a ranking truncated to clip+1 items gives the same clipped metrics except through the ideal gain, which needs the
+    # label histogram of the whole database: the reason pairwise_retrieval(topk=...) relies on `all_ids` completion
+    assert rank.shape[1] > 251
