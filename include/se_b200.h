@@ -227,6 +227,17 @@ int se_pairwise_dist(const float* F, int ldF, int N, int D, int row0, int rows, 
 int se_row_topk(const float* dist, int64_t ld, int rows, int n, int k, float* out_val, int32_t* out_idx, int ldo,
                 void* stream);
 
+/* ClassHierarchy.hierarchical_precision(retrieved, labels, ks, compute_ahp=clip, ignore_qids=True) of the reference
+ * (class_hierarchy.py:211-316) on the first K1 = max(ks, clip) + 1 ranks of Q queries (query ids q0 .. q0+Q-1 are
+ * database indices; ranks [Q, ldr] int32, e.g. from se_row_topk).  labels [N] int32 class indices (< C);
+ * wup_lut / lcs_height_lut [C, C] float64 = wup_similarity / lcs_height of the hierarchy; best_wup / best_lcs [C, K1]
+ * float64 = per query class the cumulative sums of the descending class similarities of the WHOLE database
+ * (ranking independent, class_hierarchy.py:268,280).  out [Q, 2*(nks + (clip > 0))] float64 per query:
+ * P@ks[0] (WUP), P@ks[0] (LCS_HEIGHT), ..., AHP@clip (WUP), AHP@clip (LCS_HEIGHT).  nks <= 8. */
+int se_hier_precision(const int32_t* ranks, int ldr, int Q, int K1, int q0, const int32_t* labels, int C,
+                      const double* wup_lut, const double* lcs_height_lut, const double* best_wup, const double* best_lcs,
+                      const int32_t* ks, int nks, int clip, double* out, void* stream);
+
 /* ------------------------------------------------------------------ plan runner
  * Runs a host-built array of ops (one training step is ~900 launches) in one call so that
  * neither Python nor ctypes sits between launches.  Each op is an opcode plus the argument

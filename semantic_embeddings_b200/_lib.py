@@ -52,6 +52,7 @@ _SIGS = {
     'se_tc_capabilities': (c_int, []),
     'se_conv2d_fwd': (c_int, [POINTER(ConvDesc), _P, _P, _P, _P, _P, c_int, _P, c_int, _P]),
     'se_conv2d_fwd_ex': (c_int, [POINTER(ConvDesc), _P, _P, _P, _P, _P, _P, c_int, _P, c_int, _P]),
+    'se_hier_precision': (c_int, [_P, c_int, c_int, c_int, c_int, _P, c_int, _P, _P, _P, _P, _P, c_int, c_int, _P, _P]),
     'se_row_topk': (c_int, [_P, c_int64, c_int, c_int, c_int, _P, _P, c_int, _P]),
     'se_conv_bn_fwd': (c_int, [POINTER(ConvDesc), _P, _P, _P, _P, _P, c_int, _P, _P, _P, c_float, c_float, _P, _P, _P, _P, _P,
                                c_int, _P, _P, c_int, _P]),

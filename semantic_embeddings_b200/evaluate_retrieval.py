@@ -115,3 +115,47 @@ def pairwise_retrieval(features, normalize=False, return_generator=True, topk=No
     else:
         gen = ((i, ret.tolist()) for i, ret in enumerate(ranking))
     return gen if return_generator else dict(gen)
+
+
+def hierarchical_precision_topk(topk_idx, labels, wup_lut, lcs_height_lut, ks=(1, 10, 50, 100), clip_ahp=250, q0=0):
+    """`ClassHierarchy.hierarchical_precision(retrieved, labels, ks, compute_ahp=clip_ahp)` (class_hierarchy.py:211-316)
+    on device rankings: topk_idx int32 [Q, >= max(ks, clip_ahp) + 1] (row_topk / pairwise_ranking(topk=...)), labels the
+    class INDEX of every database item, the two [C, C] look-up tables of the hierarchy (wup_similarity, lcs_height).
+    Returns (averages, per-query arrays) keyed by the reference's metric names.  se_hier_precision does the per-query
+    work; the ranking-independent ideal gains come from the label histogram on the host."""
+    import ctypes
+    import torch
+    dev = topk_idx.device
+    labels_np = np.asarray(labels, dtype=np.int64)
+    ks = [int(k) for k in ks]
+    clip = int(clip_ahp) if clip_ahp else 0
+    K1 = max(ks + [clip]) + 1
+    if topk_idx.shape[1] < K1:
+        raise ValueError('need the first %d ranks of every query, got %d' % (K1, topk_idx.shape[1]))
+    wup = np.ascontiguousarray(wup_lut, dtype=np.float64)
+    lcsh = np.ascontiguousarray(lcs_height_lut, dtype=np.float64)
+    C = wup.shape[0]
+    best_w = np.empty((C, K1))
+    best_l = np.empty((C, K1))
+    for c in range(C):       # class_hierarchy.py:268,280: cumsum(sorted(similarities of the whole database, reverse=True))
+        best_w[c] = np.cumsum(np.sort(wup[c, labels_np])[::-1])[:K1]
+        best_l[c] = np.cumsum(np.sort(1.0 - lcsh[c, labels_np])[::-1])[:K1]
+    t = lambda a, dt: torch.as_tensor(np.ascontiguousarray(a), dtype=dt).to(dev)
+    lab_d, wup_d, lcs_d = t(labels_np, torch.int32), t(wup, torch.float64), t(lcsh, torch.float64)
+    bw_d, bl_d = t(best_w, torch.float64), t(best_l, torch.float64)
+    idx = topk_idx if topk_idx.dtype == torch.int32 else topk_idx.to(torch.int32)
+    Q = idx.shape[0]
+    M = 2 * (len(ks) + (1 if clip else 0))
+    out = torch.empty((Q, M), dtype=torch.float64, device=dev)
+    ks_arr = (ctypes.c_int32 * len(ks))(*ks)
+    _lib.call('se_hier_precision', _lib.ptr(idx), idx.stride(0), Q, K1, int(q0), _lib.ptr(lab_d), C, _lib.ptr(wup_d), _lib.ptr(lcs_d),
+              _lib.ptr(bw_d), _lib.ptr(bl_d), ks_arr, len(ks), clip, _lib.ptr(out), _lib.stream_ptr())
+    res = out.cpu().numpy()
+    per = {}
+    for i, k in enumerate(ks):
+        per['P@%d (WUP)' % k] = res[:, 2 * i]
+        per['P@%d (LCS_HEIGHT)' % k] = res[:, 2 * i + 1]
+    if clip:
+        per['AHP@%d (WUP)' % clip] = res[:, 2 * len(ks)]
+        per['AHP@%d (LCS_HEIGHT)' % clip] = res[:, 2 * len(ks) + 1]
+    return {m: float(v.mean()) for m, v in per.items()}, per

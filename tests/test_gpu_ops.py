@@ -628,3 +628,42 @@ def test_pairwise_ranking_topk_equals_full_ranking_prefix():
     full_d = pairwise_retrieval(dict(as_dict), False, return_generator=False)
     top_d = pairwise_retrieval(dict(as_dict), False, return_generator=False, topk=20)
     assert all(top_d[q] == full_d[q][:20] for q in ids)
+
+
+def test_hierarchical_precision_kernel_matches_the_reference_metrics():
+    """se_hier_precision on the first 251 ranks vs (a) the numbers ClassHierarchy.hierarchical_precision of the reference
+    produced for the same rankings (fixture prec250_*) and (b) oracle/hierarchy.py; float64, <= 1e-12 per query.
+    Also end to end: distance kernel -> se_row_topk -> se_hier_precision on the fixture features."""
+    from oracle import hierarchy as ohier
+    from semantic_embeddings_b200.evaluate_retrieval import hierarchical_precision_topk, pairwise_ranking
+    fx = np.load(os.path.join(G, 'retrieval_ref.npz'))
+    rank, labels = fx['rank_sq_unit'].astype(np.int64), fx['labels']
+    top = torch.as_tensor(rank[:, :251].astype(np.int32)).cuda()
+    avg, per = hierarchical_precision_topk(top, labels, fx['wup_lut'], fx['lcs_height_lut'], ks=(1, 10, 50, 100), clip_ahp=250)
+    assert sorted(per.keys()) == [str(n) for n in fx['prec250_names']]
+    for k, name in enumerate(fx['prec250_names']):
+        np.testing.assert_allclose(per[str(name)], fx['prec250_per_query'][k], rtol=0, atol=1e-12, err_msg=str(name))
+        assert abs(avg[str(name)] - fx['prec250_avg'][k]) < 1e-12
+    _, oper = ohier.hierarchical_precision(rank, labels, fx['wup_lut'], fx['lcs_height_lut'], ks=(1, 10), compute_ahp=40)
+    _, gper = hierarchical_precision_topk(top[:, :41].contiguous(), labels, fx['wup_lut'], fx['lcs_height_lut'], ks=(1, 10), clip_ahp=40)
+    for name in oper:
+        np.testing.assert_allclose(gper[name], oper[name], rtol=0, atol=1e-12, err_msg=name)
+    # the query is not always rank 0 (duplicates / other items at distance 0): put it at rank 3 for every third query and
+    # outside the evaluated prefix for every fifth one -- the removal logic of class_hierarchy.py:289-297
+    rank2 = rank.copy()
+    for q in range(0, len(rank2), 3):
+        rank2[q, [0, 3]] = rank2[q, [3, 0]]
+    for q in range(1, len(rank2), 5):
+        pos = int(np.nonzero(rank2[q] == q)[0][0])
+        rank2[q] = np.concatenate((np.delete(rank2[q], pos), [q]))
+    _, oper = ohier.hierarchical_precision(rank2, labels, fx['wup_lut'], fx['lcs_height_lut'], ks=(1, 5, 10), compute_ahp=40)
+    top2 = torch.as_tensor(rank2[:, :41].astype(np.int32)).cuda()
+    _, gper = hierarchical_precision_topk(top2, labels, fx['wup_lut'], fx['lcs_height_lut'], ks=(1, 5, 10), clip_ahp=40)
+    for name in oper:
+        np.testing.assert_allclose(gper[name], oper[name], rtol=0, atol=1e-12, err_msg=name)
+    # end to end on the GPU: the fixture's unit-norm features give the reference's ranking wherever it is unambiguous,
+    # so the averaged metrics agree to the level of the few ambiguous swaps
+    gtop = torch.as_tensor(pairwise_ranking(fx['feat_unit'].astype(np.float32), False, topk=251).astype(np.int32)).cuda()
+    gavg, _ = hierarchical_precision_topk(gtop, labels, fx['wup_lut'], fx['lcs_height_lut'], ks=(1, 10, 50, 100), clip_ahp=250)
+    for k, name in enumerate(fx['prec250_names']):
+        assert abs(gavg[str(name)] - fx['prec250_avg'][k]) < 2e-3, (name, gavg[str(name)], fx['prec250_avg'][k])
