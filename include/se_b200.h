@@ -17,9 +17,12 @@
  *     into a CUDA graph.
  *   - activations are float32 NHWC; conv kernels are float32 HWIO (Keras layout); dense
  *     kernels are (in,out).  `mode` selects the arithmetic of contraction kernels:
- *     SE_MODE_F32 = fp32 FFMA (parity mode), SE_MODE_TF32 = tcgen05 kind::tf32, fp32
- *     accumulate in TMEM (fast mode; falls back to F32 for shapes the tensor path does not
- *     cover -- never to the CPU).
+ *     SE_MODE_F32 = fp32 FFMA; SE_MODE_TF32 = tcgen05 kind::tf32 (operands truncated to a
+ *     10-bit mantissa, fp32 accumulate in TMEM: ~1e-3 relative, outside the reference's fp32
+ *     semantics, kept for comparison); SE_MODE_TF32X3 = tcgen05 kind::tf32 with error
+ *     compensation (every operand split into hi + lo, hi*hi + hi*lo + lo*hi in one fp32
+ *     accumulator: fp32-level results, the mode the training path runs and is benchmarked in).
+ *     Shapes the tensor path does not cover fall back to the fp32 kernels -- never to the CPU.
  */
 #ifndef SE_B200_H
 #define SE_B200_H
@@ -37,6 +40,7 @@ extern "C" {
 
 #define SE_MODE_F32 0
 #define SE_MODE_TF32 1
+#define SE_MODE_TF32X3 2
 
 /* head variants: learn_image_embeddings.py --loss (lines 62, 127-130, 164-171) */
 #define SE_LOSS_INV_CORR 0     /* l2norm wrapper + 1 - <t,x>      */
@@ -79,6 +83,21 @@ int se_conv2d_fwd(const se_conv_desc* d, const float* x, const float* w, const f
  * (SE_MODE_TF32) consumes K-major operands; without w_t the call uses the fp32 kernels. */
 int se_conv2d_fwd_ex(const se_conv_desc* d, const float* x, const float* w, const float* w_t, const float* bias,
                      const float* residual, float* y, int relu, double* stats, int mode, void* stream);
+/* Auxiliary copies of a convolution kernel w (HWIO) that the tensor-core paths consume; any may be NULL (the call
+ * then uses the fp32 kernels):  w_t = [kh][kw][Cout][Cin] (K-major B operand of the forward GEMM);  w_t_lo / w_lo =
+ * the low parts w - tf32_trunc(w) in the transposed / the HWIO order (SE_MODE_TF32X3).  se_split_filters writes all
+ * three for every kernel of a flat parameter buffer in one launch. */
+typedef struct {
+  const float* w_t;
+  const float* w_t_lo;
+  const float* w_lo;
+} se_conv_aux;
+int se_conv2d_fwd_aux(const se_conv_desc* d, const float* x, const float* w, const se_conv_aux* aux, const float* bias,
+                      const float* residual, float* y, int relu, double* stats, int mode, void* stream);
+int se_conv2d_dgrad_aux(const se_conv_desc* d, const float* dy, const float* w, const se_conv_aux* aux, float* dx, float beta,
+                        int mode, void* stream);
+/* se_transpose_filters + PL[off + i] = lo(P[off + i]), PTL[off + (tap, co, ci)] = lo(P[off + (tap, ci, co)]) */
+int se_split_filters(const float* P, float* PT, float* PL, float* PTL, const int64_t* table, int n, void* stream);
 /* PT[off + (tap, co, ci)] = P[off + (tap, ci, co)] for n kernels of a flat buffer, one launch.
  * table: host array of n x {element offset, taps, Cin, Cout} (int64). */
 int se_transpose_filters(const float* P, float* PT, const int64_t* table, int n, void* stream);

@@ -11,7 +11,8 @@ from ctypes import POINTER, c_char_p, c_double, c_float, c_int, c_int32, c_int64
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'libse_b200.so')
 
-SE_MODE_F32, SE_MODE_TF32 = 0, 1
+SE_MODE_F32, SE_MODE_TF32, SE_MODE_TF32X3 = 0, 1, 2
+MODE_NAMES = {0: 'f32', 1: 'tf32', 2: 'tf32x3'}
 SE_LOSS_INV_CORR, SE_LOSS_UNNORM_CORR, SE_LOSS_MSE = 0, 1, 2
 SE_PDIST_SQEUCLID, SE_PDIST_NEGDOT = 0, 1
 
@@ -34,6 +35,10 @@ class Residual(ctypes.Structure):
     _fields_ = [('ptr', c_void_p), ('C', c_int32), ('pad_lo', c_int32), ('pool', c_int32), ('H', c_int32), ('W', c_int32)]
 
 
+class ConvAux(ctypes.Structure):
+    _fields_ = [('w_t', c_void_p), ('w_t_lo', c_void_p), ('w_lo', c_void_p)]
+
+
 class L2Segment(ctypes.Structure):
     _fields_ = [('begin', c_int64), ('end', c_int64), ('l2', c_float)]
 
@@ -52,6 +57,9 @@ _SIGS = {
     'se_tc_capabilities': (c_int, []),
     'se_conv2d_fwd': (c_int, [POINTER(ConvDesc), _P, _P, _P, _P, _P, c_int, _P, c_int, _P]),
     'se_conv2d_fwd_ex': (c_int, [POINTER(ConvDesc), _P, _P, _P, _P, _P, _P, c_int, _P, c_int, _P]),
+    'se_conv2d_fwd_aux': (c_int, [POINTER(ConvDesc), _P, _P, POINTER(ConvAux), _P, _P, _P, c_int, _P, c_int, _P]),
+    'se_conv2d_dgrad_aux': (c_int, [POINTER(ConvDesc), _P, _P, POINTER(ConvAux), _P, c_float, c_int, _P]),
+    'se_split_filters': (c_int, [_P, _P, _P, _P, POINTER(c_int64), c_int, _P]),
     'se_hier_precision': (c_int, [_P, c_int, c_int, c_int, c_int, _P, c_int, _P, _P, _P, _P, _P, c_int, c_int, _P, _P]),
     'se_row_topk': (c_int, [_P, c_int64, c_int, c_int, c_int, _P, _P, c_int, _P]),
     'se_conv_bn_fwd': (c_int, [POINTER(ConvDesc), _P, _P, _P, _P, _P, c_int, _P, _P, _P, c_float, c_float, _P, _P, _P, _P, _P,

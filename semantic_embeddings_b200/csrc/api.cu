@@ -43,13 +43,14 @@ int conv_fwd_simt(const se_conv_desc*, const float*, const float*, const float*,
 int conv_dgrad_simt(const se_conv_desc*, const float*, const float*, float*, float, cudaStream_t);
 int conv_wgrad_simt(const se_conv_desc*, const float*, const float*, float*, float*, cudaStream_t);
 // conv_tc.cu (tcgen05 kind::tf32); each returns SE_ERR_UNSUPPORTED for shapes it does not cover
-int conv_fwd_tc(const se_conv_desc*, const float*, const float*, const float*, const float*, float*, int, double*, cudaStream_t);
-int conv_dgrad_tc(const se_conv_desc*, const float*, const float*, float*, float, cudaStream_t);
+int conv_fwd_tc(const se_conv_desc*, const float*, const float*, const float*, const float*, const float*, float*, int, double*,
+                cudaStream_t);
+int conv_dgrad_tc(const se_conv_desc*, const float*, const float*, const float*, float*, float, cudaStream_t);
 int conv_bn_fwd_tc(const se_conv_desc* d, const float* x, const float* w_t, const float* bias, float* y, int relu, double* stats,
                    const float* gamma, const float* beta, float eps, float momentum, float* moving_mean, float* moving_var,
                    float* save_mean, float* save_invstd, const float* bn_res, int bn_relu, float* bn_out,
                    unsigned long long* counter, cudaStream_t st);
-int conv_wgrad_tc(const se_conv_desc*, const float*, const float*, float*, float*, cudaStream_t);
+int conv_wgrad_tc(const se_conv_desc*, const float*, const float*, float*, float*, int x3, cudaStream_t);
 
 static int check_desc(const se_conv_desc* d) {
   if (!d) { set_error("null conv descriptor"); return SE_ERR_ARG; }
@@ -91,17 +92,27 @@ extern "C" int se_init(void) {
 namespace se { int tc_capabilities(); }
 extern "C" int se_tc_capabilities(void) { return se::tc_capabilities(); }
 
-extern "C" int se_conv2d_fwd_ex(const se_conv_desc* d, const float* x, const float* w, const float* w_t,
-                                const float* bias, const float* residual, float* y, int relu, double* stats, int mode,
-                                void* stream) {
+extern "C" int se_conv2d_fwd_aux(const se_conv_desc* d, const float* x, const float* w, const se_conv_aux* aux,
+                                 const float* bias, const float* residual, float* y, int relu, double* stats, int mode,
+                                 void* stream) {
   int rc = check_desc(d);
   if (rc) return rc;
   SE_REQUIRE(x && w && y, "null pointer");
-  if (mode == SE_MODE_TF32 && w_t) {
-    rc = conv_fwd_tc(d, x, w_t, bias, residual, y, relu, stats, as_stream(stream));
+  if (mode == SE_MODE_TF32 && aux && aux->w_t) {
+    rc = conv_fwd_tc(d, x, aux->w_t, nullptr, bias, residual, y, relu, stats, as_stream(stream));
+    if (rc != SE_ERR_UNSUPPORTED) return rc;
+  } else if (mode == SE_MODE_TF32X3 && aux && aux->w_t && aux->w_t_lo) {
+    rc = conv_fwd_tc(d, x, aux->w_t, aux->w_t_lo, bias, residual, y, relu, stats, as_stream(stream));
     if (rc != SE_ERR_UNSUPPORTED) return rc;
   }
   return conv_fwd_simt(d, x, w, bias, residual, y, relu, stats, as_stream(stream));
+}
+
+extern "C" int se_conv2d_fwd_ex(const se_conv_desc* d, const float* x, const float* w, const float* w_t,
+                                const float* bias, const float* residual, float* y, int relu, double* stats, int mode,
+                                void* stream) {
+  se_conv_aux aux = {w_t, nullptr, nullptr};
+  return se_conv2d_fwd_aux(d, x, w, &aux, bias, residual, y, relu, stats, mode, stream);
 }
 
 extern "C" int se_conv_bn_fwd(const se_conv_desc* d, const float* x, const float* w, const float* w_t, const float* bias,
@@ -129,22 +140,35 @@ extern "C" int se_conv2d_fwd(const se_conv_desc* d, const float* x, const float*
   return se_conv2d_fwd_ex(d, x, w, nullptr, bias, residual, y, relu, stats, mode, stream);
 }
 
-namespace se { int transpose_filters(const float* P, float* PT, const long long* table, int n, cudaStream_t st); }
+namespace se {
+int transpose_filters(const float* P, float* PT, float* PL, float* PTL, const long long* table, int n, cudaStream_t st);
+}
 extern "C" int se_transpose_filters(const float* P, float* PT, const int64_t* table, int n, void* stream) {
   SE_REQUIRE(P && PT && table && n >= 0, "bad arguments");
-  return se::transpose_filters(P, PT, reinterpret_cast<const long long*>(table), n, as_stream(stream));
+  return se::transpose_filters(P, PT, nullptr, nullptr, reinterpret_cast<const long long*>(table), n, as_stream(stream));
+}
+extern "C" int se_split_filters(const float* P, float* PT, float* PL, float* PTL, const int64_t* table, int n, void* stream) {
+  SE_REQUIRE(P && PT && PL && PTL && table && n >= 0, "bad arguments");
+  return se::transpose_filters(P, PT, PL, PTL, reinterpret_cast<const long long*>(table), n, as_stream(stream));
 }
 
-extern "C" int se_conv2d_dgrad(const se_conv_desc* d, const float* dy, const float* w, float* dx, float beta, int mode,
-                               void* stream) {
+extern "C" int se_conv2d_dgrad_aux(const se_conv_desc* d, const float* dy, const float* w, const se_conv_aux* aux, float* dx,
+                                   float beta, int mode, void* stream) {
   int rc = check_desc(d);
   if (rc) return rc;
   SE_REQUIRE(dy && w && dx, "null pointer");
   if (mode == SE_MODE_TF32) {
-    rc = conv_dgrad_tc(d, dy, w, dx, beta, as_stream(stream));
+    rc = conv_dgrad_tc(d, dy, w, nullptr, dx, beta, as_stream(stream));
+    if (rc != SE_ERR_UNSUPPORTED) return rc;
+  } else if (mode == SE_MODE_TF32X3 && aux && aux->w_lo) {
+    rc = conv_dgrad_tc(d, dy, w, aux->w_lo, dx, beta, as_stream(stream));
     if (rc != SE_ERR_UNSUPPORTED) return rc;
   }
   return conv_dgrad_simt(d, dy, w, dx, beta, as_stream(stream));
+}
+extern "C" int se_conv2d_dgrad(const se_conv_desc* d, const float* dy, const float* w, float* dx, float beta, int mode,
+                               void* stream) {
+  return se_conv2d_dgrad_aux(d, dy, w, nullptr, dx, beta, mode, stream);
 }
 
 extern "C" int se_conv2d_wgrad(const se_conv_desc* d, const float* x, const float* dy, float* dw, float* dbias, int mode,
@@ -152,8 +176,8 @@ extern "C" int se_conv2d_wgrad(const se_conv_desc* d, const float* x, const floa
   int rc = check_desc(d);
   if (rc) return rc;
   SE_REQUIRE(x && dy && dw, "null pointer");
-  if (mode == SE_MODE_TF32) {
-    rc = conv_wgrad_tc(d, x, dy, dw, dbias, as_stream(stream));
+  if (mode == SE_MODE_TF32 || mode == SE_MODE_TF32X3) {
+    rc = conv_wgrad_tc(d, x, dy, dw, dbias, mode == SE_MODE_TF32X3, as_stream(stream));
     if (rc != SE_ERR_UNSUPPORTED) return rc;
   }
   return conv_wgrad_simt(d, x, dy, dw, dbias, as_stream(stream));
@@ -248,8 +272,9 @@ static int run_ops_impl(const se_op* ops, int n, int mode, void* stream, bool* f
           transposing = false;
           *forked = false;
         }
-        rc = se_conv2d_fwd_ex(&d, (const float*)p[0], (const float*)p[1], (const float*)p[6], (const float*)p[2],
-                              (const float*)p[3], (float*)p[4], i[12], (double*)p[5], i[13] >= 0 ? i[13] : mode, stream);
+        se_conv_aux aux = {(const float*)p[6], (const float*)p[7], nullptr};
+        rc = se_conv2d_fwd_aux(&d, (const float*)p[0], (const float*)p[1], &aux, (const float*)p[2],
+                               (const float*)p[3], (float*)p[4], i[12], (double*)p[5], i[13] >= 0 ? i[13] : mode, stream);
         break;
       }
       case SE_OP_CONV_BN_FWD: {
@@ -270,7 +295,9 @@ static int run_ops_impl(const se_op* ops, int n, int mode, void* stream, bool* f
       }
       case SE_OP_CONV_DGRAD: {
         se_conv_desc d = desc_from(i);
-        rc = se_conv2d_dgrad(&d, (const float*)p[0], (const float*)p[1], (float*)p[2], f[0], i[13] >= 0 ? i[13] : mode, stream);
+        se_conv_aux aux = {nullptr, nullptr, (const float*)p[3]};
+        rc = se_conv2d_dgrad_aux(&d, (const float*)p[0], (const float*)p[1], &aux, (float*)p[2], f[0],
+                                 i[13] >= 0 ? i[13] : mode, stream);
         break;
       }
       case SE_OP_CONV_WGRAD: {
@@ -351,7 +378,7 @@ static int run_ops_impl(const se_op* ops, int n, int mode, void* stream, bool* f
         break;
       }
       case SE_OP_TRANSPOSE_FILTERS:
-        if (mode == SE_MODE_TF32) {
+        if (mode == SE_MODE_TF32 || mode == SE_MODE_TF32X3) {
           // the transposed filter copies are first needed by the first tensor-core convolution: the transposition runs
           // on the side stream beside the statistics memset, the stem convolution and its BatchNorm
           void* ts = stream;
@@ -362,7 +389,10 @@ static int run_ops_impl(const se_op* ops, int n, int mode, void* stream, bool* f
             *forked = true;
             transposing = true;
           }
-          rc = se_transpose_filters((const float*)p[0], (float*)p[1], (const int64_t*)p[2], i[0], ts);
+          if (mode == SE_MODE_TF32X3 && p[3] && p[4])
+            rc = se_split_filters((const float*)p[0], (float*)p[1], (float*)p[3], (float*)p[4], (const int64_t*)p[2], i[0], ts);
+          else
+            rc = se_transpose_filters((const float*)p[0], (float*)p[1], (const int64_t*)p[2], i[0], ts);
         }
         break;
       case SE_OP_SGD_PREPARE:

@@ -55,6 +55,7 @@ struct ConvTcParams {
   int stages, stage_bytes, a_bytes, acc_stride, tmem_cols, nacc, b_merged;
   int stage_out;            // output staging bytes per epilogue warp: 4096 (two sub-buffers) or 2048
   int res, res_b_bytes, nt; // resident-weights mode: B loaded once per CTA, MMAs of `nt` tiles interleaved
+  int res_bl_off;           // X3: byte offset of the resident low-part weights inside the resident block
   const float* bias;
   const float* residual;
   float* out;
@@ -78,6 +79,22 @@ struct ConvTcParams {
 };
 
 constexpr int CT_THREADS = 384;   // warp 0 TMA, warp 1 MMA, warp 2 TMEM alloc, warps 4-7 / 8-11 two epilogue groups
+constexpr int CT_THREADS_X3 = 448; // + warps 3, 12, 13: operand splitters of the error-compensated mode (see conv_tc_kernel)
+constexpr int CT_NCONV = 96;       // splitter threads
+
+// x -> x - tf32_trunc(x): the part of an fp32 operand that kind::tf32 (which reads the upper 19 bits of the word,
+// i.e. truncates the mantissa to 10 bits) does not see.  Exact in fp32 (the difference has <= 13 significant bits).
+__device__ __forceinline__ float tf32_lo(float x) { return x - __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
+__device__ __forceinline__ void split_lo_inplace(uint8_t* base, int bytes, int tid, int nthreads) {
+  float4* q = reinterpret_cast<float4*>(base);
+  const int n = bytes >> 4;
+#pragma unroll 4
+  for (int i = tid; i < n; i += nthreads) {
+    float4 v = q[i];
+    v.x = tf32_lo(v.x); v.y = tf32_lo(v.y); v.z = tf32_lo(v.z); v.w = tf32_lo(v.w);
+    q[i] = v;
+  }
+}
 
 // column sums of a 32 x NC block held one row per lane (v[j] = column j of this lane's row):
 // after the butterfly lane L holds the total of column L (NC == 32) or L >> 1 (NC == 16).
@@ -220,9 +237,20 @@ __device__ __forceinline__ void conv_tc_epilogue_block(const ConvTcParams& p, co
   if (dbg) dbg[3] = clock64();
 }
 
+// X3 = error-compensated arithmetic ("3xTF32"): every fp32 operand is the sum of the part kind::tf32 reads (hi =
+// mantissa truncated to 10 bits) and a remainder lo = x - hi (<= 13 significant bits, of which tf32 keeps the top 10),
+// and the product is accumulated as A_hi*B_hi + A_hi*B_lo + A_lo*B_hi in the same fp32 TMEM accumulator (the dropped
+// A_lo*B_lo and the truncation of lo are ~2^-21 relative: fp32-level results from tensor-core tiles).  Weights: lo is
+// a second (resident or streamed) B tile written once per step by se_split_filters.  Activations: no second tile --
+// pass 1 issues A*B_hi and A*B_lo on the tile as TMA delivered it (the hardware truncation IS the hi part), the
+// splitter warps (3, 12, 13) then rewrite the tile IN PLACE as lo, and pass 2 issues A_lo*B_hi.  The MMA thread runs
+// the two passes as two cursors over the same stage sequence (whichever is ready goes next), so pass 1 of the next
+// tile overlaps the split of the previous one.
+template <int X3>
 __global__ void __maxnreg__(128)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-               const __grid_constant__ CUtensorMap map_o, const __grid_constant__ CUtensorMap map_z, ConvTcParams p) {
+               const __grid_constant__ CUtensorMap map_bl, const __grid_constant__ CUtensorMap map_o,
+               const __grid_constant__ CUtensorMap map_z, ConvTcParams p) {
   pdl_trigger();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -236,7 +264,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   uint64_t* t_empty = t_full + CT_MAX_ACC;
   uint64_t* b_full = t_empty + CT_MAX_ACC;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(b_full + 1);
-  float* s_bias = reinterpret_cast<float*>(bars + 2 * CT_MAX_STAGES + 2 * CT_MAX_ACC + 4);    // [Nc] (zeros without a bias)
+  uint64_t* hi_done = bars + 2 * CT_MAX_STAGES + 2 * CT_MAX_ACC + 4;       // X3: pass-1 MMAs of a stage have read it
+  uint64_t* lo_ready = hi_done + CT_MAX_STAGES;                            // X3: the stage now holds the lo parts
+  float* s_bias = reinterpret_cast<float*>(lo_ready + CT_MAX_STAGES);      // [Nc] (zeros without a bias)
   float* s_stats = s_bias + p.Nc;                                                              // [8 warps][2 * Nc]
 
   const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
@@ -253,6 +283,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     for (int s = 0; s < p.stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
     for (int a = 0; a < p.nacc; ++a) { mbar_init(&t_full[a], 1); mbar_init(&t_empty[a], 128 * ((p.BN + 31) >> 5)); }
     mbar_init(b_full, 1);
+    if (X3) for (int s = 0; s < p.stages; ++s) { mbar_init(&hi_done[s], 1); mbar_init(&lo_ready[s], CT_NCONV); }
     fence_barrier_init();
     fence_proxy_async();
   }
@@ -261,12 +292,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   uint32_t tmem_base = 0;
   if (warp == 0) {
     __syncwarp();
-    asm volatile("barrier.arrive 3, %0;" ::"r"(CT_THREADS) : "memory");   // named barrier 3: never shared with the final __syncthreads
+    asm volatile("barrier.arrive 3, %0;" ::"r"(X3 ? CT_THREADS_X3 : CT_THREADS) : "memory");   // named barrier 3: never shared with the final __syncthreads
   } else {
     if (warp == 2) tmem_alloc(tmem_slot, p.tmem_cols);
-    if (p.stats) for (int i = threadIdx.x - 32; i < 16 * p.Nc; i += CT_THREADS - 32) s_stats[i] = 0.f;
+    if (p.stats) for (int i = threadIdx.x - 32; i < 16 * p.Nc; i += (X3 ? CT_THREADS_X3 : CT_THREADS) - 32) s_stats[i] = 0.f;
     fence_before_sync();
-    asm volatile("barrier.sync 3, %0;" ::"r"(CT_THREADS) : "memory");
+    asm volatile("barrier.sync 3, %0;" ::"r"(X3 ? CT_THREADS_X3 : CT_THREADS) : "memory");
     fence_after_sync();
     tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);   // provably warp-uniform (see tc.cuh elect_one)
   }
@@ -276,13 +307,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     // ===================== TMA producer
     int stage = 0, phase = 0, tr_n = 0;
     CT_TRACE(0, 0);
-    const uint32_t tx = p.rg * (p.a_bytes + b_rows * row_bytes);
+    const uint32_t tx = p.rg * (p.a_bytes + (X3 ? 2 : 1) * b_rows * row_bytes);
     if (p.res && t_begin < t_end) {
       // weights once per CTA: three boxes of 3*BN rows (one per filter row; see the tap order note below)
-      mbar_expect_tx(b_full, 3 * b_rows * row_bytes);
+      mbar_expect_tx(b_full, (X3 ? 2 : 1) * 3 * b_rows * row_bytes);
       for (int r = 0; r < 3; ++r) {
         const int tap0 = p.flip ? 8 - (r * 3 + 2) : r * 3;
         tma_load_2d(res_b + r * b_rows * row_bytes, &map_b, b_full, 0, tap0 * p.Nc);
+        if (X3) tma_load_2d(res_b + p.res_bl_off + r * b_rows * row_bytes, &map_bl, b_full, 0, tap0 * p.Nc);
       }
     }
     for (int t = t_begin; p.res && t < t_end; ++t) {
@@ -320,11 +352,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
               // index is reversed, so the box starts at tap 8-(3r+2) and holds the s-blocks in the order 2,1,0.
               const int tap0 = p.flip ? 8 - (r * 3 + 2) : r * 3;
               tma_load_2d(sbr, &map_b, &full[stage], kb * p.cblk, tap0 * p.Nc);
+              if (X3) tma_load_2d(sbr + p.rg * b_rows * row_bytes, &map_bl, &full[stage], kb * p.cblk, tap0 * p.Nc);
             } else {
               for (int s = 0; s < 3; ++s) {
                 const int tap = r * 3 + s;
                 const int btap = p.flip ? 8 - tap : tap;
                 tma_load_2d(sbr + s * p.BN * row_bytes, &map_b, &full[stage], kb * p.cblk, btap * p.Nc + tn * p.BN);
+                if (X3)
+                  tma_load_2d(sbr + p.rg * b_rows * row_bytes + s * p.BN * row_bytes, &map_bl, &full[stage], kb * p.cblk,
+                              btap * p.Nc + tn * p.BN);
               }
             }
           }
@@ -339,7 +375,67 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     const uint32_t sbo = 8 * row_bytes;
     int stage = 0, phase = 0, tr_n = 0;
     CT_TRACE(1, 0);
-    if (p.res && t_begin < t_end) {
+    if (X3 && t_begin < t_end) {
+      // ---- error-compensated issue loop.  A "unit" is one pipeline stage: a whole tile (resident weights) or one
+      // (filter-row group, channel block) of a tile.  Cursor 1 issues pass 1 of unit u1 (A*B_hi, A*B_lo on the raw tile),
+      // cursor 2 pass 2 of unit u2 <= u1 (A_lo*B_hi after the splitters rewrote the tile); ready work goes first.
+      const uint32_t dhi = umma_desc_hi_kmajor(sbo, row_bytes);
+      const uint32_t tiles_u32 = smem_u32(tiles);
+      const uint32_t bres = smem_u32(res_b);
+      const int kst = p.cblk / 8;
+      const int rows_u = p.res ? 3 : p.rg;                         // filter rows per unit
+      const int upt = p.res ? 1 : (3 / p.rg) * p.kblocks;          // units per tile
+      const int U = (t_end - t_begin) * upt;
+      const uint32_t b_row = b_rows * row_bytes;                   // bytes of one filter row of B
+      const uint32_t lo_off = p.res ? (uint32_t)p.res_bl_off : (uint32_t)p.rg * b_row;
+      if (p.res) mbar_wait(b_full, 0);
+      int u1 = 0, s1 = 0, ph1 = 0, k1 = 0, a1 = 0, aph1 = 0;
+      int u2 = 0, s2 = 0, ph2 = 0, k2 = 0, a2 = 0;
+      bool acc_ok = false;
+      while (u2 < U) {
+        if (u1 < U) {
+          if (k1 == 0 && !acc_ok) acc_ok = mbar_try_wait(&t_empty[a1], aph1 ^ 1);
+          if ((k1 != 0 || acc_ok) && mbar_try_wait(&full[s1], ph1)) {
+            fence_after_sync();
+            const uint32_t a0 = tiles_u32 + s1 * p.stage_bytes;
+            const uint32_t b0 = p.res ? bres : a0 + p.rg * p.a_bytes;
+            const uint32_t d_tmem = tmem_base + a1 * p.acc_stride;
+            for (int rr = 0; rr < rows_u; ++rr) {
+              for (int ks = 0; ks < kst; ++ks) {
+                const uint64_t da = umma_desc_join(dhi, a0 + rr * p.a_bytes + ks * 32);
+                const uint64_t dbh = umma_desc_join(dhi, b0 + rr * b_row + ks * 32);
+                const uint64_t dbl = umma_desc_join(dhi, b0 + lo_off + rr * b_row + ks * 32);
+                if ((k1 | rr | ks) == 0) mma_tf32_c<false>(d_tmem, da, dbh, idesc);
+                else mma_tf32_c<true>(d_tmem, da, dbh, idesc);
+                mma_tf32_c<true>(d_tmem, da, dbl, idesc);
+              }
+            }
+            mma_commit(&hi_done[s1]);
+            ++u1;
+            if (++s1 == p.stages) { s1 = 0; ph1 ^= 1; }
+            if (++k1 == upt) { k1 = 0; acc_ok = false; if (++a1 == p.nacc) { a1 = 0; aph1 ^= 1; } }
+          }
+        }
+        if (u2 < u1 && mbar_try_wait(&lo_ready[s2], ph2)) {
+          fence_after_sync();
+          const uint32_t a0 = tiles_u32 + s2 * p.stage_bytes;
+          const uint32_t b0 = p.res ? bres : a0 + p.rg * p.a_bytes;
+          const uint32_t d_tmem = tmem_base + a2 * p.acc_stride;
+          for (int rr = 0; rr < rows_u; ++rr) {
+            for (int ks = 0; ks < kst; ++ks) {
+              const uint64_t da = umma_desc_join(dhi, a0 + rr * p.a_bytes + ks * 32);
+              const uint64_t dbh = umma_desc_join(dhi, b0 + rr * b_row + ks * 32);
+              mma_tf32_c<true>(d_tmem, da, dbh, idesc);
+            }
+          }
+          mma_commit(&empty[s2]);
+          ++u2;
+          if (++s2 == p.stages) { s2 = 0; ph2 ^= 1; }
+          if (++k2 == upt) { k2 = 0; mma_commit(&t_full[a2]); if (++a2 == p.nacc) a2 = 0; }
+        }
+      }
+    }
+    if (!X3 && p.res && t_begin < t_end) {
       // Small layers are bound by the instruction stream of this single issuing thread: everything that does
       // not change inside a group of tiles is hoisted, descriptors are (constant high word | address), and the
       // MMAs of up to four tiles are interleaved (independent accumulators back to back).
@@ -391,7 +487,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         CT_TRACE(1, 3);
       }
     }
-    for (int t = t_begin; !p.res && t < t_end; ++t) {
+    for (int t = t_begin; !X3 && !p.res && t < t_end; ++t) {
       const int i = t - t_begin, acc = i % p.nacc, acc_phase = (i / p.nacc) & 1;
       mbar_wait(&t_empty[acc], acc_phase ^ 1);
       CT_TRACE(1, 1);
@@ -419,6 +515,21 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         if (++stage == p.stages) { stage = 0; phase ^= 1; }
       }
       mma_commit(&t_full[acc]);
+    }
+  } else if (X3 && (warp == 3 || warp >= 12)) {
+    // ===================== operand splitters (X3): stage by stage, in the producer's order
+    const int tid_c = (warp == 3 ? 0 : warp - 11) * 32 + lane;
+    const int upt = p.res ? 1 : (3 / p.rg) * p.kblocks;
+    const int U = max(0, t_end - t_begin) * upt;
+    const int bytes = (p.res ? 3 : p.rg) * p.a_bytes;
+    int stage = 0, phase = 0;
+    for (int u = 0; u < U; ++u) {
+      mbar_wait(&full[stage], phase);              // (the TMA writes of this stage are visible to this thread)
+      mbar_wait(&hi_done[stage], phase);           // pass-1 MMAs have finished reading the raw tile
+      split_lo_inplace(tiles + (size_t)stage * p.stage_bytes, bytes, tid_c, CT_NCONV);
+      fence_proxy_async();                         // generic-proxy writes -> visible to the tensor core
+      mbar_arrive(&lo_ready[stage]);
+      if (++stage == p.stages) { stage = 0; phase ^= 1; }
     }
   } else if (warp >= 4) {
     // ===================== epilogue: two groups of 4 warps; a warp owns one TMEM lane quarter
@@ -617,8 +728,11 @@ struct TrEntry { long long off; int taps, cin, cout; };
 constexpr int TR_MAX = 160;
 struct TrTable { TrEntry e[TR_MAX]; int n; };
 
+// PL / PTL (both or neither): the low parts w - tf32_trunc(w) in the HWIO and the transposed order (error-compensated
+// mode: B_lo operands of the backward-data and the forward kernel)
 __global__ void __launch_bounds__(256)
-transpose_filters_kernel(const float* __restrict__ P, float* __restrict__ PT, const __grid_constant__ TrTable tab) {
+transpose_filters_kernel(const float* __restrict__ P, float* __restrict__ PT, float* __restrict__ PL, float* __restrict__ PTL,
+                         const __grid_constant__ TrTable tab) {
   pdl_grid_sync();
   for (int li = blockIdx.y; li < tab.n; li += gridDim.y) {
     const TrEntry e = tab.e[li];
@@ -629,7 +743,10 @@ transpose_filters_kernel(const float* __restrict__ P, float* __restrict__ PT, co
       long long t2 = i / e.cin;
       int co = (int)(t2 % e.cout);
       int tap = (int)(t2 / e.cout);
-      PT[e.off + i] = P[e.off + ((long long)tap * e.cin + ci) * e.cout + co];
+      const long long src = e.off + ((long long)tap * e.cin + ci) * e.cout + co;
+      const float v = P[src];
+      PT[e.off + i] = v;
+      if (PTL) { const float l = tf32_lo(v); PTL[e.off + i] = l; PL[src] = l; }
     }
   }
 }
@@ -655,7 +772,7 @@ static int pick_bn(int Nc) {
   return 16;
 }
 
-size_t conv_wgrad_tc_smem(const se_conv_desc* d, int* tmem_cols);   // conv_wgrad_tc.cu
+size_t conv_wgrad_tc_smem(const se_conv_desc* d, int* tmem_cols, int x3);   // conv_wgrad_tc.cu
 constexpr int WG_COOP_SMEM_MAX = 116 * 1024;
 
 struct ConvTcBn {            // fused BatchNorm arguments of conv_tc_launch (null = plain convolution)
@@ -665,8 +782,10 @@ struct ConvTcBn {            // fused BatchNorm arguments of conv_tc_launch (nul
 
 static int conv_tc_launch(const se_conv_desc* d, const float* a_tensor, int Kc, const float* bmat, int Nc, int flip,
                           const float* bias, const float* residual, float* out, int relu, float beta, double* stats,
-                          cudaStream_t st, const ConvTcBn* bn = nullptr) {
+                          cudaStream_t st, const ConvTcBn* bn = nullptr, const float* bmat_lo = nullptr) {
   ConvTcParams p;
+  const int x3 = bmat_lo ? 1 : 0;       // error-compensated mode: bmat_lo = the low parts of bmat (se_split_filters)
+  if (x3 && bn) return SE_ERR_UNSUPPORTED;
   p.bn = 0; p.bn_relu = 0; p.bn_eps = 0.f; p.bn_momentum = 0.f;
   p.bn_gamma = p.bn_beta = p.bn_res = nullptr;
   p.bn_moving_mean = p.bn_moving_var = p.bn_save_mean = p.bn_save_invstd = p.bn_out = nullptr;
@@ -699,7 +818,7 @@ static int conv_tc_launch(const se_conv_desc* d, const float* a_tensor, int Kc, 
   static const bool no_coop = getenv("SE_NO_SIDE_STREAM") != nullptr;
   if (flip && !no_coop) {
     int wg_cols = 0;
-    const size_t wg = conv_wgrad_tc_smem(d, &wg_cols);
+    const size_t wg = conv_wgrad_tc_smem(d, &wg_cols, x3);
     if (wg > 0 && wg <= (size_t)WG_COOP_SMEM_MAX && wg_cols <= 256) {
       if (pick_bn(Nc) == 16) p.stage_out = 2048;          // one sub-buffer per warp buys the input pipeline a stage
       budget = 225 * 1024 - (int)wg - 2048 - 8 * p.stage_out;
@@ -709,10 +828,10 @@ static int conv_tc_launch(const se_conv_desc* d, const float* a_tensor, int Kc, 
   const int full_budget = CT_SMEM_BUDGET;
  retry:
   p.rg = 3;
-  p.stage_bytes = 3 * p.a_bytes + ceil_div(9 * p.BN * p.cblk * 4, 1024) * 1024;
+  p.stage_bytes = 3 * p.a_bytes + (1 + x3) * ceil_div(9 * p.BN * p.cblk * 4, 1024) * 1024;
   if (2 * p.stage_bytes > budget) {
     p.rg = 1;
-    p.stage_bytes = p.a_bytes + ceil_div(3 * p.BN * p.cblk * 4, 1024) * 1024;
+    p.stage_bytes = p.a_bytes + (1 + x3) * ceil_div(3 * p.BN * p.cblk * 4, 1024) * 1024;
   }
   p.stages = min(CT_MAX_STAGES, budget / p.stage_bytes);
   if (p.stages < 2) {
@@ -720,14 +839,15 @@ static int conv_tc_launch(const se_conv_desc* d, const float* a_tensor, int Kc, 
     return SE_ERR_UNSUPPORTED;
   }
   // resident-weights mode: every tile of the CTA uses the same 9*BN x Kc weight block
-  p.res = 0; p.res_b_bytes = 0; p.nt = 1;
+  p.res = 0; p.res_b_bytes = 0; p.res_bl_off = 0; p.nt = 1;
   static const char* dbg_nores = getenv("SE_CT_NORES");
-  const int wbytes = ceil_div(9 * p.BN * Kc * 4, 1024) * 1024;
-  if (!dbg_nores && p.tiles_n == 1 && p.kblocks == 1 && wbytes <= 40 * 1024) {
-    p.res = 1; p.res_b_bytes = wbytes; p.rg = 3;
+  const int wbytes = (1 + x3) * ceil_div(9 * p.BN * Kc * 4, 1024) * 1024;
+  if (!dbg_nores && p.tiles_n == 1 && p.kblocks == 1 && wbytes <= (1 + x3) * 40 * 1024 &&
+      ((budget - wbytes) / (3 * p.a_bytes) >= 2 || budget != full_budget)) {
+    p.res = 1; p.res_b_bytes = wbytes; p.res_bl_off = wbytes / 2; p.rg = 3;
     p.stage_bytes = 3 * p.a_bytes;
     p.stages = min(CT_MAX_STAGES, (budget - wbytes) / p.stage_bytes);
-    if (p.stages < 2 && budget != full_budget) { budget = full_budget; tmem_budget = 512; p.stage_out = CT_STAGE_OUT; goto retry; }
+    if (p.stages < 2) { budget = full_budget; tmem_budget = 512; p.stage_out = CT_STAGE_OUT; goto retry; }
     static const char* dbg_nt = getenv("SE_CT_NT");
     p.nt = dbg_nt ? atoi(dbg_nt) : 2;   // measured: 2 beats 4 (first epilogue starts earlier) and 1 (MMA bubbles)
     p.nt = max(1, min(min(p.nt, 4), p.stages - 1));
@@ -765,7 +885,7 @@ static int conv_tc_launch(const se_conv_desc* d, const float* a_tensor, int Kc, 
   if (stats && (size_t)16 * Nc * sizeof(float) > 24 * 1024) return SE_ERR_UNSUPPORTED;
   if (beta != 0.f && (beta != 1.f || residual || relu)) return SE_ERR_UNSUPPORTED;   // accumulate = bulk reduce-add of the raw result
 
-  CUtensorMap ma, mb;
+  CUtensorMap ma, mb, mbl;
   {
     uint64_t dims[4] = {(uint64_t)Kc, (uint64_t)d->W, (uint64_t)d->H, (uint64_t)d->N};
     uint64_t strides[3] = {(uint64_t)Kc * 4, (uint64_t)d->W * Kc * 4, (uint64_t)d->H * d->W * Kc * 4};
@@ -776,6 +896,9 @@ static int conv_tc_launch(const se_conv_desc* d, const float* a_tensor, int Kc, 
     uint64_t bstrides[1] = {(uint64_t)Kc * 4};
     uint32_t bbox[2] = {(uint32_t)p.cblk, (uint32_t)(p.b_merged ? 3 * p.BN : p.BN)};
     if (!make_tmap(&mb, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(bmat), bdims, bstrides, bbox, sw)) return SE_ERR_CUDA;
+    mbl = mb;
+    if (x3 && !make_tmap(&mbl, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(bmat_lo), bdims, bstrides, bbox, sw))
+      return SE_ERR_CUDA;
   }
   CUtensorMap mo, mz;
   {
@@ -788,15 +911,17 @@ static int conv_tc_launch(const se_conv_desc* d, const float* a_tensor, int Kc, 
     if (bn && !make_tmap(&mz, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, bn->out, odims, ostrides, obox, CU_TENSOR_MAP_SWIZZLE_64B))
       return SE_ERR_CUDA;
   }
-  const size_t smem = (size_t)p.res_b_bytes + (size_t)p.stages * p.stage_bytes + 8 * p.stage_out + (2 * CT_MAX_STAGES + 2 * CT_MAX_ACC + 4) * 8 + Nc * 4 + (stats ? 16 * Nc * 4 : 0) + (bn ? 2 * Nc * 4 : 0) + 1024 + 64;
+  const size_t smem = (size_t)p.res_b_bytes + (size_t)p.stages * p.stage_bytes + 8 * p.stage_out + (4 * CT_MAX_STAGES + 2 * CT_MAX_ACC + 4) * 8 + Nc * 4 + (stats ? 16 * Nc * 4 : 0) + (bn ? 2 * Nc * 4 : 0) + 1024 + 64;
   if (smem > 227 * 1024) return SE_ERR_UNSUPPORTED;
   int grid = min(sm_count(), p.tiles_m * p.tiles_n);
-  launch(conv_tc_kernel, dim3(grid), dim3(CT_THREADS), smem, st, ma, mb, mo, mz, p);
+  if (x3) launch(conv_tc_kernel<1>, dim3(grid), dim3(CT_THREADS_X3), smem, st, ma, mb, mbl, mo, mz, p);
+  else launch(conv_tc_kernel<0>, dim3(grid), dim3(CT_THREADS), smem, st, ma, mb, mbl, mo, mz, p);
   return check_launch("conv_tc_kernel");
 }
 
 int init_conv_tc() {
-  if (cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) {
+  if (cudaFuncSetAttribute(conv_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess ||
+      cudaFuncSetAttribute(conv_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) {
     set_error("init_conv_tc: cannot raise the shared-memory limit");
     return SE_ERR_CUDA;
   }
@@ -810,12 +935,13 @@ static int ensure_init() {
 }
 
 // forward needs the transposed kernel copy w_t = [tap][co][ci]; without it the caller falls back to the fp32 kernels
-int conv_fwd_tc(const se_conv_desc* d, const float* x, const float* w_t, const float* bias, const float* residual, float* y,
-                int relu, double* stats, cudaStream_t st) {
+// w_t_lo != null selects the error-compensated arithmetic (w_t_lo = low parts of w_t, se_split_filters)
+int conv_fwd_tc(const se_conv_desc* d, const float* x, const float* w_t, const float* w_t_lo, const float* bias,
+                const float* residual, float* y, int relu, double* stats, cudaStream_t st) {
   if (!w_t || !tc_shape_ok(d, d->Cin, d->Cout)) return SE_ERR_UNSUPPORTED;
   int rc = ensure_init();
   if (rc) return rc;
-  return conv_tc_launch(d, x, d->Cin, w_t, d->Cout, 0, bias, residual, y, relu, 0.f, stats, st);
+  return conv_tc_launch(d, x, d->Cin, w_t, d->Cout, 0, bias, residual, y, relu, 0.f, stats, st, nullptr, w_t_lo);
 }
 
 // convolution + training-mode BatchNorm (+ same-shape residual, + ReLU) in one launch; y receives the convolution
@@ -834,15 +960,16 @@ int conv_bn_fwd_tc(const se_conv_desc* d, const float* x, const float* w_t, cons
   return conv_tc_launch(d, x, d->Cin, w_t, d->Cout, 0, bias, nullptr, y, relu, 0.f, stats, st, &bn);
 }
 
-int conv_dgrad_tc(const se_conv_desc* d, const float* dy, const float* w, float* dx, float beta, cudaStream_t st) {
+int conv_dgrad_tc(const se_conv_desc* d, const float* dy, const float* w, const float* w_lo, float* dx, float beta,
+                  cudaStream_t st) {
   if (!tc_shape_ok(d, d->Cout, d->Cin)) return SE_ERR_UNSUPPORTED;
   int rc = ensure_init();
   if (rc) return rc;
-  return conv_tc_launch(d, dy, d->Cout, w, d->Cin, 1, nullptr, nullptr, dx, 0, beta, nullptr, st);
+  return conv_tc_launch(d, dy, d->Cout, w, d->Cin, 1, nullptr, nullptr, dx, 0, beta, nullptr, st, nullptr, w_lo);
 }
 
 
-int transpose_filters(const float* P, float* PT, const long long* table, int n, cudaStream_t st) {
+int transpose_filters(const float* P, float* PT, float* PL, float* PTL, const long long* table, int n, cudaStream_t st) {
   for (int base = 0; base < n; base += TR_MAX) {
     TrTable tab;
     tab.n = min(TR_MAX, n - base);
@@ -854,7 +981,7 @@ int transpose_filters(const float* P, float* PT, const long long* table, int n, 
     }
     long long gx = ceil_div<long long>(maxtot, 256);
     dim3 grid((unsigned)(gx < 64 ? gx : 64), (unsigned)tab.n);
-    launch(transpose_filters_kernel, dim3(grid), dim3(256), 0, st, P, PT, tab);
+    launch(transpose_filters_kernel, dim3(grid), dim3(256), 0, st, P, PT, PL, PTL, tab);
     int rc = check_launch("transpose_filters_kernel");
     if (rc) return rc;
   }

@@ -44,6 +44,14 @@ struct WgTcParams {
   float* dbias;
 };
 
+__device__ __forceinline__ float wg_tf32_lo(float x) { return x - __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
+
+// X3 = error-compensated arithmetic (see conv_tc.cu): dW = X_hi*dY_hi + X_hi*dY_lo + X_lo*dY_hi in one fp32 accumulator.
+// hi is what kind::tf32 reads of the raw tile (mantissa truncated to 10 bits); the epilogue warps, idle until the last
+// tile, produce the lo parts: warp 2 writes dY_lo into a second (small) dY buffer of the stage as soon as the tile has
+// landed, warps 3-5 rewrite the three X buffers IN PLACE as X_lo once pass 1 (X*dY_hi, X*dY_lo) has read them, then
+// pass 2 issues X_lo*dY_hi.  The MMA warp runs the passes as two cursors over the stage sequence.
+template <int X3>
 __global__ void __launch_bounds__(192, 1)
 conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_dy, WgTcParams p) {
   pdl_trigger();
@@ -56,6 +64,9 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
   uint64_t* empty = bars + 4;
   uint64_t* done = bars + 8;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
+  uint64_t* ylo_ready = bars + 10;          // X3: dY_lo of the stage written
+  uint64_t* hi_done = bars + 14;            // X3: pass-1 MMAs have read the stage
+  uint64_t* lo_ready = bars + 18;           // X3: the X buffers of the stage hold X_lo
 
   const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
   const int per_cta = (p.tiles_m + gridDim.x - 1) / gridDim.x;
@@ -75,6 +86,7 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
     prefetch_tmap(&map_x); prefetch_tmap(&map_dy);
     for (int s = 0; s < p.stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
     mbar_init(done, 1);
+    if (X3) for (int s = 0; s < p.stages; ++s) { mbar_init(&ylo_ready[s], 32); mbar_init(&hi_done[s], 1); mbar_init(&lo_ready[s], 96); }
     fence_barrier_init();
   }
   fence_proxy_async();                      // generic-proxy writes of the ones tile -> visible to the tensor core
@@ -119,7 +131,74 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
       const int ksteps = (p.debug & 4) ? 0 : p.PT / 8;
       int stage = 0, phase = 0;
       uint32_t acc = 0;
-      for (int t = t_begin; t < t_end; ++t) {
+      if (X3) {
+        const int T = t_end - t_begin;
+        int u1 = 0, s1 = 0, ph1 = 0, u2 = 0, s2 = 0, ph2 = 0;
+        while (u2 < T) {
+          int ok1 = 0;
+          if (u1 < T) ok1 = mbar_try_wait(&full[s1], ph1) && mbar_try_wait(&ylo_ready[s1], ph1);
+          ok1 = __shfl_sync(0xffffffffu, ok1, 0);          // one decision for the warp (elect_one needs convergence)
+          if (ok1) {
+            fence_after_sync();
+            const uint32_t sb = tiles_u32 + (uint32_t)s1 * p.stage_bytes;
+            const uint32_t dyb = sb + 3 * p.xbuf_bytes, dyl = dyb + p.dy_bytes;
+            uint32_t img_off = 0, rem = 0;
+            for (int ks = 0; ks < ksteps; ++ks) {
+              const uint64_t db = ((uint64_t)hi << 32) | (uint64_t)((((dyb + ks * 1024) & 0x3FFFFu) >> 4) | lbo_b);
+              const uint64_t dl = ((uint64_t)hi << 32) | (uint64_t)((((dyl + ks * 1024) & 0x3FFFFu) >> 4) | lbo_b);
+              const uint32_t a0 = sb + img_off + rem * 128;
+              if (elect_one()) {
+#pragma unroll
+                for (int s = 0; s < 3; ++s) {
+                  const uint64_t da = ((uint64_t)hi << 32) | (uint64_t)((((a0 + s * p.xbuf_bytes) & 0x3FFFFu) >> 4) | lbo_a);
+                  mma_tf32(tmem_base + s * p.ncols, da, db, idesc, acc);
+                  mma_tf32(tmem_base + s * p.ncols, da, dl, idesc, 1);
+                }
+                if (p.G == 4) {
+                  mma_tf32(tmem_base + 3 * p.ncols, ((uint64_t)hi << 32) | (uint64_t)ones_lo, db, idesc, acc);
+                  mma_tf32(tmem_base + 3 * p.ncols, ((uint64_t)hi << 32) | (uint64_t)ones_lo, dl, idesc, 1);
+                }
+              }
+              __syncwarp();
+              acc = 1;
+              rem += 8;
+              if ((int)rem == p.img_px) { rem = 0; img_off += p.img_stride; }
+            }
+            if (elect_one()) mma_commit(&hi_done[s1]);
+            __syncwarp();
+            ++u1;
+            if (++s1 == p.stages) { s1 = 0; ph1 ^= 1; }
+          }
+          int ok2 = 0;
+          if (u2 < u1) ok2 = mbar_try_wait(&lo_ready[s2], ph2);
+          ok2 = __shfl_sync(0xffffffffu, ok2, 0);
+          if (ok2) {
+            fence_after_sync();
+            const uint32_t sb = tiles_u32 + (uint32_t)s2 * p.stage_bytes;
+            const uint32_t dyb = sb + 3 * p.xbuf_bytes;
+            uint32_t img_off = 0, rem = 0;
+            for (int ks = 0; ks < ksteps; ++ks) {
+              const uint64_t db = ((uint64_t)hi << 32) | (uint64_t)((((dyb + ks * 1024) & 0x3FFFFu) >> 4) | lbo_b);
+              const uint32_t a0 = sb + img_off + rem * 128;
+              if (elect_one()) {
+#pragma unroll
+                for (int s = 0; s < 3; ++s) {
+                  const uint64_t da = ((uint64_t)hi << 32) | (uint64_t)((((a0 + s * p.xbuf_bytes) & 0x3FFFFu) >> 4) | lbo_a);
+                  mma_tf32(tmem_base + s * p.ncols, da, db, idesc, 1);
+                }
+              }
+              __syncwarp();
+              rem += 8;
+              if ((int)rem == p.img_px) { rem = 0; img_off += p.img_stride; }
+            }
+            if (elect_one()) mma_commit(&empty[s2]);
+            __syncwarp();
+            ++u2;
+            if (++s2 == p.stages) { s2 = 0; ph2 ^= 1; }
+          }
+        }
+      }
+      for (int t = t_begin; !X3 && t < t_end; ++t) {
         mbar_wait(&full[stage], phase);
         fence_after_sync();
         const uint32_t sb = tiles_u32 + (uint32_t)stage * p.stage_bytes;
@@ -150,6 +229,40 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
     } else {
       // ===================== epilogue: TMEM -> reductions into dW / dbias (4 warps, one lane quarter each)
       const int q4 = warp & 3;                              // TMEM lane quarter == vertical tap r (quarter 3: bias row)
+      if (X3) {
+        // operand splitters until the last tile has been issued (then these warps run the epilogue as usual)
+        int stage = 0, phase = 0;
+        for (int t = t_begin; t < t_end; ++t) {
+          uint8_t* sb = tiles + (size_t)stage * p.stage_bytes;
+          mbar_wait(&full[stage], phase);
+          if (warp == 2) {
+            const float4* src = reinterpret_cast<const float4*>(sb + 3 * p.xbuf_bytes);
+            float4* dst = reinterpret_cast<float4*>(sb + 3 * p.xbuf_bytes + p.dy_bytes);
+            const int n = p.dy_bytes >> 4;
+#pragma unroll 4
+            for (int i = lane; i < n; i += 32) {
+              float4 v = src[i];
+              v.x = wg_tf32_lo(v.x); v.y = wg_tf32_lo(v.y); v.z = wg_tf32_lo(v.z); v.w = wg_tf32_lo(v.w);
+              dst[i] = v;
+            }
+            fence_proxy_async();
+            mbar_arrive(&ylo_ready[stage]);
+          } else {
+            mbar_wait(&hi_done[stage], phase);
+            float4* q = reinterpret_cast<float4*>(sb);
+            const int n = (3 * p.xbuf_bytes) >> 4;
+#pragma unroll 4
+            for (int i = (warp - 3) * 32 + lane; i < n; i += 96) {
+              float4 v = q[i];
+              v.x = wg_tf32_lo(v.x); v.y = wg_tf32_lo(v.y); v.z = wg_tf32_lo(v.z); v.w = wg_tf32_lo(v.w);
+              q[i] = v;
+            }
+            fence_proxy_async();
+            mbar_arrive(&lo_ready[stage]);
+          }
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        }
+      }
       if (q4 < 3 || p.G == 4) {
         mbar_wait(done, 0);
         fence_after_sync();
@@ -191,7 +304,8 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
 }
 
 int init_conv_wgrad_tc() {
-  if (cudaFuncSetAttribute(conv_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) {
+  if (cudaFuncSetAttribute(conv_wgrad_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess ||
+      cudaFuncSetAttribute(conv_wgrad_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) {
     set_error("init_conv_wgrad_tc: cannot raise the shared-memory limit");
     return SE_ERR_CUDA;
   }
@@ -204,7 +318,7 @@ int init_conv_wgrad_tc() {
 // dgrad kernel to the rest (conv_wgrad_tc_smem() is what it asks).
 constexpr int WG_COOP_SMEM = 116 * 1024;
 
-static int plan_wgrad(const se_conv_desc* d, bool with_bias, WgTcParams* pp, size_t* smem_out) {
+static int plan_wgrad(const se_conv_desc* d, bool with_bias, int x3, WgTcParams* pp, size_t* smem_out) {
   if (d->kh != 3 || d->kw != 3 || d->stride != 1 || d->pad_t != 1 || d->pad_l != 1 || d->Ho != d->H || d->Wo != d->W)
     return SE_ERR_UNSUPPORTED;
   const int Cin = d->Cin, Cout = d->Cout, W = d->W, H = d->H;
@@ -225,8 +339,8 @@ static int plan_wgrad(const se_conv_desc* d, bool with_bias, WgTcParams* pp, siz
   p.nnb = ceil_div(ceil_div(Cout, gz), 32);
   p.ncols = 32 * p.nnb;
   p.dy_bytes = p.PT * 128 * p.nnb;
-  p.stage_bytes = ceil_div(3 * p.xbuf_bytes + p.dy_bytes, 1024) * 1024;
-  const int fixed = (with_bias ? 1024 : 0) + 16 * 8 + 1024 + 64;
+  p.stage_bytes = ceil_div(3 * p.xbuf_bytes + (1 + x3) * p.dy_bytes, 1024) * 1024;
+  const int fixed = (with_bias ? 1024 : 0) + 24 * 8 + 1024 + 64;
   if (2 * p.stage_bytes + fixed <= WG_COOP_SMEM) p.stages = 2;
   else p.stages = min(4, (200 * 1024) / p.stage_bytes);
   if (p.stages < 1) return SE_ERR_UNSUPPORTED;
@@ -236,22 +350,22 @@ static int plan_wgrad(const se_conv_desc* d, bool with_bias, WgTcParams* pp, siz
 }
 
 // dynamic shared memory the wgrad kernel of this layer will take, and its TMEM columns (0 when it cannot run)
-size_t conv_wgrad_tc_smem(const se_conv_desc* d, int* tmem_cols) {
+size_t conv_wgrad_tc_smem(const se_conv_desc* d, int* tmem_cols, int x3) {
   WgTcParams p;
   size_t smem = 0;
-  if (plan_wgrad(d, true, &p, &smem) != SE_OK) return 0;
+  if (plan_wgrad(d, true, x3, &p, &smem) != SE_OK) return 0;
   int cols = 32;
   while (cols < p.G * p.ncols) cols <<= 1;
   if (tmem_cols) *tmem_cols = cols;
   return smem;
 }
 
-int conv_wgrad_tc(const se_conv_desc* d, const float* x, const float* dy, float* dw, float* dbias, cudaStream_t st) {
+int conv_wgrad_tc(const se_conv_desc* d, const float* x, const float* dy, float* dw, float* dbias, int x3, cudaStream_t st) {
   if ((reinterpret_cast<uintptr_t>(dw) & 15) != 0 || (dbias && (reinterpret_cast<uintptr_t>(dbias) & 15) != 0))
     return SE_ERR_UNSUPPORTED;
   WgTcParams p;
   size_t smem = 0;
-  int rc = plan_wgrad(d, dbias != nullptr, &p, &smem);
+  int rc = plan_wgrad(d, dbias != nullptr, x3, &p, &smem);
   if (rc != SE_OK) return rc;
   static bool inited = false;
   if (!inited) { rc = init_conv_wgrad_tc(); if (rc) return rc; inited = true; }
@@ -278,7 +392,8 @@ int conv_wgrad_tc(const se_conv_desc* d, const float* x, const float* dy, float*
   }
   const int gy = ceil_div(Cin, 32);
   const int gx = max(1, min(p.tiles_m, sm_count() / (gy * gz)));
-  launch(conv_wgrad_tc_kernel, dim3(gx, gy, gz), dim3(192), smem, st, mx, mdy, p);
+  if (x3) launch(conv_wgrad_tc_kernel<1>, dim3(gx, gy, gz), dim3(192), smem, st, mx, mdy, p);
+  else launch(conv_wgrad_tc_kernel<0>, dim3(gx, gy, gz), dim3(192), smem, st, mx, mdy, p);
   return check_launch("conv_wgrad_tc_kernel");
 }
 

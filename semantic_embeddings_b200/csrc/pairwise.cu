@@ -97,7 +97,7 @@ using namespace se;
 
 extern "C" int64_t se_pairwise_workspace_bytes(int N, int D, int mode) {
   long long f = 2LL * N;
-  if (mode == SE_MODE_TF32) f += pairwise_tc_workspace_floats(N, D);
+  if (mode != SE_MODE_F32) f += pairwise_tc_workspace_floats(N, D);
   return (f + 64) * (long long)sizeof(float);
 }
 
@@ -113,7 +113,7 @@ extern "C" int se_pairwise_dist(const float* F, int ldF, int N, int D, int row0,
   launch(pairwise_prep_kernel, dim3(ceil_div(N, 8)), dim3(256), 0, st, F, ldF, N, D, normalize, sq, invn);
   int rc = check_launch("pairwise_prep_kernel");
   if (rc) return rc;
-  if (mode == SE_MODE_TF32) {
+  if (mode != SE_MODE_F32) {   // SE_MODE_TF32 and SE_MODE_TF32X3: the tensor path is the error-compensated split-fp16 kernel
     rc = pairwise_tc(F, ldF, N, D, row0, rows, pdist_mode, normalize, out, ldout, ws, st);
     if (rc != SE_ERR_UNSUPPORTED) return rc;   // shapes the tensor path does not cover use the fp32 tiles
   }

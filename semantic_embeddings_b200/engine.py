@@ -117,7 +117,11 @@ class Engine:
         self.G = torch.zeros(off, **f32)
         self.V = torch.zeros(off, **f32)
         # K-major ([tap][co][ci]) copies of the conv kernels for the tcgen05 forward path, refreshed once per step
-        self.PT = torch.zeros(off, **f32) if self.mode == _lib.SE_MODE_TF32 else None
+        tc = self.mode in (_lib.SE_MODE_TF32, _lib.SE_MODE_TF32X3)
+        self.PT = torch.zeros(off, **f32) if tc else None
+        # error-compensated mode: low parts (w - tf32_trunc(w)) of the kernels in the HWIO and the transposed order
+        self.PL = torch.zeros(off, **f32) if self.mode == _lib.SE_MODE_TF32X3 else None
+        self.PTL = torch.zeros(off, **f32) if self.mode == _lib.SE_MODE_TF32X3 else None
         convs = [n for n in self.nodes if n.op == 'conv']
         self.tr_table = (ctypes.c_int64 * (4 * max(1, len(convs))))()
         for k, n in enumerate(convs):
@@ -244,7 +248,8 @@ class Engine:
         nbytes = lambda t: t.numel() * t.element_size()
         fwd.append(self._op(_lib.OP_MEMSET, p=[self.stats, nbytes(self.stats)]))
         if self.PT is not None and self.n_tr:
-            tr = self._op(_lib.OP_TRANSPOSE_FILTERS, [self.n_tr], p=[self.P, self.PT, ctypes.addressof(self.tr_table)])
+            tr = self._op(_lib.OP_TRANSPOSE_FILTERS, [self.n_tr],
+                          p=[self.P, self.PT, ctypes.addressof(self.tr_table), self.PL, self.PTL])
             fwd.append(tr)
             inf.append(tr)
         scale = 1.0 / (self.B * self.world)
@@ -273,6 +278,7 @@ class Engine:
                     off, c = self.bn_slot[stats_by_conv[n.name].name]
                     st = self.stats[off:off + 2 * c]
                 Wt = self._pview(n.name + '/kernel', self.PT) if (self.PT is not None and n.op == 'conv') else None
+                Wtl = self._pview(n.name + '/kernel', self.PTL) if (self.PTL is not None and n.op == 'conv') else None
                 m = stats_by_conv.get(n.name)
                 if (m is not None and Wt is not None and res is None and self.fuse_conv_bn
                         and (not m.attrs['residual'] or (m.attrs['res_pool'] == 1 and m.attrs['res_pad_lo'] == 0
@@ -289,8 +295,8 @@ class Engine:
                          self.stats[off + 4 * c + 1:off + 4 * c + 2]]))
                     fused_bn.add(m.name)
                 else:
-                    fwd.append(self._op(_lib.OP_CONV_FWD, d + [relu], p=[A[n.inputs[0].name], W, b, res, out, st, Wt]))
-                inf.append(self._op(_lib.OP_CONV_FWD, d + [relu], p=[A[n.inputs[0].name], W, b, res, out, None, Wt]))
+                    fwd.append(self._op(_lib.OP_CONV_FWD, d + [relu], p=[A[n.inputs[0].name], W, b, res, out, st, Wt, Wtl]))
+                inf.append(self._op(_lib.OP_CONV_FWD, d + [relu], p=[A[n.inputs[0].name], W, b, res, out, None, Wt, Wtl]))
             elif n.op == 'bn':
                 x = n.inputs[0]
                 c = x.shape[-1]
@@ -392,7 +398,8 @@ class Engine:
                 bwd.append(self._op(_lib.OP_CONV_WGRAD, d, p=[A[x.name], dY, dW, db]))
                 dx, beta = gb(x)
                 if dx is not None:
-                    bwd.append(self._op(_lib.OP_CONV_DGRAD, d, [beta], [dY, W, dx]))
+                    Wl = self._pview(n.name + '/kernel', self.PL) if (self.PL is not None and n.op == 'conv') else None
+                    bwd.append(self._op(_lib.OP_CONV_DGRAD, d, [beta], [dY, W, dx, Wl]))
                 if n.attrs.get('residual'):
                     dr, br = gb(n.inputs[1])
                     bwd.append(self._op(_lib.OP_ADD_BWD, [0, dY.numel()], [br, 0.0], [dY, None, dr, None]))

@@ -103,6 +103,12 @@ STEP_CASES = [
     ('resnet-110-fc-cls', 'resnet-110-fc', 'cifar100', 8, 'inv_corr', 0.1, True),
     ('simple-mse', 'simple', 'cifar100', 6, 'mse', 0.0, False),
     ('wrn-28-10-cls', 'wrn-28-10', 'cifar100', 4, 'inv_corr', 0.1, False),
+    # the same gate in the arithmetic the training path runs and bench.py measures (SE_MODE_TF32X3: tcgen05 tiles with
+    # error compensation); the cases above run the fp32 FFMA kernels
+    ('simple-x3', 'simple', 'cifar100', 8, 'inv_corr', 0.0, False, 2),
+    ('resnet-110-fc-x3', 'resnet-110-fc', 'cifar100', 8, 'inv_corr', 0.0, False, 2),
+    ('resnet-110-fc-cls-x3', 'resnet-110-fc', 'cifar100', 8, 'inv_corr', 0.1, True, 2),
+    ('wrn-28-10-cls-x3', 'wrn-28-10', 'cifar100', 4, 'inv_corr', 0.1, False, 2),
 ]
 
 
@@ -180,7 +186,8 @@ def test_two_training_steps_match_oracle(case):
     from oracle import train as otrain
     from semantic_embeddings_b200 import utils
     from semantic_embeddings_b200.engine import Engine
-    tag, arch, key, B, loss, cls_weight, nesterov = case
+    tag, arch, key, B, loss, cls_weight, nesterov = case[:7]
+    mode = case[7] if len(case) > 7 else 0
     emb = class_matrix(key) if key else np.eye(64)
     C, D = emb.shape
     om = omodels.build_network(D, arch, input_channels=3, seed=21)
@@ -191,7 +198,7 @@ def test_two_training_steps_match_oracle(case):
         omodels.randomize(cls.params, seed=24)
     graph = utils.build_network(D, arch, input_channels=3)
     eng = Engine(graph, B, emb, loss=loss, cls_weight=cls_weight, num_classes=C, nesterov=nesterov, clipnorm=10.0,
-                 use_cuda_graph=(tag == 'resnet-110-fc'))
+                 mode=mode, use_cuda_graph=tag.startswith('resnet-110-fc'))
     vel = otrain.make_velocity(om, cls if cls_weight > 0 else None)
     emb_t = torch.as_tensor(emb.astype(np.float32)).double()
     g = torch.Generator().manual_seed(31)
@@ -250,7 +257,7 @@ def test_two_training_steps_match_oracle(case):
         vtot = float(np.sqrt(sum(float(v.norm()) ** 2 for v in vel.values())))
         e['velocity'] = max([rel_l2(ev[n], vel[n].numpy()) for n in vel if float(vel[n].norm()) > 1e-3 * vtot] or [0.0])
         errs[step] = e
-        report('train_step', case=tag, step=step, worst_grad_tensor=worst_name, **e)
+        report('train_step', case=tag, mode=mode, step=step, worst_grad_tensor=worst_name, **e)
     for step, e in errs.items():
         gtol = max(2e-3, 5 * e['grad_floor_f32_oracle'], 1.5 * e['relu_flip_quantum'])
         assert e['loss'] < 1e-4 and e['emb'] < 1e-4, (step, e)

@@ -72,7 +72,7 @@ CONV_CASES = [
 
 
 @pytest.mark.parametrize('case', CONV_CASES, ids=lambda c: 'x'.join(str(v) for v in c[:7]))
-@pytest.mark.parametrize('mode', [0, 1], ids=['f32', 'tf32'])
+@pytest.mark.parametrize('mode', [0, 1, 2], ids=['f32', 'tf32', 'tf32x3'])
 def test_conv_fwd_dgrad_wgrad(case, mode):
     from oracle import nn as onn
     from semantic_embeddings_b200.graph import same_pad
@@ -106,17 +106,34 @@ def test_conv_fwd_dgrad_wgrad(case, mode):
     tab = (ctypes.c_int64 * 4)(0, k * k, Cin, Cout)
     L.call('se_transpose_filters', L.ptr(wd), L.ptr(wtd), tab, 1, sptr())
     assert torch.equal(wtd.view(k * k, Cout, Cin), wd.view(k * k, Cin, Cout).transpose(1, 2))
-    L.call('se_conv2d_fwd_ex', d, L.ptr(xd), L.ptr(wd), L.ptr(wtd), L.ptr(bd), None, L.ptr(yd), 0, L.ptr(stats), mode, sptr())
-    tol = 2e-5 if mode == 0 else 4e-3       # tf32 inputs: 10-bit mantissa
+    aux = None
+    if mode == 2:
+        # error-compensated mode: low parts of the kernel (w - tf32_trunc(w)), both orders, from se_split_filters
+        wld, wtld = torch.empty_like(wd), torch.empty_like(wd)
+        L.call('se_split_filters', L.ptr(wd), L.ptr(wtd), L.ptr(wld), L.ptr(wtld), tab, 1, sptr())
+        lo = wd - (wd.view(torch.int32) & -8192).view(torch.float32)
+        assert torch.equal(wld, lo) and torch.equal(wtld.view(k * k, Cout, Cin), lo.view(k * k, Cin, Cout).transpose(1, 2))
+        aux = L.ConvAux(L.ptr(wtd), L.ptr(wtld), L.ptr(wld))
+        L.call('se_conv2d_fwd_aux', d, L.ptr(xd), L.ptr(wd), aux, L.ptr(bd), None, L.ptr(yd), 0, L.ptr(stats), mode, sptr())
+    else:
+        L.call('se_conv2d_fwd_ex', d, L.ptr(xd), L.ptr(wd), L.ptr(wtd), L.ptr(bd), None, L.ptr(yd), 0, L.ptr(stats), mode, sptr())
+    tol = 4e-3 if mode == 1 else 2e-5       # single-pass tf32 inputs: 10-bit mantissa; tf32x3 must be at fp32 level
     e_y = relerr(yd.cpu(), y.detach())
     ys = y.detach().reshape(-1, Cout)
     e_s = relerr(stats.cpu()[:Cout], ys.sum(0))
     e_q = relerr(stats.cpu()[Cout:], (ys ** 2).sum(0))
     dxd = torch.full((N, H, W, Cin), 7.0, device='cuda')
-    L.call('se_conv2d_dgrad', d, L.ptr(dyd), L.ptr(wd), L.ptr(dxd), 0.0, mode, sptr())
+
+    def dgrad(beta):
+        if aux is not None:
+            L.call('se_conv2d_dgrad_aux', d, L.ptr(dyd), L.ptr(wd), aux, L.ptr(dxd), beta, mode, sptr())
+        else:
+            L.call('se_conv2d_dgrad', d, L.ptr(dyd), L.ptr(wd), L.ptr(dxd), beta, mode, sptr())
+
+    dgrad(0.0)
     e_dx = relerr(dxd.cpu(), grads[0])
     # beta = 1 accumulates
-    L.call('se_conv2d_dgrad', d, L.ptr(dyd), L.ptr(wd), L.ptr(dxd), 1.0, mode, sptr())
+    dgrad(1.0)
     e_dx2 = relerr(dxd.cpu(), 2 * grads[0])
     dwd = torch.zeros(k, k, Cin, Cout, device='cuda')
     dbd = torch.zeros(Cout, device='cuda') if b is not None else None
@@ -126,6 +143,35 @@ def test_conv_fwd_dgrad_wgrad(case, mode):
     report('conv', case=str(case), mode=mode, y=e_y, sum=e_s, sumsq=e_q, dx=e_dx, dw=e_dw, db=e_db)
     assert e_y < tol and e_dx < tol and e_dx2 < tol and e_dw < tol and e_db < tol, (e_y, e_dx, e_dx2, e_dw, e_db)
     assert e_s < max(tol, 1e-4) and e_q < tol * 2, (e_s, e_q)
+
+
+def test_tf32_operands_are_truncated_by_the_tensor_core():
+    """The error-compensated mode (SE_MODE_TF32X3) rests on one hardware fact: kind::tf32 reads the upper 19 bits of an
+    fp32 operand word, i.e. TRUNCATES the mantissa to 10 bits (so hi = x & 0xffffe000 needs no conversion pass and
+    lo = x - hi is exact).  Single-pass SE_MODE_TF32 on full-precision inputs must therefore equal (to fp32
+    accumulation error) the float64 convolution of the truncated operands, and differ measurably from the convolution of
+    round-to-nearest operands."""
+    import ctypes
+    from oracle import nn as onn
+    L = _lib()
+    N, H, W, C = 4, 32, 32, 32
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(N, H, W, C, generator=g)
+    w = torch.randn(3, 3, C, C, generator=g) * 0.06
+    trunc = lambda t: (t.contiguous().view(torch.int32) & -8192).view(torch.float32)
+    rne = lambda t: ((t.contiguous().view(torch.int32) + 0x0FFF + ((t.contiguous().view(torch.int32) >> 13) & 1)) & -8192).view(torch.float32)
+    y_tr = onn.conv2d(trunc(x).double(), trunc(w).double(), None, 1, 'same')
+    y_rn = onn.conv2d(rne(x).double(), rne(w).double(), None, 1, 'same')
+    d = L.ConvDesc(N, H, W, C, C, 3, 3, 1, 1, 1, H, W)
+    xd, wd = dev(x), dev(w)
+    wtd = torch.empty_like(wd)
+    tab = (ctypes.c_int64 * 4)(0, 9, C, C)
+    L.call('se_transpose_filters', L.ptr(wd), L.ptr(wtd), tab, 1, sptr())
+    yd = torch.empty(N, H, W, C, device='cuda')
+    L.call('se_conv2d_fwd_ex', d, L.ptr(xd), L.ptr(wd), L.ptr(wtd), None, None, L.ptr(yd), 0, None, 1, sptr())
+    e_tr, e_rn = relerr(yd.cpu(), y_tr), relerr(yd.cpu(), y_rn)
+    report('tf32_truncation', vs_truncated=e_tr, vs_rounded=e_rn)
+    assert e_tr < 5e-6 and e_rn > 20 * e_tr, (e_tr, e_rn)
 
 
 def test_conv_epilogue_bias_relu_residual_stats():
