@@ -1,24 +1,30 @@
-"""Times one conv layer (fwd / dgrad / wgrad) in both arithmetic modes with CUDA events."""
+"""Times one conv layer (fwd / dgrad / wgrad) per arithmetic mode with CUDA events (50 launches replayed from a graph)."""
 import ctypes, json, os, sys
 import numpy as np, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from semantic_embeddings_b200 import _lib as L
 
-def bench(N, H, C, Co, reps=50):
+MODES = {'x3': 2, 'tc': 1, 'f32': 0}
+
+
+def bench(N, H, C, Co, reps=50, modes=('x3', 'tc')):
     L.load(); L.check(L.load().se_init())
     d = L.ConvDesc(N, H, H, C, Co, 3, 3, 1, 1, 1, H, H)
     x = torch.randn(N, H, H, C, device='cuda'); w = torch.randn(3, 3, C, Co, device='cuda') * 0.1
-    wt = torch.empty_like(w); y = torch.empty(N, H, H, Co, device='cuda'); dy = torch.randn_like(y); dx = torch.empty_like(x)
+    wt, wl, wtl = torch.empty_like(w), torch.empty_like(w), torch.empty_like(w)
+    y = torch.empty(N, H, H, Co, device='cuda'); dy = torch.randn_like(y); dx = torch.empty_like(x)
     dw = torch.zeros_like(w); db = torch.zeros(Co, device='cuda'); b = torch.zeros(Co, device='cuda')
     stats = torch.zeros(2 * Co, dtype=torch.float64, device='cuda')
     tab = (ctypes.c_int64 * 4)(0, 9, C, Co)
     sp = L.stream_ptr
-    L.call('se_transpose_filters', w.data_ptr(), wt.data_ptr(), tab, 1, sp())
+    L.call('se_split_filters', w.data_ptr(), wt.data_ptr(), wl.data_ptr(), wtl.data_ptr(), tab, 1, sp())
+    aux = L.ConvAux(wt.data_ptr(), wtl.data_ptr(), wl.data_ptr())
     out = {}
-    for mode in (1, 0):
+    for mname in modes:
+        mode = MODES[mname]
         fns = {
-            'fwd': lambda: L.call('se_conv2d_fwd_ex', d, x.data_ptr(), w.data_ptr(), wt.data_ptr(), b.data_ptr(), None, y.data_ptr(), 0, stats.data_ptr(), mode, sp()),
-            'dgrad': lambda: L.call('se_conv2d_dgrad', d, dy.data_ptr(), w.data_ptr(), dx.data_ptr(), 0.0, mode, sp()),
+            'fwd': lambda: L.call('se_conv2d_fwd_aux', d, x.data_ptr(), w.data_ptr(), aux, b.data_ptr(), None, y.data_ptr(), 0, stats.data_ptr(), mode, sp()),
+            'dgrad': lambda: L.call('se_conv2d_dgrad_aux', d, dy.data_ptr(), w.data_ptr(), aux, dx.data_ptr(), 0.0, mode, sp()),
             'wgrad': lambda: L.call('se_conv2d_wgrad', d, x.data_ptr(), dy.data_ptr(), dw.data_ptr(), db.data_ptr(), mode, sp()),
         }
         for name, fn in fns.items():
@@ -30,10 +36,11 @@ def bench(N, H, C, Co, reps=50):
             g.replay(); torch.cuda.synchronize()
             a, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record(); g.replay(); e.record(); torch.cuda.synchronize()
-            out['%s_%s' % (name, 'tc' if mode else 'f32')] = round(1000 * a.elapsed_time(e) / reps, 2)
+            out['%s_%s' % (name, mname)] = round(1000 * a.elapsed_time(e) / reps, 2)
     return out
+
 
 if __name__ == '__main__':
     shapes = [(128, 32, 16, 16), (128, 16, 32, 32), (128, 8, 64, 64), (64, 32, 160, 160)]
     for s in shapes:
-        print(json.dumps({'shape': s, 'env': {k: v for k, v in os.environ.items() if k.startswith('SE_CT')}, 'us': bench(*s)}))
+        print(json.dumps({'shape': s, 'env': {k: v for k, v in os.environ.items() if k.startswith('SE_')}, 'us': bench(*s)}))

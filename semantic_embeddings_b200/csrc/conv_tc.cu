@@ -79,17 +79,29 @@ struct ConvTcParams {
 };
 
 constexpr int CT_THREADS = 384;   // warp 0 TMA, warp 1 MMA, warp 2 TMEM alloc, warps 4-7 / 8-11 two epilogue groups
-constexpr int CT_THREADS_X3 = 448; // + warps 3, 12, 13: operand splitters of the error-compensated mode (see conv_tc_kernel)
-constexpr int CT_NCONV = 96;       // splitter threads
+constexpr int CT_THREADS_X3 = 416; // + warps 3 and 12: operand splitters of the error-compensated mode (see conv_tc_kernel);
+                                   // 13 warps x 128 registers leave room for the co-resident weight-gradient kernel
+constexpr int CT_NCONV = 64;       // splitter threads
 
 // x -> x - tf32_trunc(x): the part of an fp32 operand that kind::tf32 (which reads the upper 19 bits of the word,
 // i.e. truncates the mantissa to 10 bits) does not see.  Exact in fp32 (the difference has <= 13 significant bits).
 __device__ __forceinline__ float tf32_lo(float x) { return x - __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
+// bytes is a multiple of 8 * 16 * nthreads for every tile shape of this kernel except the smallest (handled by the tail)
 __device__ __forceinline__ void split_lo_inplace(uint8_t* base, int bytes, int tid, int nthreads) {
   float4* q = reinterpret_cast<float4*>(base);
   const int n = bytes >> 4;
-#pragma unroll 4
-  for (int i = tid; i < n; i += nthreads) {
+  int i = tid;
+  for (; i + 7 * nthreads < n; i += 8 * nthreads) {      // eight independent 16-byte loads in flight per thread
+    float4 v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = q[i + j * nthreads];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      v[j].x = tf32_lo(v[j].x); v[j].y = tf32_lo(v[j].y); v[j].z = tf32_lo(v[j].z); v[j].w = tf32_lo(v[j].w);
+      q[i + j * nthreads] = v[j];
+    }
+  }
+  for (; i < n; i += nthreads) {
     float4 v = q[i];
     v.x = tf32_lo(v.x); v.y = tf32_lo(v.y); v.z = tf32_lo(v.z); v.w = tf32_lo(v.w);
     q[i] = v;
@@ -243,7 +255,7 @@ __device__ __forceinline__ void conv_tc_epilogue_block(const ConvTcParams& p, co
 // A_lo*B_lo and the truncation of lo are ~2^-21 relative: fp32-level results from tensor-core tiles).  Weights: lo is
 // a second (resident or streamed) B tile written once per step by se_split_filters.  Activations: no second tile --
 // pass 1 issues A*B_hi and A*B_lo on the tile as TMA delivered it (the hardware truncation IS the hi part), the
-// splitter warps (3, 12, 13) then rewrite the tile IN PLACE as lo, and pass 2 issues A_lo*B_hi.  The MMA thread runs
+// splitter warps (3 and 12) then rewrite the tile IN PLACE as lo, and pass 2 issues A_lo*B_hi.  The MMA thread runs
 // the two passes as two cursors over the same stage sequence (whichever is ready goes next), so pass 1 of the next
 // tile overlaps the split of the previous one.
 template <int X3>
@@ -376,63 +388,47 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     int stage = 0, phase = 0, tr_n = 0;
     CT_TRACE(1, 0);
     if (X3 && t_begin < t_end) {
-      // ---- error-compensated issue loop.  A "unit" is one pipeline stage: a whole tile (resident weights) or one
-      // (filter-row group, channel block) of a tile.  Cursor 1 issues pass 1 of unit u1 (A*B_hi, A*B_lo on the raw tile),
-      // cursor 2 pass 2 of unit u2 <= u1 (A_lo*B_hi after the splitters rewrote the tile); ready work goes first.
+      // ---- error-compensated mode, pass 1 (A*B_hi, A*B_lo on the tile as TMA delivered it).  A "unit" is one pipeline
+      // stage: a whole tile (resident weights) or one (filter-row group, channel block) of a tile.  Pass 2 (A_lo*B_hi
+      // once the splitters have rewritten the stage) is issued by a second thread (warp 2): each thread's instruction
+      // stream -- barrier waits, descriptor arithmetic, commits -- is what bounds small layers, so it is split in two;
+      // the order pass 1 -> split -> pass 2 of a stage is carried by the hi_done / lo_ready barriers.
       const uint32_t dhi = umma_desc_hi_kmajor(sbo, row_bytes);
-      const uint32_t tiles_u32 = smem_u32(tiles);
-      const uint32_t bres = smem_u32(res_b);
+      const uint32_t tiles_lo = ((smem_u32(tiles) & 0x3FFFFu) >> 4) | (1u << 16);     // descriptor low words: address >> 4
+      const uint32_t bres_lo = ((smem_u32(res_b) & 0x3FFFFu) >> 4) | (1u << 16);
       const int kst = p.cblk / 8;
       const int rows_u = p.res ? 3 : p.rg;                         // filter rows per unit
       const int upt = p.res ? 1 : (3 / p.rg) * p.kblocks;          // units per tile
       const int U = (t_end - t_begin) * upt;
-      const uint32_t b_row = b_rows * row_bytes;                   // bytes of one filter row of B
-      const uint32_t lo_off = p.res ? (uint32_t)p.res_bl_off : (uint32_t)p.rg * b_row;
+      const uint32_t a_step = (uint32_t)p.a_bytes >> 4, b_step = (uint32_t)(b_rows * row_bytes) >> 4;
+      const uint32_t stage_step = (uint32_t)p.stage_bytes >> 4;
+      const uint32_t lo_delta = p.res ? (uint32_t)p.res_bl_off >> 4 : (uint32_t)p.rg * b_step;
       if (p.res) mbar_wait(b_full, 0);
-      int u1 = 0, s1 = 0, ph1 = 0, k1 = 0, a1 = 0, aph1 = 0;
-      int u2 = 0, s2 = 0, ph2 = 0, k2 = 0, a2 = 0;
-      bool acc_ok = false;
-      while (u2 < U) {
-        if (u1 < U) {
-          if (k1 == 0 && !acc_ok) acc_ok = mbar_try_wait(&t_empty[a1], aph1 ^ 1);
-          if ((k1 != 0 || acc_ok) && mbar_try_wait(&full[s1], ph1)) {
-            fence_after_sync();
-            const uint32_t a0 = tiles_u32 + s1 * p.stage_bytes;
-            const uint32_t b0 = p.res ? bres : a0 + p.rg * p.a_bytes;
-            const uint32_t d_tmem = tmem_base + a1 * p.acc_stride;
-            for (int rr = 0; rr < rows_u; ++rr) {
-              for (int ks = 0; ks < kst; ++ks) {
-                const uint64_t da = umma_desc_join(dhi, a0 + rr * p.a_bytes + ks * 32);
-                const uint64_t dbh = umma_desc_join(dhi, b0 + rr * b_row + ks * 32);
-                const uint64_t dbl = umma_desc_join(dhi, b0 + lo_off + rr * b_row + ks * 32);
-                if ((k1 | rr | ks) == 0) mma_tf32_c<false>(d_tmem, da, dbh, idesc);
-                else mma_tf32_c<true>(d_tmem, da, dbh, idesc);
-                mma_tf32_c<true>(d_tmem, da, dbl, idesc);
-              }
-            }
-            mma_commit(&hi_done[s1]);
-            ++u1;
-            if (++s1 == p.stages) { s1 = 0; ph1 ^= 1; }
-            if (++k1 == upt) { k1 = 0; acc_ok = false; if (++a1 == p.nacc) { a1 = 0; aph1 ^= 1; } }
+      int s1 = 0, ph1 = 0, k1 = 0, a1 = 0, aph1 = 0;
+      for (int u1 = 0; u1 < U; ++u1) {
+        if (k1 == 0) mbar_wait(&t_empty[a1], aph1 ^ 1);
+        mbar_wait(&full[s1], ph1);
+        fence_after_sync();
+        CT_TRACE(1, 2);
+        const uint32_t d_tmem = tmem_base + a1 * p.acc_stride;
+        uint32_t da_r = tiles_lo + s1 * stage_step;
+        uint32_t db_r = p.res ? bres_lo : da_r + p.rg * a_step;
+        for (int rr = 0; rr < rows_u; ++rr) {
+          uint32_t da = da_r, db = db_r;
+          for (int ks = 0; ks < kst; ++ks) {
+            const uint64_t qa = ((uint64_t)dhi << 32) | da, qh = ((uint64_t)dhi << 32) | db,
+                           ql = ((uint64_t)dhi << 32) | (db + lo_delta);
+            if ((k1 | rr | ks) == 0) mma_tf32_c<false>(d_tmem, qa, qh, idesc);
+            else mma_tf32_c<true>(d_tmem, qa, qh, idesc);
+            mma_tf32_c<true>(d_tmem, qa, ql, idesc);
+            da += 2; db += 2;                                      // next 8 channels: 32 bytes
           }
+          da_r += a_step; db_r += b_step;
         }
-        if (u2 < u1 && mbar_try_wait(&lo_ready[s2], ph2)) {
-          fence_after_sync();
-          const uint32_t a0 = tiles_u32 + s2 * p.stage_bytes;
-          const uint32_t b0 = p.res ? bres : a0 + p.rg * p.a_bytes;
-          const uint32_t d_tmem = tmem_base + a2 * p.acc_stride;
-          for (int rr = 0; rr < rows_u; ++rr) {
-            for (int ks = 0; ks < kst; ++ks) {
-              const uint64_t da = umma_desc_join(dhi, a0 + rr * p.a_bytes + ks * 32);
-              const uint64_t dbh = umma_desc_join(dhi, b0 + rr * b_row + ks * 32);
-              mma_tf32_c<true>(d_tmem, da, dbh, idesc);
-            }
-          }
-          mma_commit(&empty[s2]);
-          ++u2;
-          if (++s2 == p.stages) { s2 = 0; ph2 ^= 1; }
-          if (++k2 == upt) { k2 = 0; mma_commit(&t_full[a2]); if (++a2 == p.nacc) a2 = 0; }
-        }
+        mma_commit(&hi_done[s1]);
+        CT_TRACE(1, 3);
+        if (++s1 == p.stages) { s1 = 0; ph1 ^= 1; }
+        if (++k1 == upt) { k1 = 0; if (++a1 == p.nacc) { a1 = 0; aph1 ^= 1; } }
       }
     }
     if (!X3 && p.res && t_begin < t_end) {
@@ -516,19 +512,57 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       }
       mma_commit(&t_full[acc]);
     }
+  } else if (X3 && warp == 2 && elect_one()) {
+    // ===================== MMA issuer, pass 2 of the error-compensated mode: A_lo * B_hi
+    if (t_begin < t_end) {
+      const uint32_t idesc = umma_idesc(2 /*tf32*/, CT_BM, 3 * p.BN);
+      const uint32_t dhi = umma_desc_hi_kmajor(8 * row_bytes, row_bytes);
+      const uint32_t tiles_lo = ((smem_u32(tiles) & 0x3FFFFu) >> 4) | (1u << 16);
+      const uint32_t bres_lo = ((smem_u32(res_b) & 0x3FFFFu) >> 4) | (1u << 16);
+      const int kst = p.cblk / 8;
+      const int rows_u = p.res ? 3 : p.rg;
+      const int upt = p.res ? 1 : (3 / p.rg) * p.kblocks;
+      const int U = (t_end - t_begin) * upt;
+      const uint32_t a_step = (uint32_t)p.a_bytes >> 4, b_step = (uint32_t)(b_rows * row_bytes) >> 4;
+      const uint32_t stage_step = (uint32_t)p.stage_bytes >> 4;
+      int s2 = 0, ph2 = 0, k2 = 0, a2 = 0, tr_n = 0;
+      for (int u2 = 0; u2 < U; ++u2) {
+        mbar_wait(&lo_ready[s2], ph2);
+        fence_after_sync();
+        CT_TRACE(4, 4);
+        const uint32_t d_tmem = tmem_base + a2 * p.acc_stride;
+        uint32_t da_r = tiles_lo + s2 * stage_step;
+        uint32_t db_r = p.res ? bres_lo : da_r + p.rg * a_step;
+        for (int rr = 0; rr < rows_u; ++rr) {
+          uint32_t da = da_r, db = db_r;
+          for (int ks = 0; ks < kst; ++ks) {
+            mma_tf32_c<true>(d_tmem, ((uint64_t)dhi << 32) | da, ((uint64_t)dhi << 32) | db, idesc);
+            da += 2; db += 2;
+          }
+          da_r += a_step; db_r += b_step;
+        }
+        mma_commit(&empty[s2]);
+        if (++k2 == upt) { k2 = 0; mma_commit(&t_full[a2]); if (++a2 == p.nacc) a2 = 0; }
+        CT_TRACE(4, 5);
+        if (++s2 == p.stages) { s2 = 0; ph2 ^= 1; }
+      }
+    }
   } else if (X3 && (warp == 3 || warp >= 12)) {
     // ===================== operand splitters (X3): stage by stage, in the producer's order
-    const int tid_c = (warp == 3 ? 0 : warp - 11) * 32 + lane;
+    const int tid_c = (warp == 3 ? 0 : 32) + lane;
     const int upt = p.res ? 1 : (3 / p.rg) * p.kblocks;
     const int U = max(0, t_end - t_begin) * upt;
     const int bytes = (p.res ? 3 : p.rg) * p.a_bytes;
     int stage = 0, phase = 0;
+    int tr_n = (tid_c == 0) ? 0 : 1000;
     for (int u = 0; u < U; ++u) {
       mbar_wait(&full[stage], phase);              // (the TMA writes of this stage are visible to this thread)
       mbar_wait(&hi_done[stage], phase);           // pass-1 MMAs have finished reading the raw tile
+      CT_TRACE(3, 1);
       split_lo_inplace(tiles + (size_t)stage * p.stage_bytes, bytes, tid_c, CT_NCONV);
       fence_proxy_async();                         // generic-proxy writes -> visible to the tensor core
       mbar_arrive(&lo_ready[stage]);
+      CT_TRACE(3, 2);
       if (++stage == p.stages) { stage = 0; phase ^= 1; }
     }
   } else if (warp >= 4) {
@@ -773,7 +807,7 @@ static int pick_bn(int Nc) {
 }
 
 size_t conv_wgrad_tc_smem(const se_conv_desc* d, int* tmem_cols, int x3);   // conv_wgrad_tc.cu
-constexpr int WG_COOP_SMEM_MAX = 116 * 1024;
+constexpr int WG_COOP_SMEM_MAX = 120 * 1024;
 
 struct ConvTcBn {            // fused BatchNorm arguments of conv_tc_launch (null = plain convolution)
   const float* gamma; const float* beta; float eps, momentum; float* moving_mean; float* moving_var;

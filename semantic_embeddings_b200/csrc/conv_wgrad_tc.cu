@@ -29,6 +29,15 @@ namespace se {
 
 using namespace tc;
 
+// conv_wgrad_pk.cu: the "packed" error-compensated variant for layers with Cin, Cout <= 16 (its own operand layout)
+int init_conv_wgrad_pk();
+size_t conv_wgrad_pk_smem(const se_conv_desc* d, int* tmem_cols);
+int conv_wgrad_pk(const se_conv_desc* d, const float* x, const float* dy, float* dw, float* dbias, cudaStream_t st);
+static bool wgrad_is_packed(const se_conv_desc* d, int x3) {
+  static const bool no_pack = getenv("SE_WG_NO_PACK") != nullptr;
+  return x3 && d->Cin <= 16 && d->Cout <= 16 && !no_pack;
+}
+
 struct WgTcParams {
   int N, H, W, Cin, Cout;
   int Hb, Nb, PT;              // pixel tile: Hb rows of one image (Nb == 1) or Nb whole images; PT = W*Hb*Nb pixels
@@ -51,6 +60,13 @@ __device__ __forceinline__ float wg_tf32_lo(float x) { return x - __uint_as_floa
 // tile, produce the lo parts: warp 2 writes dY_lo into a second (small) dY buffer of the stage as soon as the tile has
 // landed, warps 3-5 rewrite the three X buffers IN PLACE as X_lo once pass 1 (X*dY_hi, X*dY_lo) has read them, then
 // pass 2 issues X_lo*dY_hi.  The MMA warp runs the passes as two cursors over the stage sequence.
+// Layers with Cin, Cout <= 16 use the "packed" variant of conv_wgrad_pk.cu instead (lo parts in the zero-filled channel
+// slots of the 32-channel boxes: no second pass).
+//
+// Measured (B200, 16 -> 16 channels at 32x32, batch 128): consecutive MMAs that share their B descriptor cost ~35 cycles
+// each, an MMA with a new B operand ~100 more (the MN-major B slab is re-staged) -- so dY, the small operand, is B and
+// every k-step issues all MMAs of one B slab back to back.  The alternative layout (one X box, three shifted dY boxes
+// stacked along N) moves fewer bytes but changes B every MMA and was 25 % slower.
 template <int X3>
 __global__ void __launch_bounds__(192, 1)
 conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_dy, WgTcParams p) {
@@ -131,7 +147,7 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
       const int ksteps = (p.debug & 4) ? 0 : p.PT / 8;
       int stage = 0, phase = 0;
       uint32_t acc = 0;
-      if (X3) {
+      if (X3 == 1) {
         const int T = t_end - t_begin;
         int u1 = 0, s1 = 0, ph1 = 0, u2 = 0, s2 = 0, ph2 = 0;
         while (u2 < T) {
@@ -148,16 +164,19 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
               const uint64_t dl = ((uint64_t)hi << 32) | (uint64_t)((((dyl + ks * 1024) & 0x3FFFFu) >> 4) | lbo_b);
               const uint32_t a0 = sb + img_off + rem * 128;
               if (elect_one()) {
+                // all MMAs of one B slab back to back (a new B operand costs far more than a new A operand)
 #pragma unroll
                 for (int s = 0; s < 3; ++s) {
                   const uint64_t da = ((uint64_t)hi << 32) | (uint64_t)((((a0 + s * p.xbuf_bytes) & 0x3FFFFu) >> 4) | lbo_a);
                   mma_tf32(tmem_base + s * p.ncols, da, db, idesc, acc);
+                }
+                if (p.G == 4) mma_tf32(tmem_base + 3 * p.ncols, ((uint64_t)hi << 32) | (uint64_t)ones_lo, db, idesc, acc);
+#pragma unroll
+                for (int s = 0; s < 3; ++s) {
+                  const uint64_t da = ((uint64_t)hi << 32) | (uint64_t)((((a0 + s * p.xbuf_bytes) & 0x3FFFFu) >> 4) | lbo_a);
                   mma_tf32(tmem_base + s * p.ncols, da, dl, idesc, 1);
                 }
-                if (p.G == 4) {
-                  mma_tf32(tmem_base + 3 * p.ncols, ((uint64_t)hi << 32) | (uint64_t)ones_lo, db, idesc, acc);
-                  mma_tf32(tmem_base + 3 * p.ncols, ((uint64_t)hi << 32) | (uint64_t)ones_lo, dl, idesc, 1);
-                }
+                if (p.G == 4) mma_tf32(tmem_base + 3 * p.ncols, ((uint64_t)hi << 32) | (uint64_t)ones_lo, dl, idesc, 1);
               }
               __syncwarp();
               acc = 1;
@@ -229,7 +248,7 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
     } else {
       // ===================== epilogue: TMEM -> reductions into dW / dbias (4 warps, one lane quarter each)
       const int q4 = warp & 3;                              // TMEM lane quarter == vertical tap r (quarter 3: bias row)
-      if (X3) {
+      if (X3 == 1) {
         // operand splitters until the last tile has been issued (then these warps run the epilogue as usual)
         int stage = 0, phase = 0;
         for (int t = t_begin; t < t_end; ++t) {
@@ -305,7 +324,8 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
 
 int init_conv_wgrad_tc() {
   if (cudaFuncSetAttribute(conv_wgrad_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess ||
-      cudaFuncSetAttribute(conv_wgrad_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) {
+      cudaFuncSetAttribute(conv_wgrad_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess ||
+      init_conv_wgrad_pk() != SE_OK) {
     set_error("init_conv_wgrad_tc: cannot raise the shared-memory limit");
     return SE_ERR_CUDA;
   }
@@ -316,7 +336,7 @@ int init_conv_wgrad_tc() {
 // Co-residency with the backward-data kernel of the same layer (se_run_ops issues wgrad on a side stream): when two
 // pipeline stages fit in ~half of the SM's shared memory the kernel takes only those, and conv_tc.cu sizes the
 // dgrad kernel to the rest (conv_wgrad_tc_smem() is what it asks).
-constexpr int WG_COOP_SMEM = 116 * 1024;
+constexpr int WG_COOP_SMEM = 120 * 1024;
 
 static int plan_wgrad(const se_conv_desc* d, bool with_bias, int x3, WgTcParams* pp, size_t* smem_out) {
   if (d->kh != 3 || d->kw != 3 || d->stride != 1 || d->pad_t != 1 || d->pad_l != 1 || d->Ho != d->H || d->Wo != d->W)
@@ -327,17 +347,17 @@ static int plan_wgrad(const se_conv_desc* d, bool with_bias, int x3, WgTcParams*
   if (W > 64 || (W & (W - 1)) != 0 || W < 8) return SE_ERR_UNSUPPORTED;
   WgTcParams& p = *pp;
   p.N = d->N; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout;
+  p.G = with_bias ? 4 : 3;
+  // output channels per CTA: at most 128 (4 accumulators x 128 columns = the 512 TMEM columns), in 32-channel blocks
+  const int gz = ceil_div(Cout, 128);
+  p.nnb = ceil_div(ceil_div(Cout, gz), 32);
+  p.ncols = 32 * p.nnb;
   p.PT = max(64, 2 * W);
   if (W * H >= p.PT) { if (H % (p.PT / W) != 0) return SE_ERR_UNSUPPORTED; p.Hb = p.PT / W; p.Nb = 1; }
   else { if (p.PT % (W * H) != 0) return SE_ERR_UNSUPPORTED; p.Hb = H; p.Nb = p.PT / (W * H); }
   p.img_px = p.Hb * W;
   p.img_stride = (p.Hb + 2) * W * 128;
   p.xbuf_bytes = p.Nb * p.img_stride;
-  p.G = with_bias ? 4 : 3;
-  // output channels per CTA: at most 128 (4 accumulators x 128 columns = the 512 TMEM columns), in 32-channel blocks
-  const int gz = ceil_div(Cout, 128);
-  p.nnb = ceil_div(ceil_div(Cout, gz), 32);
-  p.ncols = 32 * p.nnb;
   p.dy_bytes = p.PT * 128 * p.nnb;
   p.stage_bytes = ceil_div(3 * p.xbuf_bytes + (1 + x3) * p.dy_bytes, 1024) * 1024;
   const int fixed = (with_bias ? 1024 : 0) + 24 * 8 + 1024 + 64;
@@ -353,6 +373,7 @@ static int plan_wgrad(const se_conv_desc* d, bool with_bias, int x3, WgTcParams*
 size_t conv_wgrad_tc_smem(const se_conv_desc* d, int* tmem_cols, int x3) {
   WgTcParams p;
   size_t smem = 0;
+  if (wgrad_is_packed(d, x3)) return conv_wgrad_pk_smem(d, tmem_cols);
   if (plan_wgrad(d, true, x3, &p, &smem) != SE_OK) return 0;
   int cols = 32;
   while (cols < p.G * p.ncols) cols <<= 1;
@@ -365,6 +386,7 @@ int conv_wgrad_tc(const se_conv_desc* d, const float* x, const float* dy, float*
     return SE_ERR_UNSUPPORTED;
   WgTcParams p;
   size_t smem = 0;
+  if (wgrad_is_packed(d, x3)) return conv_wgrad_pk(d, x, dy, dw, dbias, st);
   int rc = plan_wgrad(d, dbias != nullptr, x3, &p, &smem);
   if (rc != SE_OK) return rc;
   static bool inited = false;
