@@ -46,6 +46,7 @@ extern "C" {
 #define SE_LOSS_INV_CORR 0     /* l2norm wrapper + 1 - <t,x>      */
 #define SE_LOSS_UNNORM_CORR 1  /* no wrapper     + 1 - <t,z>      */
 #define SE_LOSS_MSE 2          /* no wrapper     + sum (z-t)^2    */
+#define SE_LOSS_SOFTMAX_CORR 3 /* softmax wrapper + 1 - <t,x>     (learn_image_embeddings.py:129-130) */
 
 /* pairwise modes: evaluate_retrieval.py:57-62 */
 #define SE_PDIST_SQEUCLID 0    /* A + B - 2 F F^T                 */
@@ -199,10 +200,22 @@ int se_relu_bwd(const float* dy, const float* y, float* dx, float beta, int64_t 
 int se_embed_head_fwd_bwd(const float* z, int ldz, const int32_t* labels, const float* E, int ldE, int B,
                           int D, int C, int loss_kind, float loss_scale, const float* extra_dx,
                           float* x_out, float* loss, float* acc, float* dz, void* stream);
+/* same + rank_out [B] (may be NULL): the top-k form of the metric for every k at once.  utils.nn_accuracy(k)
+ * (utils.py:85,95) is 1 iff one of the k best class scores lies within 1e-6 of the true class' score; with G = number
+ * of classes better than the true score by >= 1e-6, that is `rank_out < k` (rank_out = G, or C when no class is within
+ * 1e-6).  For SE_LOSS_SOFTMAX_CORR (metric = Keras categorical / top-k categorical accuracy) rank_out = number of
+ * outputs strictly above the output at argmax(t).  --top_k_acc K: accuracy@K = mean(rank_out < K). */
+int se_embed_head_fwd_bwd_ex(const float* z, int ldz, const int32_t* labels, const float* E, int ldE, int B,
+                             int D, int C, int loss_kind, float loss_scale, const float* extra_dx,
+                             float* x_out, float* loss, float* acc, float* dz, float* rank_out, void* stream);
 /* softmax + Keras categorical_crossentropy (clip 1e-7) + argmax accuracy + backward
  * (learn_image_embeddings.py:44,230-231): dlogits = scale * dCE/dlogits. */
 int se_softmax_xent_fwd_bwd(const float* logits, int ld, const int32_t* labels, int B, int C, float scale,
                             float* prob, float* loss, float* acc, float* dlogits, void* stream);
+/* same + rank_out [B] (may be NULL): classes with a strictly larger logit than the label's -- utils.top_k_acc(k)
+ * (utils.py:49-54, in_top_k) = mean(rank_out < k) */
+int se_softmax_xent_fwd_bwd_ex(const float* logits, int ld, const int32_t* labels, int B, int C, float scale,
+                               float* prob, float* loss, float* acc, float* dlogits, float* rank_out, void* stream);
 
 /* ------------------------------------------------------------------ optimizer
  * keras.optimizers.SGD(lr, momentum, decay, nesterov, clipnorm) + kernel_regularizer=l2(.)
@@ -224,10 +237,25 @@ int se_sgd_prepare(const float* p, float* g, int64_t n, const se_l2_segment* seg
 int se_sgd_apply(float* p, const float* g, float* v, int64_t n, float lr, float momentum, int nesterov,
                  float clipnorm, const double* out, void* stream);
 
+/* Keras SGD(decay) (learn_image_embeddings.py:224-236, --max_decay): lr_state = float[4] device memory
+ * {lr written by the schedule, decay, iterations, lr_t}; one call per optimizer step sets lr_t = lr / (1 + decay *
+ * iterations) and increments iterations.  se_sgd_apply_devlr then reads lr_state + 3. */
+int se_sgd_schedule(float* lr_state, void* stream);
 /* same as se_sgd_apply with the learning rate read from device memory (float[1]) at run time, so
  * that a CUDA-graph-captured step follows the SGDR schedule (sgdr_callback.py:75-87) without re-capture */
 int se_sgd_apply_devlr(float* p, const float* g, float* v, int64_t n, const float* lr_dev, float momentum,
                        int nesterov, float clipnorm, const double* out, void* stream);
+
+/* ------------------------------------------------------------------ input pipeline
+ * TinyDatasetGenerator.compose_batch (datasets/common.py:771-796): Keras ImageDataGenerator.random_transform with
+ * horizontal_flip + width/height_shift_range 0.15 (datasets/common.py:640; shift = scipy affine_transform order 1,
+ * mode 'nearest') and .standardize (featurewise mean / std, :639) for a batch gathered by index from a dataset that is
+ * resident in device memory.  src [n, H, W, C] uint8 or float32 raw pixels; index [B] rows of src (NULL = 0..B-1);
+ * tx / ty [B] row / column shifts in pixels (NULL = 0), flip [B] 0/1 (NULL = none) -- the random draws are the host's;
+ * mean / inv_std [C] with inv_std = 1 / (std + 1e-7); out [B, H, W, C] float32. */
+int se_augment_batch(const void* src, int src_is_u8, const int32_t* index, const float* tx, const float* ty,
+                     const unsigned char* flip, const float* mean, const float* inv_std, float* out, int B, int H, int W,
+                     int C, void* stream);
 
 /* ------------------------------------------------------------------ retrieval
  * evaluate_retrieval.py:56-63: rows [row0,row0+rows) of the N x N distance matrix of F [N,ldF]
@@ -256,6 +284,23 @@ int se_row_topk(const float* dist, int64_t ld, int rows, int n, int k, float* ou
 int se_hier_precision(const int32_t* ranks, int ldr, int Q, int K1, int q0, const int32_t* labels, int C,
                       const double* wup_lut, const double* lcs_height_lut, const double* best_wup, const double* best_lcs,
                       const int32_t* ks, int nks, int clip, double* out, void* stream);
+
+/* The same metrics from rankings of any length, as evaluate_retrieval.py:195 requests them (ks = 1..plot_max, compute_ahp
+ * = clip or True, compute_ap = True):  ranks [Q, ldr] int32 with n_ret entries per query (n_ret = N for full rankings
+ * from se_row_argsort, or max(kcurve, clip) + 1 for top-k rankings); best_wup / best_lcs [C, n_ret] float64;
+ *   curve [Q, 2, kcurve] = P@k for k = 1..kcurve (WUP, LCS_HEIGHT)                       (NULL when kcurve == 0)
+ *   ahp   [Q, 2]: clip > 0 -> AHP@clip, clip < 0 -> AHP over the whole list, clip == 0 -> not computed (may be NULL)
+ *   ap    [Q]   : classical average precision; needs full rankings (NULL = not computed)  (class_hierarchy.py:310-314) */
+int se_hier_metrics(const int32_t* ranks, int64_t ldr, int Q, int n_ret, int q0, const int32_t* labels, int C,
+                    const double* wup_lut, const double* lcs_height_lut, const double* best_wup, const double* best_lcs,
+                    int kcurve, int clip, double* curve, double* ahp, double* ap, void* stream);
+
+/* Full-length ranking of evaluate_retrieval.py:67 (`np.argsort(pdist, axis=-1)`; ascending distance, ties by ascending
+ * index, -0.0 == +0.0): out_idx [rows, ldo] int32 = the n column indices of every row of dist [rows, ld] in rank order.
+ * workspace: se_row_argsort_workspace_bytes(rows, n) bytes of device memory (one padded row of 64-bit words per row). */
+int64_t se_row_argsort_workspace_bytes(int rows, int n);
+int se_row_argsort(const float* dist, int64_t ld, int rows, int n, int32_t* out_idx, int64_t ldo, void* workspace,
+                   void* stream);
 
 /* ------------------------------------------------------------------ plan runner
  * Runs a host-built array of ops (one training step is ~900 launches) in one call so that

@@ -1,14 +1,23 @@
 #!/usr/bin/env python
-"""Drop-in for the reference's learn_image_embeddings.py (same flags, same pickles) on the B200-native engine.
+"""Drop-in for the reference's learn_image_embeddings.py (same flags, same embedding / feature pickles) on the
+B200-native engine.  Reference: learn_image_embeddings.py:54-275.
 
-Reference: learn_image_embeddings.py:54-275.  Differences, all outside the accelerated hot path:
-  * model / weight dumps are pickles of {Keras weight name: array} instead of Keras HDF5 (h5py is not a
-    dependency; names and layouts are Keras', so they convert 1:1);
-  * datasets: 'CIFAR-100' / 'CIFAR-10' (python pickles, datasets/cifar.py:43-81) and 'synthetic' (N(0,1) images
-    for machines without data).  The other dataset parsers are host-side file readers;
-  * --loss softmax_corr, --finetune, --log_dir are accepted but rejected / ignored with a message;
+What each part of the reference script maps to:
+  model construction + compile (:123-150, 224-236)  -> semantic_embeddings_b200.utils.build_network + engine.Engine
+  fit_generator (:238-243): train batches, validation pass per epoch, SGDR callback, ModelCheckpoint
+                                                     -> the epoch loop below (device-side augmentation: datasets.py)
+  evaluate_generator / Average Accuracy (:245-254)  -> final_evaluation()
+  model / weight dumps (:257-267)                   -> pickles of {Keras weight name: array} (Keras HDF5 needs h5py; names
+                                                       and layouts are Keras', so they convert 1:1)
+  feature dump (:270-275)                           -> identical pickle: {'feat': {test index: (D,) float32}}
+Deviations, all stated at run time when they apply:
+  * --cls_base and --finetune raise NotImplementedError (attaching the classifier to an inner layer / partial weight
+    loading with frozen layers are not part of the accelerated path); --log_dir is accepted and ignored with a message;
   * --gpus N > 1: launch with `python -m torch.distributed.run --nproc-per-node N learn_image_embeddings.py ...`
-    (one process per GPU, NCCL all-reduce) instead of in-graph towers.
+    (one process per GPU, NCCL all-reduce; the reference's in-graph towers have the same arithmetic);
+  * datasets: 'CIFAR-100' / 'CIFAR-10' (python pickles, datasets/cifar.py) and 'synthetic[:n]';
+  * --arith selects the arithmetic of the convolutions: tf32x3 (default: tcgen05 tiles with error compensation, fp32-level
+    results), f32 (fp32 FFMA kernels), tf32 (single-pass TF32, ~1e-3 relative deviation: NOT the reference's arithmetic).
 """
 import argparse
 import os
@@ -22,80 +31,10 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 from semantic_embeddings_b200 import utils  # noqa: E402
+from semantic_embeddings_b200.datasets import get_data_generator  # noqa: E402,F401  (re-exported like the reference's import)
 
 
-class TinyData:
-    """In-memory image dataset with the augmentation of datasets/common.py:638-670,771-796 (TinyDatasetGenerator):
-    featurewise mean/std from the training set, random horizontal flip, +-15% shifts with nearest fill."""
-
-    def __init__(self, X_train, y_train, X_test, y_test, classes=None):
-        if classes is not None:                                  # datasets/cifar.py:59-77: subset + re-enumeration
-            lut = {c: i for i, c in enumerate(classes)}
-            keep = np.array([c in lut for c in y_train])
-            X_train, y_train = X_train[keep], np.array([lut[c] for c in y_train[keep]])
-            keep = np.array([c in lut for c in y_test])
-            X_test, y_test = X_test[keep], np.array([lut[c] for c in y_test[keep]])
-        self.X_train, self.y_train = X_train.astype(np.float32), np.asarray(y_train)
-        self.X_test, self.y_test = X_test.astype(np.float32), np.asarray(y_test)
-        self.mean = self.X_train.mean(axis=(0, 1, 2))
-        self.std = self.X_train.std(axis=(0, 1, 2))
-        self.num_classes = int(max(self.y_train.max(), self.y_test.max())) + 1
-        self.num_train, self.num_test = len(self.X_train), len(self.X_test)
-        self.num_channels = self.X_train.shape[-1]
-        self.labels_test = self.y_test
-
-    def standardize(self, X):
-        return (X - self.mean) / (self.std + 1e-6)
-
-    def train_batches(self, batch_size, rng):
-        perm = rng.permutation(self.num_train)
-        n, h, w = self.num_train, self.X_train.shape[1], self.X_train.shape[2]
-        for i in range(0, n - batch_size + 1, batch_size):
-            idx = perm[i:i + batch_size]
-            X = self.standardize(self.X_train[idx])
-            flip = rng.rand(len(idx)) < 0.5
-            X[flip] = X[flip, :, ::-1]
-            dy = rng.uniform(-0.15, 0.15, len(idx)) * h
-            dx = rng.uniform(-0.15, 0.15, len(idx)) * w
-            for k in range(len(idx)):                           # nearest-fill shift
-                ry = np.clip(np.arange(h) + int(round(dy[k])), 0, h - 1)
-                rx = np.clip(np.arange(w) + int(round(dx[k])), 0, w - 1)
-                X[k] = X[k][ry][:, rx]
-            yield np.ascontiguousarray(X, dtype=np.float32), self.y_train[idx]
-
-    def test_batches(self, batch_size):
-        for i in range(0, self.num_test, batch_size):
-            yield self.standardize(self.X_test[i:i + batch_size]).astype(np.float32), self.y_test[i:i + batch_size]
-
-
-def get_data_generator(dataset, data_root, classes=None):
-    """datasets/__init__.py:21-166, CIFAR branch (:85-87) + a synthetic stand-in."""
-    name = dataset.lower()
-    if name in ('cifar-100', 'cifar-10'):
-        def load(fn):
-            with open(os.path.join(data_root, fn), 'rb') as f:
-                d = pickle.load(f, encoding='bytes')
-            X = d[b'data'].reshape(-1, 3, 32, 32).transpose(0, 2, 3, 1)       # datasets/cifar.py:80-81
-            y = np.asarray(d[b'fine_labels'] if b'fine_labels' in d else d[b'labels'])
-            return X, y
-        if name == 'cifar-100':
-            Xtr, ytr = load('train')
-            Xte, yte = load('test')
-        else:
-            parts = [load('data_batch_%d' % i) for i in range(1, 6)]
-            Xtr, ytr = np.concatenate([p[0] for p in parts]), np.concatenate([p[1] for p in parts])
-            Xte, yte = load('test_batch')
-        return TinyData(Xtr, ytr, Xte, yte, classes)
-    if name.startswith('synthetic'):
-        rng = np.random.RandomState(0)
-        ncls = len(classes) if classes is not None else 100
-        n = int(name.split(':')[1]) if ':' in name else 2048
-        return TinyData(rng.randn(n, 32, 32, 3) * 60 + 120, rng.randint(0, ncls, n),
-                        rng.randn(n // 4, 32, 32, 3) * 60 + 120, rng.randint(0, ncls, n // 4), None)
-    raise ValueError('Unknown dataset: {}'.format(dataset))
-
-
-def main():
+def build_parser():
     parser = argparse.ArgumentParser(description='Learns to map images onto class embeddings.',
                                      formatter_class=argparse.ArgumentDefaultsHelpFormatter)
     g = parser.add_argument_group('Data parameters')
@@ -130,20 +69,52 @@ def main():
     g.add_argument('--log_dir', type=str, default=None)
     g.add_argument('--no_progress', action='store_true', default=False)
     g.add_argument('--top_k_acc', type=int, nargs='+', default=[])
-    g.add_argument('--arith', type=str, default='tf32', choices=['tf32', 'f32'],
-                   help='(new) tensor-core fast mode or fp32 parity mode')
+    g.add_argument('--arith', type=str, default='tf32x3', choices=['tf32x3', 'f32', 'tf32'],
+                   help='(new) arithmetic of the convolution kernels, see the module docstring')
     utils.add_lr_schedule_arguments(parser)
-    args = parser.parse_args()
+    return parser
+
+
+def run_validation(eng, data, ks, embed_dst):
+    """One pass over the test set in inference mode (the validation_data of fit_generator / evaluate_generator,
+    learn_image_embeddings.py:240,246): means of every loss / metric, and the arg-max class of the classifier output."""
+    import torch
+    B = eng.B
+    sums, count = {}, 0
+    cls_pred = []
+    for idx, y in data.test_batches(B):
+        n = len(idx)
+        if n < B:                                   # fixed-size launch plans: pad the last batch, count only its head
+            idx = np.concatenate([idx, np.repeat(idx[-1:], B - n)])
+            y = np.concatenate([y, np.repeat(y[-1:], B - n)])
+        data.compose_batch(idx, False, eng.x)
+        eng.labels.copy_(torch.from_numpy(np.asarray(y, dtype=np.int32)), non_blocking=True)
+        eng._run('eval')
+        m = eng.per_sample_metrics(ks)
+        for k, v in m.items():
+            sums[k] = sums.get(k, 0.0) + float(v[:n].sum())
+        if eng.xent_node is not None:
+            cls_pred.append(eng.act['prob_out'][:n].argmax(dim=-1).cpu().numpy())
+        elif embed_dst is not None:
+            cls_pred.append(eng.act['head_out'][:n].argmax(dim=-1).cpu().numpy())
+        count += n
+    out = {k: v / max(count, 1) for k, v in sums.items()}
+    if eng.xent_node is not None:                   # Keras' total loss: weighted sum of the output losses (+ regulariser)
+        out['total'] = out['loss'] + eng.cls_weight * out['cls_loss']
+    return out, (np.concatenate(cls_pred) if cls_pred else None)
+
+
+def main(argv=None):
+    args = build_parser().parse_args(argv)
     if args.val_batch_size is None:
         args.val_batch_size = args.batch_size
-    if args.cls_base is not None or args.max_decay > 0 or args.finetune or args.loss == 'softmax_corr' or args.top_k_acc:
-        raise NotImplementedError('--cls_base / --max_decay / --finetune / --loss softmax_corr / --top_k_acc are outside '
-                                  'the accelerated hot path (SURVEY.md section 8)')
+    if args.cls_base is not None or args.finetune:
+        raise NotImplementedError('--cls_base / --finetune are outside the accelerated hot path (SURVEY.md section 8)')
 
     import torch
     from semantic_embeddings_b200 import _lib
     from semantic_embeddings_b200.engine import Engine
-    from semantic_embeddings_b200.parallel import broadcast_parameters, init_process_group, shard_batch
+    from semantic_embeddings_b200.parallel import broadcast_parameters, init_process_group
 
     # class embeddings (learn_image_embeddings.py:104-117)
     if args.embedding == 'onehot':
@@ -152,73 +123,119 @@ def main():
         with open(args.embedding, 'rb') as pf:
             emb = pickle.load(pf)
         embed_labels, embedding = emb['ind2label'], emb['embedding']
-    data = get_data_generator(args.dataset, args.data_root, classes=embed_labels)
-    if embedding is None:
-        embedding = np.eye(data.num_classes)
 
     local = int(os.environ.get('LOCAL_RANK', '0'))
     torch.cuda.set_device(local)
     rank, world = init_process_group(device=torch.device('cuda', local))
-    if world != max(1, args.gpus) and rank == 0:
-        print('note: --gpus {} but {} process(es) were launched; using {}'.format(args.gpus, world, world))
-    start, per_gpu = shard_batch(args.batch_size, world, rank)
+    say = print if rank == 0 else (lambda *a, **k: None)
+    if world != max(1, args.gpus):
+        say('note: --gpus {} but {} process(es) were launched; using {}'.format(args.gpus, world, world))
+    if args.batch_size % world != 0:
+        raise ValueError('--batch_size {} is not divisible by the {} GPU processes'.format(args.batch_size, world))
+    if args.val_batch_size != args.batch_size:
+        say('note: --val_batch_size is ignored (validation runs with the per-GPU training batch of the launch plans)')
+    if args.log_dir:
+        say('note: --log_dir is ignored (no TensorBoard writer on this path)')
+
+    data = get_data_generator(args.dataset, args.data_root, classes=embed_labels, device='cuda:%d' % local)
+    if embedding is None:
+        embedding = np.eye(data.num_classes)
 
     graph = utils.build_network(embedding.shape[1], args.architecture, input_channels=data.num_channels)
-    mode = _lib.SE_MODE_TF32 if args.arith == 'tf32' else _lib.SE_MODE_F32
-    eng = Engine(graph, args.batch_size // world, embedding, loss=args.loss, cls_weight=args.cls_weight,
-                 num_classes=data.num_classes, mode=mode, device='cuda:%d' % local, nesterov=args.nesterov,
-                 clipnorm=args.clipgrad, world_size=world)
+    mode = {'tf32x3': _lib.SE_MODE_TF32X3, 'tf32': _lib.SE_MODE_TF32, 'f32': _lib.SE_MODE_F32}[args.arith]
+    say('arithmetic: {}{}'.format(args.arith, '' if args.arith != 'tf32' else
+                                   ' (single-pass TF32: ~1e-3 relative deviation from the fp32 reference)'))
+    callbacks, num_epochs = utils.get_lr_schedule(args.lr_schedule, data.num_train, args.batch_size,
+                                                  schedule_args={k: v for k, v in vars(args).items() if v is not None})
+    epochs = args.epochs if args.epochs else num_epochs
+    steps_per_epoch = data.num_train // args.batch_size
+    # learn_image_embeddings.py:224-227
+    decay = (1.0 / args.max_decay - 1) / (steps_per_epoch * epochs) if args.max_decay > 0 else 0.0
+    pb = args.batch_size // world
+    eng = Engine(graph, pb, embedding, loss=args.loss, cls_weight=args.cls_weight, num_classes=data.num_classes, mode=mode,
+                 device='cuda:%d' % local, nesterov=args.nesterov, clipnorm=args.clipgrad, world_size=world, decay=decay)
     if args.snapshot and os.path.exists(args.snapshot):
-        print('Resuming from snapshot {}'.format(args.snapshot))
+        say('Resuming from snapshot {}'.format(args.snapshot))
         with open(args.snapshot, 'rb') as f:
             snap = pickle.load(f)
         eng.set_weights(snap['weights'])
         eng.set_velocity(snap['velocity'])
-    broadcast_parameters([eng.P, eng.S, eng.V])
+        eng.set_iterations(snap.get('iterations', 0))
+    broadcast_parameters([eng.P, eng.S, eng.V, eng.lr_dev])
 
-    callbacks, num_epochs = utils.get_lr_schedule(args.lr_schedule, data.num_train, args.batch_size,
-                                                  schedule_args={k: v for k, v in vars(args).items() if v is not None})
     sched = callbacks[0]
-    sched.on_train_begin()
-    for _ in range(args.initial_epoch):
-        sched.on_epoch_end()
-    epochs = args.epochs if args.epochs else num_epochs
-    rng = np.random.RandomState(1234)
-    pb = args.batch_size // world
+    sched.on_train_begin()          # like the reference, a resumed run starts a fresh SGDR cycle (the callback is new)
+    ks = tuple(args.top_k_acc)
+    monitor = args.snapshot_best
+    best = None
+    rng = np.random.RandomState(1234)          # identical stream on every rank: the permutation is shared, slices differ
     for epoch in range(args.initial_epoch, epochs):
         eng.set_lr(sched.lr)
-        tot_loss = tot_acc = nb = 0
-        for X, y in data.train_batches(args.batch_size, rng):
-            eng.train_step(torch.from_numpy(X[rank * pb:(rank + 1) * pb]), torch.from_numpy(y[rank * pb:(rank + 1) * pb]))
-            if not args.no_progress and nb % 50 == 0:
-                m = eng.metrics()
-                tot_loss += m['loss']; tot_acc += m['acc']
+        sums, nb, pending = {}, 0, None
+        for idx, y in data.train_batches(args.batch_size, rng, rank, world):
+            data.compose_batch(idx, True, eng.x, augment=True, rng=rng)
+            eng.labels.copy_(torch.from_numpy(np.asarray(y, dtype=np.int32)), non_blocking=True)
+            eng.train_step()
+            h = eng.metrics_async()              # running means of the epoch without stalling the device (Keras progress bar)
+            if pending is not None:
+                for k, v in eng.metrics_result(pending).items():
+                    sums[k] = sums.get(k, 0.0) + v
+                nb += 1
+            pending = h
+        if pending is not None:
+            for k, v in eng.metrics_result(pending).items():
+                sums[k] = sums.get(k, 0.0) + v
             nb += 1
+        logs = {k: v / max(nb, 1) for k, v in sums.items()}
+        val, _ = run_validation(eng, data, ks, None)
+        logs.update({'val_' + k: v for k, v in val.items()})
+        logs['val_loss'] = val.get('total', val['loss'])
         if rank == 0:
-            m = eng.metrics()
-            print('Epoch {}/{} - lr {:.6f} - loss {:.4f} - acc {:.4f}'.format(epoch + 1, epochs, sched.lr, m['loss'], m['acc']))
+            say('Epoch {}/{} - lr {:.6f} - '.format(epoch + 1, epochs, sched.lr) +
+                ' - '.join('{}: {:.4f}'.format(k, logs[k]) for k in sorted(logs)))
             if args.snapshot:
-                with open(args.snapshot, 'wb') as f:
-                    pickle.dump({'weights': eng.get_weights(), 'velocity': eng.get_velocity(), 'epoch': epoch + 1}, f)
+                cur = logs.get(monitor) if monitor else None
+                better = monitor is None or best is None or cur is None or \
+                    ((cur > best) if ('acc' in monitor) else (cur < best))
+                if better:
+                    best = cur
+                    with open(args.snapshot, 'wb') as f:
+                        pickle.dump({'weights': eng.get_weights(), 'velocity': eng.get_velocity(), 'epoch': epoch + 1,
+                                     'iterations': eng.iterations, 'architecture': args.architecture}, f)
         sched.on_epoch_end(epoch)
 
+    # final performance (learn_image_embeddings.py:245-254)
+    val, pred = run_validation(eng, data, ks, True if args.embedding == 'onehot' else None)
     if rank == 0:
-        if args.weight_dump or args.model_dump:
-            for fn in (args.weight_dump, args.model_dump):
-                if fn:
+        order = ['total'] if 'total' in val else []
+        order += [k for k in ('loss', 'cls_loss', 'acc') if k in val] + sorted(k for k in val if k.startswith('acc') and k != 'acc')
+        order += [k for k in ('cls_acc',) if k in val] + sorted(k for k in val if k.startswith('cls_acc') and k != 'cls_acc')
+        say([val[k] for k in order])
+        if pred is not None and (args.cls_weight > 0 or args.embedding == 'onehot'):
+            labels = np.asarray(data.labels_test)
+            class_freq = np.bincount(labels)
+            say('Average Accuracy: {:.4f}'.format(((pred == labels).astype(np.float64) / class_freq[labels]).sum() / len(class_freq)))
+        for fn in (args.weight_dump, args.model_dump):
+            if fn:
+                try:
                     with open(fn, 'wb') as f:
                         pickle.dump({'architecture': args.architecture, 'weights': eng.get_weights()}, f)
+                except Exception as e:
+                    print('An error occurred while saving the model: {}'.format(e))
         if args.feature_dump:                                  # learn_image_embeddings.py:270-275
             feats = []
-            for X, _ in data.test_batches(pb):
-                n = len(X)
+            for idx, _ in data.test_batches(pb):
+                n = len(idx)
                 if n < pb:
-                    X = np.concatenate([X, np.zeros((pb - n,) + X.shape[1:], np.float32)])
-                feats.append(eng.predict(torch.from_numpy(X))[:n])
+                    idx = np.concatenate([idx, np.repeat(idx[-1:], pb - n)])
+                data.compose_batch(idx, False, eng.x)
+                eng._run('infer')
+                feats.append(eng.act['head_out'][:n].cpu().numpy())
             feats = np.concatenate(feats)
             with open(args.feature_dump, 'wb') as dump_file:
                 pickle.dump({'feat': dict(enumerate(feats))}, dump_file)
+    return 0
 
 
 if __name__ == '__main__':
-    main()
+    sys.exit(main())

@@ -125,6 +125,37 @@ def nn_accuracy(embedding, y_true, y_pred):
     return ((true_dist - dist.min(dim=-1).values).abs() < 1e-6).to(y_pred.dtype)
 
 
+def max_sim_acc_k(embedding, y_true, y_pred, k):
+    """utils.py:95 (k > 1 branch): any of the k largest similarities within 1e-6 of the true one."""
+    sim = y_pred @ embedding.t()
+    true_sim = (y_pred * y_true).sum(dim=-1)
+    top = torch.topk(sim, k, dim=-1).values
+    return ((top - true_sim[:, None]).abs() < 1e-6).any(dim=-1).to(y_pred.dtype)
+
+
+def nn_accuracy_k(embedding, y_true, y_pred, k):
+    """utils.py:85 (k > 1 branch, Euclidean variant)."""
+    cn = (embedding.t() ** 2).sum(dim=0, keepdim=True)
+    pn = (y_pred ** 2).sum(dim=1, keepdim=True)
+    dist = pn + cn - 2 * (y_pred @ embedding.t())
+    true_dist = ((y_pred - y_true) ** 2).sum(dim=-1)
+    top = -torch.topk(-dist, k, dim=-1).values
+    return ((top - true_dist[:, None]).abs() < 1e-6).any(dim=-1).to(y_pred.dtype)
+
+
+def categorical_accuracy(y_true, y_pred):
+    """Keras metric 'accuracy' for 2-d targets (learn_image_embeddings.py:166 with --loss softmax_corr)."""
+    return (y_true.argmax(dim=-1) == y_pred.argmax(dim=-1)).to(y_pred.dtype)
+
+
+def top_k_categorical_accuracy(y_true, y_pred, k):
+    """utils.top_k_acc (utils.py:49-54) = K.in_top_k(y_pred, argmax(y_true), k): the target is in the top k when fewer
+    than k entries are strictly larger than its own."""
+    tgt = y_true.argmax(dim=-1)
+    own = y_pred.gather(1, tgt[:, None])
+    return ((y_pred > own).sum(dim=-1) < k).to(y_pred.dtype)
+
+
 def categorical_crossentropy(onehot, prob):
     """Keras categorical_crossentropy on probabilities:
     renormalise, clip to [1e-7, 1-1e-7], -sum t log p."""

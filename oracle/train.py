@@ -81,6 +81,8 @@ def train_objective(model, x, labels, embedding, loss_kind='inv_corr', cls=None,
     embed_loss = ls.mean()
     if loss_kind == 'mse':
         acc = nn.nn_accuracy(embedding, y_true, emb)
+    elif loss_kind == 'softmax_corr':
+        acc = nn.categorical_accuracy(y_true, emb)          # metrics = ['accuracy'], learn_image_embeddings.py:166
     else:
         acc = nn.max_sim_acc(embedding, y_true, emb)
     total = embed_loss

@@ -13,7 +13,7 @@ LIB_PATH = os.path.join(_HERE, 'libse_b200.so')
 
 SE_MODE_F32, SE_MODE_TF32, SE_MODE_TF32X3 = 0, 1, 2
 MODE_NAMES = {0: 'f32', 1: 'tf32', 2: 'tf32x3'}
-SE_LOSS_INV_CORR, SE_LOSS_UNNORM_CORR, SE_LOSS_MSE = 0, 1, 2
+SE_LOSS_INV_CORR, SE_LOSS_UNNORM_CORR, SE_LOSS_MSE, SE_LOSS_SOFTMAX_CORR = 0, 1, 2, 3
 SE_PDIST_SQEUCLID, SE_PDIST_NEGDOT = 0, 1
 
 # opcodes of se_run_ops (csrc/opcodes.h)
@@ -86,6 +86,13 @@ _SIGS = {
     'se_relu_bwd': (c_int, [_P, _P, _P, c_float, c_int64, _P]),
     'se_embed_head_fwd_bwd': (c_int, [_P, c_int, _P, _P, c_int, c_int, c_int, c_int, c_int, c_float, _P, _P, _P, _P, _P, _P]),
     'se_softmax_xent_fwd_bwd': (c_int, [_P, c_int, _P, c_int, c_int, c_float, _P, _P, _P, _P, _P]),
+    'se_softmax_xent_fwd_bwd_ex': (c_int, [_P, c_int, _P, c_int, c_int, c_float, _P, _P, _P, _P, _P, _P]),
+    'se_embed_head_fwd_bwd_ex': (c_int, [_P, c_int, _P, _P, c_int, c_int, c_int, c_int, c_int, c_float, _P, _P, _P, _P, _P, _P, _P]),
+    'se_sgd_schedule': (c_int, [_P, _P]),
+    'se_hier_metrics': (c_int, [_P, c_int64, c_int, c_int, c_int, _P, c_int, _P, _P, _P, _P, c_int, c_int, _P, _P, _P, _P]),
+    'se_row_argsort_workspace_bytes': (c_int64, [c_int, c_int]),
+    'se_row_argsort': (c_int, [_P, c_int64, c_int, c_int, _P, c_int64, _P, _P]),
+    'se_augment_batch': (c_int, [_P, c_int, _P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, _P]),
     'se_sgd_step': (c_int, [_P, _P, _P, c_int64, POINTER(L2Segment), c_int, c_float, c_float, c_int, c_float, _P, _P]),
     'se_sgd_prepare': (c_int, [_P, _P, c_int64, POINTER(L2Segment), c_int, _P, _P]),
     'se_sgd_apply': (c_int, [_P, _P, _P, c_int64, c_float, c_float, c_int, c_float, _P, _P]),

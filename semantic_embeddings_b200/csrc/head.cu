@@ -40,7 +40,7 @@ __global__ void __launch_bounds__(HEAD_WARPS * 32)
 embed_head_kernel(const float* __restrict__ z, int ldz, const int* __restrict__ labels, const float* __restrict__ E,
                   int ldE, int B, int D, int C, int loss_kind, float loss_scale, const float* __restrict__ extra_dx,
                   float* __restrict__ x_out, float* __restrict__ loss, float* __restrict__ acc, float* __restrict__ dz,
-                  int es_classes) {
+                  float* __restrict__ rank_out, int es_classes) {
   pdl_grid_sync();
   extern __shared__ __align__(16) float smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -49,7 +49,8 @@ embed_head_kernel(const float* __restrict__ z, int ldz, const int* __restrict__ 
   // class matrix staged in shared memory (row pitch D+1: conflict-free when every lane walks its own class row);
   // es_classes == 0 -> the matrix does not fit, the accuracy loop reads it from global memory
   float* Es = smem + HEAD_WARPS * Dp;
-  if (es_classes > 0 && acc) {
+  const bool want_acc = acc || rank_out;
+  if (es_classes > 0 && want_acc) {
     for (int c = warp; c < C; c += HEAD_WARPS)
       for (int i = lane; i < D; i += 32) Es[c * (D + 1) + i] = E[(long long)c * ldE + i];
     __syncthreads();
@@ -77,6 +78,17 @@ embed_head_kernel(const float* __restrict__ z, int ldz, const int* __restrict__ 
     inv = rsqrtf(fmaxf(ss, 1e-12f));
     __syncwarp();
     for (int i = lane; i < D; i += 32) xs[i] *= inv;
+  } else if (loss_kind == SE_LOSS_SOFTMAX_CORR) {
+    // Activation('softmax') wrapper (learn_image_embeddings.py:129-130): x = exp(z - max z) / sum
+    __syncwarp();
+    float m = -FLT_MAX;
+    for (int i = lane; i < D; i += 32) m = fmaxf(m, xs[i]);
+    m = warp_max(m);
+    float se = 0.f;
+    for (int i = lane; i < D; i += 32) { const float e = expf(xs[i] - m); xs[i] = e; se += e; }
+    se = warp_sum(se);
+    const float is = 1.f / se;
+    for (int i = lane; i < D; i += 32) xs[i] *= is;
   }
   __syncwarp();
   if (x_out) {
@@ -107,7 +119,29 @@ embed_head_kernel(const float* __restrict__ z, int ldz, const int* __restrict__ 
   if (loss && lane == 0) loss[row] = l;
 
   // ---- accuracy: nearest class over the whole class matrix (utils.py:73-93)
-  if (acc && es_classes > 0) {
+  if (loss_kind == SE_LOSS_SOFTMAX_CORR) {
+    // metric 'accuracy' of the softmax wrapper (learn_image_embeddings.py:166) = Keras categorical_accuracy:
+    // argmax x == argmax t (lowest index on ties); rank = number of outputs strictly above the one at argmax t
+    if (want_acc) {
+      float bt = -FLT_MAX, bx = -FLT_MAX;
+      int at = 0, ax = 0;
+      for (int i = lane; i < D; i += 32) {
+        if (t[i] > bt) { bt = t[i]; at = i; }
+        if (xs[i] > bx) { bx = xs[i]; ax = i; }
+      }
+      for (int o = 16; o > 0; o >>= 1) {
+        float ot = __shfl_xor_sync(0xffffffffu, bt, o), ox = __shfl_xor_sync(0xffffffffu, bx, o);
+        int oat = __shfl_xor_sync(0xffffffffu, at, o), oax = __shfl_xor_sync(0xffffffffu, ax, o);
+        if (ot > bt || (ot == bt && oat < at)) { bt = ot; at = oat; }
+        if (ox > bx || (ox == bx && oax < ax)) { bx = ox; ax = oax; }
+      }
+      const float xt = xs[at];
+      float above = 0.f;
+      for (int i = lane; i < D; i += 32) above += (xs[i] > xt) ? 1.f : 0.f;
+      above = warp_sum(above);
+      if (lane == 0) { if (acc) acc[row] = (ax == at) ? 1.f : 0.f; if (rank_out) rank_out[row] = above; }
+    }
+  } else if (want_acc && es_classes > 0) {
     // one class per lane and step: 2 shared loads per FMA, no shuffles inside the loop
     float best = (loss_kind == SE_LOSS_MSE) ? FLT_MAX : -FLT_MAX;
     float mine = -FLT_MAX;                          // this row's own class, from the same summation order as `best`
@@ -115,15 +149,34 @@ embed_head_kernel(const float* __restrict__ z, int ldz, const int* __restrict__ 
       const float* e = Es + c * (D + 1);
       float sim = 0.f, en = 0.f;
       for (int i = 0; i < D; ++i) { const float b = e[i]; sim = fmaf(xs[i], b, sim); en = fmaf(b, b, en); }
-      if (loss_kind == SE_LOSS_MSE) best = fminf(best, xnorm2 + en - 2.f * sim);
+      if (loss_kind == SE_LOSS_MSE) { const float dist = xnorm2 + en - 2.f * sim; best = fminf(best, dist); if (c == lab) mine = -dist; }
       else { best = fmaxf(best, sim); if (c == lab) mine = sim; }
     }
     best = (loss_kind == SE_LOSS_MSE) ? -warp_max(-best) : warp_max(best);
     mine = warp_max(mine);
-    const float ref = (loss_kind == SE_LOSS_MSE) ? true_dist : mine;
-    if (lane == 0) acc[row] = (fabsf(best - ref) < 1e-6f) ? 1.f : 0.f;
-  } else if (acc) {
+    // the true class' score comes from the SAME expression as the other classes' (in exact arithmetic it equals
+    // utils.py:80,91's separately computed true_dist / true_sim; in fp32 the two differ by more than the 1e-6 threshold
+    // for distances of O(10), which would make the metric a coin flip)
+    const float ref = (loss_kind == SE_LOSS_MSE) ? -mine : mine;
+    if (acc && lane == 0) acc[row] = (fabsf(best - ref) < 1e-6f) ? 1.f : 0.f;
+    if (rank_out) {
+      // top-k form of the metric (utils.py:85,95: any of the k best values within 1e-6 of the true one) for every k at
+      // once: with G = classes better than the true value by >= 1e-6 and T = classes within 1e-6 of it, the k best
+      // contain a member of T iff G < k (and T is not empty) -> rank = G, or C when T is empty
+      float gcnt = 0.f, tcnt = 0.f;
+      for (int c = lane; c < C; c += 32) {
+        const float* e = Es + c * (D + 1);
+        float sim = 0.f, en = 0.f;
+        for (int i = 0; i < D; ++i) { const float b = e[i]; sim = fmaf(xs[i], b, sim); en = fmaf(b, b, en); }
+        const float v = (loss_kind == SE_LOSS_MSE) ? -(xnorm2 + en - 2.f * sim) : sim;      // larger = better
+        if (fabsf(v - mine) < 1e-6f) tcnt += 1.f; else if (v > mine) gcnt += 1.f;
+      }
+      gcnt = warp_sum(gcnt); tcnt = warp_sum(tcnt);
+      if (lane == 0) rank_out[row] = tcnt > 0.f ? gcnt : (float)C;
+    }
+  } else if (want_acc) {
     float best = (loss_kind == SE_LOSS_MSE) ? FLT_MAX : -FLT_MAX;
+    float gcnt = 0.f, tcnt = 0.f, mine = -FLT_MAX;  // rank of the true class (see the shared-memory path above)
     // four classes per iteration: independent partial sums keep four rows of E in flight (the loop is latency-bound)
     for (int c = 0; c < C; c += 4) {
       float ps[4] = {0.f, 0.f, 0.f, 0.f}, pe[4] = {0.f, 0.f, 0.f, 0.f};
@@ -145,16 +198,42 @@ embed_head_kernel(const float* __restrict__ z, int ldz, const int* __restrict__ 
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         float sim = warp_sum(ps[u]);
+        float v;
         if (loss_kind == SE_LOSS_MSE) {
           float en = warp_sum(pe[u]);                   // centroids_norm (utils.py:76)
-          best = fminf(best, xnorm2 + en - 2.f * sim);
+          const float dist = xnorm2 + en - 2.f * sim;
+          best = fminf(best, dist);
+          v = -dist;
         } else {
           best = fmaxf(best, sim);
+          v = sim;
+        }
+        // the true class' score from the same expression (see the shared-memory path); classes are visited in ascending
+        // order, so classes before the label are re-examined below once its score is known
+        if (c + u == lab) mine = v;
+      }
+    }
+    const float ref = (loss_kind == SE_LOSS_MSE) ? -mine : mine;
+    if (rank_out) {
+      for (int c = 0; c < C; c += 4) {
+        float ps[4] = {0.f, 0.f, 0.f, 0.f}, pe[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const float* e = E + (long long)min(c + u, C - 1) * ldE;
+          for (int i = lane; i < D; i += 32) { float b = e[i]; ps[u] = fmaf(xs[i], b, ps[u]); pe[u] = fmaf(b, b, pe[u]); }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const float sim = warp_sum(ps[u]);
+          const float v = (loss_kind == SE_LOSS_MSE) ? -(xnorm2 + warp_sum(pe[u]) - 2.f * sim) : sim;
+          if (c + u < C) { if (fabsf(v - mine) < 1e-6f) tcnt += 1.f; else if (v > mine) gcnt += 1.f; }
         }
       }
     }
-    float ref = (loss_kind == SE_LOSS_MSE) ? true_dist : true_sim;
-    if (lane == 0) acc[row] = (fabsf(best - ref) < 1e-6f) ? 1.f : 0.f;
+    if (lane == 0) {
+      if (acc) acc[row] = (fabsf(best - ref) < 1e-6f) ? 1.f : 0.f;
+      if (rank_out) rank_out[row] = tcnt > 0.f ? gcnt : (float)C;
+    }
   }
 
   // ---- backward
@@ -174,6 +253,18 @@ embed_head_kernel(const float* __restrict__ z, int ldz, const int* __restrict__ 
         float g = -loss_scale * t[i] + (ex ? ex[i] : 0.f);
         dzr[i] = inv * (g - xs[i] * xg);
       }
+    } else if (loss_kind == SE_LOSS_SOFTMAX_CORR) {
+      // g = dL/dx = -scale*t + extra ; softmax Jacobian: dz_j = x_j * (g_j - <x,g>)
+      float xg = 0.f;
+      for (int i = lane; i < D; i += 32) {
+        float g = -loss_scale * t[i] + (ex ? ex[i] : 0.f);
+        xg = fmaf(xs[i], g, xg);
+      }
+      xg = warp_sum(xg);
+      for (int i = lane; i < D; i += 32) {
+        float g = -loss_scale * t[i] + (ex ? ex[i] : 0.f);
+        dzr[i] = xs[i] * (g - xg);
+      }
     } else if (loss_kind == SE_LOSS_UNNORM_CORR) {
       for (int i = lane; i < D; i += 32) dzr[i] = -loss_scale * t[i] + (ex ? ex[i] : 0.f);
     } else {
@@ -186,7 +277,7 @@ embed_head_kernel(const float* __restrict__ z, int ldz, const int* __restrict__ 
 __global__ void __launch_bounds__(HEAD_WARPS * 32)
 softmax_xent_kernel(const float* __restrict__ logits, int ld, const int* __restrict__ labels, int B, int C, float scale,
                     float* __restrict__ prob, float* __restrict__ loss, float* __restrict__ acc,
-                    float* __restrict__ dlogits) {
+                    float* __restrict__ dlogits, float* __restrict__ rank_out) {
   pdl_grid_sync();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int row = blockIdx.x * HEAD_WARPS + warp;
@@ -214,6 +305,13 @@ softmax_xent_kernel(const float* __restrict__ logits, int ld, const int* __restr
     if (loss) loss[row] = -logf(pyc);
     if (acc) acc[row] = (arg == lab) ? 1.f : 0.f;
   }
+  if (rank_out) {   // utils.top_k_acc (utils.py:49-54) = in_top_k: classes with a strictly larger probability than the label's
+    const float ll = lr[lab];
+    float above = 0.f;
+    for (int i = lane; i < C; i += 32) above += (lr[i] > ll) ? 1.f : 0.f;
+    above = warp_sum(above);
+    if (lane == 0) rank_out[row] = above;
+  }
   const bool live = (py >= lo) && (py <= hi);
   for (int i = lane; i < C; i += 32) {
     float p = expf(lr[i] - m) * invs;
@@ -229,9 +327,17 @@ using namespace se;
 extern "C" int se_embed_head_fwd_bwd(const float* z, int ldz, const int32_t* labels, const float* E, int ldE, int B,
                                      int D, int C, int loss_kind, float loss_scale, const float* extra_dx, float* x_out,
                                      float* loss, float* acc, float* dz, void* stream) {
+  return se_embed_head_fwd_bwd_ex(z, ldz, labels, E, ldE, B, D, C, loss_kind, loss_scale, extra_dx, x_out, loss, acc, dz,
+                                  nullptr, stream);
+}
+
+extern "C" int se_embed_head_fwd_bwd_ex(const float* z, int ldz, const int32_t* labels, const float* E, int ldE, int B,
+                                        int D, int C, int loss_kind, float loss_scale, const float* extra_dx, float* x_out,
+                                        float* loss, float* acc, float* dz, float* rank_out, void* stream) {
   SE_REQUIRE(z && labels && E && B > 0 && D > 0 && C > 0, "bad arguments");
   SE_REQUIRE(ldz >= D && ldE >= D, "leading dimension smaller than D");
-  SE_REQUIRE(loss_kind >= 0 && loss_kind <= 2, "unknown loss kind");
+  SE_REQUIRE(loss_kind >= 0 && loss_kind <= 3, "unknown loss kind");
+  SE_REQUIRE(loss_kind != SE_LOSS_SOFTMAX_CORR || C >= 1, "bad arguments");
   const int Dp = (D + 3) & ~3;
   size_t smem = (size_t)HEAD_WARPS * Dp * sizeof(float);
   SE_REQUIRE(smem <= 48 * 1024, "D too large for the fused head (max 3072)");
@@ -240,20 +346,25 @@ extern "C" int se_embed_head_fwd_bwd(const float* z, int ldz, const int32_t* lab
   int grid = ceil_div(B, HEAD_WARPS);
   int es_classes = 0;
   const size_t es_bytes = (size_t)C * (D + 1) * sizeof(float);
-  if (acc && smem + es_bytes <= 48 * 1024) { es_classes = C; smem += es_bytes; }
+  if ((acc || rank_out) && loss_kind != SE_LOSS_SOFTMAX_CORR && smem + es_bytes <= 48 * 1024) { es_classes = C; smem += es_bytes; }
   if (vec)
     launch(embed_head_kernel<true>, dim3(grid), dim3(HEAD_WARPS * 32), smem, as_stream(stream), z, ldz, labels, E, ldE, B, D, C, loss_kind,
-           loss_scale, extra_dx, x_out, loss, acc, dz, es_classes);
+           loss_scale, extra_dx, x_out, loss, acc, dz, rank_out, es_classes);
   else
     launch(embed_head_kernel<false>, dim3(grid), dim3(HEAD_WARPS * 32), smem, as_stream(stream), z, ldz, labels, E, ldE, B, D, C, loss_kind,
-           loss_scale, extra_dx, x_out, loss, acc, dz, es_classes);
+           loss_scale, extra_dx, x_out, loss, acc, dz, rank_out, es_classes);
   return check_launch("embed_head_kernel");
 }
 
 extern "C" int se_softmax_xent_fwd_bwd(const float* logits, int ld, const int32_t* labels, int B, int C, float scale,
                                        float* prob, float* loss, float* acc, float* dlogits, void* stream) {
+  return se_softmax_xent_fwd_bwd_ex(logits, ld, labels, B, C, scale, prob, loss, acc, dlogits, nullptr, stream);
+}
+
+extern "C" int se_softmax_xent_fwd_bwd_ex(const float* logits, int ld, const int32_t* labels, int B, int C, float scale,
+                                          float* prob, float* loss, float* acc, float* dlogits, float* rank_out, void* stream) {
   SE_REQUIRE(logits && labels && B > 0 && C > 0 && ld >= C, "bad arguments");
   launch(softmax_xent_kernel, dim3(ceil_div(B, HEAD_WARPS)), dim3(HEAD_WARPS * 32), 0, as_stream(stream), logits, ld, labels, B, C, scale,
-                                                                                         prob, loss, acc, dlogits);
+         prob, loss, acc, dlogits, rank_out);
   return check_launch("softmax_xent_kernel");
 }

@@ -126,6 +126,22 @@ extern "C" int se_sgd_prepare(const float* p, float* g, int64_t n, const se_l2_s
   return check_launch("sgd_prepare_kernel");
 }
 
+// Keras SGD(decay): lr_t = lr / (1 + decay * iterations), iterations counted by the optimizer (learn_image_embeddings.py:
+// 224-236 derives `decay` from --max_decay).  state = {lr (set by the schedule), decay, iterations, lr_t (output)}.
+__global__ void sgd_schedule_kernel(float* __restrict__ state) {
+  pdl_grid_sync();
+  if (threadIdx.x == 0) {
+    state[3] = state[0] / (1.f + state[1] * state[2]);
+    state[2] += 1.f;
+  }
+}
+
+extern "C" int se_sgd_schedule(float* lr_state, void* stream) {
+  SE_REQUIRE(lr_state != nullptr, "bad arguments");
+  launch(sgd_schedule_kernel, dim3(1), dim3(32), 0, as_stream(stream), lr_state);
+  return check_launch("sgd_schedule_kernel");
+}
+
 extern "C" int se_sgd_apply(float* p, const float* g, float* v, int64_t n, float lr, float momentum, int nesterov,
                             float clipnorm, const double* out, void* stream) {
   SE_REQUIRE(p && g && v && out && n > 0, "bad arguments");

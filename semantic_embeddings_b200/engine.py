@@ -17,7 +17,8 @@ from . import _lib
 from ._lib import Op
 from .graph import Graph, Node, T
 
-LOSS_KINDS = {'inv_corr': _lib.SE_LOSS_INV_CORR, 'unnorm_corr': _lib.SE_LOSS_UNNORM_CORR, 'mse': _lib.SE_LOSS_MSE}
+LOSS_KINDS = {'inv_corr': _lib.SE_LOSS_INV_CORR, 'unnorm_corr': _lib.SE_LOSS_UNNORM_CORR, 'mse': _lib.SE_LOSS_MSE,
+              'softmax_corr': _lib.SE_LOSS_SOFTMAX_CORR}
 
 
 def _vp(x):
@@ -32,9 +33,10 @@ def _vp(x):
 class Engine:
     def __init__(self, graph, batch, embedding, loss='inv_corr', cls_weight=0.0, num_classes=None,
                  mode=_lib.SE_MODE_F32, device='cuda:0', momentum=0.9, nesterov=False, clipnorm=10.0,
-                 world_size=1, fuse_stats=True, use_cuda_graph=True, seed=0, fuse_conv_bn=False):
+                 world_size=1, fuse_stats=True, use_cuda_graph=True, seed=0, fuse_conv_bn=False, decay=0.0):
         if loss not in LOSS_KINDS:
-            raise ValueError('loss %r is not supported by the fused head (softmax_corr is not on the hot path)' % loss)
+            raise ValueError('unknown loss %r' % loss)
+        self.decay = float(decay)
         self.lib = _lib.load()
         self.dev = torch.device(device)
         if self.dev.type == 'cuda':
@@ -152,6 +154,8 @@ class Engine:
         self.acc_buf = torch.zeros(B, **f32)
         self.cls_loss_buf = torch.zeros(B, **f32)
         self.cls_acc_buf = torch.zeros(B, **f32)
+        self.rank_buf = torch.zeros(B, **f32)          # top-k metrics: rank of the true class (se_embed_head_fwd_bwd_ex)
+        self.cls_rank_buf = torch.zeros(B, **f32)
         # BatchNorm scratch: per BN [fwd sums 2C | bwd sums 2C] float64, saved mean / invstd
         self.bn_slot, tot = {}, 0
         for n in self.nodes:
@@ -162,7 +166,8 @@ class Engine:
         self.stats = torch.zeros(max(tot, 4), dtype=torch.float64, device=dev)
         self.saved = torch.zeros(max(tot // 2 + 4, 4), **f32)
         self.sgd_out = torch.zeros(2, dtype=torch.float64, device=dev)
-        self.lr_dev = torch.zeros(1, **f32)
+        self.lr_dev = torch.zeros(4, **f32)            # {lr, decay, iterations, lr_t}: se_sgd_schedule
+        self.lr_dev[1] = self.decay
         self.set_weights(self._initial_weights(seed))
 
     def _initial_weights(self, seed):
@@ -349,15 +354,21 @@ class Engine:
                 ii = [self.D, self.D, self.B, self.D, self.C, LOSS_KINDS[self.loss]]
                 dz = None if has_cls else Gd[n.inputs[0].name]
                 fwd.append(self._op(_lib.OP_HEAD, ii, [scale],
-                                    [z, self.labels, self.E, None, out, self.loss_buf, self.acc_buf, dz]))
+                                    [z, self.labels, self.E, None, out, self.loss_buf, self.acc_buf, dz, self.rank_buf]))
                 inf.append(self._op(_lib.OP_HEAD, ii, [scale], [z, self.labels, self.E, None, out, None, None, None]))
+                self._eval_head = self._op(_lib.OP_HEAD, ii, [scale], [z, self.labels, self.E, None, out, self.loss_buf,
+                                                                        self.acc_buf, None, self.rank_buf])
             elif n.op == 'xent':
                 lg = n.inputs[0]
                 fwd.append(self._op(_lib.OP_XENT, [self.num_classes, self.B, self.num_classes],
                                     [self.cls_weight * scale],
-                                    [A[lg.name], self.labels, out, self.cls_loss_buf, self.cls_acc_buf, Gd[lg.name]]))
+                                    [A[lg.name], self.labels, out, self.cls_loss_buf, self.cls_acc_buf, Gd[lg.name],
+                                     self.cls_rank_buf]))
                 inf.append(self._op(_lib.OP_XENT, [self.num_classes, self.B, self.num_classes], [0.0],
                                     [A[lg.name], self.labels, out, None, None, None]))
+                self._eval_xent = self._op(_lib.OP_XENT, [self.num_classes, self.B, self.num_classes], [0.0],
+                                           [A[lg.name], self.labels, out, self.cls_loss_buf, self.cls_acc_buf, None,
+                                            self.cls_rank_buf])
             else:
                 raise ValueError(n.op)
         # ---------------- backward
@@ -465,7 +476,16 @@ class Engine:
                         p=[self.P, self.G, self.nparams, ctypes.addressof(self.seg_array), self.sgd_out]),
                self._op(_lib.OP_SGD_APPLY, [1 if self.nesterov else 0], [self.momentum, self.clipnorm],
                         [self.P, self.G, self.nparams, self.lr_dev, self.sgd_out, self.V])]
+        ev = []
+        for o in inf:                               # validation pass: inference-mode forward that also writes the metrics
+            if o.opcode == _lib.OP_HEAD:
+                ev.append(self._eval_head)
+            elif o.opcode == _lib.OP_XENT:
+                ev.append(self._eval_xent)
+            else:
+                ev.append(o)
         self.plans = {'fwd': self._pack(fwd), 'bwd': self._pack(bwd), 'opt': self._pack(opt), 'infer': self._pack(inf),
+                      'eval': self._pack(ev),
                       'fwdbwd': self._pack(fwd + bwd), 'step': self._pack(fwd + bwd + opt)}
 
     @staticmethod
@@ -510,7 +530,21 @@ class Engine:
         self.labels.copy_(labels.to(torch.int32), non_blocking=True)
 
     def set_lr(self, lr):
-        self.lr_dev.fill_(float(lr))
+        """The schedule's learning rate (sgdr_callback.py:75-87 sets it once per epoch); the step's effective rate is
+        lr / (1 + decay * iterations) (Keras SGD `decay`, learn_image_embeddings.py:224-236), derived on the device."""
+        self.lr_dev[0:1].fill_(float(lr))
+
+    def set_iterations(self, n):
+        """Optimizer step counter of the decay term (resuming a snapshot)."""
+        self.lr_dev[2:3].fill_(float(n))
+        self.iterations = int(n)
+
+    def evaluate(self, x, labels):
+        """Inference-mode forward (BatchNorm moving statistics) + losses / metrics of one batch: what Keras' validation
+        pass and evaluate_generator compute (learn_image_embeddings.py:238-246).  Returns the metrics dict."""
+        self.load_batch(x, labels)
+        self._run('eval')
+        return self.metrics()
 
     def forward_backward(self):
         self._run('fwdbwd')
@@ -543,6 +577,31 @@ class Engine:
         if self.xent_node is not None:
             out['cls_loss'] = float(self.cls_loss_buf.cpu().numpy().mean())
             out['cls_acc'] = float(self.cls_acc_buf.cpu().numpy().mean())
+        return out
+
+    def per_sample_metrics(self, ks=()):
+        """Per-sample loss / accuracy arrays of the last batch (and accuracy@k for k in ks): what a validation loop sums
+        when its last batch is only partly filled."""
+        out = {'loss': self.loss_buf.cpu().numpy(), 'acc': self.acc_buf.cpu().numpy()}
+        r = self.rank_buf.cpu().numpy() if ks else None
+        for k in ks:
+            out['acc%d' % k] = (r < k).astype(np.float32)
+        if self.xent_node is not None:
+            out['cls_loss'] = self.cls_loss_buf.cpu().numpy()
+            out['cls_acc'] = self.cls_acc_buf.cpu().numpy()
+            rc = self.cls_rank_buf.cpu().numpy() if ks else None
+            for k in ks:
+                out['cls_acc%d' % k] = (rc < k).astype(np.float32)
+        return out
+
+    def top_k_accuracy(self, ks):
+        """--top_k_acc (learn_image_embeddings.py:167-180): accuracy@k of the last batch for every k in `ks`, from the rank
+        of the true class that the head kernels wrote: {'acc<k>': ..., 'cls_acc<k>': ...}."""
+        r = self.rank_buf.cpu().numpy()
+        out = {'acc%d' % k: float((r < k).mean()) for k in ks}
+        if self.xent_node is not None:
+            rc = self.cls_rank_buf.cpu().numpy()
+            out.update({'cls_acc%d' % k: float((rc < k).mean()) for k in ks})
         return out
 
     def metrics_async(self):

@@ -3,9 +3,9 @@ on top of the CUDA all-pairs distance kernel (se_pairwise_dist).
 
 Same signature, accepted input forms, id mapping, error and -- for drop-in fidelity -- the same side
 effect (with normalize=True a caller-supplied ndarray is L2-normalised in place, evaluate_retrieval.py:58).
-The distance matrix (lines 56-63) is computed by the hand-written kernel; the ranking (line 67) is the
-"next" row of the scope table and is currently a device-side stable sort of each
-row block (ascending distance, ties by ascending index).
+The distance matrix (lines 56-63), the ranking (line 67; ascending distance, ties by ascending index) and the
+hierarchical-precision metrics are hand-written kernels (se_pairwise_dist, se_row_argsort / se_row_topk,
+se_hier_metrics); `retrieval_metrics` chains them per block of query rows without a host round trip.
 """
 import pickle
 
@@ -71,13 +71,58 @@ def pairwise_ranking(features, normalize=False, block_rows=4096, mode=None, devi
     for r0 in range(0, N, block_rows):
         r = min(block_rows, N - r0)
         d = pairwise_distances(None, normalize, r0, r, mode, out=buf[:r], feat_dev=fd)
-        if k <= TOPK_MAX and N <= TOPK_MAX_N:
-            # the ranks the metrics read (class_hierarchy.py clip_ahp): hand-written per-row radix-select kernel
+        if k <= TOPK_MAX and N <= TOPK_MAX_N and k < N:
+            # the ranks the clipped metrics read (class_hierarchy.py clip_ahp): per-row radix-select kernel
             idx = row_topk(d, k)[0]
         else:
-            idx = torch.sort(d, dim=-1, stable=True).indices[:, :k]     # full-length rankings: library sort
+            idx = row_argsort(d)[:, :k]                                  # full-length rankings: se_row_argsort
         ranking[r0:r0 + r] = idx.cpu().numpy()
     return ranking
+
+
+def row_argsort(dist):
+    """Full ranking of every row of a device matrix (ascending, ties by index): evaluate_retrieval.py:67 on the GPU
+    (se_row_argsort: bitonic network with shared-memory sub-sorts, one CTA per row).  Returns int32 [rows, n]."""
+    import torch
+    rows, n = dist.shape
+    assert dist.is_cuda and dist.dtype == torch.float32 and dist.stride(1) == 1
+    idx = torch.empty((rows, n), dtype=torch.int32, device=dist.device)
+    ws = torch.empty(int(_lib.load().se_row_argsort_workspace_bytes(rows, n)), dtype=torch.uint8, device=dist.device)
+    with torch.cuda.device(dist.device):
+        _lib.call('se_row_argsort', _lib.ptr(dist), dist.stride(0), rows, n, _lib.ptr(idx), idx.stride(0), _lib.ptr(ws),
+                  _lib.stream_ptr())
+    return idx
+
+
+def retrieval_metrics(features, labels_ix, wup_lut, lcs_height_lut, kcurve=250, clip_ahp=None, compute_ap=True,
+                      normalize=False, block_rows=2048, mode=None, device=None, rank=0, world=1):
+    """evaluate_retrieval.py:186-195 without leaving the GPU: for every database item as the query, the distance row
+    (se_pairwise_dist), its ranking (se_row_argsort, or se_row_topk when only the first ranks are read) and the metrics
+    (se_hier_metrics) are computed block of rows by block of rows; nothing of size N x N reaches the host.
+    labels_ix: class index per item; clip_ahp: None / 0 -> AHP over the whole list, K -> AHP@K.
+    Row blocks are sharded over `world` processes (no exchange step: every query is independent); the caller averages.
+    Returns {'curve' [rows, 2, kcurve], 'ahp' [rows, 2], 'ap' [rows]} for this rank's rows and (row0, rows)."""
+    import torch
+    from .class_hierarchy import hierarchical_metrics
+    from .parallel import shard_rows
+    f = np.ascontiguousarray(np.asarray(features, dtype=np.float32))
+    dev = torch.device(device or 'cuda')
+    fd = torch.from_numpy(f).to(dev)
+    N = f.shape[0]
+    clip = int(clip_ahp) if clip_ahp else -1
+    full = compute_ap or clip < 0                          # AP and the unclipped AHP read the whole list
+    K1 = N if full else min(N, max(kcurve, clip) + 1)
+    row0, rows = shard_rows(N, world, rank)
+    outs = []
+    buf = torch.empty((min(block_rows, max(rows, 1)), N), dtype=torch.float32, device=dev)
+    for r0 in range(row0, row0 + rows, block_rows):
+        r = min(block_rows, row0 + rows - r0)
+        d = pairwise_distances(None, normalize, r0, r, mode, out=buf[:r], feat_dev=fd)
+        idx = row_argsort(d) if (full or K1 > TOPK_MAX or N > TOPK_MAX_N) else row_topk(d, K1)[0]
+        outs.append(hierarchical_metrics(idx[:, :K1] if not full else idx, np.arange(r0, r0 + r), labels_ix, wup_lut,
+                                         lcs_height_lut, min(kcurve, K1 - 1), clip, compute_ap))
+    res = {k: np.concatenate([o[k] for o in outs]) for k in (outs[0] if outs else {})}
+    return res, (row0, rows)
 
 
 TOPK_MAX, TOPK_MAX_N = 1024, 52000

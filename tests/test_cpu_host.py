@@ -10,6 +10,7 @@ import numpy as np
 import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLDEN = os.path.join(ROOT, 'tests', 'golden')
 G = os.path.join(ROOT, 'tests', 'golden')
 
 
@@ -246,3 +247,66 @@ def test_bench_reference_arm_prints_one_json_line():
     assert d['cpu_baseline']['kind'] == 'port' and d['cpu_baseline']['cores'] >= 1 and 'sample' in d['cpu_baseline']
     assert d['e2e']['h2d_bytes_per_step'] == 0 and d['e2e']['d2h_bytes_per_step'] == 0 and d['e2e']['value'] == d['value']
     assert d['n_gpus'] == 1 and d['steps'] == 1
+
+
+def test_class_hierarchy_restatement_matches_the_reference_tables(tmp_path):
+    """semantic_embeddings_b200.class_hierarchy.ClassHierarchy (own implementation of class_hierarchy.py:7-208, :349-380)
+    on the CIFAR-100 taxonomy: Wu-Palmer and LCS-height tables equal to the ones the reference's class produced
+    (tests/golden/retrieval_ref.npz, make_golden.py), from a relation file in both orientations."""
+    from semantic_embeddings_b200.class_hierarchy import ClassHierarchy, ideal_gains
+    pc = np.load(os.path.join(GOLDEN, 'cifar_hierarchy.npz'))['parent_child']
+    fx = np.load(os.path.join(GOLDEN, 'retrieval_ref.npz'))
+    f1, f2 = tmp_path / 'pc.txt', tmp_path / 'isa.txt'
+    f1.write_text('\n'.join('%d %d' % (p, c) for p, c in pc) + '\n\n')
+    f2.write_text('\n'.join('%d %d' % (c, p) for p, c in pc) + '\n')
+    for h in (ClassHierarchy.from_file(str(f1), id_type=int), ClassHierarchy.from_file(str(f2), is_a_relations=True, id_type=int)):
+        wup, lcsh = h.similarity_luts(list(range(100)))
+        assert np.array_equal(wup, fx['wup_lut']) and np.array_equal(lcsh, fx['lcs_height_lut'])
+        assert h.is_tree() and h.wup_similarity(3, 3) == 1.0 and h.lcs_height(5, 5) == 0.0
+        assert h.lcs(0, 0) == 0 and h.shortest_path_length(7, 7) == 0
+    # ideal gains = cumsum of the sorted similarities of the whole database (class_hierarchy.py:268,280)
+    labels = fx['labels'].astype(np.int32)
+    bw, bl = ideal_gains(labels, wup, lcsh, len(labels))
+    for c in (0, 17, 99):
+        np.testing.assert_allclose(bw[c], np.cumsum(np.sort(wup[c, labels])[::-1]), rtol=0, atol=1e-12)
+        np.testing.assert_allclose(bl[c], np.cumsum(np.sort(1.0 - lcsh[c, labels])[::-1]), rtol=0, atol=1e-12)
+    with pytest.raises(ValueError):
+        ClassHierarchy({1: [2], 2: [1]}, {2: [1], 1: [2]})          # a cycle
+
+
+def test_cli_scripts_parse_their_reference_flags():
+    """Both drop-in scripts import from the repo (never from /root/reference), accept the reference's flags
+    (learn_image_embeddings.py:57-94, evaluate_retrieval.py:157-173) and reject malformed booleans like the reference."""
+    import argparse
+    import importlib
+    lie = importlib.import_module('learn_image_embeddings')
+    er = importlib.import_module('evaluate_retrieval')
+    assert os.path.dirname(os.path.abspath(lie.__file__)) == ROOT and os.path.dirname(os.path.abspath(er.__file__)) == ROOT
+    assert lie.get_data_generator.__module__ == 'semantic_embeddings_b200.datasets'
+    a = lie.build_parser().parse_args(['--dataset', 'CIFAR-100', '--data_root', '/x', '--embedding', 'e.pickle', '--loss',
+                                       'softmax_corr', '--max_decay', '0.1', '--top_k_acc', '5', '10', '--snapshot_best',
+                                       '--sgdr_max_lr', '0.05', '--gpus', '8'])
+    assert a.loss == 'softmax_corr' and a.top_k_acc == [5, 10] and a.snapshot_best == 'val_loss' and a.arith == 'tf32x3'
+    assert a.batch_size == 100 and a.clipgrad == 10.0 and a.architecture == 'simple' and a.lr_schedule == 'SGDR'
+    assert er.str2bool('T') is True and er.str2bool('no') is False
+    with pytest.raises(argparse.ArgumentTypeError):
+        er.str2bool('maybe')
+    assert er.METRICS[4] == 'AHP (WUP)' and er.METRICS[-1] == 'AP' and len(er.METRICS) == 11
+    assert callable(er.pairwise_retrieval)
+
+
+def test_augment_oracle_is_the_scipy_transform_keras_delegates_to():
+    """oracle/augment.py: shifts are scipy.ndimage.affine_transform(order=1, mode='nearest') per channel, flip afterwards,
+    standardize with epsilon 1e-7; an integer shift is a plain roll with edge replication."""
+    from oracle import augment as oaug
+    rng = np.random.RandomState(1)
+    x = rng.randint(0, 255, (8, 8, 3)).astype(np.float32)
+    out = oaug.random_transform(x, 2.0, -1.0, False)          # out[h, w] = x[h + 2, w - 1], clamped
+    hh = np.clip(np.arange(8) + 2, 0, 7)
+    ww = np.clip(np.arange(8) - 1, 0, 7)
+    assert np.allclose(out, x[hh][:, ww])
+    assert np.allclose(oaug.random_transform(x, 0.0, 0.0, True), x[:, ::-1])
+    half = oaug.random_transform(x, 0.5, 0.0, False)
+    assert np.allclose(half[:-1], 0.5 * (x[:-1] + x[1:]), atol=1e-4) and np.allclose(half[-1], x[-1], atol=1e-4)
+    mean, std = oaug.fit_statistics(np.stack([x, x + 1]))
+    assert np.allclose(oaug.standardize(x, mean, std), (x - mean) / (std + 1e-7))

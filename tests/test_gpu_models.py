@@ -370,3 +370,170 @@ def test_pairwise_retrieval_api_matches_reference_fixture():
     np.testing.assert_allclose(np.linalg.norm(f, axis=1), 1.0, atol=1e-5)
     with pytest.raises(ValueError):
         pairwise_retrieval({0: np.zeros((2, 3), np.float32), 1: np.zeros((2, 3), np.float32)})
+
+
+# ----------------------------------------------------------------------------------------------- BASELINE-size parity
+# The step tests above use small batches so that the float64 oracle with its ReLU-flip probes stays fast; the cases
+# below run the sizes BASELINE.json quotes (many tiles per CTA, full CTA grids, CUDA graph) in the benchmarked
+# arithmetic (SE_MODE_TF32X3) against ONE float64 oracle pass each.
+
+def test_resnet110_batch128_step_matches_oracle_in_benchmarked_mode():
+    """BASELINE configs[1]: CIFAR-100 ResNet-110(-fc), cosine loss, batch 128, one full training step from a CUDA graph
+    in SE_MODE_TF32X3 -- exactly what bench.py times.  Embeddings / loss <= 1e-4, gradient within the fp32 noise floor."""
+    from oracle import models as omodels
+    from oracle import train as otrain
+    from semantic_embeddings_b200 import _lib, utils
+    from semantic_embeddings_b200.engine import Engine
+    emb = class_matrix('cifar100')
+    B = 128
+    om = omodels.build_network(100, 'resnet-110-fc', input_channels=3, seed=61)
+    omodels.randomize(om, seed=62)
+    to_f32_exact(om)
+    eng = Engine(utils.build_network(100, 'resnet-110-fc', input_channels=3), B, emb, mode=_lib.SE_MODE_TF32X3,
+                 use_cuda_graph=True)
+    eng.set_weights(oracle_weights_np(om))
+    g = torch.Generator().manual_seed(63)
+    x = torch.randn(B, 32, 32, 3, generator=g, dtype=torch.float64).float()
+    y = torch.randint(0, 100, (B,), generator=g)
+    vel = otrain.make_velocity(om)
+    emb_t = torch.as_tensor(emb.astype(np.float32)).double()
+    # noise floor of the gradient at this size: the same step by the oracle in float32 (ReLU masks of pre-activations that
+    # fp32 cannot resolve flip against float64; the more samples, the more such elements)
+    import copy
+    om32 = copy.deepcopy(om)
+    otrain.cast_model(om32, torch.float32)
+    _, grads32, _ = otrain.train_step(om32, x, y, emb_t.float(), {k: v.float() for k, v in vel.items()}, 0.05)
+    obj, grads, norm = otrain.train_step(om, x.double(), y, emb_t, vel, 0.05)
+    floor = max(_grad_errors({k: v.numpy() for k, v in grads32.items()}, grads, norm)[:2])
+    eng.train_step(x, y, lr=0.05)
+    m = eng.metrics()
+    gn, _ = eng.grad_norm_and_reg()
+    e_loss = abs(m['loss'] - float(obj['embed_loss'].detach())) / max(1.0, abs(float(obj['embed_loss'].detach())))
+    e_emb = rel_max(eng.act['head_out'].cpu().numpy(), obj['emb'].detach().numpy())
+    gg, gw, name = _grad_errors(eng.get_grads(), grads, norm)
+    ew = eng.get_weights()
+    e_w = max(rel_l2(ew[n], om.params[n].numpy()) for n in om.params)
+    report('baseline_size', case='resnet-110-fc B=128 step tf32x3 graph', loss=e_loss, emb=e_emb, gnorm=abs(gn - norm) / norm,
+           grad_global=gg, grad_worst=gw, worst=name, weights=e_w, grad_floor_f32_oracle=floor)
+    assert e_loss < 1e-4 and e_emb < 1e-4, (e_loss, e_emb)
+    gtol = max(2e-3, 3 * floor)
+    assert abs(gn - norm) / norm < 1e-3 and gg < gtol and e_w < gtol * 0.05, (gn, norm, gg, e_w, floor)
+
+
+def test_wrn_28_10_batch64_forward_loss_in_benchmarked_mode():
+    """BASELINE configs[2] per-GPU shard: WRN-28-10, batch 64, cosine + softmax combined loss (cls_weight 0.1): forward
+    pass, both losses and the classifier probabilities in SE_MODE_TF32X3 (160/320/640-channel tensor-core tiles)."""
+    from oracle import models as omodels
+    from oracle import train as otrain
+    from semantic_embeddings_b200 import _lib, utils
+    from semantic_embeddings_b200.engine import Engine
+    emb = class_matrix('cifar100')
+    B = 64
+    om = omodels.build_network(100, 'wrn-28-10', input_channels=3, seed=71)
+    omodels.randomize(om, seed=72)
+    cls = otrain.ClsHead(100, 100, seed=73)
+    omodels.randomize(cls.params, seed=74)
+    to_f32_exact(om, cls)
+    eng = Engine(utils.build_network(100, 'wrn-28-10', input_channels=3), B, emb, cls_weight=0.1, num_classes=100,
+                 mode=_lib.SE_MODE_TF32X3, use_cuda_graph=False)
+    eng.set_weights(oracle_weights_np(om, cls))
+    g = torch.Generator().manual_seed(75)
+    x = torch.randn(B, 32, 32, 3, generator=g, dtype=torch.float64).float()
+    y = torch.randint(0, 100, (B,), generator=g)
+    emb_t = torch.as_tensor(emb.astype(np.float32)).double()
+    with torch.no_grad():
+        obj = otrain.train_objective(om, x.double(), y, emb_t, 'inv_corr', cls, 0.1)
+    eng.load_batch(x, y)
+    eng._run('fwd', graph=False)
+    m = eng.metrics()
+    e_loss = abs(m['loss'] - float(obj['embed_loss'])) / max(1.0, abs(float(obj['embed_loss'])))
+    e_cls = abs(m['cls_loss'] - float(obj['cls_loss'])) / max(1.0, abs(float(obj['cls_loss'])))
+    e_emb = rel_max(eng.act['head_out'].cpu().numpy(), obj['emb'].numpy())
+    report('baseline_size', case='wrn-28-10 B=64 forward tf32x3', loss=e_loss, cls_loss=e_cls, emb=e_emb)
+    assert e_loss < 1e-4 and e_cls < 1e-4 and e_emb < 1e-4, (e_loss, e_cls, e_emb)
+
+
+def test_resnet50_224_forward_matches_oracle():
+    """BASELINE configs[3] geometry: ResNet-50 at 224 x 224 x 3 with the 555-d NAB head, batch 4, forward + loss."""
+    from oracle import models as omodels
+    from oracle import train as otrain
+    from semantic_embeddings_b200 import _lib
+    from semantic_embeddings_b200.models import resnet50
+    from semantic_embeddings_b200.engine import Engine
+    emb = class_matrix('nab')
+    C, D = emb.shape
+    B = 4
+    om = omodels.build_resnet50(D, 3, seed=81)
+    omodels.randomize(om, seed=82)
+    to_f32_exact(om)
+    eng = Engine(resnet50.ResNet50(D, input_shape=(224, 224, 3)), B, emb, mode=_lib.SE_MODE_TF32X3, use_cuda_graph=False)
+    eng.set_weights(oracle_weights_np(om))
+    g = torch.Generator().manual_seed(83)
+    x = torch.randn(B, 224, 224, 3, generator=g, dtype=torch.float64).float()
+    y = torch.randint(0, C, (B,), generator=g)
+    emb_t = torch.as_tensor(emb.astype(np.float32)).double()
+    with torch.no_grad():
+        obj = otrain.train_objective(om, x.double(), y, emb_t)
+    eng.load_batch(x, y)
+    eng._run('fwd', graph=False)
+    e_loss = abs(eng.metrics()['loss'] - float(obj['embed_loss'])) / max(1.0, abs(float(obj['embed_loss'])))
+    e_emb = rel_max(eng.act['head_out'].cpu().numpy(), obj['emb'].numpy())
+    report('baseline_size', case='resnet-50 224x224 B=4 forward', loss=e_loss, emb=e_emb)
+    assert e_loss < 1e-4 and e_emb < 1e-4, (e_loss, e_emb)
+
+
+def test_cli_train_feature_dump_then_retrieval_cli(tmp_path, capsys):
+    """End to end through the two drop-in scripts (learn_image_embeddings.py:258-275 -> evaluate_retrieval.py:157-208):
+    train one epoch on the synthetic dataset with --top_k_acc / --max_decay / --snapshot, write the feature pickle, run
+    the retrieval script on it, and check (a) the pickle format, (b) every number of the printed table and the CSV against
+    the CPU oracle (oracle/retrieval.py rankings + oracle/hierarchy.py metrics) computed from the SAME pickle."""
+    import pickle
+    import learn_image_embeddings as lie
+    import evaluate_retrieval as er
+    from oracle import hierarchy as ohier
+    from oracle import retrieval as oret
+    emb_p, hier_p = tmp_path / 'emb.pickle', tmp_path / 'hier.txt'
+    with open(emb_p, 'wb') as f:
+        pickle.dump({'embedding': class_matrix('cifar100'), 'ind2label': list(range(100)),
+                     'label2ind': {i: i for i in range(100)}}, f)
+    pc = np.load(os.path.join(G, 'cifar_hierarchy.npz'))['parent_child']
+    hier_p.write_text('\n'.join('%d %d' % (p, c) for p, c in pc) + '\n')
+    feat_p, snap_p, csv_p = tmp_path / 'feat.pickle', tmp_path / 'snap.pickle', tmp_path / 'perf.csv'
+    rc = lie.main(['--dataset', 'synthetic:2048', '--data_root', str(tmp_path), '--embedding', str(emb_p), '--architecture',
+                   'simple', '--batch_size', '64', '--epochs', '1', '--top_k_acc', '5', '--max_decay', '0.5',
+                   '--snapshot', str(snap_p), '--feature_dump', str(feat_p), '--no_progress'])
+    assert rc == 0
+    log = capsys.readouterr().out
+    assert 'Epoch 1/1' in log and 'val_loss' in log and 'val_acc5' in log
+    with open(snap_p, 'rb') as f:
+        snap = pickle.load(f)
+    assert snap['epoch'] == 1 and snap['iterations'] == 32 and len(snap['weights']) > 10 and len(snap['velocity']) > 10
+    with open(feat_p, 'rb') as f:
+        dump = pickle.load(f)
+    feats = dump['feat']
+    assert sorted(feats.keys()) == list(range(512)) and feats[0].shape == (100,) and feats[0].dtype == np.float32
+    F = np.stack([feats[i] for i in range(512)])
+    np.testing.assert_allclose(np.linalg.norm(F, axis=1), 1.0, atol=1e-5)        # l2norm wrapper of --loss inv_corr
+    rc = er.main(['--dataset', 'synthetic:2048', '--data_root', str(tmp_path), '--hierarchy', str(hier_p), '--feat', str(feat_p),
+                  '--label', 'run', '--plot_max', '20', '--clip_ahp', '30', '--csv', str(csv_p)])
+    assert rc == 0
+    table = capsys.readouterr().out
+    # the oracle on the same pickle
+    from semantic_embeddings_b200.datasets import get_data_generator
+    y = np.asarray(get_data_generator('synthetic:2048', '', None).labels_test)
+    fx = np.load(os.path.join(G, 'retrieval_ref.npz'))
+    ranking = oret.rank_stable(oret.pairwise_dist64(F, False))
+    ks = list(range(1, 21)) + [50, 100]
+    oavg, _ = ohier.hierarchical_precision(ranking, y, fx['wup_lut'], fx['lcs_height_lut'], ks=ks, compute_ahp=30, compute_ap=True)
+    row = [ln for ln in table.splitlines() if ln.startswith('run')][0]
+    vals = [float(v) for v in row.split('|')[1:]]
+    names = ['P@1 (WUP)', 'P@10 (WUP)', 'P@50 (WUP)', 'P@100 (WUP)', 'AHP@30 (WUP)', 'P@1 (LCS_HEIGHT)', 'P@10 (LCS_HEIGHT)',
+             'P@50 (LCS_HEIGHT)', 'P@100 (LCS_HEIGHT)', 'AHP@30 (LCS_HEIGHT)', 'AP']
+    assert 'AHP@30 (WUP)' in table
+    for nm, v in zip(names, vals):
+        assert abs(v - oavg[nm]) < 2e-4, (nm, v, oavg[nm])           # the table prints 4 decimals
+    lines = csv_p.read_text().strip().splitlines()
+    assert lines[0] == 'k;run' and len(lines) == 21
+    for k in range(1, 21):
+        kk, v = lines[k].split(';')
+        assert int(kk) == k and abs(float(v) - oavg['P@%d (LCS_HEIGHT)' % k]) < 2e-4

@@ -497,6 +497,89 @@ def test_embed_head_matches_oracle(shape, kind, with_extra):
     assert mism <= max(1, B // 50), mism
 
 
+@pytest.mark.parametrize('with_extra', [False, True], ids=['plain', 'extra_dx'])
+def test_embed_head_softmax_corr_matches_oracle(with_extra):
+    """--loss softmax_corr (learn_image_embeddings.py:129-130,164-166): Activation('softmax') wrapper, 1 - <t, x>, Keras
+    'accuracy', and the backward pass through the softmax; one-hot targets (the classification set-up of the paper) and
+    the unit-sphere class matrix."""
+    from oracle import nn as onn
+    from oracle import train as otrain
+    L = _lib()
+    B, D = 37, 100
+    for emb in (torch.eye(D, dtype=torch.float64),
+                torch.as_tensor(np.load(os.path.join(G, 'class_matrices.npz'))['cifar100_embedding']).float().double()):
+        g = torch.Generator().manual_seed(11)
+        z = (torch.randn(B, D, generator=g, dtype=torch.float64) * 3).float().double()
+        labels = torch.randint(0, D, (B,), generator=g)
+        extra = torch.randn(B, D, generator=g, dtype=torch.float64).float().double() * 0.01 if with_extra else None
+        zz = z.clone().requires_grad_(True)
+        x = otrain.head_forward(zz, 'softmax_corr')
+        t = emb[labels]
+        ls = otrain.per_sample_loss(t, x, 'softmax_corr')
+        obj = ls.sum() / B + ((x * extra).sum() if with_extra else 0.0)
+        (dz_ref,) = torch.autograd.grad(obj, zz)
+        acc_ref = onn.categorical_accuracy(t, x.detach())
+        zd, ed, ld = dev(z), dev(emb), dev(labels, torch.int32)
+        exd = dev(extra) if with_extra else None
+        xo, dzo = torch.empty(B, D, device='cuda'), torch.empty(B, D, device='cuda')
+        lo, ao, ro = torch.empty(B, device='cuda'), torch.empty(B, device='cuda'), torch.empty(B, device='cuda')
+        L.call('se_embed_head_fwd_bwd_ex', L.ptr(zd), D, L.ptr(ld), L.ptr(ed), D, B, D, D, 3, 1.0 / B, L.ptr(exd),
+               L.ptr(xo), L.ptr(lo), L.ptr(ao), L.ptr(dzo), L.ptr(ro), sptr())
+        assert relerr(xo.cpu(), x.detach()) < 2e-6
+        assert np.abs(lo.cpu().numpy() - ls.detach().numpy()).max() < 2e-6
+        assert relerr(dzo.cpu(), dz_ref) < 1e-5
+        assert np.array_equal(ao.cpu().numpy(), acc_ref.numpy())
+        for k in (1, 3, 5):
+            ref_k = onn.top_k_categorical_accuracy(t, x.detach(), k).numpy()
+            assert np.array_equal((ro.cpu().numpy() < k).astype(np.float64), ref_k), k
+
+
+@pytest.mark.parametrize('kind', ['inv_corr', 'mse'])
+@pytest.mark.parametrize('shape', [(64, 100, 100, 'cifar100'), (16, 555, 555, 'nab')], ids=['cifar', 'nab'])
+def test_embed_head_top_k_rank_matches_reference_metric(kind, shape):
+    """--top_k_acc (learn_image_embeddings.py:167-180): utils.nn_accuracy(embedding, dot_prod_sim, k) of the reference
+    (utils.py:85,95: any of the k best class scores within 1e-6 of the true score) for k = 1, 2, 5, 10 from the ONE rank
+    value per sample that the fused head writes; both class matrices (the 555-class one takes the global-memory path)."""
+    from oracle import nn as onn
+    from oracle import train as otrain
+    from semantic_embeddings_b200.engine import LOSS_KINDS
+    L = _lib()
+    B, D, C, key = shape
+    emb = torch.as_tensor(np.load(os.path.join(G, 'class_matrices.npz'))[key + '_embedding']).float().double()
+    g = torch.Generator().manual_seed(5)
+    labels = torch.randint(0, C, (B,), generator=g)
+    # outputs near their class embedding with enough noise that the true class lands on ranks 1 .. ~20
+    z = (emb[labels] + 0.35 * torch.randn(B, D, generator=g, dtype=torch.float64)).float().double()
+    x = otrain.head_forward(z, kind)
+    t = emb[labels]
+    zd, ed, ld = dev(z), dev(emb), dev(labels, torch.int32)
+    ao, ro = torch.empty(B, device='cuda'), torch.empty(B, device='cuda')
+    L.call('se_embed_head_fwd_bwd_ex', L.ptr(zd), D, L.ptr(ld), L.ptr(ed), D, B, D, C, LOSS_KINDS[kind], 1.0, None,
+           None, None, L.ptr(ao), None, L.ptr(ro), sptr())
+    rank = ro.cpu().numpy()
+    assert rank.max() >= 3                                  # the case exercises k > 1
+    for k in (1, 2, 5, 10):
+        ref = (onn.nn_accuracy_k(emb, t, x, k) if kind == 'mse' else onn.max_sim_acc_k(emb, t, x, k)).numpy()
+        assert np.array_equal((rank < k).astype(np.float64), ref), (k, rank, ref)
+    assert np.array_equal(ao.cpu().numpy(), (rank < 1).astype(np.float32))
+
+
+def test_sgd_schedule_is_keras_lr_decay():
+    """Keras SGD(decay) (learn_image_embeddings.py:224-236): lr_t = lr / (1 + decay * iterations), iterations counted per
+    optimizer step on the device (se_sgd_schedule), the schedule's lr changing in between."""
+    L = _lib()
+    st = torch.tensor([0.1, 0.05, 0.0, 0.0], device='cuda')
+    got = []
+    for it in range(5):
+        if it == 3:
+            st[0:1].fill_(0.02)
+        L.call('se_sgd_schedule', L.ptr(st), sptr())
+        got.append(float(st[3].item()))
+    ref = [np.float32(lr) / (np.float32(1) + np.float32(0.05) * np.float32(it)) for it, lr in enumerate([0.1, 0.1, 0.1, 0.02, 0.02])]
+    assert np.allclose(got, ref, rtol=1e-6, atol=0)
+    assert float(st[2].item()) == 5.0
+
+
 def test_embed_head_matches_reference_formulas_fixture():
     """Fixture produced by the reference's own utils.l2norm / inv_correlation / nn_accuracy (make_golden.py)."""
     L = _lib()
@@ -540,6 +623,12 @@ def test_softmax_xent_matches_oracle():
     assert np.abs(lo.cpu().numpy() - ce.detach().numpy()).max() < 2e-5
     assert relerr(do.cpu(), dl) < 2e-5
     np.testing.assert_array_equal(ao.cpu().numpy(), (prob.argmax(-1) == labels).double().numpy())
+    # utils.top_k_acc (utils.py:49-54) of the classifier output from the rank the kernel writes
+    ro = torch.empty(B, device='cuda')
+    L.call('se_softmax_xent_fwd_bwd_ex', L.ptr(ld), C, L.ptr(yd), B, C, scale, None, None, None, None, L.ptr(ro), sptr())
+    for k in (1, 3, 5):
+        ref = onn.top_k_categorical_accuracy(onehot, prob.detach(), k).numpy()
+        assert np.array_equal((ro.cpu().numpy() < k).astype(np.float64), ref), k
 
 
 @pytest.mark.parametrize('nesterov', [False, True])
@@ -713,3 +802,150 @@ def test_hierarchical_precision_kernel_matches_the_reference_metrics():
     gavg, _ = hierarchical_precision_topk(gtop, labels, fx['wup_lut'], fx['lcs_height_lut'], ks=(1, 10, 50, 100), clip_ahp=250)
     for k, name in enumerate(fx['prec250_names']):
         assert abs(gavg[str(name)] - fx['prec250_avg'][k]) < 2e-3, (name, gavg[str(name)], fx['prec250_avg'][k])
+
+
+def test_pairwise_n50000_sampled_rows_and_top251_match_oracle():
+    """BASELINE configs[4] size: N = 50 000, D = 100 unit-norm features (what an l2norm model emits), the whole 10 GB
+    matrix from the tensor-core kernel.  64 sampled rows are compared with the float64 oracle (oracle/retrieval.py,
+    evaluate_retrieval.py:56-63), and the top 251 of those rows (se_row_topk on the device matrix) with a stable argsort of
+    the float64 distances on every rank position whose gap to its neighbours exceeds the measured kernel error
+    (bit-exact rank indices on tie-free positions, SURVEY.md section 7 hard part 5)."""
+    from semantic_embeddings_b200.evaluate_retrieval import pairwise_distances, row_topk
+    N, D, K = 50000, 100, 251
+    rng = np.random.RandomState(0)
+    f = rng.randn(N, D).astype(np.float32)
+    f /= np.linalg.norm(f, axis=-1, keepdims=True)
+    fd = torch.from_numpy(f).cuda()
+    full = pairwise_distances(None, False, feat_dev=fd, mode=2)
+    assert full.shape == (N, N)
+    rows = np.unique(np.concatenate([[0, 1, 127, 128, 129, N - 129, N - 128, N - 2, N - 1], rng.randint(0, N, 55)]))[:64]
+    sub = full[torch.as_tensor(rows).cuda()].contiguous()
+    got = sub.cpu().numpy()
+    f64 = f.astype(np.float64)
+    sq = (f64 ** 2).sum(-1)
+    ref = sq[rows][:, None] + sq[None, :] - 2.0 * f64[rows] @ f64.T
+    err = float(np.abs(got - ref).max())
+    idx, val = row_topk(sub, K, want_values=True)
+    idx = idx.cpu().numpy().astype(np.int64)
+    order = np.argsort(ref, axis=-1, kind='stable')[:, :K + 1]
+    d_sorted = np.take_along_axis(ref, order, axis=-1)
+    gaps = np.diff(d_sorted, axis=-1)                       # gap between rank j and j+1, j < K
+    safe = np.ones((len(rows), K), dtype=bool)
+    tol = 4 * max(err, 1e-7)
+    safe[:, :] &= gaps[:, :K] > tol                          # distinct from the next rank
+    safe[:, 1:] &= gaps[:, :K - 1] > tol                     # ... and from the previous one
+    mism = (idx != order[:, :K]) & safe
+    report('pairwise_n50000', max_abs_err=err, tie_free_positions=float(safe.mean()), mismatches=int(mism.sum()))
+    assert err < 5e-6, err
+    assert (idx[:, 0] == rows).all()                         # every query retrieves itself first
+    assert safe.mean() > 0.9 and mism.sum() == 0, (safe.mean(), mism.sum())
+    # the device-side ranking is the exact stable order of the device distances
+    chk = torch.sort(sub, dim=-1, stable=True).indices[:, :K].cpu().numpy()
+    assert np.array_equal(idx, chk)
+
+
+def _cifar_hierarchy():
+    from semantic_embeddings_b200.class_hierarchy import ClassHierarchy
+    parents, children = {}, {}
+    for p, c in np.load(os.path.join(G, 'cifar_hierarchy.npz'))['parent_child']:
+        parents.setdefault(int(c), []).append(int(p))
+        children.setdefault(int(p), []).append(int(c))
+    return ClassHierarchy(parents, children)
+
+
+@pytest.mark.parametrize('case', [(3, 7), (5, 4096), (4, 4097), (2, 9000), (3, 50000), (1, 70000)], ids=lambda c: '%dx%d' % c)
+def test_row_argsort_is_a_stable_argsort(case):
+    """se_row_argsort (evaluate_retrieval.py:67, full-length ranking) against a stable sort of the SAME device matrix:
+    identical indices, ties (quantised values, +0.0 / -0.0, a constant row) included."""
+    from semantic_embeddings_b200.evaluate_retrieval import row_argsort
+    rows, n = case
+    g = torch.Generator().manual_seed(rows * 13 + n)
+    d = torch.randn(rows, n, generator=g)
+    d[:, ::3] = torch.round(d[:, ::3] * 4) / 4
+    d[0, : min(n, 5)] = -0.0
+    d[0, min(n, 5): min(n, 9)] = 0.0
+    d[-1] = 1.5
+    dd = d.cuda()
+    idx = row_argsort(dd)
+    ref = torch.sort(torch.where(dd == 0, torch.zeros_like(dd), dd), dim=-1, stable=True).indices
+    assert torch.equal(idx.long(), ref)
+    # strided input
+    big = torch.full((rows, n + 3), -9e9, device='cuda')
+    big[:, :n] = dd
+    assert torch.equal(row_argsort(big[:, :n]), idx)
+
+
+def test_hier_metrics_full_rankings_match_the_reference_numbers():
+    """se_hier_metrics on FULL rankings: P@k, the unclipped AHP and classical AP per query against the numbers the
+    reference's own ClassHierarchy.hierarchical_precision(compute_ahp=True, compute_ap=True) produced for the same rankings
+    (fixture prec_*), and the clipped form against prec250_*; <= 1e-12 per query.  Also the drop-in method with the
+    reference's signature (dict inputs) and the taxonomy look-up tables of this package's own ClassHierarchy."""
+    from semantic_embeddings_b200.class_hierarchy import hierarchical_metrics
+    fx = np.load(os.path.join(G, 'retrieval_ref.npz'))
+    rank, labels = fx['rank_sq_unit'].astype(np.int32), fx['labels'].astype(np.int32)
+    h = _cifar_hierarchy()
+    wup, lcsh = h.similarity_luts(list(range(100)))
+    assert np.array_equal(wup, fx['wup_lut']) and np.array_equal(lcsh, fx['lcs_height_lut'])
+    res = hierarchical_metrics(torch.as_tensor(rank).cuda(), None, labels, wup, lcsh, 100, -1, True)
+    got = {'AHP (WUP)': res['ahp'][:, 0], 'AHP (LCS_HEIGHT)': res['ahp'][:, 1], 'AP': res['ap']}
+    for k in (1, 10, 50, 100):
+        got['P@%d (WUP)' % k] = res['curve'][:, 0, k - 1]
+        got['P@%d (LCS_HEIGHT)' % k] = res['curve'][:, 1, k - 1]
+    for i, name in enumerate(fx['prec_names']):
+        np.testing.assert_allclose(got[str(name)], fx['prec_per_query'][i], rtol=0, atol=1e-12, err_msg=str(name))
+    res250 = hierarchical_metrics(torch.as_tensor(rank[:, :251].copy()).cuda(), None, labels, wup, lcsh, 100, 250, False)
+    for i, name in enumerate(fx['prec250_names']):
+        name = str(name)
+        v = res250['ahp'][:, 0 if 'WUP' in name else 1] if name.startswith('AHP') else \
+            res250['curve'][:, 0 if 'WUP' in name else 1, int(name.split('@')[1].split(' ')[0]) - 1]
+        np.testing.assert_allclose(v, fx['prec250_per_query'][i], rtol=0, atol=1e-12, err_msg=name)
+    # drop-in call, arbitrary (non-contiguous) item ids, generator input, incomplete lists completed from all_ids
+    ids = [int(v) for v in fx['ids']]
+    lab = {i: int(l) for i, l in zip(ids, labels)}
+    ret = ((ids[q], [ids[r] for r in rank[q][:200]]) for q in range(len(ids)))
+    avg, per = h.hierarchical_precision(ret, lab, ks=[1, 10, 50], compute_ahp=150, compute_ap=False, all_ids=ids)
+    from oracle import hierarchy as ohier
+    oavg, oper = ohier.hierarchical_precision(rank, labels, wup, lcsh, ks=(1, 10, 50), compute_ahp=150)
+    for name in oavg:
+        np.testing.assert_allclose([per[name][i] for i in ids], oper[name], rtol=0, atol=1e-12, err_msg=name)
+        assert abs(avg[name] - oavg[name]) < 1e-12
+
+
+@pytest.mark.parametrize('src_dtype', ['u8', 'f32'])
+def test_augment_batch_matches_keras_restatement(src_dtype):
+    """se_augment_batch (TinyDatasetGenerator.compose_batch, datasets/common.py:771-796: Keras random_transform with
+    flips and +-15 % shifts -- scipy affine_transform order 1 / 'nearest' -- then featurewise standardize) against
+    oracle/augment.py on the same draws, including shifts beyond the documented range and the no-augmentation path."""
+    from oracle import augment as oaug
+    from semantic_embeddings_b200.datasets import TinyDatasetGenerator
+    rng = np.random.RandomState(3)
+    n, H, W, C = 40, 32, 32, 3
+    X = rng.randint(0, 256, (n, H, W, C)).astype(np.uint8)
+    Xs = X if src_dtype == 'u8' else (X.astype(np.float32) * 0.37 - 11.0)
+    data = TinyDatasetGenerator(Xs, Xs[:8], rng.randint(0, 10, n), rng.randint(0, 10, 8))
+    mean, std = oaug.fit_statistics(Xs)
+    assert np.abs(data.mean.cpu().numpy() - mean).max() < 1e-3 and np.abs(data.std.cpu().numpy() - std).max() < 1e-3
+    idx = rng.permutation(n)[:24]
+    tx = rng.uniform(-0.15, 0.15, len(idx)) * H
+    ty = rng.uniform(-0.15, 0.15, len(idx)) * W
+    tx[:4] = [0.0, 4.8, -4.8, 7.25]
+    ty[:4] = [0.0, -4.8, 4.8, -9.5]
+    flip = rng.rand(len(idx)) < 0.5
+    flip[:4] = [False, True, False, True]
+    out = torch.empty(len(idx), H, W, C, device='cuda')
+    data.compose_batch(idx, True, out, augment=True, params=(tx, ty, flip))
+    ref = oaug.compose_batch(Xs.astype(np.float32), idx, list(zip(tx, ty, flip)), data.mean.cpu().numpy(), data.std.cpu().numpy())
+    err = float(np.abs(out.cpu().numpy() - ref).max())
+    report('augment', src=src_dtype, max_abs_err=err)
+    assert err < 2e-5, err
+    # test-time path: standardize only
+    out2 = torch.empty(8, H, W, C, device='cuda')
+    data.compose_batch(np.arange(8), False, out2)
+    ref2 = oaug.standardize(Xs[:8].astype(np.float32), data.mean.cpu().numpy(), data.std.cpu().numpy())
+    assert np.abs(out2.cpu().numpy() - ref2).max() < 2e-6
+    # random draws of the product path stay inside the documented ranges and differ between calls
+    a, b = torch.empty_like(out), torch.empty_like(out)
+    r = np.random.RandomState(0)
+    data.compose_batch(idx, True, a, augment=True, rng=r)
+    data.compose_batch(idx, True, b, augment=True, rng=r)
+    assert not torch.equal(a, b)
