@@ -297,9 +297,11 @@ def run_native(args):
     mode = {'tf32x3': L.SE_MODE_TF32X3, 'tf32': L.SE_MODE_TF32, 'f32': L.SE_MODE_F32}[args.mode]
     caps = L.load().se_tc_capabilities()
     emb = np.load(os.path.join(ROOT, 'tests', 'golden', 'class_matrices.npz'))['cifar100_embedding']
-    B = args.batch
+    # weak scaling (default): the per-GPU batch is the config's 128; strong scaling: the GLOBAL batch is 128
+    B = args.batch if args.scaling == 'weak' else max(1, args.batch // world)
     graph = utils.build_network(100, ARCH, input_channels=3)
-    eng = Engine(graph, B, emb, mode=mode, device=str(dev), world_size=world, use_cuda_graph=not args.no_graph)
+    eng = Engine(graph, B, emb, mode=mode, device=str(dev), world_size=world, use_cuda_graph=not args.no_graph,
+                 comm=args.comm)
     eng.set_lr(0.1)
 
     # synthetic data: N(0,1) images, seed 1000+rank; a small pool cycled through
@@ -402,10 +404,14 @@ def run_native(args):
         tc = bool(mode != L.SE_MODE_F32 and (caps & 7))
         line = {
             'metric': METRIC, 'value': value, 'unit': 'images/s', 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
-            'ms_per_step': ms_res / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+            'ms_per_step': ms_res / args.steps, 'higher_is_better': True, 'scaling': args.scaling, 'vs_baseline': None,
             'dtype': (args.mode if tc else 'f32'), 'data': 'synthetic',
             'config': {'workload': WORKLOAD, 'per_gpu_batch': B, 'global_batch': gb, 'parallelism': 'dp%d' % world,
                        'arith_mode': args.mode, 'tc_capabilities': caps, 'cuda_graph': not args.no_graph,
+                       'gradient_exchange': ('none' if world == 1 else
+                                             ('NCCL inside the library: %d bucketed all-reduces overlapped with the backward '
+                                              'pass, captured in the step graph' % eng.grad_buckets) if eng.comm_native
+                                             else 'torch.distributed all_reduce of the flat buffer between two graphs'),
                        'l2_policy': 'activations+gradients touched per step (~%.1f GB) exceed the 126 MB L2; '
                                     'retrieval output 10 GB' % (eng_bytes(eng) / 1e9)},
             'e2e': {'value': e2e, 'unit': 'images/s', 'ms_per_step': ms_e2e / args.steps,
@@ -442,6 +448,9 @@ def main():
     # tf32 = single-pass (outside the gate, for comparison only); f32 = fp32 FFMA kernels
     ap.add_argument('--mode', default='tf32x3', choices=['tf32x3', 'tf32', 'f32'])
     ap.add_argument('--batch', type=int, default=PER_GPU_BATCH)
+    ap.add_argument('--scaling', default='weak', choices=['weak', 'strong'],
+                    help='weak: --batch images per GPU (the driver contract); strong: --batch images in total')
+    ap.add_argument('--comm', default='auto', choices=['auto', 'native', 'torch'])
     ap.add_argument('--retrieval-n', type=int, default=50000)
     ap.add_argument('--skip-retrieval', action='store_true')
     ap.add_argument('--skip-cpu-baseline', action='store_true')

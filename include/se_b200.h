@@ -246,6 +246,21 @@ int se_sgd_schedule(float* lr_state, void* stream);
 int se_sgd_apply_devlr(float* p, const float* g, float* v, int64_t n, const float* lr_dev, float momentum,
                        int nesterov, float clipnorm, const double* out, void* stream);
 
+/* ------------------------------------------------------------------ data-parallel gradient exchange
+ * keras.utils.multi_gpu_model (learn_image_embeddings.py:133,148) -> one process per GPU + NCCL.  The communicator lives
+ * inside the library so that the plan runner can issue bucketed all-reduces on its own stream while the backward pass
+ * continues and capture them in the step's CUDA graph (SE_OP_ALLREDUCE in se_run_ops).  NCCL is taken from the
+ * libnccl.so.2 already loaded in the process; SE_ERR_UNSUPPORTED when there is none.
+ *   se_comm_unique_id: rank 0 creates the 128-byte NCCL id, the caller distributes it (any out-of-band channel);
+ *   se_comm_init:      collective over all ranks, current CUDA device = this rank's GPU;
+ *   se_allreduce_sum:  in-place SUM over all ranks of buf[0:n] on `stream` (per-sample losses are pre-scaled by
+ *                      1/global_batch, so the sum IS the gradient of the global mean loss). */
+int se_comm_unique_id(void* id_out, int bytes);
+int se_comm_init(int rank, int world, const void* unique_id, int bytes);
+int se_comm_world(void);
+int se_allreduce_sum(float* buf, int64_t n, void* stream);
+int se_comm_destroy(void);
+
 /* ------------------------------------------------------------------ input pipeline
  * TinyDatasetGenerator.compose_batch (datasets/common.py:771-796): Keras ImageDataGenerator.random_transform with
  * horizontal_flip + width/height_shift_range 0.15 (datasets/common.py:640; shift = scipy affine_transform order 1,

@@ -20,7 +20,7 @@ SE_PDIST_SQEUCLID, SE_PDIST_NEGDOT = 0, 1
 OP_CONV_FWD, OP_CONV_DGRAD, OP_CONV_WGRAD, OP_BN_STATS, OP_BN_FWD_TRAIN, OP_BN_FWD_INFER, OP_BN_BWD, \
     OP_SHORTCUT_BWD, OP_AVGPOOL_FWD, OP_AVGPOOL_BWD, OP_MAXPOOL_FWD, OP_MAXPOOL_BWD, OP_GAP_FWD, OP_GAP_BWD, \
     OP_ADD_FWD, OP_ADD_BWD, OP_HEAD, OP_XENT, OP_MEMSET, OP_SGD_PREPARE, OP_SGD_APPLY, OP_TRANSPOSE_FILTERS, \
-    OP_CONV_BN_FWD = range(1, 24)
+    OP_CONV_BN_FWD, OP_ALLREDUCE = range(1, 25)
 
 
 class SeError(RuntimeError):
@@ -89,6 +89,11 @@ _SIGS = {
     'se_softmax_xent_fwd_bwd_ex': (c_int, [_P, c_int, _P, c_int, c_int, c_float, _P, _P, _P, _P, _P, _P]),
     'se_embed_head_fwd_bwd_ex': (c_int, [_P, c_int, _P, _P, c_int, c_int, c_int, c_int, c_int, c_float, _P, _P, _P, _P, _P, _P, _P]),
     'se_sgd_schedule': (c_int, [_P, _P]),
+    'se_comm_unique_id': (c_int, [_P, c_int]),
+    'se_comm_init': (c_int, [c_int, c_int, _P, c_int]),
+    'se_comm_world': (c_int, []),
+    'se_allreduce_sum': (c_int, [_P, c_int64, _P]),
+    'se_comm_destroy': (c_int, []),
     'se_hier_metrics': (c_int, [_P, c_int64, c_int, c_int, c_int, _P, c_int, _P, _P, _P, _P, c_int, c_int, _P, _P, _P, _P]),
     'se_row_argsort_workspace_bytes': (c_int64, [c_int, c_int]),
     'se_row_argsort': (c_int, [_P, c_int64, c_int, c_int, _P, c_int64, _P, _P]),

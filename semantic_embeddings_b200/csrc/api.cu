@@ -241,6 +241,32 @@ static bool side_stream_ready() {
   return true;
 }
 
+namespace se {
+cudaStream_t comm_stream();
+bool comm_ready();
+int comm_allreduce_ranges(float* base, const long long* off, const long long* cnt, int nranges, cudaStream_t st);
+}
+static cudaEvent_t g_ev_comm_main = nullptr, g_ev_comm_side = nullptr, g_ev_comm_done = nullptr;
+static bool g_comm_pending = false;      // all-reduces in flight on the communication stream (joined before the optimizer)
+static bool comm_events_ready() {
+  if (!g_ev_comm_main) {
+    if (cudaEventCreateWithFlags(&g_ev_comm_main, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&g_ev_comm_side, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&g_ev_comm_done, cudaEventDisableTiming) != cudaSuccess) {
+      g_ev_comm_main = nullptr;
+      return false;
+    }
+  }
+  return true;
+}
+static void join_comm(void* stream) {
+  if (g_comm_pending) {
+    cudaEventRecord(g_ev_comm_done, se::comm_stream());
+    cudaStreamWaitEvent(as_stream(stream), g_ev_comm_done, 0);
+    g_comm_pending = false;
+  }
+}
+
 static int run_ops_impl(const se_op* ops, int n, int mode, void* stream, bool* forked);
 
 extern "C" int se_run_ops(const se_op* ops, int n, int mode, void* stream) {
@@ -251,6 +277,7 @@ extern "C" int se_run_ops(const se_op* ops, int n, int mode, void* stream) {
     cudaEventRecord(g_ev_join, g_side);
     cudaStreamWaitEvent(as_stream(stream), g_ev_join, 0);
   }
+  join_comm(stream);
   return rc;
 }
 
@@ -395,7 +422,28 @@ static int run_ops_impl(const se_op* ops, int n, int mode, void* stream, bool* f
             rc = se_transpose_filters((const float*)p[0], (float*)p[1], (const int64_t*)p[2], i[0], ts);
         }
         break;
+      case SE_OP_ALLREDUCE: {
+        // p[0] = flat gradient buffer, i[0] = number of ranges, p[1 + 2k] / p[2 + 2k] = element offset / count of range k.
+        // The ranges hold gradients that every op up to here has finished writing: weight gradients on the side stream,
+        // BatchNorm / bias gradients on the main stream.  The exchange runs on the communication stream behind both and
+        // overlaps the rest of the backward pass; the optimizer joins it.
+        if (!se::comm_ready() || !comm_events_ready()) { set_error("SE_OP_ALLREDUCE without a communicator (se_comm_init)"); return SE_ERR_ARG; }
+        cudaStream_t cs = se::comm_stream();
+        cudaEventRecord(g_ev_comm_main, as_stream(stream));
+        cudaStreamWaitEvent(cs, g_ev_comm_main, 0);
+        if (*forked) {
+          cudaEventRecord(g_ev_comm_side, g_side);
+          cudaStreamWaitEvent(cs, g_ev_comm_side, 0);
+        }
+        long long off[7], cnt[7];
+        const int nr = i[0] < 7 ? i[0] : 7;
+        for (int r = 0; r < nr; ++r) { off[r] = (long long)(uintptr_t)p[1 + 2 * r]; cnt[r] = (long long)(uintptr_t)p[2 + 2 * r]; }
+        rc = se::comm_allreduce_ranges((float*)p[0], off, cnt, nr, cs);
+        g_comm_pending = true;
+        break;
+      }
       case SE_OP_SGD_PREPARE:
+        join_comm(stream);
         if (*forked) {   // the optimizer reads every gradient: the side branch joins here
           cudaEventRecord(g_ev_join, g_side);
           cudaStreamWaitEvent(as_stream(stream), g_ev_join, 0);

@@ -25,4 +25,5 @@ enum {
   SE_OP_SGD_APPLY = 21,
   SE_OP_TRANSPOSE_FILTERS = 22,
   SE_OP_CONV_BN_FWD = 23,
+  SE_OP_ALLREDUCE = 24,
 };

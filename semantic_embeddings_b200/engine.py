@@ -33,7 +33,8 @@ def _vp(x):
 class Engine:
     def __init__(self, graph, batch, embedding, loss='inv_corr', cls_weight=0.0, num_classes=None,
                  mode=_lib.SE_MODE_F32, device='cuda:0', momentum=0.9, nesterov=False, clipnorm=10.0,
-                 world_size=1, fuse_stats=True, use_cuda_graph=True, seed=0, fuse_conv_bn=False, decay=0.0):
+                 world_size=1, fuse_stats=True, use_cuda_graph=True, seed=0, fuse_conv_bn=False, decay=0.0,
+                 grad_buckets=3, comm='auto'):
         if loss not in LOSS_KINDS:
             raise ValueError('unknown loss %r' % loss)
         self.decay = float(decay)
@@ -50,6 +51,13 @@ class Engine:
         self.cls_weight = float(cls_weight)
         self.momentum, self.nesterov, self.clipnorm = float(momentum), bool(nesterov), float(clipnorm or 0.0)
         self.world = int(world_size)
+        self.grad_buckets = max(1, int(grad_buckets))
+        # data-parallel gradient exchange: 'native' = the library's own NCCL communicator, bucketed all-reduces issued by
+        # the plan runner on its communication stream and captured in the step graph; 'torch' = one all_reduce of the
+        # flat buffer through torch.distributed between two graphs; 'auto' = native when it can be set up
+        self.comm_native = False
+        if self.world > 1 and comm in ('auto', 'native') and self.dev.type == 'cuda':
+            self.comm_native = self._init_native_comm(required=(comm == 'native'))
         self.fuse_stats = fuse_stats
         self.fuse_conv_bn = fuse_conv_bn and fuse_stats
         self.use_cuda_graph = use_cuda_graph
@@ -64,6 +72,45 @@ class Engine:
         self._build_plans()
         self._graphs = {}
         self.iterations = 0
+
+    def _init_native_comm(self, required):
+        """se_comm_init over the ranks of the default torch.distributed group (which only carries the 128-byte NCCL id)."""
+        import torch.distributed as dist
+        if not dist.is_initialized():
+            if required:
+                raise RuntimeError('comm="native" needs an initialised torch.distributed group to distribute the NCCL id')
+            return False
+        if self.lib.se_comm_world() == self.world:
+            return True                                   # a communicator of this process already exists
+        rank = dist.get_rank()
+        idb = (ctypes.c_ubyte * 128)()
+        ok = torch.zeros(1, dtype=torch.int32, device=self.dev)
+        if rank == 0:
+            ok[0] = 1 if self.lib.se_comm_unique_id(idb, 128) == 0 else 0
+        t = torch.tensor(list(bytes(idb)), dtype=torch.uint8, device=self.dev)
+        dist.broadcast(ok, 0)
+        if int(ok.item()) == 0:
+            if required:
+                raise _lib.SeError('se_comm_unique_id failed: ' + self.lib.se_last_error().decode())
+            return False
+        dist.broadcast(t, 0)
+        idb = (ctypes.c_ubyte * 128)(*t.cpu().tolist())
+        rc = self.lib.se_comm_init(rank, self.world, idb, 128)
+        flag = torch.tensor([1 if rc == 0 else 0], dtype=torch.int32, device=self.dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if int(flag.item()) == 0:
+            if rc == 0:
+                self.lib.se_comm_destroy()
+            if required:
+                raise _lib.SeError('se_comm_init failed: ' + self.lib.se_last_error().decode())
+            return False
+        # first collective outside any capture: NCCL sets up its channels lazily
+        probe = torch.ones(1024, dtype=torch.float32, device=self.dev)
+        _lib.check(self.lib.se_allreduce_sum(probe.data_ptr(), probe.numel(), _lib.stream_ptr()), 'se_allreduce_sum')
+        torch.cuda.synchronize(self.dev)
+        if float(probe[0].item()) != float(self.world):
+            raise _lib.SeError('se_allreduce_sum returned %r instead of the world size %d' % (float(probe[0].item()), self.world))
+        return True
 
     # ------------------------------------------------------------------ graph extension: head (+ classifier)
     def _extend_graph(self):
@@ -373,6 +420,7 @@ class Engine:
                 raise ValueError(n.op)
         # ---------------- backward
         written = set()
+        final = {}                         # trainable parameter -> number of backward ops after which its gradient is complete
 
         def gb(t):
             """(gradient tensor, beta) for the next contribution to tensor t; None when t needs no gradient."""
@@ -407,6 +455,9 @@ class Engine:
                 dW = self._pview(n.name + '/kernel', self.G)
                 db = self._pview(n.name + '/bias', self.G) if n.attrs['use_bias'] else None
                 bwd.append(self._op(_lib.OP_CONV_WGRAD, d, p=[A[x.name], dY, dW, db]))
+                final[n.name + '/kernel'] = len(bwd)
+                if n.attrs['use_bias']:
+                    final[n.name + '/bias'] = len(bwd)
                 dx, beta = gb(x)
                 if dx is not None:
                     Wl = self._pview(n.name + '/kernel', self.PL) if (self.PL is not None and n.op == 'conv') else None
@@ -444,6 +495,7 @@ class Engine:
                 bwd.append(self._op(_lib.OP_BN_BWD, [c, rows, relu, relu_in, early], [beta, bres],
                                     [A[x.name], A[n.output.name], dY, self._pview(n.name + '/gamma'), sm, si, dx, dres,
                                      self._pview(n.name + '/gamma', self.G), self._pview(n.name + '/beta', self.G), scratch]))
+                final[n.name + '/gamma'] = final[n.name + '/beta'] = len(bwd)
                 if sc_op is not None:
                     bwd.append(sc_op)
             elif n.op == 'avgpool2':
@@ -487,6 +539,46 @@ class Engine:
         self.plans = {'fwd': self._pack(fwd), 'bwd': self._pack(bwd), 'opt': self._pack(opt), 'infer': self._pack(inf),
                       'eval': self._pack(ev),
                       'fwdbwd': self._pack(fwd + bwd), 'step': self._pack(fwd + bwd + opt)}
+        if self.world > 1:
+            # data parallel: the same step with bucketed all-reduces inside the backward pass (one graph, no host in between)
+            self.plans['step_dp'] = self._pack(fwd + self._with_allreduce(bwd, final) + opt)
+
+    def _with_allreduce(self, bwd, final):
+        """Backward plan with SE_OP_ALLREDUCE ops: the flat gradient buffer is cut into `grad_buckets` buckets in the order
+        the backward pass completes it (last layers first); a bucket's exchange is issued right after the op that writes
+        its last gradient and overlaps everything below it.  A bucket is a few contiguous ranges of the buffer (parameters
+        are laid out in forward order inside each L2 segment, so what a stretch of the backward pass completes is one run
+        per segment)."""
+        missing = [n for n in self.offsets if n not in final]
+        assert not missing, 'no backward op writes the gradient of %s' % missing
+        size = lambda n: (int(np.prod(self.offsets[n][1])) + 3) // 4 * 4
+        order = sorted(self.offsets, key=lambda n: (final[n], self.offsets[n][0]))
+        # cuts at equal shares of the backward pass's OPS (a proxy for time), not of the bytes: what is still to be
+        # exchanged when the last gradient lands is then only the last stretch's share (for ResNet-110 the 16-channel
+        # stage: 5 % of the parameters), and the big early buckets have the rest of the backward pass to hide behind
+        cuts = sorted({max(1, (len(bwd) * k) // self.grad_buckets) for k in range(1, self.grad_buckets)}) + [len(bwd)]
+        out, start, self.bucket_ranges = [], 0, []
+        done = set()
+        for cut in cuts:
+            out += list(bwd[start:cut])
+            names = [n for n in order if final[n] <= cut and n not in done]
+            done.update(names)
+            runs = []
+            for off, sz in sorted((self.offsets[n][0], size(n)) for n in names):
+                if runs and runs[-1][0] + runs[-1][1] == off:
+                    runs[-1][1] += sz
+                else:
+                    runs.append([off, sz])
+            for g0 in range(0, len(runs), 7):             # an op carries up to 7 ranges
+                grp = runs[g0:g0 + 7]
+                pp = [self.G]
+                for off, sz in grp:
+                    pp += [off, sz]
+                out.append(self._op(_lib.OP_ALLREDUCE, [len(grp)], p=pp))
+            self.bucket_ranges.append(runs)
+            start = cut
+        assert done == set(self.offsets)
+        return out
 
     @staticmethod
     def _pack(ops):
@@ -559,7 +651,9 @@ class Engine:
             self.load_batch(x, labels)
         if lr is not None:
             self.set_lr(lr)
-        if self.world > 1 or allreduce is not None:
+        if self.world > 1 and self.comm_native and allreduce is None:
+            self._run('step_dp')                          # forward, backward with overlapped all-reduces, optimizer: one graph
+        elif self.world > 1 or allreduce is not None:
             self._run('fwdbwd')
             (allreduce or self._allreduce)(self.G)
             self._run('opt')
