@@ -35,6 +35,16 @@ METRIC = 'images/sec training ResNet-110 CIFAR-100 at 1/2/4/8 B200; retrieval Gp
 # the same string on both arms (native / --impl reference): the driver compares config.workload
 WORKLOAD = ('CIFAR-100 ResNet-110 (%s) cosine loss vs cifar100.unitsphere, SGD momentum 0.9 + clipnorm 10 + L2 2e-4, '
             'batch %d/GPU, synthetic 32x32x3' % (ARCH, PER_GPU_BATCH))
+# the other training configurations of BASELINE.json (extra lines: `--workload config3|config4`; the driver's default
+# run is configs[1] above).  arch, class matrix, per-GPU batch, input size, classifier weight, description
+WORKLOADS = {
+    'config2': dict(arch=ARCH, emb='cifar100', batch=PER_GPU_BATCH, size=32, cls_weight=0.0, name=WORKLOAD),
+    'config3': dict(arch='wrn-28-10', emb='cifar100', batch=64, size=32, cls_weight=0.1,
+                    name='CIFAR-100 WRN-28-10 cosine + softmax combined loss (cls_weight 0.1), batch 64/GPU (512 on 8 GPUs), '
+                         'synthetic 32x32x3'),
+    'config4': dict(arch='resnet-50', emb='nab', batch=32, size=224, cls_weight=0.0,
+                    name='NABirds-shape ResNet-50 224x224x3, nab.unitsphere head (555-d), batch 32/GPU (256 on 8 GPUs), synthetic'),
+}
 
 
 def traffic_lookup(kernel):
@@ -296,19 +306,22 @@ def run_native(args):
     pk = peaks()
     mode = {'tf32x3': L.SE_MODE_TF32X3, 'tf32': L.SE_MODE_TF32, 'f32': L.SE_MODE_F32}[args.mode]
     caps = L.load().se_tc_capabilities()
-    emb = np.load(os.path.join(ROOT, 'tests', 'golden', 'class_matrices.npz'))['cifar100_embedding']
-    # weak scaling (default): the per-GPU batch is the config's 128; strong scaling: the GLOBAL batch is 128
-    B = args.batch if args.scaling == 'weak' else max(1, args.batch // world)
-    graph = utils.build_network(100, ARCH, input_channels=3)
+    wl = WORKLOADS[args.workload]
+    emb = np.load(os.path.join(ROOT, 'tests', 'golden', 'class_matrices.npz'))[wl['emb'] + '_embedding']
+    ncls, size = emb.shape[0], wl['size']
+    batch = args.batch if args.batch else wl['batch']
+    # weak scaling (default): the per-GPU batch is the config's; strong scaling: that many images in total
+    B = batch if args.scaling == 'weak' else max(1, batch // world)
+    graph = utils.build_network(emb.shape[1], wl['arch'], input_channels=3)
     eng = Engine(graph, B, emb, mode=mode, device=str(dev), world_size=world, use_cuda_graph=not args.no_graph,
-                 comm=args.comm)
+                 comm=args.comm, cls_weight=wl['cls_weight'], num_classes=ncls)
     eng.set_lr(0.1)
 
     # synthetic data: N(0,1) images, seed 1000+rank; a small pool cycled through
     gen = torch.Generator().manual_seed(1000 + rank)
     pool = 4
-    xs_host = [torch.randn(B, 32, 32, 3, generator=gen).pin_memory() for _ in range(pool)]
-    ys_host = [torch.randint(0, 100, (B,), generator=gen, dtype=torch.int32).pin_memory() for _ in range(pool)]
+    xs_host = [torch.randn(B, size, size, 3, generator=gen).pin_memory() for _ in range(pool)]
+    ys_host = [torch.randint(0, ncls, (B,), generator=gen, dtype=torch.int32).pin_memory() for _ in range(pool)]
     xs_dev = [x.to(dev) for x in xs_host]
     ys_dev = [y.to(dev) for y in ys_host]
 
@@ -369,7 +382,7 @@ def run_native(args):
         roof, breakdown, prof_total, conv_flops = profile_step(eng, L, pk)
 
     retrieval = None
-    if not args.skip_retrieval:
+    if not args.skip_retrieval and args.workload == 'config2':
         n, d = args.retrieval_n, 100
         ms_r, rows, chk, rank_ms = bench_retrieval(L, rank, world, dev, n, d, 5, mode)
         if world > 1:
@@ -393,7 +406,7 @@ def run_native(args):
                                            'kernel': 'row_topk_kernel (radix select + bitonic sort in shared memory)'}
 
     cpu = None
-    if rank == 0 and world == 1 and not args.skip_cpu_baseline:
+    if rank == 0 and world == 1 and not args.skip_cpu_baseline and args.workload == 'config2':
         ips, ms_cpu, info = cpu_reference_arm(steps=3, warmup=1, budget_s=25.0)
         cpu = {'value': ips, 'unit': 'images/s', 'cores': info['cores'], 'kind': 'port',
                'sample': '3 timed steps of %d images after 1 warm-up (float32 torch-CPU restatement of the Keras '
@@ -406,7 +419,7 @@ def run_native(args):
             'metric': METRIC, 'value': value, 'unit': 'images/s', 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
             'ms_per_step': ms_res / args.steps, 'higher_is_better': True, 'scaling': args.scaling, 'vs_baseline': None,
             'dtype': (args.mode if tc else 'f32'), 'data': 'synthetic',
-            'config': {'workload': WORKLOAD, 'per_gpu_batch': B, 'global_batch': gb, 'parallelism': 'dp%d' % world,
+            'config': {'workload': wl['name'] if (args.workload != 'config2' or B != PER_GPU_BATCH) else WORKLOAD, 'per_gpu_batch': B, 'global_batch': gb, 'parallelism': 'dp%d' % world,
                        'arith_mode': args.mode, 'tc_capabilities': caps, 'cuda_graph': not args.no_graph,
                        'gradient_exchange': ('none' if world == 1 else
                                              ('NCCL inside the library: %d bucketed all-reduces overlapped with the backward '
@@ -447,7 +460,9 @@ def main():
     # tf32x3 = tcgen05 tiles with error compensation (meets the 1e-4 parity gate; the mode the training CLI runs);
     # tf32 = single-pass (outside the gate, for comparison only); f32 = fp32 FFMA kernels
     ap.add_argument('--mode', default='tf32x3', choices=['tf32x3', 'tf32', 'f32'])
-    ap.add_argument('--batch', type=int, default=PER_GPU_BATCH)
+    ap.add_argument('--batch', type=int, default=0, help='per-GPU batch (default: the workload\'s)')
+    ap.add_argument('--workload', default='config2', choices=sorted(WORKLOADS),
+                    help='BASELINE.json training configuration; the driver contract is config2 (ResNet-110, batch 128)')
     ap.add_argument('--scaling', default='weak', choices=['weak', 'strong'],
                     help='weak: --batch images per GPU (the driver contract); strong: --batch images in total')
     ap.add_argument('--comm', default='auto', choices=['auto', 'native', 'torch'])

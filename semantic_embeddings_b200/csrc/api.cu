@@ -98,11 +98,17 @@ extern "C" int se_conv2d_fwd_aux(const se_conv_desc* d, const float* x, const fl
   int rc = check_desc(d);
   if (rc) return rc;
   SE_REQUIRE(x && w && y, "null pointer");
-  if (mode == SE_MODE_TF32 && aux && aux->w_t) {
-    rc = conv_fwd_tc(d, x, aux->w_t, nullptr, bias, residual, y, relu, stats, as_stream(stream));
-    if (rc != SE_ERR_UNSUPPORTED) return rc;
-  } else if (mode == SE_MODE_TF32X3 && aux && aux->w_t && aux->w_t_lo) {
-    rc = conv_fwd_tc(d, x, aux->w_t, aux->w_t_lo, bias, residual, y, relu, stats, as_stream(stream));
+  const bool tc1 = mode == SE_MODE_TF32 && aux && aux->w_t;
+  const bool tc3 = mode == SE_MODE_TF32X3 && aux && aux->w_t && aux->w_t_lo;
+  if (tc1 || tc3) {
+    const float* lo = tc3 ? aux->w_t_lo : nullptr;
+    rc = conv_fwd_tc(d, x, aux->w_t, lo, bias, residual, y, relu, stats, as_stream(stream));
+    if (rc == SE_ERR_UNSUPPORTED && stats) {
+      // wide layers (640 output channels): the per-warp statistics slots of the fused epilogue do not fit in shared
+      // memory -- run the tensor-core convolution without them and take the BatchNorm sums in a separate pass over y
+      rc = conv_fwd_tc(d, x, aux->w_t, lo, bias, residual, y, relu, nullptr, as_stream(stream));
+      if (rc == SE_OK) return se_bn_stats(y, (int64_t)d->N * d->Ho * d->Wo, d->Cout, stats, stream);
+    }
     if (rc != SE_ERR_UNSUPPORTED) return rc;
   }
   return conv_fwd_simt(d, x, w, bias, residual, y, relu, stats, as_stream(stream));
