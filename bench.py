@@ -240,7 +240,7 @@ def profile_step(eng, L, pk):
     return roof, breakdown, total, conv_flops
 
 
-def bench_retrieval(L, rank, world, dev, n, d, reps, mode):
+def bench_retrieval(L, rank, world, dev, n, d, reps, mode, pk_hbm=6567.4):
     """All-pairs distance (evaluate_retrieval.py:56-63), rows sharded over ranks, no exchange step."""
     import torch
     from semantic_embeddings_b200.evaluate_retrieval import pairwise_distances
@@ -277,7 +277,43 @@ def bench_retrieval(L, rank, world, dev, n, d, reps, mode):
         b.record()
         torch.cuda.synchronize(dev)
         rank_ms = a.elapsed_time(b) / 3.0
-    return ms, rows, chk, rank_ms
+    extra = {}
+    if rows > 0 and world == 1 and n <= 52000:
+        from semantic_embeddings_b200.evaluate_retrieval import pairwise_topk, row_argsort
+        from semantic_embeddings_b200.class_hierarchy import hierarchical_metrics
+        k = min(251, n)
+        # fused distance + top-251 (se_pairwise_topk): no N x N matrix
+        pairwise_topk(k=k, feat_dev=fd)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(3):
+            _, _, fused = pairwise_topk(k=k, feat_dev=fd)
+        b.record()
+        torch.cuda.synchronize(dev)
+        extra['fused_topk'] = {'ms': a.elapsed_time(b) / 3.0, 'k': k, 'fused': bool(fused),
+                               'gpairs_per_s': float(n) * n / (a.elapsed_time(b) / 3.0 / 1000.0) / 1e9,
+                               'kernels': 'pairwise_tc_kernel<0> on a 4096-column sample + row_topk_kernel (thresholds), '
+                                          'pairwise_tc_kernel<1> (candidate sweep), pairwise_topk_finish_kernel',
+                               'note': 'includes the status read-back; the matrix-write bound of the unfused kernel at this '
+                                       'size is %.2f ms' % (4.0 * n * n / pk_hbm / 1e6)}
+        # full-length ranking (se_row_argsort) and P@k / AHP / AP (se_hier_metrics) for a block of 2048 query rows
+        blk = min(2048, rows)
+        sub = out[:blk]
+        row_argsort(sub)
+        a.record()
+        idx = row_argsort(sub)
+        b.record()
+        torch.cuda.synchronize(dev)
+        extra['ranking_full'] = {'rows': blk, 'ms': a.elapsed_time(b), 'ms_all_rows_extrapolated': a.elapsed_time(b) * n / blk,
+                                 'kernel': 'row_argsort_kernel (bitonic network, shared-memory sub-sorts)'}
+        labels = rng.randint(0, 100, n).astype(np.int32)
+        hier = np.load(os.path.join(ROOT, 'tests', 'golden', 'retrieval_ref.npz'))
+        t0 = time.perf_counter()
+        hierarchical_metrics(idx, np.arange(blk), labels, hier['wup_lut'], hier['lcs_height_lut'], 250, -1, True)
+        torch.cuda.synchronize(dev)
+        extra['metrics_full'] = {'rows': blk, 'wall_ms_incl_host_setup': 1000.0 * (time.perf_counter() - t0),
+                                 'kernel': 'hier_metrics_kernel (P@1..250, unclipped AHP, AP from full rankings)'}
+    return ms, rows, chk, rank_ms, extra
 
 
 def run_native(args):
@@ -384,7 +420,7 @@ def run_native(args):
     retrieval = None
     if not args.skip_retrieval and args.workload == 'config2':
         n, d = args.retrieval_n, 100
-        ms_r, rows, chk, rank_ms = bench_retrieval(L, rank, world, dev, n, d, 5, mode)
+        ms_r, rows, chk, rank_ms, r_extra = bench_retrieval(L, rank, world, dev, n, d, 5, mode, pk['hbm_gbs'])
         if world > 1:
             t = torch.tensor([ms_r], device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -399,6 +435,7 @@ def run_native(args):
                                   'traffic': traffic_lookup('pairwise_dist') if (n == 50000 and world == 1) else None,
                                   'algorithmic_bytes_per_launch': per_gpu_bytes, 'peak_source': pk['source']},
                      'arithmetic': 'tcgen05 kind::f16, split-fp16 x3 (fp32-level accuracy)' if (mode != L.SE_MODE_F32 and caps & 8) else 'fp32 FFMA'}
+        retrieval.update(r_extra)
         if rank_ms is not None:
             # per-row top-251 of this rank's row block; bound: one read of the block (4 bytes per pair)
             retrieval['ranking_top251'] = {'ms': rank_ms, 'gpairs_per_s': float(rows) * n / (rank_ms / 1000.0) / 1e9,

@@ -281,6 +281,17 @@ int64_t se_pairwise_workspace_bytes(int N, int D, int mode);
 int se_pairwise_dist(const float* F, int ldF, int N, int D, int row0, int rows, int pdist_mode,
                      int normalize, float* out, int64_t ldout, void* workspace, int mode, void* stream);
 
+/* Fused distance + ranking: the k nearest items (ascending distance, ties by index) of
+ * query rows [row0, row0+rows) WITHOUT writing the rows x N distance matrix -- sample-based per-row thresholds, a
+ * tensor-core sweep that keeps only the entries below them, a per-row sort of those candidates.  Distances are the
+ * ones se_pairwise_dist would store (same arithmetic), so out_idx equals se_row_topk of that matrix.
+ * status [1] device int32: 0 = exact; non-zero = some row found fewer than k or more than 4096 candidates (pathological
+ * distance distributions) and the caller must use se_pairwise_dist + se_row_topk instead.  k <= 1024, D <= 128.
+ * out_idx [rows, ldo] int32, out_val [rows, ldo] float32 (may be NULL). */
+int64_t se_pairwise_topk_workspace_bytes(int N, int D, int rows);
+int se_pairwise_topk(const float* F, int ldF, int N, int D, int row0, int rows, int pdist_mode, int normalize, int k,
+                     int32_t* out_idx, float* out_val, int ldo, void* workspace, int32_t* status, void* stream);
+
 /* Ranking step of evaluate_retrieval.py:67 (`np.argsort(pdist, axis=-1)`) restricted to what the metrics read
  * (class_hierarchy.py:242-244,273,283: the first clip_ahp+1 ranks): for each of `rows` rows of dist [rows, ld] the k
  * smallest of its n values in ascending order, ties by ascending index (a stable argsort's prefix; -0.0 == +0.0).

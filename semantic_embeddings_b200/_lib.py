@@ -89,6 +89,8 @@ _SIGS = {
     'se_softmax_xent_fwd_bwd_ex': (c_int, [_P, c_int, _P, c_int, c_int, c_float, _P, _P, _P, _P, _P, _P]),
     'se_embed_head_fwd_bwd_ex': (c_int, [_P, c_int, _P, _P, c_int, c_int, c_int, c_int, c_int, c_float, _P, _P, _P, _P, _P, _P, _P]),
     'se_sgd_schedule': (c_int, [_P, _P]),
+    'se_pairwise_topk_workspace_bytes': (c_int64, [c_int, c_int, c_int]),
+    'se_pairwise_topk': (c_int, [_P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, _P, _P, c_int, _P, _P, _P]),
     'se_comm_unique_id': (c_int, [_P, c_int]),
     'se_comm_init': (c_int, [c_int, c_int, _P, c_int]),
     'se_comm_world': (c_int, []),

@@ -56,6 +56,10 @@ struct ConvTcParams {
   int stage_out;            // output staging bytes per epilogue warp: 4096 (two sub-buffers) or 2048
   int res, res_b_bytes, nt; // resident-weights mode: B loaded once per CTA, MMAs of `nt` tiles interleaved
   int res_bl_off;           // X3: byte offset of the resident low-part weights inside the resident block
+  int single;               // resident-weights mode, whole image rows: ONE input box of Hb+2 rows per tile; the three filter
+                            // rows read it at offsets of a_tap bytes (descriptor start addresses) instead of three shifted boxes
+  int a_tap;                // bytes between the A slabs of consecutive filter rows inside a stage (a_bytes, or W * row_bytes)
+  int a_stage_bytes;        // bytes of input data in a resident-mode stage (what TMA fills and the splitters rewrite)
   const float* bias;
   const float* residual;
   float* out;
@@ -337,9 +341,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       else { n0 = tm * p.Nb; h0 = 0; }
       mbar_wait(&empty[stage], phase ^ 1);
       CT_TRACE(0, 1);
-      mbar_expect_tx(&full[stage], 3 * p.a_bytes);
+      mbar_expect_tx(&full[stage], p.a_stage_bytes);
       uint8_t* sa = tiles + (size_t)stage * p.stage_bytes;
-      for (int r = 0; r < 3; ++r) tma_load_4d(sa + r * p.a_bytes, &map_a, &full[stage], 0, 0, h0 + r - 1, n0);
+      if (p.single) tma_load_4d(sa, &map_a, &full[stage], 0, 0, h0 - 1, n0);      // rows h0-1 .. h0+Hb: halo rows included
+      else for (int r = 0; r < 3; ++r) tma_load_4d(sa + r * p.a_bytes, &map_a, &full[stage], 0, 0, h0 + r - 1, n0);
       CT_TRACE(0, 2);
       if (++stage == p.stages) { stage = 0; phase ^= 1; }
     }
@@ -400,7 +405,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       const int rows_u = p.res ? 3 : p.rg;                         // filter rows per unit
       const int upt = p.res ? 1 : (3 / p.rg) * p.kblocks;          // units per tile
       const int U = (t_end - t_begin) * upt;
-      const uint32_t a_step = (uint32_t)p.a_bytes >> 4, b_step = (uint32_t)(b_rows * row_bytes) >> 4;
+      const uint32_t a_step = (uint32_t)(p.res ? p.a_tap : p.a_bytes) >> 4, b_step = (uint32_t)(b_rows * row_bytes) >> 4;
       const uint32_t stage_step = (uint32_t)p.stage_bytes >> 4;
       const uint32_t lo_delta = p.res ? (uint32_t)p.res_bl_off >> 4 : (uint32_t)p.rg * b_step;
       if (p.res) mbar_wait(b_full, 0);
@@ -464,7 +469,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         for (int r = 0; r < 3; ++r) {
           for (int ks = 0; ks < kst; ++ks) {
             const uint64_t db = umma_desc_join(dhi, bres + r * b_rows * row_bytes + ks * 32);
-            const uint32_t aoff = r * p.a_bytes + ks * 32;
+            const uint32_t aoff = r * p.a_tap + ks * 32;
             if ((r | ks) == 0) {
 #pragma unroll
               for (int j = 0; j < 4; ++j)
@@ -523,7 +528,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       const int rows_u = p.res ? 3 : p.rg;
       const int upt = p.res ? 1 : (3 / p.rg) * p.kblocks;
       const int U = (t_end - t_begin) * upt;
-      const uint32_t a_step = (uint32_t)p.a_bytes >> 4, b_step = (uint32_t)(b_rows * row_bytes) >> 4;
+      const uint32_t a_step = (uint32_t)(p.res ? p.a_tap : p.a_bytes) >> 4, b_step = (uint32_t)(b_rows * row_bytes) >> 4;
       const uint32_t stage_step = (uint32_t)p.stage_bytes >> 4;
       int s2 = 0, ph2 = 0, k2 = 0, a2 = 0, tr_n = 0;
       for (int u2 = 0; u2 < U; ++u2) {
@@ -552,7 +557,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     const int tid_c = (warp == 3 ? 0 : 32) + lane;
     const int upt = p.res ? 1 : (3 / p.rg) * p.kblocks;
     const int U = max(0, t_end - t_begin) * upt;
-    const int bytes = (p.res ? 3 : p.rg) * p.a_bytes;
+    const int bytes = p.res ? p.a_stage_bytes : p.rg * p.a_bytes;
     int stage = 0, phase = 0;
     int tr_n = (tid_c == 0) ? 0 : 1000;
     for (int u = 0; u < U; ++u) {
@@ -873,13 +878,20 @@ static int conv_tc_launch(const se_conv_desc* d, const float* a_tensor, int Kc, 
     return SE_ERR_UNSUPPORTED;
   }
   // resident-weights mode: every tile of the CTA uses the same 9*BN x Kc weight block
-  p.res = 0; p.res_b_bytes = 0; p.res_bl_off = 0; p.nt = 1;
+  p.res = 0; p.res_b_bytes = 0; p.res_bl_off = 0; p.nt = 1; p.single = 0; p.a_tap = p.a_bytes; p.a_stage_bytes = 3 * p.a_bytes;
   static const char* dbg_nores = getenv("SE_CT_NORES");
   const int wbytes = (1 + x3) * ceil_div(9 * p.BN * Kc * 4, 1024) * 1024;
+  static const bool no_single = getenv("SE_CT_NO_SINGLE") != nullptr;
+  const int single = (p.Nb == 1 && d->W % 8 == 0 && !no_single) ? 1 : 0;
+  const int a_stage = single ? (p.Hb + 2) * d->W * p.cblk * 4 : 3 * p.a_bytes;
+  const int res_stage = ceil_div(a_stage, 1024) * 1024;
   if (!dbg_nores && p.tiles_n == 1 && p.kblocks == 1 && wbytes <= (1 + x3) * 40 * 1024 &&
-      ((budget - wbytes) / (3 * p.a_bytes) >= 2 || budget != full_budget)) {
+      ((budget - wbytes) / res_stage >= 2 || budget != full_budget)) {
     p.res = 1; p.res_b_bytes = wbytes; p.res_bl_off = wbytes / 2; p.rg = 3;
-    p.stage_bytes = 3 * p.a_bytes;
+    p.single = single;
+    p.a_tap = single ? d->W * p.cblk * 4 : p.a_bytes;
+    p.a_stage_bytes = a_stage;
+    p.stage_bytes = res_stage;
     p.stages = min(CT_MAX_STAGES, (budget - wbytes) / p.stage_bytes);
     if (p.stages < 2) { budget = full_budget; tmem_budget = 512; p.stage_out = CT_STAGE_OUT; goto retry; }
     static const char* dbg_nt = getenv("SE_CT_NT");
@@ -923,7 +935,7 @@ static int conv_tc_launch(const se_conv_desc* d, const float* a_tensor, int Kc, 
   {
     uint64_t dims[4] = {(uint64_t)Kc, (uint64_t)d->W, (uint64_t)d->H, (uint64_t)d->N};
     uint64_t strides[3] = {(uint64_t)Kc * 4, (uint64_t)d->W * Kc * 4, (uint64_t)d->H * d->W * Kc * 4};
-    uint32_t box[4] = {(uint32_t)p.cblk, (uint32_t)p.Wb, (uint32_t)p.Hb, (uint32_t)p.Nb};
+    uint32_t box[4] = {(uint32_t)p.cblk, (uint32_t)p.Wb, (uint32_t)(p.single ? p.Hb + 2 : p.Hb), (uint32_t)p.Nb};
     CUtensorMapSwizzle sw = p.cblk == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
     if (!make_tmap(&ma, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(a_tensor), dims, strides, box, sw)) return SE_ERR_CUDA;
     uint64_t bdims[2] = {(uint64_t)Kc, (uint64_t)9 * Nc};

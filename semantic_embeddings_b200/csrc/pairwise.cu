@@ -90,6 +90,9 @@ pairwise_f32_kernel(const float* __restrict__ F, int ldF, int N, int D, int row0
 int pairwise_tc(const float* F, int ldF, int N, int D, int row0, int rows, int pmode, int normalize, float* out,
                 long long ldout, float* ws, cudaStream_t st);  // pairwise_tc.cu
 long long pairwise_tc_workspace_floats(int N, int D);
+long long pairwise_topk_extra_bytes(int N, int D, int rows);
+int pairwise_tc_topk(const float* F, int ldF, int N, int D, int row0, int rows, int pmode, int k, int* out_idx, float* out_val,
+                     int ldo, float* ws, int* status, cudaStream_t st);
 
 }  // namespace se
 
@@ -121,4 +124,21 @@ extern "C" int se_pairwise_dist(const float* F, int ldF, int N, int D, int row0,
   dim3 grid(ceil_div(N, BN), ceil_div(rows, BM));
   launch(pairwise_f32_kernel<BM, BN, 4, 4>, dim3(grid), dim3(256), 0, st, F, ldF, N, D, row0, rows, pdist_mode, sq, invn, out, ldout);
   return check_launch("pairwise_f32_kernel");
+}
+
+extern "C" int64_t se_pairwise_topk_workspace_bytes(int N, int D, int rows) {
+  return se_pairwise_workspace_bytes(N, D, SE_MODE_TF32X3) + pairwise_topk_extra_bytes(N, D, rows) + 8192;
+}
+
+extern "C" int se_pairwise_topk(const float* F, int ldF, int N, int D, int row0, int rows, int pdist_mode, int normalize, int k,
+                                int32_t* out_idx, float* out_val, int ldo, void* workspace, int32_t* status, void* stream) {
+  SE_REQUIRE(F && out_idx && workspace && status, "null pointer");
+  SE_REQUIRE(N > 0 && D > 0 && ldF >= D && row0 >= 0 && rows > 0 && row0 + rows <= N && k > 0 && ldo >= k, "bad shape");
+  SE_REQUIRE(pdist_mode == SE_PDIST_SQEUCLID || pdist_mode == SE_PDIST_NEGDOT, "unknown pairwise mode");
+  cudaStream_t st = as_stream(stream);
+  float* ws = reinterpret_cast<float*>(workspace);
+  launch(pairwise_prep_kernel, dim3(ceil_div(N, 8)), dim3(256), 0, st, F, ldF, N, D, normalize, ws, ws + N);
+  int rc = check_launch("pairwise_prep_kernel");
+  if (rc) return rc;
+  return pairwise_tc_topk(F, ldF, N, D, row0, rows, pdist_mode, k, out_idx, out_val, ldo, ws, status, st);
 }

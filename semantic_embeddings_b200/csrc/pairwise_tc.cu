@@ -35,8 +35,21 @@ constexpr int PW_SMEM = 2 * PW_MAXKB * PW_A_BYTES + PW_STAGES * 2 * PW_B_BYTES +
 
 struct PwParams {
   int N, row0, rows, pmode, tiles_m, tiles_n, kblocks, ksteps_total;
-  const float* sq;       // squared norms of the (normalised) rows, [N]
+  const float* sq;       // squared norms of the (normalised) query rows, [N]
+  const float* sq_b;     // squared norms of the column items (== sq for the all-pairs matrix; a sample's norms otherwise)
   const float* scal;     // scal[1] = 4^e: undoes the power-of-two input scaling
+  // fused ranking (se_pairwise_topk).  EPI == 2, sample pass: every (row, 128-column half tile) adds the SECOND smallest of
+  // its 128 distances to tau_sum[row] -- the mean of those order statistics (quantile ~2/129 of the row) is the row's
+  // candidate threshold.  EPI == 1, sweep: entries below the threshold become (value, column) candidates in the region
+  // of the writing (row, column half, part of the row block) -- a lane owns its row for the CTA's whole stretch of the
+  // row block, so the fill count lives in a register and no atomics are needed.
+  float* tau_sum;        // [rows]   EPI 2: accumulates; EPI 1: threshold = tau_sum[row] * tau_scale
+  float tau_scale;       // 1 / (number of half tiles of the sample pass)
+  int* cnt;              // [rows, 4] candidates per region (may exceed capr: the finishing kernel reports it)
+  float* cand_val;       // [rows, 4, capr]
+  int* cand_idx;         // [rows, 4, capr]
+  int capr, ncols;       // ncols: number of valid columns
+  int jsel;              // EPI 2: which order statistic (0-based, < 8) of a half tile feeds the threshold
 };
 
 // ---- prep: fp32 features -> scaled fp16 (h, l) matrices with row pitch KW
@@ -77,8 +90,12 @@ pairwise_split_kernel(const float* __restrict__ F, int ldF, int N, int D, int KW
 }
 
 // ---- main kernel
+// map_h / map_l: split operands of the query rows (A); map_bh / map_bl: of the column items (B; the same arrays for the
+// all-pairs matrix).  EPI 0: distances out through map_out; EPI 1: thresholded candidates (fused ranking).
+template <int EPI>
 __global__ void __launch_bounds__(128 + 32 * PW_EPI_WARPS, 1)
 pairwise_tc_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_constant__ CUtensorMap map_l,
+                   const __grid_constant__ CUtensorMap map_bh, const __grid_constant__ CUtensorMap map_bl,
                    const __grid_constant__ CUtensorMap map_out, PwParams p) {
   pdl_trigger();
   extern __shared__ uint8_t smem_raw[];
@@ -102,7 +119,7 @@ pairwise_tc_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_const
   const int t_end = min(total_tiles, t_begin + per_cta);
 
   if (warp == 0 && lane == 0) {
-    prefetch_tmap(&map_h); prefetch_tmap(&map_l); prefetch_tmap(&map_out);
+    prefetch_tmap(&map_h); prefetch_tmap(&map_l); prefetch_tmap(&map_bh); prefetch_tmap(&map_bl); prefetch_tmap(&map_out);
     for (int s = 0; s < PW_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
     mbar_init(a_full, 1); mbar_init(a_empty, 1);
     for (int a = 0; a < 2; ++a) { mbar_init(&t_full[a], 1); mbar_init(&t_empty[a], 32 * PW_EPI_WARPS); }
@@ -138,10 +155,10 @@ pairwise_tc_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_const
         mbar_expect_tx(&full[stage], 2 * PW_B_BYTES);
         uint8_t* bh = sB + (stage * 2 + 0) * PW_B_BYTES;
         uint8_t* bl = sB + (stage * 2 + 1) * PW_B_BYTES;
-        tma_load_2d_hint(bh, &map_h, &full[stage], kb * PW_KB, tn * PW_BN, keep);
-        tma_load_2d_hint(bh + PW_A_BYTES, &map_h, &full[stage], kb * PW_KB, tn * PW_BN + 128, keep);
-        tma_load_2d_hint(bl, &map_l, &full[stage], kb * PW_KB, tn * PW_BN, keep);
-        tma_load_2d_hint(bl + PW_A_BYTES, &map_l, &full[stage], kb * PW_KB, tn * PW_BN + 128, keep);
+        tma_load_2d_hint(bh, &map_bh, &full[stage], kb * PW_KB, tn * PW_BN, keep);
+        tma_load_2d_hint(bh + PW_A_BYTES, &map_bh, &full[stage], kb * PW_KB, tn * PW_BN + 128, keep);
+        tma_load_2d_hint(bl, &map_bl, &full[stage], kb * PW_KB, tn * PW_BN, keep);
+        tma_load_2d_hint(bl + PW_A_BYTES, &map_bl, &full[stage], kb * PW_KB, tn * PW_BN + 128, keep);
         if (++stage == PW_STAGES) { stage = 0; phase ^= 1; }
       }
     }
@@ -192,6 +209,7 @@ pairwise_tc_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_const
     const uint64_t stream_out = l2_policy_evict_first();   // the distances are written once and not read by this kernel
     constexpr int CHUNKS = PW_BN / 2 / 32;              // 4 blocks of 32 columns per warp and tile
     int acc = 0, acc_phase = 0;
+    int e_tm = -1, e_pos = 0, e_region = 0;              // EPI 1: row block / fill count / region of this lane's candidates
     for (int t = t_begin; t < t_end; ++t) {
       const int tm = t / p.tiles_n, tn = t % p.tiles_n;
       const int r_local = q4 * 32 + lane;               // row inside the tile == TMEM lane
@@ -199,7 +217,21 @@ pairwise_tc_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_const
       const float a_sq = p.sq[gi];                      // (rows past N read workspace padding; clipped at the store)
       // squared norms of this warp's 128 columns: lane i keeps columns 4i..4i+3, handed out by shuffles below
       // (issued before the accumulator wait so that the L2 latency is off the critical path)
-      const float4 sqv = __ldg(reinterpret_cast<const float4*>(p.sq + tn * PW_BN + half * (PW_BN / 2)) + lane);
+      const float4 sqv = __ldg(reinterpret_cast<const float4*>(p.sq_b + tn * PW_BN + half * (PW_BN / 2)) + lane);
+      const int lrow = tm * PW_BM + r_local;             // row inside this call's row range
+      const bool row_ok = lrow < p.rows;
+      float tau = 0.f;
+      if (EPI == 1) {
+        tau = row_ok ? p.tau_sum[lrow] * p.tau_scale : 0.f;
+        if (tm != e_tm) {                                // a new row block: flush the previous block's fill count
+          if (e_tm >= 0 && e_tm * PW_BM + r_local < p.rows) p.cnt[(long long)(e_tm * PW_BM + r_local) * 4 + e_region] = e_pos;
+          e_tm = tm; e_pos = 0;
+          e_region = half * 2 + ((t_begin > tm * p.tiles_n) ? 1 : 0);
+        }
+      }
+      float ms[8];                                         // EPI 2: the eight smallest distances of this half tile, ascending
+#pragma unroll
+      for (int i = 0; i < 8; ++i) ms[i] = 3.0e38f;
       mbar_wait(&t_full[acc], acc_phase);
       fence_after_sync();
       for (int c = 0; c < CHUNKS; ++c) {
@@ -226,6 +258,52 @@ pairwise_tc_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_const
             o[q] = make_float4((a_sq + bx) - 2.f * c0, (a_sq + by) - 2.f * c1, (a_sq + bz) - 2.f * c2, (a_sq + bw) - 2.f * c3);
           }
         }
+        if (EPI == 1) {
+          // branch-free pass mask (bit i = column j0 + i is a candidate), then the few set bits are handled one by one;
+          // the values are parked in this warp's staging rows so that the rare path can fetch entry i by index
+          unsigned mask = 0;
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            mask |= (o[q].x < tau ? 1u : 0u) << (4 * q) | (o[q].y < tau ? 1u : 0u) << (4 * q + 1) |
+                    (o[q].z < tau ? 1u : 0u) << (4 * q + 2) | (o[q].w < tau ? 1u : 0u) << (4 * q + 3);
+          }
+          const int nvalid = p.ncols - j0;                   // columns of this block inside the matrix
+          if (nvalid < 32) mask &= nvalid > 0 ? ((1u << nvalid) - 1u) : 0u;
+          if (!row_ok) mask = 0;
+          if (__any_sync(0xffffffffu, mask != 0)) {
+            float* rowbuf = reinterpret_cast<float*>(ob + lane * 128);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) *reinterpret_cast<float4*>(rowbuf + 4 * q) = o[q];     // own row only: no sync needed
+            float* cv = p.cand_val + ((long long)lrow * 4 + e_region) * p.capr;
+            int* ci = p.cand_idx + ((long long)lrow * 4 + e_region) * p.capr;
+            while (mask) {
+              const int i = __ffs(mask) - 1;
+              mask &= mask - 1;
+              if (e_pos < p.capr) { cv[e_pos] = rowbuf[i]; ci[e_pos] = j0 + i; }
+              ++e_pos;
+            }
+          }
+          continue;
+        }
+        if (EPI == 2) {
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const float vv[4] = {o[q].x, o[q].y, o[q].z, o[q].w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              float x = (j0 + 4 * q + e < p.ncols) ? vv[e] : 3.0e38f;
+#pragma unroll
+              for (int i = 0; i < 8; ++i) { const float lo = fminf(ms[i], x); x = fmaxf(ms[i], x); ms[i] = lo; }
+            }
+          }
+          if (c == CHUNKS - 1 && row_ok) {
+            float sel = ms[0];
+#pragma unroll
+            for (int i = 1; i < 8; ++i) if (i == p.jsel) sel = ms[i];
+            atomicAdd(&p.tau_sum[lrow], sel);
+          }
+          continue;
+        }
         if (lane == 0) tma_store_wait_read<0>();        // the previous store of this warp has read the buffer
         __syncwarp();
         // SWIZZLE_128B staging: 16-byte chunk q of row r lives at chunk (q ^ (r & 7))
@@ -241,6 +319,8 @@ pairwise_tc_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_const
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
+    if (EPI == 1 && e_tm >= 0 && e_tm * PW_BM + (q4 * 32 + lane) < p.rows)
+      p.cnt[(long long)(e_tm * PW_BM + q4 * 32 + lane) * 4 + e_region] = e_pos;
     if (lane == 0) tma_store_wait_all<0>();
   }
 
@@ -252,7 +332,9 @@ pairwise_tc_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_const
 int init_pairwise_tc() {
   static bool configured = false;
   if (!configured) {
-    if (cudaFuncSetAttribute(pairwise_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PW_SMEM) != cudaSuccess) {
+    if (cudaFuncSetAttribute(pairwise_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, PW_SMEM) != cudaSuccess ||
+        cudaFuncSetAttribute(pairwise_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, PW_SMEM) != cudaSuccess ||
+        cudaFuncSetAttribute(pairwise_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, PW_SMEM) != cudaSuccess) {
       set_error("pairwise_tc: cannot reserve %d bytes of shared memory", PW_SMEM);
       return SE_ERR_CUDA;
     }
@@ -267,54 +349,223 @@ long long pairwise_tc_workspace_floats(int N, int D) {
   return 64 + 64 + (long long)N * KW + 1024;
 }
 
-int pairwise_tc(const float* F, int ldF, int N, int D, int row0, int rows, int pmode, int normalize, float* out,
-                long long ldout, float* ws, cudaStream_t st) {
-  const int KW = ceil_div(D, 16) * 16;
-  const int kblocks = ceil_div(KW, PW_KB);
-  if (kblocks > PW_MAXKB) return SE_ERR_UNSUPPORTED;                       // D > 128: fp32 tiles
-  if ((ldout % 4) != 0 || (reinterpret_cast<uintptr_t>(out) & 15) != 0) return SE_ERR_UNSUPPORTED;  // TMA store alignment
-  float* sq = ws;
-  float* norms = ws + N;
+// ---- host side: operand preparation (shared by the matrix and the fused-ranking entry points) and the launch
+struct PwLayout {
+  float* sq; float* norms; float* scal; __half* Fh; __half* Fl; int KW, kblocks;
+};
+
+static int pw_prepare(const float* F, int ldF, int N, int D, float* ws, cudaStream_t st, PwLayout* L) {
+  L->KW = ceil_div(D, 16) * 16;
+  L->kblocks = ceil_div(L->KW, PW_KB);
+  if (L->kblocks > PW_MAXKB) return SE_ERR_UNSUPPORTED;                    // D > 128: fp32 tiles
+  L->sq = ws;
+  L->norms = ws + N;
   uintptr_t base = (reinterpret_cast<uintptr_t>(ws + 2LL * N) + 255) & ~(uintptr_t)255;
-  float* scal = reinterpret_cast<float*>(base);
-  __half* Fh = reinterpret_cast<__half*>(base + 256);
-  __half* Fl = Fh + (long long)N * KW;
-  if (cudaMemsetAsync(scal, 0, 256, st) != cudaSuccess) { set_error("pairwise_tc: memset failed"); return SE_ERR_CUDA; }
+  L->scal = reinterpret_cast<float*>(base);
+  L->Fh = reinterpret_cast<__half*>(base + 256);
+  L->Fl = L->Fh + (long long)N * L->KW;
+  if (cudaMemsetAsync(L->scal, 0, 256, st) != cudaSuccess) { set_error("pairwise_tc: memset failed"); return SE_ERR_CUDA; }
   long long w1 = ceil_div<long long>((long long)N * D, 256), cap = (long long)sm_count() * 8;
   int g1 = (int)(w1 < cap ? w1 : cap);
-  launch(pairwise_absmax_kernel, dim3(g1), dim3(256), 0, st, F, ldF, N, D, norms, reinterpret_cast<unsigned*>(scal));
+  launch(pairwise_absmax_kernel, dim3(g1), dim3(256), 0, st, F, ldF, N, D, L->norms, reinterpret_cast<unsigned*>(L->scal));
   int rc = check_launch("pairwise_absmax_kernel");
   if (rc) return rc;
-  long long w2 = ceil_div<long long>((long long)N * KW, 256);
+  long long w2 = ceil_div<long long>((long long)N * L->KW, 256);
   int g2 = (int)(w2 < cap ? w2 : cap);
-  launch(pairwise_split_kernel, dim3(g2), dim3(256), 0, st, F, ldF, N, D, KW, norms, scal, Fh, Fl);
-  rc = check_launch("pairwise_split_kernel");
-  if (rc) return rc;
+  launch(pairwise_split_kernel, dim3(g2), dim3(256), 0, st, F, ldF, N, D, L->KW, L->norms, L->scal, L->Fh, L->Fl);
+  return check_launch("pairwise_split_kernel");
+}
 
-  CUtensorMap mh, ml, mo;
+struct PwEpi { int kind; float* tau_sum; float tau_scale; int* cnt; float* cand_val; int* cand_idx; int capr; int jsel; };
+
+// rows [row0, row0+rows) of the N query items against `ncols` column items given by (Bh, Bl, sq_b)
+static int pw_launch(const PwLayout& L, int N, int row0, int rows, const __half* Bh, const __half* Bl, const float* sq_b,
+                     int ncols, int pmode, float* out, long long ldout, const PwEpi* e1, cudaStream_t st) {
+  if (!e1 && ((ldout % 4) != 0 || (reinterpret_cast<uintptr_t>(out) & 15) != 0)) return SE_ERR_UNSUPPORTED;  // TMA store alignment
+  CUtensorMap mh, ml, mbh, mbl, mo;
   {
-    uint64_t dims[2] = {(uint64_t)KW, (uint64_t)N};
-    uint64_t strides[1] = {(uint64_t)KW * 2};
+    uint64_t dims[2] = {(uint64_t)L.KW, (uint64_t)N};
+    uint64_t strides[1] = {(uint64_t)L.KW * 2};
     uint32_t box[2] = {PW_KB, 128};
-    if (!make_tmap(&mh, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, Fh, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B) ||
-        !make_tmap(&ml, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, Fl, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B))
+    if (!make_tmap(&mh, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, L.Fh, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B) ||
+        !make_tmap(&ml, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, L.Fl, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B))
       return SE_ERR_CUDA;
-    uint64_t odims[2] = {(uint64_t)N, (uint64_t)rows};
-    uint64_t ostrides[1] = {(uint64_t)ldout * 4};
-    uint32_t obox[2] = {32, 32};
-    if (!make_tmap(&mo, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, out, odims, ostrides, obox, CU_TENSOR_MAP_SWIZZLE_128B))
+    uint64_t bdims[2] = {(uint64_t)L.KW, (uint64_t)ncols};
+    if (!make_tmap(&mbh, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<__half*>(Bh), bdims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B) ||
+        !make_tmap(&mbl, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<__half*>(Bl), bdims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B))
       return SE_ERR_CUDA;
+    mo = mh;
+    if (!e1) {
+      uint64_t odims[2] = {(uint64_t)ncols, (uint64_t)rows};
+      uint64_t ostrides[1] = {(uint64_t)ldout * 4};
+      uint32_t obox[2] = {32, 32};
+      if (!make_tmap(&mo, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, out, odims, ostrides, obox, CU_TENSOR_MAP_SWIZZLE_128B))
+        return SE_ERR_CUDA;
+    }
   }
   PwParams p;
   p.N = N; p.row0 = row0; p.rows = rows; p.pmode = pmode;
-  p.tiles_m = ceil_div(rows, PW_BM); p.tiles_n = ceil_div(N, PW_BN);
-  p.kblocks = kblocks; p.ksteps_total = KW / 16;
-  p.sq = sq; p.scal = scal;
+  p.tiles_m = ceil_div(rows, PW_BM); p.tiles_n = ceil_div(ncols, PW_BN);
+  p.kblocks = L.kblocks; p.ksteps_total = L.KW / 16;
+  p.sq = L.sq; p.sq_b = sq_b; p.scal = L.scal; p.ncols = ncols;
+  p.tau_sum = nullptr; p.tau_scale = 0.f; p.cnt = nullptr; p.cand_val = nullptr; p.cand_idx = nullptr; p.capr = 0; p.jsel = 1;
+  if (e1) { p.jsel = e1->jsel; p.tau_sum = e1->tau_sum; p.tau_scale = e1->tau_scale; p.cnt = e1->cnt; p.cand_val = e1->cand_val; p.cand_idx = e1->cand_idx; p.capr = e1->capr; }
   int rc0 = init_pairwise_tc();
   if (rc0) return rc0;
   int grid = min(sm_count(), p.tiles_m * p.tiles_n);
-  launch(pairwise_tc_kernel, dim3(grid), dim3(128 + 32 * PW_EPI_WARPS), PW_SMEM, st, mh, ml, mo, p);
+  // candidate sweep: a row block may be shared by at most two CTAs (regions are per (row, column half, part))
+  if (e1 && e1->kind == 1) grid = max(1, min(grid, p.tiles_m));
+  if (e1 && e1->kind == 1) launch(pairwise_tc_kernel<1>, dim3(grid), dim3(128 + 32 * PW_EPI_WARPS), PW_SMEM, st, mh, ml, mbh, mbl, mo, p);
+  else if (e1) launch(pairwise_tc_kernel<2>, dim3(grid), dim3(128 + 32 * PW_EPI_WARPS), PW_SMEM, st, mh, ml, mbh, mbl, mo, p);
+  else launch(pairwise_tc_kernel<0>, dim3(grid), dim3(128 + 32 * PW_EPI_WARPS), PW_SMEM, st, mh, ml, mbh, mbl, mo, p);
   return check_launch("pairwise_tc_kernel");
+}
+
+int pairwise_tc(const float* F, int ldF, int N, int D, int row0, int rows, int pmode, int normalize, float* out,
+                long long ldout, float* ws, cudaStream_t st) {
+  PwLayout L;
+  int rc = pw_prepare(F, ldF, N, D, ws, st, &L);
+  if (rc) return rc;
+  return pw_launch(L, N, row0, rows, L.Fh, L.Fl, L.sq, N, pmode, out, ldout, nullptr, st);
+}
+
+// ---------------------------------------------------------------------------------------- fused distance + top-k
+// the k nearest items of every query WITHOUT the rows x N distance matrix in HBM.
+//   1. sample pass (EPI 2): distances to a strided sample of S <= 4096 column items; every (row, 128-column half tile)
+//      contributes the j-th smallest of its distances (j = 2..8 by k / N), and their mean -- roughly the j/129 quantile of
+//      the row -- is the row's candidate threshold (~3 k of the N entries: j = 2 for k = 251 at N = 50 000);
+//   2. sweep (EPI 1): the tensor-core kernel over all N columns keeps the entries below the threshold as (value, column)
+//      candidates in per-(row, column half, part) regions -- no atomics, nothing else is written;
+//   3. one CTA per row sorts its candidates as (key, column) words and writes the first k.
+// The values are the ones the matrix kernel would have stored (same arithmetic), so the result equals se_row_topk on the
+// written matrix -- provided every row found at least k candidates and no region overflowed, which status[0] reports
+// (0 = exact; otherwise the caller falls back to the matrix path).  The threshold is a statistical estimate; exactness
+// never depends on it, only the fallback rate does.
+constexpr int PT_SAMPLE = 4096, PT_CAPR = 1024, PT_CAP = 4 * PT_CAPR, PT_THREADS = 512;
+
+__global__ void __launch_bounds__(256)
+pairwise_sample_kernel(const __half* __restrict__ Fh, const __half* __restrict__ Fl, const float* __restrict__ sq, int KW,
+                       int S, int stride, __half* __restrict__ Sh, __half* __restrict__ Sl, float* __restrict__ sq_s) {
+  pdl_grid_sync();
+  const long long total = (long long)S * KW;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int r = (int)(i / KW), k = (int)(i % KW);
+    const long long src = (long long)r * stride * KW + k;
+    Sh[i] = Fh[src];
+    Sl[i] = Fl[src];
+    if (k == 0) sq_s[r] = sq[(long long)r * stride];
+  }
+}
+
+__device__ __forceinline__ uint32_t pt_key(float f) {
+  if (f == 0.f) f = 0.f;
+  uint32_t u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float pt_unkey(uint32_t k) { return __uint_as_float((k & 0x80000000u) ? (k & 0x7FFFFFFFu) : ~k); }
+
+__global__ void __launch_bounds__(PT_THREADS)
+pairwise_topk_finish_kernel(const int* __restrict__ cnt, const float* __restrict__ cand_val, const int* __restrict__ cand_idx,
+                            int k, int* __restrict__ out_idx, float* __restrict__ out_val, int ldo, int* __restrict__ status) {
+  pdl_grid_sync();
+  __shared__ unsigned long long s[PT_CAP];
+  const int row = blockIdx.x;
+  int c4[4], off[5];
+  off[0] = 0;
+  bool bad = false;
+  for (int r = 0; r < 4; ++r) {
+    c4[r] = cnt[row * 4 + r];
+    if (c4[r] > PT_CAPR) bad = true;
+    off[r + 1] = off[r] + min(c4[r], PT_CAPR);
+  }
+  const int c = off[4];
+  if (bad || c < k) { if (threadIdx.x == 0) atomicOr(status, 1); return; }
+  int npad = 1;
+  while (npad < c) npad <<= 1;
+  for (int i = threadIdx.x; i < npad; i += PT_THREADS) {
+    unsigned long long w = ~0ull;
+    if (i < c) {
+      const int r = (i >= off[1]) + (i >= off[2]) + (i >= off[3]);
+      const long long src = ((long long)row * 4 + r) * PT_CAPR + (i - off[r]);
+      w = ((unsigned long long)pt_key(cand_val[src]) << 32) | (unsigned)cand_idx[src];
+    }
+    s[i] = w;
+  }
+  __syncthreads();
+  for (int kk = 2; kk <= npad; kk <<= 1) {
+    for (int j = kk >> 1; j >= 1; j >>= 1) {
+      for (int t = threadIdx.x; t < npad / 2; t += PT_THREADS) {
+        const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+        const int q = i | j;
+        const bool up = ((i & kk) == 0);
+        const unsigned long long a = s[i], b = s[q];
+        if ((a > b) == up) { s[i] = b; s[q] = a; }
+      }
+      __syncthreads();
+    }
+  }
+  for (int i = threadIdx.x; i < k; i += PT_THREADS) {
+    out_idx[(long long)row * ldo + i] = (int)(unsigned)(s[i] & 0xFFFFFFFFull);
+    if (out_val) out_val[(long long)row * ldo + i] = pt_unkey((uint32_t)(s[i] >> 32));
+  }
+}
+
+// extra workspace of the fused path, carved behind the matrix path's (all regions 256-byte aligned)
+struct PtWs {
+  __half* Sh; __half* Sl; float* sq_s; float* tau_sum; int* cnt; float* cv; int* ci; long long bytes;
+  int S;
+};
+static PtWs pt_carve(void* base, int N, int KW, int rows) {
+  PtWs w;
+  w.S = min(N, PT_SAMPLE);
+  uintptr_t p0 = (reinterpret_cast<uintptr_t>(base) + 255) & ~(uintptr_t)255, p = p0;
+  auto take = [&](long long bytes) { uintptr_t r = p; p += (bytes + 255) & ~255LL; return r; };
+  w.Sh = reinterpret_cast<__half*>(take((long long)(w.S + 256) * KW * 2));     // + one spare tile of rows for clipped reads
+  w.Sl = reinterpret_cast<__half*>(take((long long)(w.S + 256) * KW * 2));
+  w.sq_s = reinterpret_cast<float*>(take((long long)(w.S + 512) * 4));
+  w.tau_sum = reinterpret_cast<float*>(take((long long)rows * 4));
+  w.cnt = reinterpret_cast<int*>(take((long long)rows * 4 * 4));
+  w.cv = reinterpret_cast<float*>(take((long long)rows * PT_CAP * 4));
+  w.ci = reinterpret_cast<int*>(take((long long)rows * PT_CAP * 4));
+  w.bytes = (long long)(p - p0) + 256;
+  return w;
+}
+
+long long pairwise_topk_extra_bytes(int N, int D, int rows) {
+  return pt_carve(nullptr, N, ceil_div(D, 16) * 16, rows).bytes;
+}
+
+int pairwise_tc_topk(const float* F, int ldF, int N, int D, int row0, int rows, int pmode, int k, int* out_idx, float* out_val,
+                     int ldo, float* ws, int* status, cudaStream_t st) {
+  if (k < 1 || k > 1024 || k > N) return SE_ERR_UNSUPPORTED;
+  PwLayout L;
+  int rc = pw_prepare(F, ldF, N, D, ws, st, &L);
+  if (rc) return rc;
+  const PtWs w = pt_carve(L.Fl + (long long)N * L.KW + 2048, N, L.KW, rows);
+  const int S = w.S, stride = N / S;
+  if (cudaMemsetAsync(w.cnt, 0, (size_t)rows * 16, st) != cudaSuccess || cudaMemsetAsync(status, 0, 4, st) != cudaSuccess ||
+      cudaMemsetAsync(w.sq_s, 0, (size_t)(S + 512) * 4, st) != cudaSuccess ||
+      cudaMemsetAsync(w.tau_sum, 0, (size_t)rows * 4, st) != cudaSuccess) {
+    set_error("pairwise_topk: memset failed");
+    return SE_ERR_CUDA;
+  }
+  launch(pairwise_sample_kernel, dim3(min(sm_count() * 4, ceil_div(S * L.KW, 256))), dim3(256), 0, st, L.Fh, L.Fl, L.sq, L.KW, S, stride,
+         w.Sh, w.Sl, w.sq_s);
+  rc = check_launch("pairwise_sample_kernel");
+  if (rc) return rc;
+  // thresholds: mean over the sample's half tiles (128 distances each) of the j-th smallest distance, j chosen so that
+  // ~3k of the row's N entries are expected below it (j / 129 of the row).  j > 8 is not tracked: such shapes (k large
+  // against N) simply find fewer than k candidates, report status != 0 and take the matrix path.
+  int j = (int)((3LL * k * 129 + N / 2) / N);
+  j = max(2, min(8, j));
+  PwEpi e2 = {2, w.tau_sum, 0.f, nullptr, nullptr, nullptr, 0, j - 1};
+  rc = pw_launch(L, N, row0, rows, w.Sh, w.Sl, w.sq_s, S, pmode, nullptr, 0, &e2, st);
+  if (rc) return rc;
+  PwEpi e1 = {1, w.tau_sum, 1.f / (2.f * (float)ceil_div(S, PW_BN)), w.cnt, w.cv, w.ci, PT_CAPR, 0};
+  rc = pw_launch(L, N, row0, rows, L.Fh, L.Fl, L.sq, N, pmode, nullptr, 0, &e1, st);
+  if (rc) return rc;
+  launch(pairwise_topk_finish_kernel, dim3(rows), dim3(PT_THREADS), 0, st, w.cnt, w.cv, w.ci, k, out_idx, out_val, ldo, status);
+  return check_launch("pairwise_topk_finish_kernel");
 }
 
 }  // namespace se

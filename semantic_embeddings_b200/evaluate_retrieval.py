@@ -80,6 +80,46 @@ def pairwise_ranking(features, normalize=False, block_rows=4096, mode=None, devi
     return ranking
 
 
+def pairwise_topk(features=None, k=251, normalize=False, feat_dev=None, device=None, want_values=False, allow_fallback=True):
+    """The k nearest database items of every item (ascending distance, ties by index) without the N x N matrix in memory:
+    se_pairwise_topk (sample thresholds -> tensor-core sweep keeping candidates -> per-row candidate sort).  Equals
+    row_topk(pairwise_distances(...), k).  When the kernel reports that some row's candidate list was too short or too
+    long (status != 0: degenerate distance distributions, e.g. many duplicates) the matrix path is used instead.
+    Returns (int32 [N, k] device tensor, float32 values or None, fused: bool)."""
+    import torch
+    if feat_dev is None:
+        f = np.ascontiguousarray(np.asarray(features, dtype=np.float32))
+        feat_dev = torch.from_numpy(f).to(torch.device(device or 'cuda'))
+    N, D = feat_dev.shape
+    dev = feat_dev.device
+    lib = _lib.load()
+    idx = torch.empty((N, k), dtype=torch.int32, device=dev)
+    val = torch.empty((N, k), dtype=torch.float32, device=dev) if want_values else None
+    pmode = _lib.SE_PDIST_NEGDOT if normalize else _lib.SE_PDIST_SQEUCLID
+    fused = False
+    if D <= 128 and k <= 1024 and k <= N:
+        ws = torch.empty(int(lib.se_pairwise_topk_workspace_bytes(N, D, N)), dtype=torch.uint8, device=dev)
+        status = torch.zeros(1, dtype=torch.int32, device=dev)
+        with torch.cuda.device(dev):
+            _lib.call('se_pairwise_topk', feat_dev.data_ptr(), feat_dev.stride(0), N, D, 0, N, pmode, 1 if normalize else 0, k,
+                      idx.data_ptr(), _lib.ptr(val), k, ws.data_ptr(), status.data_ptr(), _lib.stream_ptr())
+        fused = int(status.item()) == 0
+        del ws
+    if not fused:
+        if not allow_fallback:
+            raise _lib.SeError('se_pairwise_topk: candidate lists out of range (status != 0)')
+        block = 4096
+        buf = torch.empty((min(block, N), N), dtype=torch.float32, device=dev)
+        for r0 in range(0, N, block):
+            r = min(block, N - r0)
+            d = pairwise_distances(None, normalize, r0, r, None, out=buf[:r], feat_dev=feat_dev)
+            i2, v2 = row_topk(d, k, want_values) if N <= TOPK_MAX_N else (row_argsort(d)[:, :k].contiguous(), None)
+            idx[r0:r0 + r] = i2
+            if want_values and v2 is not None:
+                val[r0:r0 + r] = v2
+    return idx, val, fused
+
+
 def row_argsort(dist):
     """Full ranking of every row of a device matrix (ascending, ties by index): evaluate_retrieval.py:67 on the GPU
     (se_row_argsort: bitonic network with shared-memory sub-sorts, one CTA per row).  Returns int32 [rows, n]."""

@@ -842,6 +842,13 @@ def test_pairwise_n50000_sampled_rows_and_top251_match_oracle():
     # the device-side ranking is the exact stable order of the device distances
     chk = torch.sort(sub, dim=-1, stable=True).indices[:, :K].cpu().numpy()
     assert np.array_equal(idx, chk)
+    # fused distance + ranking at full size: every one of the 50 000 rows equals the top 251 of the written matrix
+    from semantic_embeddings_b200.evaluate_retrieval import pairwise_topk
+    fi, fv, fused = pairwise_topk(k=K, feat_dev=fd, want_values=True, allow_fallback=False)
+    assert fused
+    for r0 in range(0, N, 10000):
+        ri, rv = row_topk(full[r0:r0 + 10000], K, want_values=True)
+        assert torch.equal(fi[r0:r0 + 10000], ri) and torch.equal(fv[r0:r0 + 10000], rv)
 
 
 def _cifar_hierarchy():
@@ -949,3 +956,36 @@ def test_augment_batch_matches_keras_restatement(src_dtype):
     data.compose_batch(idx, True, a, augment=True, rng=r)
     data.compose_batch(idx, True, b, augment=True, rng=r)
     assert not torch.equal(a, b)
+
+
+@pytest.mark.parametrize('case', [(3000, 100, 16, False), (12000, 100, 100, False), (12000, 64, 100, True), (30000, 128, 251, False)],
+                         ids=lambda c: 'N%d-D%d-k%d-%s' % (c[0], c[1], c[2], 'cos' if c[3] else 'sq'))
+def test_fused_pairwise_topk_equals_topk_of_the_written_matrix(case):
+    """se_pairwise_topk (fused distance + ranking, no N x N matrix) against se_row_topk of the matrix se_pairwise_dist
+    writes: identical indices AND values for every row (same arithmetic, same tie order)."""
+    from semantic_embeddings_b200.evaluate_retrieval import pairwise_distances, pairwise_topk, row_topk
+    N, D, k, normalize = case
+    rng = np.random.RandomState(N + D)
+    f = rng.randn(N, D).astype(np.float32)
+    if not normalize:
+        f /= np.linalg.norm(f, axis=-1, keepdims=True)
+    fd = torch.from_numpy(f).cuda()
+    idx, val, fused = pairwise_topk(k=k, normalize=normalize, feat_dev=fd, want_values=True, allow_fallback=False)
+    assert fused
+    full = pairwise_distances(None, normalize, feat_dev=fd, mode=2)
+    ref_i, ref_v = row_topk(full, k, want_values=True)
+    assert torch.equal(idx, ref_i) and torch.equal(val, ref_v)
+
+
+def test_fused_pairwise_topk_reports_degenerate_rows_and_falls_back():
+    """Many duplicate items: more entries tie at the threshold than a candidate list holds / fewer than k lie strictly below
+    it -> status != 0 -> the wrapper computes the same result through the matrix path."""
+    from semantic_embeddings_b200.evaluate_retrieval import pairwise_distances, pairwise_topk, row_topk
+    rng = np.random.RandomState(7)
+    base = rng.randn(8, 32).astype(np.float32)
+    f = base[rng.randint(0, 8, 6000)]                      # only 8 distinct items
+    fd = torch.from_numpy(f).cuda()
+    idx, _, fused = pairwise_topk(k=50, feat_dev=fd)
+    assert not fused
+    ref_i, _ = row_topk(pairwise_distances(None, False, feat_dev=fd, mode=2), 50)
+    assert torch.equal(idx, ref_i)
