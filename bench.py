@@ -502,7 +502,8 @@ def main():
                     help='BASELINE.json training configuration; the driver contract is config2 (ResNet-110, batch 128)')
     ap.add_argument('--scaling', default='weak', choices=['weak', 'strong'],
                     help='weak: --batch images per GPU (the driver contract); strong: --batch images in total')
-    ap.add_argument('--comm', default='auto', choices=['auto', 'native', 'torch'])
+    ap.add_argument('--comm', default='torch', choices=['auto', 'native', 'torch'],
+                    help='gradient exchange: torch.distributed all_reduce (default) or the library\'s NCCL-in-graph path')
     ap.add_argument('--retrieval-n', type=int, default=50000)
     ap.add_argument('--skip-retrieval', action='store_true')
     ap.add_argument('--skip-cpu-baseline', action='store_true')
