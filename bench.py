@@ -73,7 +73,7 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    """nvidia-smi clocks / throttle reasons sampled every 100 ms while the timed region runs."""
     Q = 'clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,' \
         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
 
@@ -83,7 +83,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
-                                          '--format=csv,noheader,nounits', '-lms', '200'],
+                                          '--format=csv,noheader,nounits', '-lms', '100'],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -292,8 +292,9 @@ def bench_retrieval(L, rank, world, dev, n, d, reps, mode, pk_hbm=6567.4):
         torch.cuda.synchronize(dev)
         extra['fused_topk'] = {'ms': a.elapsed_time(b) / 3.0, 'k': k, 'fused': bool(fused),
                                'gpairs_per_s': float(n) * n / (a.elapsed_time(b) / 3.0 / 1000.0) / 1e9,
-                               'kernels': 'pairwise_tc_kernel<0> on a 4096-column sample + row_topk_kernel (thresholds), '
-                                          'pairwise_tc_kernel<1> (candidate sweep), pairwise_topk_finish_kernel',
+                               'kernels': 'pairwise_tc_kernel<2> on a 4096-column sample (per-row thresholds in its epilogue), '
+                                          'pairwise_tc_kernel<1> (candidate sweep, nothing else written), '
+                                          'pairwise_topk_finish_kernel (per-row candidate sort)',
                                'note': 'includes the status read-back; the matrix-write bound of the unfused kernel at this '
                                        'size is %.2f ms' % (4.0 * n * n / pk_hbm / 1e6)}
         # full-length ranking (se_row_argsort) and P@k / AHP / AP (se_hier_metrics) for a block of 2048 query rows
@@ -491,7 +492,7 @@ def eng_bytes(eng):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=30)
+    ap.add_argument('--steps', type=int, default=100)
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='native', choices=['native', 'reference'])
     # tf32x3 = tcgen05 tiles with error compensation (meets the 1e-4 parity gate; the mode the training CLI runs);

@@ -8,8 +8,8 @@ tag = sys.argv[1] if len(sys.argv) > 1 else 'r1'
 ops = [json.loads(l) for l in open(os.path.join(ROOT, 'gpurun_out', 'parity_ops.jsonl'))]
 mods = [json.loads(l) for l in open(os.path.join(ROOT, 'gpurun_out', 'parity_models.jsonl'))]
 out = ['# Parity summary (B200, from gpurun_out/parity_*.jsonl of the full `pytest -m gpu` run)\n',
-       'Max-norm relative errors against the float64 CPU oracle unless noted; mode 0 = SE_MODE_F32, 1 = SE_MODE_TF32.\n',
-       '## Training steps (tests/test_gpu_models.py, SE_MODE_F32, identical fp32-rounded weights on both sides)\n',
+       'Max-norm relative errors against the float64 CPU oracle unless noted; mode 0 = SE_MODE_F32, 1 = SE_MODE_TF32 (single pass), 2 = SE_MODE_TF32X3 (error-compensated: the benchmarked mode).\n',
+       '## Training steps (tests/test_gpu_models.py; cases ending in -x3 run SE_MODE_TF32X3, the others SE_MODE_F32; identical fp32-rounded weights on both sides)\n',
        'Gradient columns: relative L2 over all parameters / worst tensor.  "f32 oracle" = the same step by the oracle in '
        'float32, "flip quantum" = the float64 oracle with the masks of its fragile ReLU inputs (|x| < 4e-6) inverted: '
        'the gradient of a ReLU network moves by that much when fp32 rounding changes the sign of a near-zero pre-activation.\n',

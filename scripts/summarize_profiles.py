@@ -67,7 +67,7 @@ def ncu_report(path, title):
         nm = r[name_i].split('(')[0] if name_i is not None else 'kernel'
         grid = r[hdr.index('Grid Size')] if 'Grid Size' in hdr else ''
         seen.setdefault((nm, grid), r)
-    keys = list(seen.keys())[:6]
+    keys = list(seen.keys())[:12]
     out.append('| metric | unit | ' + ' | '.join('`%s` %s' % (k[0].replace('se::', '')[:28], k[1]) for k in keys) + ' |')
     out.append('|---|---|' + '---:|' * len(keys))
     for w in WANT:
@@ -102,12 +102,11 @@ def ncu_report(path, title):
 
 # bench.py op-category -> (ncu report, kernel-name substring, grid) for the `roofline.traffic` field
 TRAFFIC_MAP = {
-    'pairwise_dist': ('pairwise_tc', 'pairwise_tc_kernel', None),
-    'conv_wgrad 3x3 s1 16->16 @32x32': ('train_kernels', 'conv_wgrad_tc_kernel', '148'),
-    'conv_fwd 3x3 s1 16->16 @32x32': ('train_kernels', 'conv_tc_kernel', '148'),
-    'conv_dgrad 3x3 s1 16->16 @32x32': ('train_kernels', 'conv_tc_kernel', '148'),
-    'bn_bwd C=16 rows=131072': ('train_kernels', 'bn_bwd_reg_kernel', '148'),
-    'bn_fwd C=16 rows=131072': ('train_kernels', 'bn_fwd_kernel', None),
+    'pairwise_dist': ('r2_kernels', 'pairwise_tc_kernel<0>', None),
+    'conv_wgrad 3x3 s1 16->16 @32x32': ('r2_kernels', 'conv_wgrad_pk_kernel', '148'),
+    'conv_fwd 3x3 s1 16->16 @32x32': ('r2_kernels', 'conv_tc_kernel<1>', '148'),
+    'conv_dgrad 3x3 s1 16->16 @32x32': ('r2_kernels', 'conv_tc_kernel<1>', '148'),
+    'conv_wgrad 3x3 s1 32->32 @16x16': ('r2_kernels', 'conv_wgrad_tc_kernel<1>', None),
 }
 
 
@@ -131,7 +130,7 @@ def traffic_json(tag):
                 b = float(r[ri].replace(',', '')) * scale[units[ri]] + float(r[wi].replace(',', '')) * scale[units[wi]]
                 out[cat] = {'dram_bytes_per_launch': b, 'kernel': r[ni].split('(')[0], 'source': 'profiles/%s_ncu_%s.md' % (tag, rep),
                             'note': 'ncu replays flush the caches: in a training step these tensors are L2-resident'
-                                    if rep == 'train_kernels' else 'N=50000, D=100'}
+                                    if 'pairwise' not in sub else 'N=50000, D=100'}
                 break
     with open(os.path.join(PROF, '%s_traffic.json' % tag), 'w') as f:
         json.dump(out, f, indent=1)
