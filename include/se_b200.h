@@ -137,14 +137,13 @@ int se_bn_fwd_train(const float* x, int64_t rows, int C, const double* stats, co
                     const float* beta, float eps, float momentum, float* moving_mean, float* moving_var,
                     float* save_mean, float* save_invstd, const se_residual* res, int relu, float* y,
                     void* stream);
-/* Conv2D followed by training-mode BatchNormalization (+ same-shape residual, + ReLU): the pair the reference
- * stacks in every block (models/cifar_resnet.py:96-107, models/wide_residual_network.py:28-66, models/plainnet.py).
+/* Conv2D followed by training-mode BatchNormalization (+ same-shape residual, + ReLU): the pair the reference stacks in
+ * every block (models/cifar_resnet.py:96-107, models/wide_residual_network.py:28-66, models/plainnet.py), as ONE call:
  *   y      = conv(x, w) [+ bias] [relu]                (kept: the BatchNorm backward needs it)
  *   bn_out = act( gamma*(y-mean)*rsqrt(var+eps)+beta [+ res] ), statistics / moving averages as se_bn_fwd_train
- * One launch when the tcgen05 path applies (SE_MODE_TF32, w_t given, every CTA can keep its tiles in TMEM): the batch
- * statistics are exchanged through `stats` at a grid-wide barrier (`counter`, one zeroed 64-bit word) and the
- * normalised activation is written from the accumulators.  Otherwise the call runs se_conv2d_fwd_ex and
- * se_bn_fwd_train one after the other; results are identical either way.  stats: float64 [2*Cout], caller zeroes. */
+ * = se_conv2d_fwd_ex (statistics accumulated in the convolution epilogue) + se_bn_fwd_train.  (Round 1 also had a
+ * single-launch form with a grid barrier inside the convolution kernel; measured 0.13 ms per step SLOWER than the two
+ * launches, it was removed in round 2.)  stats: float64 [2*Cout], caller zeroes; `counter` is unused. */
 int se_conv_bn_fwd(const se_conv_desc* d, const float* x, const float* w, const float* w_t, const float* bias,
                    float* y, int relu, double* stats, const float* gamma, const float* beta, float eps, float momentum,
                    float* moving_mean, float* moving_var, float* save_mean, float* save_invstd, const float* res,

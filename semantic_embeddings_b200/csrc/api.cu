@@ -46,10 +46,6 @@ int conv_wgrad_simt(const se_conv_desc*, const float*, const float*, float*, flo
 int conv_fwd_tc(const se_conv_desc*, const float*, const float*, const float*, const float*, const float*, float*, int, double*,
                 cudaStream_t);
 int conv_dgrad_tc(const se_conv_desc*, const float*, const float*, const float*, float*, float, cudaStream_t);
-int conv_bn_fwd_tc(const se_conv_desc* d, const float* x, const float* w_t, const float* bias, float* y, int relu, double* stats,
-                   const float* gamma, const float* beta, float eps, float momentum, float* moving_mean, float* moving_var,
-                   float* save_mean, float* save_invstd, const float* bn_res, int bn_relu, float* bn_out,
-                   unsigned long long* counter, cudaStream_t st);
 int conv_wgrad_tc(const se_conv_desc*, const float*, const float*, float*, float*, int x3, cudaStream_t);
 
 static int check_desc(const se_conv_desc* d) {
@@ -128,11 +124,7 @@ extern "C" int se_conv_bn_fwd(const se_conv_desc* d, const float* x, const float
   int rc = check_desc(d);
   if (rc) return rc;
   SE_REQUIRE(x && w && y && stats && gamma && beta && save_mean && save_invstd && bn_out, "null pointer");
-  if (mode == SE_MODE_TF32 && w_t && counter) {
-    rc = conv_bn_fwd_tc(d, x, w_t, bias, y, relu, stats, gamma, beta, eps, momentum, moving_mean, moving_var, save_mean,
-                        save_invstd, res, bn_relu, bn_out, reinterpret_cast<unsigned long long*>(counter), as_stream(stream));
-    if (rc != SE_ERR_UNSUPPORTED) return rc;
-  }
+  (void)counter;
   rc = se_conv2d_fwd_ex(d, x, w, w_t, bias, nullptr, y, relu, stats, mode, stream);
   if (rc) return rc;
   se_residual r;

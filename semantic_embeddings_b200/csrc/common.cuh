@@ -41,6 +41,10 @@ inline int check_launch(const char* what) {
 // griddepcontrol.wait -- which returns only when ALL prerequisite grids have completed and flushed their writes --
 // before it touches global memory.  Invariant that keeps this safe at any chain depth: no kernel reads or writes
 // global memory before its griddepcontrol.wait.  SE_NO_PDL=1 turns the attribute off (kernels then serialise fully).
+// One documented exception: bn_bwd_reg_kernel with its `early` hint READS (never writes) x, y and the saved statistics
+// before the wait.  That is safe only because those tensors were produced by the forward pass and the backward plan
+// starts with a cudaMemsetAsync of the gradient buffer -- a full stream dependency that drains every forward kernel;
+// Engine._build_plans asserts that memset when it sets the hint (removing it would turn the prefetch into a race).
 bool pdl_enabled();
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }

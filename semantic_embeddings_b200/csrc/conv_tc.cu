@@ -22,8 +22,7 @@
 // TMEM allocator, warps 4-11 two epilogue groups that share the (tile, 32-column block) work items: tcgen05.ld ->
 // combine taps -> bias (from shared memory) / residual / ReLU -> 32x16 blocks staged in shared memory in the TMA
 // SWIZZLE_64B layout -> ONE bulk tensor store per block (cp.reduce add for the accumulating dgrad); BatchNorm sum and
-// sum-of-squares of the stored values via a shuffle butterfly into per-warp slots, float64 across CTAs.  Optional
-// second epilogue pass = fused training BatchNorm (grid barrier on the statistics; see conv_tc_launch / DESIGN.md 4.1).
+// sum-of-squares of the stored values via a shuffle butterfly into per-warp slots, float64 across CTAs.
 // Backward-data launches are sized (shared memory, TMEM columns, 128 registers) to share the SM with the weight-
 // gradient kernel that se_run_ops runs on its side stream; layers with few pixel tiles split the output channels over
 // two CTAs.  No integer division per tile in the epilogue (pixel index = tile * 128 + lane).
@@ -64,20 +63,6 @@ struct ConvTcParams {
   const float* residual;
   float* out;
   double* stats;
-  // fused training-mode BatchNorm of the convolution output (forward only; every tile of the CTA keeps its own
-  // accumulator, so after a grid-wide barrier on the batch statistics a second epilogue pass re-reads TMEM and
-  // writes act(scale * conv + shift [+ residual]) -- no separate BatchNorm launch, no re-read of the conv output)
-  int bn, bn_relu;
-  float bn_eps, bn_momentum;
-  const float* bn_gamma;
-  const float* bn_beta;
-  float* bn_moving_mean;
-  float* bn_moving_var;
-  float* bn_save_mean;
-  float* bn_save_invstd;
-  const float* bn_res;      // same shape as the output, or null
-  float* bn_out;
-  unsigned long long* bn_counter;   // grid barrier arrival counter (zeroed by the caller once per step)
   long long* trace;         // debug: per-role clock64 timeline of CTA 0 (SE_CT_TRACE_PTR)
   int debug;                // bit 0: no tiles (fixed overhead only), bit 1: skip A loads, bit 2: skip epilogue stores/stats
 };
@@ -175,17 +160,6 @@ __device__ __forceinline__ void conv_tc_load_combine(const ConvTcParams& p, uint
   }
 }
 
-// 16 columns of this warp's 32 TMEM lanes <- 16 registers per lane (the fused BatchNorm keeps the finished
-// convolution values where the second epilogue pass can fetch them with one load and no neighbour shuffles)
-__device__ __forceinline__ void tmem_st_16(uint32_t taddr, const float* o) {
-  asm volatile(
-      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
-      ::"r"(taddr), "f"(o[0]), "f"(o[1]), "f"(o[2]), "f"(o[3]), "f"(o[4]), "f"(o[5]), "f"(o[6]), "f"(o[7]), "f"(o[8]),
-        "f"(o[9]), "f"(o[10]), "f"(o[11]), "f"(o[12]), "f"(o[13]), "f"(o[14]), "f"(o[15])
-      : "memory");
-}
-__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
-
 // Output staging: a warp's 32 pixels x 16 channels sit in shared memory as 32 rows of 64 bytes in the TMA
 // SWIZZLE_64B layout (16-byte chunk c of row r at chunk c ^ ((r >> 1) & 3): the 8 lanes of a store phase hit 8
 // different bank groups), and leave with ONE bulk tensor store -- full 32-byte sectors, out-of-range rows clipped by
@@ -233,10 +207,6 @@ __device__ __forceinline__ void conv_tc_epilogue_block(const ConvTcParams& p, co
     }
     tma_store_commit();
   }
-  if (p.bn) {
-#pragma unroll
-    for (int h = 0; h < NC / 16; ++h) tmem_st_16(t_addr + p.BN + c0 + 16 * h, o + 16 * h);
-  }
   if (dbg) dbg[2] = clock64();
   if (sw && !(p.debug & 4)) {
     float o2[NC];
@@ -265,8 +235,7 @@ __device__ __forceinline__ void conv_tc_epilogue_block(const ConvTcParams& p, co
 template <int X3>
 __global__ void __maxnreg__(128)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-               const __grid_constant__ CUtensorMap map_bl, const __grid_constant__ CUtensorMap map_o,
-               const __grid_constant__ CUtensorMap map_z, ConvTcParams p) {
+               const __grid_constant__ CUtensorMap map_bl, const __grid_constant__ CUtensorMap map_o, ConvTcParams p) {
   pdl_trigger();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -295,7 +264,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   const int b_rows = 3 * p.BN;                              // B rows of one filter row: (s, n)
 
   if (warp == 0 && lane == 0) {
-    prefetch_tmap(&map_a); prefetch_tmap(&map_b); prefetch_tmap(&map_o); prefetch_tmap(&map_z);
+    prefetch_tmap(&map_a); prefetch_tmap(&map_b); prefetch_tmap(&map_o);
     for (int s = 0; s < p.stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
     for (int a = 0; a < p.nacc; ++a) { mbar_init(&t_full[a], 1); mbar_init(&t_empty[a], 128 * ((p.BN + 31) >> 5)); }
     mbar_init(b_full, 1);
@@ -628,130 +597,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       blk += 2;
       while (blk >= nblk) { blk -= nblk; ++it; if (++acc == p.nacc) { acc = 0; acc_phase ^= 1; } }
     }
-    if (p.bn) {
-      // ---- batch statistics: CTA partial sums -> global, grid barrier, per-channel scale / shift
-      const int et = threadIdx.x - 128;             // 0..255 over the eight epilogue warps
-      float* coef = s_stats + 16 * p.Nc;            // [scale Nc | shift Nc]
-      tmem_st_wait();                               // pass-1 write-backs of this thread have landed in TMEM
-      fence_before_sync();
-      named_bar_sync(1, 256);
-      CT_TRACE(2, 4);
-      for (int i = et; i < 2 * p.Nc; i += 256) {
-        double v = 0.0;
-#pragma unroll
-        for (int wv = 0; wv < 8; ++wv) v += (double)s_stats[wv * 2 * p.Nc + i];
-        atomicAdd(&p.stats[i], v);
-      }
-      __threadfence();
-      named_bar_sync(1, 256);
-      CT_TRACE(2, 5);
-      if (et == 0) {
-        atomicAdd(p.bn_counter, 1ULL);
-        while (*reinterpret_cast<volatile unsigned long long*>(p.bn_counter) < (unsigned long long)gridDim.x) { }
-        __threadfence();
-      }
-      named_bar_sync(1, 256);
-      CT_TRACE(2, 6);
-      const double rows = (double)p.N * p.H * p.W;
-      for (int c = et; c < p.Nc; c += 256) {
-        // identical arithmetic to bn_fwd_kernel<true> (bn.cu): float64 moments, float32 scale / shift
-        const double inv_rows = 1.0 / rows;
-        double m = __ldcg(&p.stats[c]) * inv_rows;
-        double var = __ldcg(&p.stats[p.Nc + c]) * inv_rows - m * m;
-        if (var < 0) var = 0;
-        const float mean = (float)m;
-        const float invstd = (float)(1.0 / sqrt(var + (double)p.bn_eps));
-        const float g = p.bn_gamma[c];
-        coef[c] = g * invstd;
-        coef[p.Nc + c] = p.bn_beta[c] - mean * g * invstd;
-      }
-      named_bar_sync(1, 256);
-      fence_after_sync();
-      CT_TRACE(2, 7);
-      // ---- pass 2: items = (tile, 16-column block), dealt round-robin to the two epilogue groups; the TMEM loads of
-      // up to four items are in flight together, then each item is normalised and stored
-      const int nb16 = p.BN / 16;
-      const int sh16 = (nb16 == 1) ? 0 : (nb16 == 2) ? 1 : (nb16 == 4) ? 2 : -1;     // items -> (tile, block) without a division
-      const int nitems = max(0, t_end - t_begin) * nb16;
-      const uint32_t lane_addr = tmem_base + ((uint32_t)(q4 * 32) << 16) + p.BN;
-      if (lane == 0) tma_store_wait_read<0>();
-      __syncwarp();
-      sbuf = 0;
-      for (int base = grp; base < nitems; base += 8) {
-        uint32_t v[4][16];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int idx = base + 2 * u;
-          if (idx < nitems) {
-            const int i = sh16 >= 0 ? (idx >> sh16) : idx / nb16, blk = idx - i * nb16;
-            tmem_ld_cols<16>(lane_addr + (p.nacc > i ? i : i % p.nacc) * p.acc_stride + 16 * blk, v[u]);
-          }
-        }
-        tmem_ld_wait();
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int idx = base + 2 * u;
-          if (idx >= nitems) continue;
-          const int i = sh16 >= 0 ? (idx >> sh16) : idx / nb16, blk = idx - i * nb16;
-          const int t = t_begin + i;
-          int tm = t, tn = 0;
-          if (p.tiles_n != 1) { tm = t / p.tiles_n; tn = t - tm * p.tiles_n; }
-          const long long pix = (long long)tm * CT_BM + m;
-          const bool valid = pix < total_px;
-          const long long off = pix * p.Nc + tn * p.BN + 16 * blk;
-          const int cg = tn * p.BN + 16 * blk;
-          uint8_t* sub = stg_w + sbuf * 2048;
-          if (lane == 0) { if (p.stage_out >= 4096) tma_store_wait_read<1>(); else tma_store_wait_read<0>(); }
-          __syncwarp();
-          float4 ex[4];
-          if (p.bn_res && valid) {
-#pragma unroll
-            for (int q = 0; q < 4; ++q) ex[q] = __ldg(reinterpret_cast<const float4*>(p.bn_res + off) + q);
-          }
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const float4 sc = *reinterpret_cast<const float4*>(coef + cg + 4 * q);
-            const float4 sh = *reinterpret_cast<const float4*>(coef + p.Nc + cg + 4 * q);
-            float4 val;
-            val.x = __uint_as_float(v[u][4 * q]) * sc.x + sh.x;
-            val.y = __uint_as_float(v[u][4 * q + 1]) * sc.y + sh.y;
-            val.z = __uint_as_float(v[u][4 * q + 2]) * sc.z + sh.z;
-            val.w = __uint_as_float(v[u][4 * q + 3]) * sc.w + sh.w;
-            if (p.bn_res && valid) { val.x += ex[q].x; val.y += ex[q].y; val.z += ex[q].z; val.w += ex[q].w; }
-            if (p.bn_relu) { val.x = fmaxf(val.x, 0.f); val.y = fmaxf(val.y, 0.f); val.z = fmaxf(val.z, 0.f); val.w = fmaxf(val.w, 0.f); }
-            stage_put(sub, lane, q, val);
-          }
-          fence_proxy_async();
-          __syncwarp();
-          if (lane == 0) { tma_store_2d(&map_z, sub, cg, tm * CT_BM + q4 * 32); tma_store_commit(); }
-          if (p.stage_out >= 4096) sbuf ^= 1;
-        }
-      }
-      CT_TRACE(2, 8);
-      // saved statistics and moving averages (CTA 0; off the critical path of the other CTAs' stores)
-      if (blockIdx.x == 0) {
-        for (int c = et; c < p.Nc; c += 256) {
-          const double inv_rows = 1.0 / rows;
-          double mm = __ldcg(&p.stats[c]) * inv_rows;
-          double var = __ldcg(&p.stats[p.Nc + c]) * inv_rows - mm * mm;
-          if (var < 0) var = 0;
-          const float mean = (float)mm;
-          p.bn_save_mean[c] = mean;
-          p.bn_save_invstd[c] = (float)(1.0 / sqrt(var + (double)p.bn_eps));
-          if (p.bn_moving_mean) {
-            double uvar = var * (rows / (rows - (1.0 + (double)p.bn_eps)));
-            p.bn_moving_mean[c] = p.bn_moving_mean[c] * p.bn_momentum + mean * (1.f - p.bn_momentum);
-            p.bn_moving_var[c] = p.bn_moving_var[c] * p.bn_momentum + (float)uvar * (1.f - p.bn_momentum);
-          }
-        }
-      }
-      fence_before_sync();
-    }
   }
 
   if (warp >= 4 && lane == 0) tma_store_wait_all<0>();     // bulk stores read shared memory: drain before the CTA exits
   __syncthreads();
-  if (p.stats && !p.bn) {
+  if (p.stats) {
     for (int i = threadIdx.x; i < 2 * p.Nc; i += blockDim.x) {
       double v = 0.0;
 #pragma unroll
@@ -814,21 +664,11 @@ static int pick_bn(int Nc) {
 size_t conv_wgrad_tc_smem(const se_conv_desc* d, int* tmem_cols, int x3);   // conv_wgrad_tc.cu
 constexpr int WG_COOP_SMEM_MAX = 120 * 1024;
 
-struct ConvTcBn {            // fused BatchNorm arguments of conv_tc_launch (null = plain convolution)
-  const float* gamma; const float* beta; float eps, momentum; float* moving_mean; float* moving_var;
-  float* save_mean; float* save_invstd; const float* res; int relu; float* out; unsigned long long* counter;
-};
-
 static int conv_tc_launch(const se_conv_desc* d, const float* a_tensor, int Kc, const float* bmat, int Nc, int flip,
                           const float* bias, const float* residual, float* out, int relu, float beta, double* stats,
-                          cudaStream_t st, const ConvTcBn* bn = nullptr, const float* bmat_lo = nullptr) {
+                          cudaStream_t st, const float* bmat_lo = nullptr) {
   ConvTcParams p;
   const int x3 = bmat_lo ? 1 : 0;       // error-compensated mode: bmat_lo = the low parts of bmat (se_split_filters)
-  if (x3 && bn) return SE_ERR_UNSUPPORTED;
-  p.bn = 0; p.bn_relu = 0; p.bn_eps = 0.f; p.bn_momentum = 0.f;
-  p.bn_gamma = p.bn_beta = p.bn_res = nullptr;
-  p.bn_moving_mean = p.bn_moving_var = p.bn_save_mean = p.bn_save_invstd = p.bn_out = nullptr;
-  p.bn_counter = nullptr;
   p.N = d->N; p.H = d->H; p.W = d->W; p.Kc = Kc; p.Nc = Nc;
   p.Wb = d->W;
   if (d->W * d->H >= 128) { p.Hb = 128 / d->W; p.Nb = 1; } else { p.Hb = d->H; p.Nb = 128 / (d->W * d->H); }
@@ -839,7 +679,7 @@ static int conv_tc_launch(const se_conv_desc* d, const float* a_tensor, int Kc, 
   // few pixel tiles (64 channels at 8x8: 64 tiles for 148 SMs): split the output channels over two CTAs per tile --
   // each then streams half of the 9*Cin*Cout weights, the dominant traffic of such a layer, and half of the epilogue
   static const bool no_nsplit = getenv("SE_CT_NO_NSPLIT") != nullptr;
-  if (!no_nsplit && !bn && 2 * p.tiles_m * p.tiles_n <= sm_count() && p.BN >= 64 && (p.BN / 2) % 16 == 0) {
+  if (!no_nsplit && 2 * p.tiles_m * p.tiles_n <= sm_count() && p.BN >= 64 && (p.BN / 2) % 16 == 0) {
     p.BN /= 2;
     p.tiles_n *= 2;
   }
@@ -913,16 +753,6 @@ static int conv_tc_launch(const se_conv_desc* d, const float* a_tensor, int Kc, 
     if (tmem_budget / stride < min(2, tiles_per_cta)) tmem_budget = 512;
   }
   p.acc_stride = stride; p.nacc = min(CT_MAX_ACC, tmem_budget / stride);
-  if (bn) {
-    // every tile of a CTA needs its own accumulator until the second epilogue pass
-    const int total = p.tiles_m * p.tiles_n;
-    const int per_cta = ceil_div(total, min(sm_count(), total));
-    if (!stats || residual || beta != 0.f || per_cta > p.nacc) return SE_ERR_UNSUPPORTED;
-    p.bn = 1; p.bn_relu = bn->relu; p.bn_eps = bn->eps; p.bn_momentum = bn->momentum;
-    p.bn_gamma = bn->gamma; p.bn_beta = bn->beta; p.bn_moving_mean = bn->moving_mean; p.bn_moving_var = bn->moving_var;
-    p.bn_save_mean = bn->save_mean; p.bn_save_invstd = bn->save_invstd; p.bn_res = bn->res; p.bn_out = bn->out;
-    p.bn_counter = bn->counter;
-  }
   p.tmem_cols = 32;
   while (p.tmem_cols < p.nacc * stride) p.tmem_cols <<= 1;
   p.nt = max(1, min(p.nt, p.nacc));
@@ -946,22 +776,19 @@ static int conv_tc_launch(const se_conv_desc* d, const float* a_tensor, int Kc, 
     if (x3 && !make_tmap(&mbl, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(bmat_lo), bdims, bstrides, bbox, sw))
       return SE_ERR_CUDA;
   }
-  CUtensorMap mo, mz;
+  CUtensorMap mo;
   {
     // output(s) as [pixels][channels]: 32-pixel x 16-channel boxes, SWIZZLE_64B staging (see stage_put)
     uint64_t odims[2] = {(uint64_t)Nc, (uint64_t)d->N * d->H * d->W};
     uint64_t ostrides[1] = {(uint64_t)Nc * 4};
     uint32_t obox[2] = {16u, 32u};
     if (!make_tmap(&mo, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, out, odims, ostrides, obox, CU_TENSOR_MAP_SWIZZLE_64B)) return SE_ERR_CUDA;
-    mz = mo;
-    if (bn && !make_tmap(&mz, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, bn->out, odims, ostrides, obox, CU_TENSOR_MAP_SWIZZLE_64B))
-      return SE_ERR_CUDA;
   }
-  const size_t smem = (size_t)p.res_b_bytes + (size_t)p.stages * p.stage_bytes + 8 * p.stage_out + (4 * CT_MAX_STAGES + 2 * CT_MAX_ACC + 4) * 8 + Nc * 4 + (stats ? 16 * Nc * 4 : 0) + (bn ? 2 * Nc * 4 : 0) + 1024 + 64;
+  const size_t smem = (size_t)p.res_b_bytes + (size_t)p.stages * p.stage_bytes + 8 * p.stage_out + (4 * CT_MAX_STAGES + 2 * CT_MAX_ACC + 4) * 8 + Nc * 4 + (stats ? 16 * Nc * 4 : 0) + 1024 + 64;
   if (smem > 227 * 1024) return SE_ERR_UNSUPPORTED;
   int grid = min(sm_count(), p.tiles_m * p.tiles_n);
-  if (x3) launch(conv_tc_kernel<1>, dim3(grid), dim3(CT_THREADS_X3), smem, st, ma, mb, mbl, mo, mz, p);
-  else launch(conv_tc_kernel<0>, dim3(grid), dim3(CT_THREADS), smem, st, ma, mb, mbl, mo, mz, p);
+  if (x3) launch(conv_tc_kernel<1>, dim3(grid), dim3(CT_THREADS_X3), smem, st, ma, mb, mbl, mo, p);
+  else launch(conv_tc_kernel<0>, dim3(grid), dim3(CT_THREADS), smem, st, ma, mb, mbl, mo, p);
   return check_launch("conv_tc_kernel");
 }
 
@@ -987,23 +814,7 @@ int conv_fwd_tc(const se_conv_desc* d, const float* x, const float* w_t, const f
   if (!w_t || !tc_shape_ok(d, d->Cin, d->Cout)) return SE_ERR_UNSUPPORTED;
   int rc = ensure_init();
   if (rc) return rc;
-  return conv_tc_launch(d, x, d->Cin, w_t, d->Cout, 0, bias, residual, y, relu, 0.f, stats, st, nullptr, w_t_lo);
-}
-
-// convolution + training-mode BatchNorm (+ same-shape residual, + ReLU) in one launch; y receives the convolution
-// output (BatchNorm backward needs it), bn_out the normalised activation.  stats: float64 [2*Cout] zeroed by the
-// caller, counter: one zeroed 64-bit word.  SE_ERR_UNSUPPORTED -> the caller runs the two kernels separately.
-int conv_bn_fwd_tc(const se_conv_desc* d, const float* x, const float* w_t, const float* bias, float* y, int relu, double* stats,
-                   const float* gamma, const float* beta, float eps, float momentum, float* moving_mean, float* moving_var,
-                   float* save_mean, float* save_invstd, const float* bn_res, int bn_relu, float* bn_out,
-                   unsigned long long* counter, cudaStream_t st) {
-  if (!w_t || !tc_shape_ok(d, d->Cin, d->Cout)) return SE_ERR_UNSUPPORTED;
-  static const bool off = getenv("SE_NO_CONV_BN_FUSION") != nullptr;
-  if (off) return SE_ERR_UNSUPPORTED;
-  int rc = ensure_init();
-  if (rc) return rc;
-  ConvTcBn bn = {gamma, beta, eps, momentum, moving_mean, moving_var, save_mean, save_invstd, bn_res, bn_relu, bn_out, counter};
-  return conv_tc_launch(d, x, d->Cin, w_t, d->Cout, 0, bias, nullptr, y, relu, 0.f, stats, st, &bn);
+  return conv_tc_launch(d, x, d->Cin, w_t, d->Cout, 0, bias, residual, y, relu, 0.f, stats, st, w_t_lo);
 }
 
 int conv_dgrad_tc(const se_conv_desc* d, const float* dy, const float* w, const float* w_lo, float* dx, float beta,
@@ -1011,7 +822,7 @@ int conv_dgrad_tc(const se_conv_desc* d, const float* dy, const float* w, const 
   if (!tc_shape_ok(d, d->Cout, d->Cin)) return SE_ERR_UNSUPPORTED;
   int rc = ensure_init();
   if (rc) return rc;
-  return conv_tc_launch(d, dy, d->Cout, w, d->Cin, 1, nullptr, nullptr, dx, 0, beta, nullptr, st, nullptr, w_lo);
+  return conv_tc_launch(d, dy, d->Cout, w, d->Cin, 1, nullptr, nullptr, dx, 0, beta, nullptr, st, w_lo);
 }
 
 

@@ -33,7 +33,7 @@ def _vp(x):
 class Engine:
     def __init__(self, graph, batch, embedding, loss='inv_corr', cls_weight=0.0, num_classes=None,
                  mode=_lib.SE_MODE_F32, device='cuda:0', momentum=0.9, nesterov=False, clipnorm=10.0,
-                 world_size=1, fuse_stats=True, use_cuda_graph=True, seed=0, fuse_conv_bn=False, decay=0.0,
+                 world_size=1, fuse_stats=True, use_cuda_graph=True, seed=0, decay=0.0,
                  grad_buckets=3, comm='auto'):
         if loss not in LOSS_KINDS:
             raise ValueError('unknown loss %r' % loss)
@@ -64,7 +64,6 @@ class Engine:
         if self.world > 1 and comm == 'native' and self.dev.type == 'cuda':
             self.comm_native = self._init_native_comm(required=True)
         self.fuse_stats = fuse_stats
-        self.fuse_conv_bn = fuse_conv_bn and fuse_stats
         self.use_cuda_graph = use_cuda_graph
         emb = np.asarray(embedding, dtype=np.float32)
         self.C, self.D = emb.shape
@@ -317,7 +316,6 @@ class Engine:
                 if self.fuse_stats and prod is not None and prod.op in ('conv', 'dense'):
                     stats_by_conv[prod.name] = n
         # ---------------- forward
-        fused_bn = set()
         fwd_pos = {}                       # BatchNorm node -> index of its forward op (for the backward prefetch hint)
         for n in self.nodes:
             out = A[n.output.name]
@@ -336,23 +334,7 @@ class Engine:
                     st = self.stats[off:off + 2 * c]
                 Wt = self._pview(n.name + '/kernel', self.PT) if (self.PT is not None and n.op == 'conv') else None
                 Wtl = self._pview(n.name + '/kernel', self.PTL) if (self.PTL is not None and n.op == 'conv') else None
-                m = stats_by_conv.get(n.name)
-                if (m is not None and Wt is not None and res is None and self.fuse_conv_bn
-                        and (not m.attrs['residual'] or (m.attrs['res_pool'] == 1 and m.attrs['res_pad_lo'] == 0
-                                                         and m.inputs[1].shape == m.inputs[0].shape))):
-                    # conv + training BatchNorm (+ same-shape residual, ReLU) as one op: se_conv_bn_fwd
-                    off, c = self.bn_slot[m.name]
-                    ma = m.attrs
-                    fwd.append(self._op(
-                        _lib.OP_CONV_BN_FWD, d + [relu, -1, 1 if ma['relu'] else 0], [ma['eps'], ma['momentum']],
-                        [A[n.inputs[0].name], W, b, out, st, Wt, self._pview(m.name + '/gamma'), self._pview(m.name + '/beta'),
-                         self._pview(m.name + '/moving_mean'), self._pview(m.name + '/moving_variance'),
-                         self.saved[off // 2:off // 2 + c], self.saved[off // 2 + c:off // 2 + 2 * c],
-                         A[m.inputs[1].name] if ma['residual'] else None, A[m.output.name],
-                         self.stats[off + 4 * c + 1:off + 4 * c + 2]]))
-                    fused_bn.add(m.name)
-                else:
-                    fwd.append(self._op(_lib.OP_CONV_FWD, d + [relu], p=[A[n.inputs[0].name], W, b, res, out, st, Wt, Wtl]))
+                fwd.append(self._op(_lib.OP_CONV_FWD, d + [relu], p=[A[n.inputs[0].name], W, b, res, out, st, Wt, Wtl]))
                 inf.append(self._op(_lib.OP_CONV_FWD, d + [relu], p=[A[n.inputs[0].name], W, b, res, out, None, Wt, Wtl]))
             elif n.op == 'bn':
                 x = n.inputs[0]
@@ -376,8 +358,7 @@ class Engine:
                 pp = [A[x.name], st, self._pview(n.name + '/gamma'), self._pview(n.name + '/beta'),
                       self._pview(n.name + '/moving_mean'), self._pview(n.name + '/moving_variance'), sm, si, rp, out]
                 fwd_pos[n.name] = len(fwd)
-                if n.name not in fused_bn:
-                    fwd.append(self._op(_lib.OP_BN_FWD_TRAIN, ii, [a['eps'], a['momentum']], pp))
+                fwd.append(self._op(_lib.OP_BN_FWD_TRAIN, ii, [a['eps'], a['momentum']], pp))
                 inf.append(self._op(_lib.OP_BN_FWD_INFER, ii, [a['eps'], a['momentum']], pp))
             elif n.op == 'avgpool2':
                 h, w, c = n.inputs[0].shape
@@ -494,8 +475,12 @@ class Engine:
                         sc_op = self._op(_lib.OP_SHORTCUT_BWD,
                                          [self.B, hh, ww, c, relu, r.shape[-1], a['res_pad_lo'], a['res_pool']],
                                          [bsrc], [dY, A[n.output.name], dsrc])
-                # inputs saved by the forward pass >= 24 launches ago may be prefetched before the preceding launch has
-                # finished (csrc/bn.cu bn_bwd_reg_kernel); the last layers of the network are too close for that
+                # x, y and the saved statistics were written by the FORWARD pass; the backward plan starts with a memset of
+                # the gradient buffer (bwd[0]) -- a full stream dependency, not a programmatic dependent launch -- so every
+                # forward kernel has completed and flushed before any backward kernel starts, and bn_bwd may fetch those
+                # inputs before its griddepcontrol.wait (csrc/bn.cu bn_bwd_reg_kernel, csrc/common.cuh).  The launch-distance
+                # margin only keeps the prefetch off for the last layers, whose forward outputs are the freshest.
+                assert bwd and bwd[0].opcode == _lib.OP_MEMSET, 'the early-prefetch hint relies on the memset barrier at bwd[0]'
                 early = 1 if (len(fwd) - fwd_pos[n.name]) + len(bwd) >= 24 else 0
                 bwd.append(self._op(_lib.OP_BN_BWD, [c, rows, relu, relu_in, early], [beta, bres],
                                     [A[x.name], A[n.output.name], dY, self._pview(n.name + '/gamma'), sm, si, dx, dres,

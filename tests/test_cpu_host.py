@@ -172,12 +172,22 @@ def test_engine_builds_plans_without_a_gpu(built_lib):
     assert sum(o.i[4] for o in bn_bwd) >= len(bn_bwd) - 8
     first_early = next(k for k, o in enumerate(bn_bwd) if o.i[4])
     assert all(o.i[4] == 1 for o in bn_bwd[first_early:])
-    assert not any(o.opcode == L.OP_CONV_BN_FWD for o in fwd)               # off by default (measured slower)
-    engf = Engine(g, 2, emb, device='cpu', use_cuda_graph=False, fuse_conv_bn=True, mode=L.SE_MODE_TF32)
-    nfused = sum(1 for o in engf.plans['fwd'] if o.opcode == L.OP_CONV_BN_FWD)
-    nbn = sum(1 for n in engf.nodes if n.op == 'bn')
-    assert nfused > 100 and nfused + sum(1 for o in engf.plans['fwd'] if o.opcode == L.OP_BN_FWD_TRAIN) == nbn
-    assert sum(1 for o in engf.plans['infer'] if o.opcode == L.OP_CONV_BN_FWD) == 0   # inference: moving statistics
+    assert not any(o.opcode == L.OP_CONV_BN_FWD for o in fwd)               # convolution and BatchNorm are separate launches
+    # data-parallel plan: every gradient is exchanged exactly once, in buckets cut along the backward pass
+    for arch, kw in (('resnet-110-fc', {}), ('simple', {}), ('wrn-28-10', {'cls_weight': 0.1})):
+        e2 = Engine(utils.build_network(100, arch), 2, emb, device='cpu', use_cuda_graph=False, world_size=2, comm='torch', **kw)
+        ar = [o for o in e2.plans['step_dp'] if o.opcode == L.OP_ALLREDUCE]
+        assert len(ar) >= 3 and len(e2.plans['step_dp']) == len(e2.plans['step']) + len(ar)
+        ranges = sorted((r[0], r[1]) for bucket in e2.bucket_ranges for r in bucket)
+        assert ranges[0][0] == 0 and all(a[0] + a[1] == b[0] for a, b in zip(ranges, ranges[1:]))
+        assert ranges[-1][0] + ranges[-1][1] == e2.nparams
+        # the last bucket (what cannot overlap with anything) is the smallest share of the buffer
+        sizes = [sum(r[1] for r in bucket) for bucket in e2.bucket_ranges]
+        assert sizes[-1] == min(sizes)
+        pos = [k for k, o in enumerate(e2.plans['step_dp']) if o.opcode == L.OP_ALLREDUCE]
+        last_bwd = max(k for k, o in enumerate(e2.plans['step_dp']) if o.opcode in (L.OP_CONV_WGRAD, L.OP_BN_BWD))
+        first_opt = min(k for k, o in enumerate(e2.plans['step_dp']) if o.opcode == L.OP_SGD_PREPARE)
+        assert pos[0] < last_bwd and last_bwd < pos[-1] < first_opt
     # weight I/O round trip keeps Keras names and layouts
     g = utils.build_network(100, 'resnet-32')
     eng = Engine(g, 2, np.eye(64), device='cpu', use_cuda_graph=False)

@@ -260,7 +260,7 @@ def test_conv_bn_fused_matches_oracle_and_unfused(case):
            int(brelu), L.ptr(f['z']), L.ptr(f['counter']), 1, sptr())
     torch.cuda.synchronize()
     launches = L.launch_count() - before
-    assert launches == (1 if one_launch else 2), launches
+    assert launches == 2, launches          # convolution (statistics in its epilogue) + BatchNorm: two launches (the single-launch form was removed)
     u = buffers()
     L.call('se_conv2d_fwd_ex', d, L.ptr(xd), L.ptr(wd), L.ptr(wtd), L.ptr(bd), None, L.ptr(u['y']), int(crelu), L.ptr(u['stats']),
            1, sptr())
