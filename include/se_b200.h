@@ -15,6 +15,9 @@
  *     never allocates or frees device memory.  Kernels that need scratch take it explicitly.
  *   - `stream` is a cudaStream_t; all calls are asynchronous w.r.t. the host and capturable
  *     into a CUDA graph.
+ *   - process-wide state is limited to what se_init() / se_comm_init() create: the low-priority
+ *     side stream and the fork/join events se_run_ops uses for weight gradients, and the NCCL
+ *     communicator with its stream.  Kernels keep no state between calls.
  *   - activations are float32 NHWC; conv kernels are float32 HWIO (Keras layout); dense
  *     kernels are (in,out).  `mode` selects the arithmetic of contraction kernels:
  *     SE_MODE_F32 = fp32 FFMA; SE_MODE_TF32 = tcgen05 kind::tf32 (operands truncated to a

@@ -7,15 +7,15 @@ from semantic_embeddings_b200 import _lib as L
 MODES = {'x3': 2, 'tc': 1, 'f32': 0}
 
 
-def bench(N, H, C, Co, reps=50, modes=('x3', 'tc')):
+def bench(N, H, C, Co, k=3, reps=50, modes=('x3', 'tc')):
     L.load(); L.check(L.load().se_init())
-    d = L.ConvDesc(N, H, H, C, Co, 3, 3, 1, 1, 1, H, H)
-    x = torch.randn(N, H, H, C, device='cuda'); w = torch.randn(3, 3, C, Co, device='cuda') * 0.1
+    d = L.ConvDesc(N, H, H, C, Co, k, k, 1, k // 2, k // 2, H, H)
+    x = torch.randn(N, H, H, C, device='cuda'); w = torch.randn(k, k, C, Co, device='cuda') * 0.1
     wt, wl, wtl = torch.empty_like(w), torch.empty_like(w), torch.empty_like(w)
     y = torch.empty(N, H, H, Co, device='cuda'); dy = torch.randn_like(y); dx = torch.empty_like(x)
     dw = torch.zeros_like(w); db = torch.zeros(Co, device='cuda'); b = torch.zeros(Co, device='cuda')
     stats = torch.zeros(2 * Co, dtype=torch.float64, device='cuda')
-    tab = (ctypes.c_int64 * 4)(0, 9, C, Co)
+    tab = (ctypes.c_int64 * 4)(0, k * k, C, Co)
     sp = L.stream_ptr
     L.call('se_split_filters', w.data_ptr(), wt.data_ptr(), wl.data_ptr(), wtl.data_ptr(), tab, 1, sp())
     aux = L.ConvAux(wt.data_ptr(), wtl.data_ptr(), wl.data_ptr())
@@ -42,5 +42,8 @@ def bench(N, H, C, Co, reps=50, modes=('x3', 'tc')):
 
 if __name__ == '__main__':
     shapes = [(128, 32, 16, 16), (128, 16, 32, 32), (128, 8, 64, 64), (64, 32, 160, 160)]
+    if len(sys.argv) > 1 and sys.argv[1] == '1x1':      # ResNet-50 bottleneck 1x1 layers at batch 32
+        shapes = [(32, 56, 64, 256, 1), (32, 56, 256, 64, 1), (32, 28, 512, 128, 1), (32, 14, 256, 1024, 1), (32, 14, 1024, 256, 1),
+                  (32, 7, 2048, 512, 1)]
     for s in shapes:
-        print(json.dumps({'shape': s, 'env': {k: v for k, v in os.environ.items() if k.startswith('SE_')}, 'us': bench(*s)}))
+        print(json.dumps({'shape': s, 'env': {k: v for k, v in os.environ.items() if k.startswith('SE_')}, 'us': bench(*s, modes=('x3', 'tc', 'f32') if len(s) > 4 else ('x3', 'tc'))}))

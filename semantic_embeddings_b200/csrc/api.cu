@@ -25,6 +25,10 @@ bool pdl_enabled() {
   static const bool on = getenv("SE_NO_PDL") == nullptr;
   return on;
 }
+bool coop_enabled() {
+  static const bool on = getenv("SE_BN_COOP") != nullptr;
+  return on;
+}
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 int sm_count() {
   if (g_sms == 0) {

@@ -814,7 +814,7 @@ int se::bn_bwd(const float* x, const float* y, const float* dout, int64_t rows, 
     long long* bn_trace = bn_trace_env ? reinterpret_cast<long long*>(strtoull(bn_trace_env, nullptr, 0)) : nullptr;
     const int C4 = C >> 2;
     if (!no_fuse && !no_reg && gridf <= sms && C <= BNR_MAXC && (512 % C4) == 0 && per_l * C4 <= (long long)BNR * 512) {
-      launch(bn_bwd_reg_kernel, dim3(gridf), dim3(512), 0, as_stream(stream), x, y ? y : x, dout, rows, C, gamma, save_mean, save_invstd,
+      launch_grid_barrier(bn_bwd_reg_kernel, dim3(gridf), dim3(512), 0, as_stream(stream), x, y ? y : x, dout, rows, C, gamma, save_mean, save_invstd,
              relu, relu_in, dx, beta_dx, dres, beta_res, dgamma, dbeta, scratch, (int)per_l, early && pdl_enabled() ? 1 : 0, bn_trace);
       return check_launch("bn_bwd_reg_kernel");
     }
@@ -828,7 +828,7 @@ int se::bn_bwd(const float* x, const float* y, const float* dout, int64_t rows, 
         configured = true;
       }
       // at least 116 KB per CTA would be needed to force one CTA per SM; co-residency only needs grid <= #SMs
-      launch(bn_bwd_fused_kernel, dim3(gridf), dim3(512), smem, as_stream(stream), x, y, dout, rows, C, gamma, save_mean, save_invstd, relu,
+      launch_grid_barrier(bn_bwd_fused_kernel, dim3(gridf), dim3(512), smem, as_stream(stream), x, y, dout, rows, C, gamma, save_mean, save_invstd, relu,
                                                                     relu_in, dx, beta_dx, dres, beta_res, dgamma, dbeta,
                                                                     scratch, (int)per_l);
       return check_launch("bn_bwd_fused_kernel");

@@ -65,6 +65,26 @@ inline void launch(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, c
   cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);   // errors surface through check_launch()
 }
 
+// Kernels with a grid-wide barrier (bn.cu): SE_BN_COOP=1 launches them with the cooperative attribute -- the runtime then
+// guarantees that all CTAs are co-resident (or fails the launch) instead of relying on "grid <= #SMs and nothing else
+// holds the SMs".  Cooperative launches cannot be programmatic dependents, so the PDL attribute is dropped for them.
+bool coop_enabled();
+template <typename... KArgs, typename... Args>
+inline void launch_grid_barrier(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  if (!coop_enabled()) { launch(kern, grid, block, smem, st, std::forward<Args>(args)...); return; }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr;
+  attr.id = cudaLaunchAttributeCooperative;
+  attr.val.cooperative = 1;
+  cfg.attrs = &attr;
+  cfg.numAttrs = 1;
+  cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
+}
+
 inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 
 template <typename T>

@@ -59,6 +59,16 @@ struct ConvTcParams {
                             // rows read it at offsets of a_tap bytes (descriptor start addresses) instead of three shifted boxes
   int a_tap;                // bytes between the A slabs of consecutive filter rows inside a stage (a_bytes, or W * row_bytes)
   int a_stage_bytes;        // bytes of input data in a resident-mode stage (what TMA fills and the splitters rewrite)
+  int taps;                 // filter size: 3 (3x3, three horizontal partial sums per pixel) or 1 (1x1: a plain GEMM)
+  int flat;                 // 1x1: the A tensor is addressed as a flat [pixels][channels] matrix, tile = 128 consecutive pixels
+  int tpi;                  // pixel tiles per image (Nb == 1)
+  // "padded" tiles (image widths that do not divide 32): a tile is 128 / Wb row slots of Wb lanes; an image row is cut
+  // into NS strips of Ws output pixels, each loaded as a Wb-pixel box that starts one pixel early for strips > 0 (the
+  // left neighbour) and runs past the strip (the right neighbour; zero-filled by TMA past the image border).  Slots are
+  // ordered (strip, row) for whole-row tiles, (image, row) for whole-image tiles; rows / images past the tensor are
+  // zero-filled on load and clipped on store (4-d output map, box = Ws pixels x rpw rows).
+  int padded, NS, Ws, rpw;
+  int pad;                  // rows of 'same' padding above the image: 1 (3x3) or 0 (1x1)
   const float* bias;
   const float* residual;
   float* out;
@@ -143,6 +153,14 @@ __device__ __forceinline__ void tmem_ld_cols<16>(uint32_t taddr, uint32_t (&v)[1
 template <int NC>
 __device__ __forceinline__ void conv_tc_load_combine(const ConvTcParams& p, uint32_t t_addr, int lblk, int c0, bool has_left,
                                                      bool has_right, float (&o)[NC]) {
+  if (p.taps == 1) {                              // 1x1: the accumulator is the result
+    uint32_t v1[NC];
+    tmem_ld_cols<NC>(t_addr + c0, v1);
+    tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < NC; ++j) o[j] = __uint_as_float(v1[j]);
+    return;
+  }
   uint32_t v[NC], vl[NC], vr[NC];                 // centre (s=1), left (s=0) and right (s=2) partial sums
   tmem_ld_cols<NC>(t_addr + lblk * p.BN + c0, vl);
   tmem_ld_cols<NC>(t_addr + p.BN + c0, v);
@@ -173,7 +191,10 @@ template <int NC>
 __device__ __forceinline__ void conv_tc_epilogue_block(const ConvTcParams& p, const CUtensorMap* map_o, uint32_t t_addr, int lblk,
                                                        int c0, int tn, bool valid, bool has_left, bool has_right, int row0,
                                                        uint8_t* stg, const float* exrow, const float* s_bias, float* sw,
-                                                       int lane, long long* dbg = nullptr) {
+                                                       int lane, long long* dbg = nullptr, int srow = -1, int sc1 = 0,
+                                                       int sc3 = 0) {
+  // srow: staging row of this lane (-1: none -- a lane outside its strip); padded mode stores at (channel, sc1, row0, sc3)
+  if (!p.padded) srow = lane;
   // exrow: residual row of this pixel (forward only)
   const bool live = valid && !(p.debug & 4);
   if (dbg) dbg[0] = clock64();
@@ -194,7 +215,7 @@ __device__ __forceinline__ void conv_tc_epilogue_block(const ConvTcParams& p, co
     } else {
       val = make_float4(0.f, 0.f, 0.f, 0.f);
     }
-    stage_put(stg + (q >> 2) * 2048, lane, q & 3, val);
+    if (srow >= 0) stage_put(stg + (q >> 2) * 2048, srow, q & 3, val);
     o[4 * q] = val.x; o[4 * q + 1] = val.y; o[4 * q + 2] = val.z; o[4 * q + 3] = val.w;
   }
   fence_proxy_async();                          // the staged values -> visible to the bulk-copy engine
@@ -202,7 +223,10 @@ __device__ __forceinline__ void conv_tc_epilogue_block(const ConvTcParams& p, co
   if (lane == 0 && !(p.debug & 4)) {
 #pragma unroll
     for (int h = 0; h < NC / 16; ++h) {
-      if (p.beta != 0.f) tma_reduce_add_2d(map_o, stg + h * 2048, tn * p.BN + c0 + 16 * h, row0);   // dgrad accumulate
+      if (p.padded) {
+        if (p.beta != 0.f) tma_reduce_add_4d(map_o, stg + h * 2048, tn * p.BN + c0 + 16 * h, sc1, row0, sc3);
+        else tma_store_4d(map_o, stg + h * 2048, tn * p.BN + c0 + 16 * h, sc1, row0, sc3);
+      } else if (p.beta != 0.f) tma_reduce_add_2d(map_o, stg + h * 2048, tn * p.BN + c0 + 16 * h, row0);   // dgrad accumulate
       else tma_store_2d(map_o, stg + h * 2048, tn * p.BN + c0 + 16 * h, row0);
     }
     tma_store_commit();
@@ -260,8 +284,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   const int t_begin = blockIdx.x * per_cta;
   const int t_end = (p.debug & 1) ? t_begin : min(total_tiles, t_begin + per_cta);
   const int row_bytes = p.cblk * 4;
-  const int tiles_per_img = (p.Nb == 1) ? (p.H / p.Hb) : 1;
-  const int b_rows = 3 * p.BN;                              // B rows of one filter row: (s, n)
+  const int tiles_per_img = p.tpi;
+  const int strip_bytes = p.a_bytes / p.NS;                 // one strip of a filter row's A slab
+  const int b_rows = p.taps * p.BN;                         // B rows of one filter row: (s, n)
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&map_a); prefetch_tmap(&map_b); prefetch_tmap(&map_o);
@@ -313,7 +338,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       mbar_expect_tx(&full[stage], p.a_stage_bytes);
       uint8_t* sa = tiles + (size_t)stage * p.stage_bytes;
       if (p.single) tma_load_4d(sa, &map_a, &full[stage], 0, 0, h0 - 1, n0);      // rows h0-1 .. h0+Hb: halo rows included
-      else for (int r = 0; r < 3; ++r) tma_load_4d(sa + r * p.a_bytes, &map_a, &full[stage], 0, 0, h0 + r - 1, n0);
+      else for (int r = 0; r < 3; ++r)
+        for (int s = 0; s < p.NS; ++s)
+          tma_load_4d(sa + r * p.a_bytes + s * strip_bytes, &map_a, &full[stage], 0, s * p.Ws - (s > 0), h0 + r - 1, n0);
       CT_TRACE(0, 2);
       if (++stage == p.stages) { stage = 0; phase ^= 1; }
     }
@@ -322,7 +349,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       int n0, h0;
       if (p.Nb == 1) { n0 = tm / tiles_per_img; h0 = (tm % tiles_per_img) * p.Hb; }
       else { n0 = tm * p.Nb; h0 = 0; }
-      for (int rb = 0; rb < 3; rb += p.rg) {
+      for (int rb = 0; rb < p.taps; rb += p.rg) {
         for (int kb = 0; kb < p.kblocks; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1);
           CT_TRACE(0, 1);
@@ -331,18 +358,22 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           uint8_t* sb = sa + p.rg * p.a_bytes;
           for (int rr = 0; rr < p.rg; ++rr) {
             const int r = rb + rr;
-            if (!(p.debug & 2)) tma_load_4d(sa + rr * p.a_bytes, &map_a, &full[stage], kb * p.cblk, 0, h0 + r - 1, n0);
+            if (p.flat) tma_load_4d(sa + rr * p.a_bytes, &map_a, &full[stage], kb * p.cblk, tm * CT_BM, 0, 0);
+            else if (!(p.debug & 2))
+              for (int s = 0; s < p.NS; ++s)
+                tma_load_4d(sa + rr * p.a_bytes + s * strip_bytes, &map_a, &full[stage], kb * p.cblk, s * p.Ws - (s > 0),
+                            h0 + r - p.pad, n0);
             uint8_t* sbr = sb + rr * b_rows * row_bytes;
             if (p.b_merged) {
               // one box of 3*BN rows: taps (r,0),(r,1),(r,2) are consecutive row blocks of B.  For dgrad the tap
               // index is reversed, so the box starts at tap 8-(3r+2) and holds the s-blocks in the order 2,1,0.
-              const int tap0 = p.flip ? 8 - (r * 3 + 2) : r * 3;
+              const int tap0 = p.flip ? p.taps * p.taps - 1 - (r * p.taps + p.taps - 1) : r * p.taps;
               tma_load_2d(sbr, &map_b, &full[stage], kb * p.cblk, tap0 * p.Nc);
               if (X3) tma_load_2d(sbr + p.rg * b_rows * row_bytes, &map_bl, &full[stage], kb * p.cblk, tap0 * p.Nc);
             } else {
-              for (int s = 0; s < 3; ++s) {
-                const int tap = r * 3 + s;
-                const int btap = p.flip ? 8 - tap : tap;
+              for (int s = 0; s < p.taps; ++s) {
+                const int tap = r * p.taps + s;
+                const int btap = p.flip ? p.taps * p.taps - 1 - tap : tap;
                 tma_load_2d(sbr + s * p.BN * row_bytes, &map_b, &full[stage], kb * p.cblk, btap * p.Nc + tn * p.BN);
                 if (X3)
                   tma_load_2d(sbr + p.rg * b_rows * row_bytes + s * p.BN * row_bytes, &map_bl, &full[stage], kb * p.cblk,
@@ -357,7 +388,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     }
   } else if (warp == 1 && elect_one()) {
     // ===================== MMA issuer
-    const uint32_t idesc = umma_idesc(2 /*tf32*/, CT_BM, 3 * p.BN);
+    const uint32_t idesc = umma_idesc(2 /*tf32*/, CT_BM, p.taps * p.BN);
     const uint32_t sbo = 8 * row_bytes;
     int stage = 0, phase = 0, tr_n = 0;
     CT_TRACE(1, 0);
@@ -372,7 +403,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       const uint32_t bres_lo = ((smem_u32(res_b) & 0x3FFFFu) >> 4) | (1u << 16);
       const int kst = p.cblk / 8;
       const int rows_u = p.res ? 3 : p.rg;                         // filter rows per unit
-      const int upt = p.res ? 1 : (3 / p.rg) * p.kblocks;          // units per tile
+      const int upt = p.res ? 1 : (p.taps / p.rg) * p.kblocks;     // units per tile
       const int U = (t_end - t_begin) * upt;
       const uint32_t a_step = (uint32_t)(p.res ? p.a_tap : p.a_bytes) >> 4, b_step = (uint32_t)(b_rows * row_bytes) >> 4;
       const uint32_t stage_step = (uint32_t)p.stage_bytes >> 4;
@@ -464,7 +495,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       fence_after_sync();
       const uint32_t d_tmem = tmem_base + acc * p.acc_stride;
       uint32_t first = 1;
-      for (int it = 0; it < (3 / p.rg) * p.kblocks; ++it) {
+      for (int it = 0; it < (p.taps / p.rg) * p.kblocks; ++it) {
         mbar_wait(&full[stage], phase);
         CT_TRACE(1, 2);
         fence_after_sync();
@@ -489,13 +520,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   } else if (X3 && warp == 2 && elect_one()) {
     // ===================== MMA issuer, pass 2 of the error-compensated mode: A_lo * B_hi
     if (t_begin < t_end) {
-      const uint32_t idesc = umma_idesc(2 /*tf32*/, CT_BM, 3 * p.BN);
+      const uint32_t idesc = umma_idesc(2 /*tf32*/, CT_BM, p.taps * p.BN);
       const uint32_t dhi = umma_desc_hi_kmajor(8 * row_bytes, row_bytes);
       const uint32_t tiles_lo = ((smem_u32(tiles) & 0x3FFFFu) >> 4) | (1u << 16);
       const uint32_t bres_lo = ((smem_u32(res_b) & 0x3FFFFu) >> 4) | (1u << 16);
       const int kst = p.cblk / 8;
       const int rows_u = p.res ? 3 : p.rg;
-      const int upt = p.res ? 1 : (3 / p.rg) * p.kblocks;
+      const int upt = p.res ? 1 : (p.taps / p.rg) * p.kblocks;
       const int U = (t_end - t_begin) * upt;
       const uint32_t a_step = (uint32_t)(p.res ? p.a_tap : p.a_bytes) >> 4, b_step = (uint32_t)(b_rows * row_bytes) >> 4;
       const uint32_t stage_step = (uint32_t)p.stage_bytes >> 4;
@@ -524,7 +555,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   } else if (X3 && (warp == 3 || warp >= 12)) {
     // ===================== operand splitters (X3): stage by stage, in the producer's order
     const int tid_c = (warp == 3 ? 0 : 32) + lane;
-    const int upt = p.res ? 1 : (3 / p.rg) * p.kblocks;
+    const int upt = p.res ? 1 : (p.taps / p.rg) * p.kblocks;
     const int U = max(0, t_end - t_begin) * upt;
     const int bytes = p.res ? p.a_stage_bytes : p.rg * p.a_bytes;
     int stage = 0, phase = 0;
@@ -556,8 +587,22 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     // pixel index is tm*128 + m and only the column position inside the image row (wb) needs a division.
     const int m = q4 * 32 + lane;                   // row of the tile == TMEM lane
     const int wb = m % p.Wb;
-    const bool has_left = wb > 0, has_right = wb < p.W - 1;
+    bool has_left = wb > 0, has_right = wb < p.W - 1;
     const long long total_px = (long long)p.N * p.H * p.W;
+    // padded tiles: this lane's row slot, strip and pixel column (see ConvTcParams)
+    int pd_hr = 0, pd_img = 0, pd_w = 0, pd_w0 = 0, pd_srow = -1, pd_sub = 0;
+    if (p.padded) {
+      const int slot = m / p.Wb;
+      const int strip = (p.Nb == 1) ? slot / p.Hb : 0;
+      pd_hr = slot % p.Hb;
+      pd_img = (p.Nb == 1) ? 0 : slot / p.Hb;
+      const int wo = wb - (strip > 0 ? 1 : 0);
+      pd_w0 = strip * p.Ws;
+      pd_w = pd_w0 + wo;
+      pd_sub = slot % p.rpw;
+      if (wo >= 0 && wo < p.Ws && pd_w < p.W) pd_srow = pd_sub * p.Ws + wo;
+      has_left = pd_w > 0; has_right = pd_w < p.W - 1;
+    }
     // work items = (tile, 32-column block), dealt alternately to the two groups: with one tile per CTA and 64 output
     // channels both groups work on that tile instead of one group doing its blocks back to back
     const int nblk = (p.BN + 31) >> 5;
@@ -568,10 +613,20 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       const int t = t_begin + it;
       int tm = t, tn = 0;
       if (p.tiles_n != 1) { tm = t / p.tiles_n; tn = t - tm * p.tiles_n; }
-      const long long pix = (long long)tm * CT_BM + m;
-      const bool valid = pix < total_px;
+      long long pix = (long long)tm * CT_BM + m;
+      bool valid = pix < total_px;
+      int row0 = tm * CT_BM + q4 * 32;                // first pixel of this warp's 32 rows
+      int sc3 = 0;
+      if (p.padded) {
+        int n, h;
+        if (p.Nb == 1) { n = tm / p.tpi; h = (tm - n * p.tpi) * p.Hb + pd_hr; }
+        else { n = tm * p.Nb + pd_img; h = pd_hr; }
+        valid = pd_srow >= 0 && h < p.H && n < p.N;
+        pix = ((long long)n * p.H + h) * p.W + pd_w;
+        row0 = h - pd_sub;                            // first image row of this warp's slots
+        sc3 = n;
+      }
       const float* rrow = p.residual ? p.residual + pix * p.Nc + tn * p.BN : nullptr;
-      const int row0 = tm * CT_BM + q4 * 32;          // first pixel of this warp's 32 rows
       mbar_wait(&t_full[acc], acc_phase);
       CT_TRACE(2, 1);
       fence_after_sync();
@@ -581,13 +636,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       if (c0 + 32 <= p.BN) {
         if (lane == 0) tma_store_wait_read<0>();      // the bulk stores that read this warp's staging have drained it
         __syncwarp();
-        conv_tc_epilogue_block<32>(p, &map_o, t_addr, lblk, c0, tn, valid, has_left, has_right, row0, stg_w, rrow, s_bias, sw, lane, dbg);
+        conv_tc_epilogue_block<32>(p, &map_o, t_addr, lblk, c0, tn, valid, has_left, has_right, row0, stg_w, rrow, s_bias, sw, lane, dbg,
+                                   pd_srow, pd_w0, sc3);
         sbuf = 0;
       } else {
         if (lane == 0) { if (two_sub) tma_store_wait_read<1>(); else tma_store_wait_read<0>(); }
         __syncwarp();
         conv_tc_epilogue_block<16>(p, &map_o, t_addr, lblk, c0, tn, valid, has_left, has_right, row0, stg_w + sbuf * 2048, rrow, s_bias,
-                                   sw, lane, dbg);
+                                   sw, lane, dbg, pd_srow, pd_w0, sc3);
         if (two_sub) sbuf ^= 1;
       }
       CT_TRACE(2, 2);
@@ -641,22 +697,77 @@ transpose_filters_kernel(const float* __restrict__ P, float* __restrict__ PT, fl
 }
 
 // ---------------------------------------------------------------------------------------- host side
+// Pixel-tile geometry of a W x H image (see ConvTcParams).  Exact tiles when W divides 32 and whole rows / images fill
+// 128 pixels; otherwise padded tiles: rows (or strips of rows wider than 30 pixels) in power-of-two lane groups.
+struct ConvTcGeom { int Wb, Hb, Nb, tpi, padded, NS, Ws, rpw; };
+static int pow2_ge(int v) { int q = 1; while (q < v) q <<= 1; return q; }
+static bool plan_geometry(int W, int H, ConvTcGeom* g) {
+  static const bool no_pad = getenv("SE_CT_NO_PADDED") != nullptr;
+  g->NS = 1; g->Ws = W; g->padded = 0; g->rpw = 1;
+  if (W < 4) return false;
+  if (W <= 32 && (W & (W - 1)) == 0 && ((W * H >= 128) ? (H % (128 / W) == 0) : (128 % (W * H) == 0))) {
+    g->Wb = W;
+    if (W * H >= 128) { g->Hb = 128 / W; g->Nb = 1; g->tpi = H / g->Hb; }
+    else { g->Hb = H; g->Nb = 128 / (W * H); g->tpi = 1; }
+    return true;
+  }
+  if (no_pad) return false;
+  g->padded = 1;
+  if (W <= 32) {
+    g->Wb = max(8, pow2_ge(W));                // 8-pixel (1024-byte at 32 channels) slabs keep every box swizzle-aligned
+    g->rpw = 32 / g->Wb;
+    const int slots = 128 / g->Wb;             // row slots per tile
+    if (H >= slots || pow2_ge(H) >= slots) { g->Hb = slots; g->Nb = 1; g->tpi = (H + slots - 1) / slots; }
+    else { g->Hb = pow2_ge(H); g->Nb = slots / g->Hb; g->tpi = 1; }
+    if (g->Hb % g->rpw != 0) return false;
+    return true;
+  }
+  // wide rows: strips of Ws <= 28 outputs in 32-lane boxes (one pixel of left context for strips > 0, >= 3 spare lanes)
+  if (W > 56) return false;
+  g->Wb = 32; g->NS = 2; g->Ws = (W + 1) / 2; g->Hb = 2; g->Nb = 1; g->tpi = (H + 1) / 2;
+  return true;
+}
+
 static bool tc_shape_ok(const se_conv_desc* d, int Kc, int Nc) {
   if (d->kh != 3 || d->kw != 3 || d->stride != 1 || d->pad_t != 1 || d->pad_l != 1 || d->Ho != d->H || d->Wo != d->W)
     return false;
   if (Kc % 16 != 0 || Nc % 16 != 0) return false;
   if (Kc > 16 && Kc % 32 != 0) return false;
-  const int W = d->W, H = d->H;
-  if (W > 32 || (W & (W - 1)) != 0 || W < 4) return false;         // whole image rows per warp: W divides 32
-  if (W * H >= 128) { if (H % (128 / W) != 0) return false; }
-  else { if ((128 % (W * H)) != 0) return false; }
-  return true;
+  ConvTcGeom g;
+  return plan_geometry(d->W, d->H, &g);
 }
 
-// output channels per N tile: the MMA N is 3*BNc (<= 240) and two accumulators must fit the 512 TMEM columns
-static int pick_bn(int Nc) {
-  if (Nc <= 80) return Nc;
-  for (int bn = 80; bn >= 16; bn -= 16)
+// 1x1 / stride 1 / no padding: a GEMM over the flat pixel list, any image size
+static bool tc_shape_ok_1x1(const se_conv_desc* d, int Kc, int Nc) {
+  static const bool off = getenv("SE_CT_NO_1X1") != nullptr;
+  if (off || d->kh != 1 || d->kw != 1 || d->stride != 1 || d->pad_t != 0 || d->pad_l != 0 || d->Ho != d->H || d->Wo != d->W)
+    return false;
+  if (Kc % 16 != 0 || Nc % 16 != 0) return false;
+  if (Kc > 16 && Kc % 32 != 0) return false;
+  return (long long)d->N * d->H * d->W >= CT_BM;
+}
+
+// 1x1 / stride 2 / no padding (the first convolution and the projection shortcut of a ResNet-50 stage, the shortcuts of
+// wide_residual_network.py:28): the GEMM of the 1x1 case over the (Ho, Wo) grid, the input (forward) or the output
+// (backward data) addressed through a tensor map of the sub-sampled VIEW x[:, ::2, ::2, :] (pixel and row strides
+// doubled) -- no gather pass.  Tiles are rows of the output grid (padded-tile geometry).
+static bool tc_shape_ok_1x1_s2(const se_conv_desc* d, int Kc, int Nc) {
+  static const bool off = getenv("SE_CT_NO_1X1") != nullptr || getenv("SE_CT_NO_S2") != nullptr;
+  if (off || d->kh != 1 || d->kw != 1 || d->stride != 2 || d->pad_t != 0 || d->pad_l != 0 || d->Ho != (d->H + 1) / 2 ||
+      d->Wo != (d->W + 1) / 2)
+    return false;
+  if (Kc % 16 != 0 || Nc % 16 != 0) return false;
+  if (Kc > 16 && Kc % 32 != 0) return false;
+  ConvTcGeom g;
+  return d->Wo <= 32 && plan_geometry(d->Wo, d->Ho, &g) && g.Hb % (32 / g.Wb) == 0;
+}
+
+// output channels per N tile: the MMA N is taps*BNc (<= 240 for 3x3, 128 for 1x1) and two accumulators must fit the
+// 512 TMEM columns
+static int pick_bn(int Nc, int taps) {
+  const int top = taps == 1 ? 128 : 80;
+  if (Nc <= top) return Nc;
+  for (int bn = top; bn >= 16; bn -= 16)
     if (Nc % bn == 0) return bn;
   return 16;
 }
@@ -666,16 +777,35 @@ constexpr int WG_COOP_SMEM_MAX = 120 * 1024;
 
 static int conv_tc_launch(const se_conv_desc* d, const float* a_tensor, int Kc, const float* bmat, int Nc, int flip,
                           const float* bias, const float* residual, float* out, int relu, float beta, double* stats,
-                          cudaStream_t st, const float* bmat_lo = nullptr) {
+                          cudaStream_t st, const float* bmat_lo = nullptr, int taps = 3, int s2 = 0) {
+  // s2 (1x1 / stride 2): tiles over the (Ho, Wo) grid; forward reads the sub-sampled view of a_tensor, backward data
+  // (flip) writes the sub-sampled view of out (after zeroing it: the other three quarters of dx are zero)
   ConvTcParams p;
+  const int gW = s2 ? d->Wo : d->W, gH = s2 ? d->Ho : d->H;      // the grid the pixel tiles cover
   const int x3 = bmat_lo ? 1 : 0;       // error-compensated mode: bmat_lo = the low parts of bmat (se_split_filters)
-  p.N = d->N; p.H = d->H; p.W = d->W; p.Kc = Kc; p.Nc = Nc;
-  p.Wb = d->W;
-  if (d->W * d->H >= 128) { p.Hb = 128 / d->W; p.Nb = 1; } else { p.Hb = d->H; p.Nb = 128 / (d->W * d->H); }
-  p.BN = pick_bn(Nc);
+  const long long total_px = (long long)d->N * gH * gW;
+  p.taps = taps; p.flat = taps == 1 && !s2; p.pad = taps == 3 ? 1 : 0;
+  p.N = d->N; p.H = gH; p.W = gW; p.Kc = Kc; p.Nc = Nc;
+  p.Wb = gW; p.tpi = 1; p.padded = 0; p.NS = 1; p.Ws = gW; p.rpw = 1;
+  if (p.flat) {
+    // a 128-pixel tile is a run of the flat [N*H*W][C] matrix: the kernel sees one "image" of 1 x total_px pixels
+    if (total_px > 0x7fffffffLL) return SE_ERR_UNSUPPORTED;
+    p.N = 1; p.H = 1; p.W = (int)total_px; p.Wb = CT_BM; p.Hb = 1; p.Nb = 1;
+  } else {
+    ConvTcGeom g;
+    if (!plan_geometry(gW, gH, &g)) return SE_ERR_UNSUPPORTED;
+    p.Wb = g.Wb; p.Hb = g.Hb; p.Nb = g.Nb; p.tpi = g.tpi; p.padded = g.padded; p.NS = g.NS; p.Ws = g.Ws; p.rpw = g.rpw;
+    if (s2 && flip && !p.padded) {
+      // the strided output view needs the 4-d store of the padded path: the same tiles, described as row slots
+      p.padded = 1; p.rpw = 32 / p.Wb;
+      if (p.Hb % p.rpw != 0) return SE_ERR_UNSUPPORTED;
+    }
+  }
+  p.BN = pick_bn(Nc, taps);
   if (p.BN % 16 != 0 || Nc % p.BN != 0) return SE_ERR_UNSUPPORTED;
   p.tiles_n = Nc / p.BN;
-  p.tiles_m = (p.Nb == 1) ? d->N * (d->H / p.Hb) : ceil_div(d->N, p.Nb);
+  if (p.flat) p.tiles_m = (int)ceil_div<long long>(total_px, CT_BM);
+  else p.tiles_m = (p.Nb == 1) ? d->N * p.tpi : ceil_div(d->N, p.Nb);
   // few pixel tiles (64 channels at 8x8: 64 tiles for 148 SMs): split the output channels over two CTAs per tile --
   // each then streams half of the 9*Cin*Cout weights, the dominant traffic of such a layer, and half of the epilogue
   static const bool no_nsplit = getenv("SE_CT_NO_NSPLIT") != nullptr;
@@ -699,18 +829,18 @@ static int conv_tc_launch(const se_conv_desc* d, const float* a_tensor, int Kc, 
     int wg_cols = 0;
     const size_t wg = conv_wgrad_tc_smem(d, &wg_cols, x3);
     if (wg > 0 && wg <= (size_t)WG_COOP_SMEM_MAX && wg_cols <= 256) {
-      if (pick_bn(Nc) == 16) p.stage_out = 2048;          // one sub-buffer per warp buys the input pipeline a stage
+      if (pick_bn(Nc, taps) == 16) p.stage_out = 2048;          // one sub-buffer per warp buys the input pipeline a stage
       budget = 225 * 1024 - (int)wg - 2048 - 8 * p.stage_out;
       tmem_budget = 256;
     }
   }
   const int full_budget = CT_SMEM_BUDGET;
  retry:
-  p.rg = 3;
-  p.stage_bytes = 3 * p.a_bytes + (1 + x3) * ceil_div(9 * p.BN * p.cblk * 4, 1024) * 1024;
+  p.rg = taps;
+  p.stage_bytes = taps * p.a_bytes + (1 + x3) * ceil_div(taps * taps * p.BN * p.cblk * 4, 1024) * 1024;
   if (2 * p.stage_bytes > budget) {
     p.rg = 1;
-    p.stage_bytes = p.a_bytes + (1 + x3) * ceil_div(3 * p.BN * p.cblk * 4, 1024) * 1024;
+    p.stage_bytes = p.a_bytes + (1 + x3) * ceil_div(taps * p.BN * p.cblk * 4, 1024) * 1024;
   }
   p.stages = min(CT_MAX_STAGES, budget / p.stage_bytes);
   if (p.stages < 2) {
@@ -722,14 +852,14 @@ static int conv_tc_launch(const se_conv_desc* d, const float* a_tensor, int Kc, 
   static const char* dbg_nores = getenv("SE_CT_NORES");
   const int wbytes = (1 + x3) * ceil_div(9 * p.BN * Kc * 4, 1024) * 1024;
   static const bool no_single = getenv("SE_CT_NO_SINGLE") != nullptr;
-  const int single = (p.Nb == 1 && d->W % 8 == 0 && !no_single) ? 1 : 0;
-  const int a_stage = single ? (p.Hb + 2) * d->W * p.cblk * 4 : 3 * p.a_bytes;
+  const int single = (p.Nb == 1 && p.NS == 1 && p.Wb % 8 == 0 && !no_single && taps == 3) ? 1 : 0;
+  const int a_stage = single ? (p.Hb + 2) * p.Wb * p.cblk * 4 : 3 * p.a_bytes;
   const int res_stage = ceil_div(a_stage, 1024) * 1024;
-  if (!dbg_nores && p.tiles_n == 1 && p.kblocks == 1 && wbytes <= (1 + x3) * 40 * 1024 &&
+  if (!dbg_nores && taps == 3 && p.tiles_n == 1 && p.kblocks == 1 && wbytes <= (1 + x3) * 40 * 1024 &&
       ((budget - wbytes) / res_stage >= 2 || budget != full_budget)) {
     p.res = 1; p.res_b_bytes = wbytes; p.res_bl_off = wbytes / 2; p.rg = 3;
     p.single = single;
-    p.a_tap = single ? d->W * p.cblk * 4 : p.a_bytes;
+    p.a_tap = single ? p.Wb * p.cblk * 4 : p.a_bytes;
     p.a_stage_bytes = a_stage;
     p.stage_bytes = res_stage;
     p.stages = min(CT_MAX_STAGES, (budget - wbytes) / p.stage_bytes);
@@ -745,7 +875,7 @@ static int conv_tc_launch(const se_conv_desc* d, const float* a_tensor, int Kc, 
   static const char* dbg_trace = getenv("SE_CT_TRACE_PTR");
   p.trace = dbg_trace ? reinterpret_cast<long long*>(strtoull(dbg_trace, nullptr, 0)) : nullptr;
   int stride = 32;
-  while (stride < 3 * p.BN) stride <<= 1;
+  while (stride < taps * p.BN) stride <<= 1;
   if (2 * stride > 512) return SE_ERR_UNSUPPORTED;
   if (tmem_budget < 512) {
     // one accumulator is enough only when a CTA has a single tile; otherwise keep the MMA / epilogue overlap
@@ -763,14 +893,22 @@ static int conv_tc_launch(const se_conv_desc* d, const float* a_tensor, int Kc, 
 
   CUtensorMap ma, mb, mbl;
   {
-    uint64_t dims[4] = {(uint64_t)Kc, (uint64_t)d->W, (uint64_t)d->H, (uint64_t)d->N};
-    uint64_t strides[3] = {(uint64_t)Kc * 4, (uint64_t)d->W * Kc * 4, (uint64_t)d->H * d->W * Kc * 4};
+    uint64_t dims[4] = {(uint64_t)Kc, (uint64_t)gW, (uint64_t)gH, (uint64_t)d->N};
+    uint64_t strides[3] = {(uint64_t)Kc * 4, (uint64_t)gW * Kc * 4, (uint64_t)gH * gW * Kc * 4};
+    if (s2 && !flip) {      // forward: x[:, ::2, ::2, :]
+      strides[0] = (uint64_t)2 * Kc * 4; strides[1] = (uint64_t)2 * d->W * Kc * 4; strides[2] = (uint64_t)d->H * d->W * Kc * 4;
+    }
     uint32_t box[4] = {(uint32_t)p.cblk, (uint32_t)p.Wb, (uint32_t)(p.single ? p.Hb + 2 : p.Hb), (uint32_t)p.Nb};
+    if (p.flat) {
+      dims[1] = (uint64_t)total_px; dims[2] = 1; dims[3] = 1;
+      strides[1] = strides[2] = (uint64_t)total_px * Kc * 4;
+      box[1] = CT_BM; box[2] = 1; box[3] = 1;
+    }
     CUtensorMapSwizzle sw = p.cblk == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
     if (!make_tmap(&ma, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(a_tensor), dims, strides, box, sw)) return SE_ERR_CUDA;
-    uint64_t bdims[2] = {(uint64_t)Kc, (uint64_t)9 * Nc};
+    uint64_t bdims[2] = {(uint64_t)Kc, (uint64_t)taps * taps * Nc};
     uint64_t bstrides[1] = {(uint64_t)Kc * 4};
-    uint32_t bbox[2] = {(uint32_t)p.cblk, (uint32_t)(p.b_merged ? 3 * p.BN : p.BN)};
+    uint32_t bbox[2] = {(uint32_t)p.cblk, (uint32_t)(p.b_merged ? taps * p.BN : p.BN)};
     if (!make_tmap(&mb, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(bmat), bdims, bstrides, bbox, sw)) return SE_ERR_CUDA;
     mbl = mb;
     if (x3 && !make_tmap(&mbl, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(bmat_lo), bdims, bstrides, bbox, sw))
@@ -779,14 +917,29 @@ static int conv_tc_launch(const se_conv_desc* d, const float* a_tensor, int Kc, 
   CUtensorMap mo;
   {
     // output(s) as [pixels][channels]: 32-pixel x 16-channel boxes, SWIZZLE_64B staging (see stage_put)
-    uint64_t odims[2] = {(uint64_t)Nc, (uint64_t)d->N * d->H * d->W};
+    uint64_t odims[2] = {(uint64_t)Nc, (uint64_t)total_px};
     uint64_t ostrides[1] = {(uint64_t)Nc * 4};
     uint32_t obox[2] = {16u, 32u};
+    if (p.padded) {
+      // [N][H][W][channels]: one strip of Ws pixels x rpw rows per warp; pixels / rows / images past the tensor are clipped
+      uint64_t odims4[4] = {(uint64_t)Nc, (uint64_t)gW, (uint64_t)gH, (uint64_t)d->N};
+      uint64_t ostrides4[3] = {(uint64_t)Nc * 4, (uint64_t)gW * Nc * 4, (uint64_t)gH * gW * Nc * 4};
+      if (s2 && flip) {     // backward data: dx[:, ::2, ::2, :]
+        ostrides4[0] = (uint64_t)2 * Nc * 4; ostrides4[1] = (uint64_t)2 * d->W * Nc * 4; ostrides4[2] = (uint64_t)d->H * d->W * Nc * 4;
+      }
+      uint32_t obox4[4] = {16u, (uint32_t)p.Ws, (uint32_t)p.rpw, 1u};
+      if (!make_tmap(&mo, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, out, odims4, ostrides4, obox4, CU_TENSOR_MAP_SWIZZLE_64B)) return SE_ERR_CUDA;
+    } else
     if (!make_tmap(&mo, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, out, odims, ostrides, obox, CU_TENSOR_MAP_SWIZZLE_64B)) return SE_ERR_CUDA;
   }
   const size_t smem = (size_t)p.res_b_bytes + (size_t)p.stages * p.stage_bytes + 8 * p.stage_out + (4 * CT_MAX_STAGES + 2 * CT_MAX_ACC + 4) * 8 + Nc * 4 + (stats ? 16 * Nc * 4 : 0) + 1024 + 64;
   if (smem > 227 * 1024) return SE_ERR_UNSUPPORTED;
   int grid = min(sm_count(), p.tiles_m * p.tiles_n);
+  if (s2 && flip && beta == 0.f &&
+      cudaMemsetAsync(out, 0, (size_t)d->N * d->H * d->W * Nc * sizeof(float), st) != cudaSuccess) {
+    set_error("conv_tc: cudaMemsetAsync failed");
+    return SE_ERR_CUDA;
+  }
   if (x3) launch(conv_tc_kernel<1>, dim3(grid), dim3(CT_THREADS_X3), smem, st, ma, mb, mbl, mo, p);
   else launch(conv_tc_kernel<0>, dim3(grid), dim3(CT_THREADS), smem, st, ma, mb, mbl, mo, p);
   return check_launch("conv_tc_kernel");
@@ -811,18 +964,23 @@ static int ensure_init() {
 // w_t_lo != null selects the error-compensated arithmetic (w_t_lo = low parts of w_t, se_split_filters)
 int conv_fwd_tc(const se_conv_desc* d, const float* x, const float* w_t, const float* w_t_lo, const float* bias,
                 const float* residual, float* y, int relu, double* stats, cudaStream_t st) {
-  if (!w_t || !tc_shape_ok(d, d->Cin, d->Cout)) return SE_ERR_UNSUPPORTED;
+  if (!w_t) return SE_ERR_UNSUPPORTED;
+  const bool k2 = tc_shape_ok_1x1_s2(d, d->Cin, d->Cout);
+  const bool k1 = k2 || tc_shape_ok_1x1(d, d->Cin, d->Cout);
+  if (!k1 && !tc_shape_ok(d, d->Cin, d->Cout)) return SE_ERR_UNSUPPORTED;
   int rc = ensure_init();
   if (rc) return rc;
-  return conv_tc_launch(d, x, d->Cin, w_t, d->Cout, 0, bias, residual, y, relu, 0.f, stats, st, w_t_lo);
+  return conv_tc_launch(d, x, d->Cin, w_t, d->Cout, 0, bias, residual, y, relu, 0.f, stats, st, w_t_lo, k1 ? 1 : 3, k2);
 }
 
 int conv_dgrad_tc(const se_conv_desc* d, const float* dy, const float* w, const float* w_lo, float* dx, float beta,
                   cudaStream_t st) {
-  if (!tc_shape_ok(d, d->Cout, d->Cin)) return SE_ERR_UNSUPPORTED;
+  const bool k2 = tc_shape_ok_1x1_s2(d, d->Cout, d->Cin);
+  const bool k1 = k2 || tc_shape_ok_1x1(d, d->Cout, d->Cin);
+  if (!k1 && !tc_shape_ok(d, d->Cout, d->Cin)) return SE_ERR_UNSUPPORTED;
   int rc = ensure_init();
   if (rc) return rc;
-  return conv_tc_launch(d, dy, d->Cout, w, d->Cin, 1, nullptr, nullptr, dx, 0, beta, nullptr, st, w_lo);
+  return conv_tc_launch(d, dy, d->Cout, w, d->Cin, 1, nullptr, nullptr, dx, 0, beta, nullptr, st, w_lo, k1 ? 1 : 3, k2);
 }
 
 

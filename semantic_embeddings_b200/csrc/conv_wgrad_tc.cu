@@ -33,13 +33,19 @@ using namespace tc;
 int init_conv_wgrad_pk();
 size_t conv_wgrad_pk_smem(const se_conv_desc* d, int* tmem_cols);
 int conv_wgrad_pk(const se_conv_desc* d, const float* x, const float* dy, float* dw, float* dbias, cudaStream_t st);
+// conv1x1_wgrad_tc.cu: 1x1 / stride 1 layers (a GEMM over the flat pixel list)
+int init_conv1x1_wgrad_tc();
+bool conv1x1_wgrad_tc_ok(const se_conv_desc* d);
+int conv1x1_wgrad_tc(const se_conv_desc* d, const float* x, const float* dy, float* dw, float* dbias, int x3, cudaStream_t st);
 static bool wgrad_is_packed(const se_conv_desc* d, int x3) {
   static const bool no_pack = getenv("SE_WG_NO_PACK") != nullptr;
   return x3 && d->Cin <= 16 && d->Cout <= 16 && !no_pack;
 }
 
 struct WgTcParams {
-  int N, H, W, Cin, Cout;
+  int N, H, W, Cin, Cout;      // W = the row pitch of the shared-memory boxes: the image width rounded up to a power of two >= 8
+                               // (TMA zero-fills the pixels past the image: they add nothing to the sums)
+  int tpi;                     // pixel tiles per image (Nb == 1); the last one may hang over the image (zero-filled rows)
   int Hb, Nb, PT;              // pixel tile: Hb rows of one image (Nb == 1) or Nb whole images; PT = W*Hb*Nb pixels
   int img_px;                  // pixels of one image inside the tile (Hb * W)
   int img_stride;              // bytes between images inside an x buffer ((Hb + 2) * W * 128)
@@ -90,7 +96,7 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
   const int t_end = min(p.tiles_m, t_begin + per_cta);
   const int ci0 = blockIdx.y * 32;
   const int co0 = blockIdx.z * p.ncols;
-  const int tiles_per_img = (p.Nb == 1) ? (p.H / p.Hb) : 1;
+  const int tiles_per_img = p.tpi;
   uint32_t tmem_cols = 32;
   while ((int)tmem_cols < p.G * p.ncols) tmem_cols <<= 1;
 
@@ -325,7 +331,7 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
 int init_conv_wgrad_tc() {
   if (cudaFuncSetAttribute(conv_wgrad_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess ||
       cudaFuncSetAttribute(conv_wgrad_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess ||
-      init_conv_wgrad_pk() != SE_OK) {
+      init_conv_wgrad_pk() != SE_OK || init_conv1x1_wgrad_tc() != SE_OK) {
     set_error("init_conv_wgrad_tc: cannot raise the shared-memory limit");
     return SE_ERR_CUDA;
   }
@@ -341,10 +347,15 @@ constexpr int WG_COOP_SMEM = 120 * 1024;
 static int plan_wgrad(const se_conv_desc* d, bool with_bias, int x3, WgTcParams* pp, size_t* smem_out) {
   if (d->kh != 3 || d->kw != 3 || d->stride != 1 || d->pad_t != 1 || d->pad_l != 1 || d->Ho != d->H || d->Wo != d->W)
     return SE_ERR_UNSUPPORTED;
-  const int Cin = d->Cin, Cout = d->Cout, W = d->W, H = d->H;
+  const int Cin = d->Cin, Cout = d->Cout, H = d->H;
   if (Cin % 16 != 0 || Cout % 16 != 0) return SE_ERR_UNSUPPORTED;
-  // vertical taps are address offsets of r*W pixels: whole 1024-byte swizzle periods need W % 8 == 0
-  if (W > 64 || (W & (W - 1)) != 0 || W < 8) return SE_ERR_UNSUPPORTED;
+  // vertical taps are address offsets of r*W pixels: whole 1024-byte swizzle periods need a row pitch that is a multiple
+  // of 8 pixels -- image rows are loaded as boxes of W (pitch) >= d->W pixels, zero-filled past the image
+  if (d->W > 64 || d->W < 4) return SE_ERR_UNSUPPORTED;
+  static const bool no_pad = getenv("SE_CT_NO_PADDED") != nullptr;
+  int W = 8;
+  while (W < d->W) W <<= 1;
+  if (no_pad && (W != d->W)) return SE_ERR_UNSUPPORTED;
   WgTcParams& p = *pp;
   p.N = d->N; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout;
   p.G = with_bias ? 4 : 3;
@@ -353,8 +364,16 @@ static int plan_wgrad(const se_conv_desc* d, bool with_bias, int x3, WgTcParams*
   p.nnb = ceil_div(ceil_div(Cout, gz), 32);
   p.ncols = 32 * p.nnb;
   p.PT = max(64, 2 * W);
-  if (W * H >= p.PT) { if (H % (p.PT / W) != 0) return SE_ERR_UNSUPPORTED; p.Hb = p.PT / W; p.Nb = 1; }
-  else { if (p.PT % (W * H) != 0) return SE_ERR_UNSUPPORTED; p.Hb = H; p.Nb = p.PT / (W * H); }
+  int Hp = 1;
+  while (Hp < H) Hp <<= 1;
+  if (W * H >= p.PT || W * Hp >= p.PT) {
+    p.Hb = p.PT / W; p.Nb = 1; p.tpi = ceil_div(H, p.Hb);
+    if (no_pad && H % p.Hb != 0) return SE_ERR_UNSUPPORTED;
+  } else {
+    // whole images: Hp >= H row slots each (the rows past the image are zero-filled)
+    p.Hb = Hp; p.Nb = p.PT / (W * Hp); p.tpi = 1;
+    if (no_pad && Hp != H) return SE_ERR_UNSUPPORTED;
+  }
   p.img_px = p.Hb * W;
   p.img_stride = (p.Hb + 2) * W * 128;
   p.xbuf_bytes = p.Nb * p.img_stride;
@@ -364,7 +383,7 @@ static int plan_wgrad(const se_conv_desc* d, bool with_bias, int x3, WgTcParams*
   if (2 * p.stage_bytes + fixed <= WG_COOP_SMEM) p.stages = 2;
   else p.stages = min(4, (200 * 1024) / p.stage_bytes);
   if (p.stages < 1) return SE_ERR_UNSUPPORTED;
-  p.tiles_m = (p.Nb == 1) ? d->N * (H / p.Hb) : ceil_div(d->N, p.Nb);
+  p.tiles_m = (p.Nb == 1) ? d->N * p.tpi : ceil_div(d->N, p.Nb);
   *smem_out = (size_t)p.stages * p.stage_bytes + fixed;
   return SE_OK;
 }
@@ -373,7 +392,10 @@ static int plan_wgrad(const se_conv_desc* d, bool with_bias, int x3, WgTcParams*
 size_t conv_wgrad_tc_smem(const se_conv_desc* d, int* tmem_cols, int x3) {
   WgTcParams p;
   size_t smem = 0;
-  if (wgrad_is_packed(d, x3)) return conv_wgrad_pk_smem(d, tmem_cols);
+  if (wgrad_is_packed(d, x3)) {
+    const size_t pk = conv_wgrad_pk_smem(d, tmem_cols);
+    if (pk > 0) return pk;                    // (0: a shape the packed kernel does not take -- the general kernel runs it)
+  }
   if (plan_wgrad(d, true, x3, &p, &smem) != SE_OK) return 0;
   int cols = 32;
   while (cols < p.G * p.ncols) cols <<= 1;
@@ -386,14 +408,19 @@ int conv_wgrad_tc(const se_conv_desc* d, const float* x, const float* dy, float*
     return SE_ERR_UNSUPPORTED;
   WgTcParams p;
   size_t smem = 0;
-  if (wgrad_is_packed(d, x3)) return conv_wgrad_pk(d, x, dy, dw, dbias, st);
+  static bool inited = false;
+  if (!inited) { int rc0 = init_conv_wgrad_tc(); if (rc0) return rc0; inited = true; }
+  if (conv1x1_wgrad_tc_ok(d)) return conv1x1_wgrad_tc(d, x, dy, dw, dbias, x3, st);
+  if (wgrad_is_packed(d, x3)) {
+    const int rc_pk = conv_wgrad_pk(d, x, dy, dw, dbias, st);
+    if (rc_pk != SE_ERR_UNSUPPORTED) return rc_pk;
+  }
   int rc = plan_wgrad(d, dbias != nullptr, x3, &p, &smem);
   if (rc != SE_OK) return rc;
-  static bool inited = false;
-  if (!inited) { rc = init_conv_wgrad_tc(); if (rc) return rc; inited = true; }
   const int Cin = d->Cin, Cout = d->Cout, W = d->W, H = d->H;
   const int gz = ceil_div(Cout, 128);
   p.dw = dw; p.dbias = dbias;
+  const uint32_t Wbox = (uint32_t)p.W;          // row pitch of the boxes (>= W)
   static const char* dbg = getenv("SE_WG_DEBUG");
   p.debug = dbg ? atoi(dbg) : 0;
 
@@ -401,13 +428,13 @@ int conv_wgrad_tc(const se_conv_desc* d, const float* x, const float* dy, float*
   {
     uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)d->N};
     uint64_t strides[3] = {(uint64_t)Cin * 4, (uint64_t)W * Cin * 4, (uint64_t)H * W * Cin * 4};
-    uint32_t box[4] = {32u, (uint32_t)W, (uint32_t)(p.Hb + 2), (uint32_t)p.Nb};
+    uint32_t box[4] = {32u, Wbox, (uint32_t)(p.Hb + 2), (uint32_t)p.Nb};
     if (!make_tmap(&mx, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(x), dims, strides, box,
                    CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B))
       return SE_ERR_CUDA;
     uint64_t ydims[4] = {(uint64_t)Cout, (uint64_t)W, (uint64_t)H, (uint64_t)d->N};
     uint64_t ystrides[3] = {(uint64_t)Cout * 4, (uint64_t)W * Cout * 4, (uint64_t)H * W * Cout * 4};
-    uint32_t ybox[4] = {32u, (uint32_t)W, (uint32_t)p.Hb, (uint32_t)p.Nb};
+    uint32_t ybox[4] = {32u, Wbox, (uint32_t)p.Hb, (uint32_t)p.Nb};
     if (!make_tmap(&mdy, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(dy), ydims, ystrides, ybox,
                    CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B))
       return SE_ERR_CUDA;

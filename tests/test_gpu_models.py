@@ -316,12 +316,14 @@ def test_fast_mode_error_is_reported_not_hidden():
     assert e_emb < 5e-2 and e_loss < 5e-2
 
 
-def test_resnet50_step_matches_oracle():
+@pytest.mark.parametrize('mode', ['f32', 'tf32x3'])
+def test_resnet50_step_matches_oracle(mode):
     """Config 4 architecture (keras.applications ResNet50 v1 + GAP + Dense 'embedding', utils.py:228-243) on a small
     64x64 input: 7x7/2 stem with explicit padding, 3x3/2 max-pool, bottleneck blocks with projection shortcuts, NAB-sized
     (555-d) head.  The backbone itself is third-party and unpinned; this checks engine vs oracle."""
     from oracle import models as omodels
     from oracle import train as otrain
+    from semantic_embeddings_b200 import _lib
     from semantic_embeddings_b200.models import resnet50
     from semantic_embeddings_b200.engine import Engine
     emb = class_matrix('nab')
@@ -331,21 +333,30 @@ def test_resnet50_step_matches_oracle():
     omodels.randomize(om, seed=52)
     to_f32_exact(om)
     graph = resnet50.ResNet50(D, input_shape=(64, 64, 3))
-    eng = Engine(graph, B, emb, use_cuda_graph=False)
+    # tf32x3: the 1x1 bottleneck convolutions with >= 128 pixels run on the tcgen05 GEMM kernels (conv_tc.cu flat mode,
+    # conv1x1_wgrad_tc.cu), the rest on the fp32 kernels
+    eng = Engine(graph, B, emb, use_cuda_graph=False, mode=_lib.SE_MODE_TF32X3 if mode == 'tf32x3' else _lib.SE_MODE_F32)
     eng.set_weights(oracle_weights_np(om))
     g = torch.Generator().manual_seed(3)
     x = torch.randn(B, 64, 64, 3, generator=g, dtype=torch.float64).float()
     y = torch.randint(0, C, (B,), generator=g)
     vel = otrain.make_velocity(om)
     emb_t = torch.as_tensor(emb.astype(np.float32)).double()
+    # noise floor of this ill-conditioned case (batch 2, BatchNorm over 8 values at the 2x2 maps): the same step by the
+    # oracle in float32 -- the embedding tolerance is 1e-4 or three times that floor, whichever is larger
+    import copy
+    om32 = copy.deepcopy(om)
+    otrain.cast_model(om32, torch.float32)
+    obj32, _, _ = otrain.train_step(om32, x, y, emb_t.float(), {k: v.float() for k, v in vel.items()}, 0.05)
     obj, grads, norm = otrain.train_step(om, x.double(), y, emb_t, vel, 0.05)
+    floor = rel_max(obj32['emb'].detach().numpy(), obj['emb'].detach().numpy())
     eng.train_step(x, y, lr=0.05)
     m = eng.metrics()
     e_loss = abs(m['loss'] - float(obj['embed_loss'].detach()))
     e_emb = rel_max(eng.act['head_out'].cpu().numpy(), obj['emb'].detach().numpy())
     gg, gw, name = _grad_errors(eng.get_grads(), grads, norm)
-    report('resnet50_step', loss=e_loss, emb=e_emb, grad_global=gg, worst=name)
-    assert e_loss < 1e-4 and e_emb < 1e-4, (e_loss, e_emb)
+    report('resnet50_step_' + mode, loss=e_loss, emb=e_emb, emb_floor_f32_oracle=floor, grad_global=gg, worst=name)
+    assert e_loss < 1e-4 and e_emb < max(1e-4, 3 * floor), (e_loss, e_emb, floor)
     assert gg < 5e-2, gg          # batch of 2 with 2x2 final maps: BN backward is ill-conditioned in fp32
 
 

@@ -68,7 +68,37 @@ CONV_CASES = [
     (1, 32, 32, 64, 320, 3, 1, 'same', False),   # tcgen05: two N tiles of 160
     (5, 4, 8, 32, 48, 3, 1, 'same', True),       # tcgen05 wgrad: two 4x8 images per pixel tile (halo rows between them)
     (3, 64, 64, 16, 16, 3, 1, 'same', False),    # tcgen05 wgrad: 64-pixel rows, 16-channel boxes zero-filled to 32
+    (2, 14, 14, 64, 256, 1, 1, 'valid', True),   # tcgen05 1x1: 392 pixels (ragged last tile), 2 K blocks, 2 N tiles of 128
+    (3, 7, 7, 256, 64, 1, 1, 'valid', True),     # tcgen05 1x1: ResNet-50 stage-5 maps, 8 K blocks
+    (1, 28, 28, 128, 512, 1, 1, 'valid', False), # tcgen05 1x1: 4 N tiles, no bias
+    (4, 8, 8, 16, 48, 1, 1, 'valid', True),      # tcgen05 1x1: 16-channel (64-byte) rows, N = 48
+    (8, 56, 56, 64, 64, 1, 1, 'valid', True),    # tcgen05 1x1: 196 pixel tiles (more than one per CTA)
+    (3, 28, 28, 32, 64, 3, 1, 'same', True),     # tcgen05 padded tiles: 28-pixel rows in 32-lane slots (ResNet-50 stage 3)
+    (5, 14, 14, 64, 32, 3, 1, 'same', True),     # tcgen05 padded tiles: two 14-pixel rows per warp, last tile hangs over the image
+    (5, 7, 7, 64, 64, 3, 1, 'same', False),      # tcgen05 padded tiles: two 7x7 images per tile (8x8 slots), odd image count
+    (2, 55, 55, 32, 32, 3, 1, 'same', True),     # tcgen05 strips: 55-pixel rows as 28 + 27, odd row count (ResNet-50 stage 2)
+    (2, 16, 12, 16, 16, 3, 1, 'same', True),     # tcgen05 padded tiles: 12-pixel rows, 16 channels
+    (1, 40, 40, 32, 48, 3, 1, 'same', False),    # tcgen05 strips: 20 + 20
+    (2, 55, 55, 64, 128, 1, 2, 'valid', True),   # tcgen05 1x1 / stride 2 through a strided tensor view: 55 -> 28 (ResNet-50 stage 3)
+    (3, 28, 28, 128, 64, 1, 2, 'valid', False),  # tcgen05 1x1 / stride 2: 28 -> 14
+    (4, 14, 14, 64, 96, 1, 2, 'valid', True),    # tcgen05 1x1 / stride 2: 14 -> 7, two images per tile
 ]
+TC_PADDED = {(3, 28, 28, 32, 64), (5, 14, 14, 64, 32), (5, 7, 7, 64, 64), (2, 55, 55, 32, 32), (1, 40, 40, 32, 48)}
+
+
+def _tc_1x1(case):
+    """(forward, dgrad, wgrad) reach the tcgen05 1x1 kernels for this case (conv_tc.cu tc_shape_ok_1x1, conv1x1_wgrad_tc.cu)"""
+    N, H, W, Cin, Cout, k, stride = case[:7]
+    if k != 1 or stride not in (1, 2):
+        return False, False, False
+    kok = lambda c: c % 16 == 0 and (c == 16 or c % 32 == 0)
+    px = N * H * W
+    if stride == 2:     # tiles over the (Ho, Wo) grid, Wo <= 32
+        ok = (W + 1) // 2 <= 32
+        return ok and kok(Cin) and Cout % 16 == 0, ok and kok(Cout) and Cin % 16 == 0, ok and Cin % 4 == 0 and Cout % 16 == 0
+    return (kok(Cin) and Cout % 16 == 0 and px >= 128, kok(Cout) and Cin % 16 == 0 and px >= 128,
+            Cin % 4 == 0 and Cout % 16 == 0 and px >= 32)
+
 
 
 @pytest.mark.parametrize('case', CONV_CASES, ids=lambda c: 'x'.join(str(v) for v in c[:7]))
@@ -143,6 +173,13 @@ def test_conv_fwd_dgrad_wgrad(case, mode):
     report('conv', case=str(case), mode=mode, y=e_y, sum=e_s, sumsq=e_q, dx=e_dx, dw=e_dw, db=e_db)
     assert e_y < tol and e_dx < tol and e_dx2 < tol and e_dw < tol and e_db < tol, (e_y, e_dx, e_dx2, e_dw, e_db)
     assert e_s < max(tol, 1e-4) and e_q < tol * 2, (e_s, e_q)
+    if mode == 1:
+        # the single-pass mode must show tensor-core (10-bit mantissa) error: proof that these layers left the FFMA kernels
+        f_tc, d_tc, w_tc = _tc_1x1(case)
+        if tuple(case[:5]) in TC_PADDED:
+            kok = lambda c: c % 16 == 0 and (c == 16 or c % 32 == 0)      # GEMM K: 16 or whole 32-channel blocks
+            f_tc, d_tc, w_tc = kok(Cin), kok(Cout), True
+        assert (not f_tc or e_y > 2e-5) and (not d_tc or e_dx > 2e-5) and (not w_tc or e_dw > 2e-5), (e_y, e_dx, e_dw)
 
 
 def test_tf32_operands_are_truncated_by_the_tensor_core():
