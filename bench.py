@@ -197,7 +197,9 @@ def op_category(op, L):
         return '%s C=%d rows=%d' % (nm, i[0], i[1]), 0.0, 4.0 * i[0] * i[1] * passes
     other = {L.OP_HEAD: 'embed_head', L.OP_SGD_PREPARE: 'sgd_prepare', L.OP_SGD_APPLY: 'sgd_apply', L.OP_MEMSET: 'memset',
              L.OP_GAP_FWD: 'gap_fwd', L.OP_GAP_BWD: 'gap_bwd', L.OP_SHORTCUT_BWD: 'shortcut_bwd', L.OP_ADD_BWD: 'add_bwd',
-             L.OP_ADD_FWD: 'add_fwd', L.OP_XENT: 'softmax_xent'}
+             L.OP_ADD_FWD: 'add_fwd', L.OP_XENT: 'softmax_xent', L.OP_TRANSPOSE_FILTERS: 'split_filters',
+             L.OP_MAXPOOL_FWD: 'maxpool_fwd', L.OP_MAXPOOL_BWD: 'maxpool_bwd', L.OP_AVGPOOL_FWD: 'avgpool_fwd',
+             L.OP_AVGPOOL_BWD: 'avgpool_bwd', L.OP_ALLREDUCE: 'allreduce'}
     return other.get(op.opcode, 'op%d' % op.opcode), 0.0, 0.0
 
 

@@ -11,8 +11,9 @@ What each part of the reference script maps to:
                                                        and layouts are Keras', so they convert 1:1)
   feature dump (:270-275)                           -> identical pickle: {'feat': {test index: (D,) float32}}
 Deviations, all stated at run time when they apply:
-  * --cls_base and --finetune raise NotImplementedError (attaching the classifier to an inner layer / partial weight
-    loading with frozen layers are not part of the accelerated path); --log_dir is accepted and ignored with a message;
+  * --cls_base raises NotImplementedError (attaching the classifier to an inner layer is not part of the accelerated
+    path); --finetune reads this package's own dumps (pickle / .npz of Keras-named arrays), not Keras HDF5; --log_dir is
+    accepted and ignored with a message;
   * --gpus N > 1: launch with `python -m torch.distributed.run --nproc-per-node N learn_image_embeddings.py ...`
     (one process per GPU, NCCL all-reduce; the reference's in-graph towers have the same arithmetic);
   * datasets: 'CIFAR-100' / 'CIFAR-10' (python pickles, datasets/cifar.py) and 'synthetic[:n]';
@@ -104,12 +105,36 @@ def run_validation(eng, data, ks, embed_dst):
     return out, (np.concatenate(cls_pred) if cls_pred else None)
 
 
+def load_weights_by_name(eng, path):
+    """model.load_weights(path, by_name=True, skip_mismatch=True) (learn_image_embeddings.py:185) for this package's own
+    dumps: a pickle written by --model_dump / --weight_dump / --snapshot ({'weights': {name: array}}) or an .npz of named
+    arrays.  (The reference's HDF5 files need h5py + Keras, which this image does not have.)  Returns (loaded, skipped)."""
+    if path.endswith('.npz'):
+        with np.load(path) as z:
+            weights = {k: z[k] for k in z.files}
+    else:
+        with open(path, 'rb') as f:
+            blob = pickle.load(f)
+        weights = blob['weights'] if isinstance(blob, dict) and 'weights' in blob else blob
+    loaded, skipped, take = [], [], {}
+    for name, a in weights.items():
+        spec = eng.pspecs.get(name)
+        if spec is not None and tuple(np.shape(a)) == tuple(spec.shape):
+            take[name] = a
+            loaded.append(name)
+        else:
+            skipped.append(name)
+    eng.set_weights(take)
+    return loaded, skipped
+
+
 def main(argv=None):
     args = build_parser().parse_args(argv)
     if args.val_batch_size is None:
         args.val_batch_size = args.batch_size
-    if args.cls_base is not None or args.finetune:
-        raise NotImplementedError('--cls_base / --finetune are outside the accelerated hot path (SURVEY.md section 8)')
+    if args.cls_base is not None:
+        raise NotImplementedError('--cls_base (classifier attached to an inner layer) is outside the accelerated hot path '
+                                  '(SURVEY.md section 8)')
 
     import torch
     from semantic_embeddings_b200 import _lib
@@ -163,20 +188,17 @@ def main(argv=None):
         eng.set_iterations(snap.get('iterations', 0))
     broadcast_parameters([eng.P, eng.S, eng.V, eng.lr_dev])
 
-    sched = callbacks[0]
-    sched.on_train_begin()          # like the reference, a resumed run starts a fresh SGDR cycle (the callback is new)
     ks = tuple(args.top_k_acc)
-    monitor = args.snapshot_best
-    best = None
     rng = np.random.RandomState(1234)          # identical stream on every rank: the permutation is shared, slices differ
-    for epoch in range(args.initial_epoch, epochs):
-        eng.set_lr(sched.lr)
+
+    def train_epoch():
+        """One pass over the training set; running means of the per-batch metrics (Keras progress bar)."""
         sums, nb, pending = {}, 0, None
         for idx, y in data.train_batches(args.batch_size, rng, rank, world):
             data.compose_batch(idx, True, eng.x, augment=True, rng=rng)
             eng.labels.copy_(torch.from_numpy(np.asarray(y, dtype=np.int32)), non_blocking=True)
             eng.train_step()
-            h = eng.metrics_async()              # running means of the epoch without stalling the device (Keras progress bar)
+            h = eng.metrics_async()              # without stalling the device
             if pending is not None:
                 for k, v in eng.metrics_result(pending).items():
                     sums[k] = sums.get(k, 0.0) + v
@@ -186,7 +208,42 @@ def main(argv=None):
             for k, v in eng.metrics_result(pending).items():
                 sums[k] = sums.get(k, 0.0) + v
             nb += 1
-        logs = {k: v / max(nb, 1) for k, v in sums.items()}
+        return {k: v / max(nb, 1) for k, v in sums.items()}
+
+    # Load pre-trained weights and train the new layers for a few epochs (learn_image_embeddings.py:183-207)
+    if args.finetune:
+        say('Loading pre-trained weights from {}'.format(args.finetune))
+        loaded, skipped = load_weights_by_name(eng, args.finetune)
+        say('  {} tensors loaded, {} skipped (unknown name or shape mismatch)'.format(len(loaded), len(skipped)))
+        broadcast_parameters([eng.P, eng.S])
+        if args.finetune_init > 0:
+            say('Pre-training new layers')
+            last = [n for n in graph.nodes if any(k.startswith(n.name + '/') for k in eng.offsets)][-1].name
+            new_layers = {'embedding', 'prob', last}      # :188-190 (the embedding model's last layer stays trainable)
+            frozen = eng.set_trainable(lambda name: name.split('/')[0] in new_layers)
+            say('  {} of {} parameter tensors frozen'.format(len(frozen), len(eng.offsets)))
+            dec = float(eng.lr_dev[1].item())
+            eng.lr_dev[1:2].fill_(0.0)                     # this phase's optimizer: SGD(lr=sgd_lr) without decay (:192-199)
+            eng.set_lr(args.sgd_lr)
+            for ep in range(args.finetune_init):
+                logs = train_epoch()
+                val, _ = run_validation(eng, data, ks, None)
+                logs.update({'val_' + k: v for k, v in val.items()})
+                say('Epoch {}/{} - '.format(ep + 1, args.finetune_init) +
+                    ' - '.join('{}: {:.4f}'.format(k, logs[k]) for k in sorted(logs)))
+            eng.set_trainable(None)
+            eng.V.zero_()                                  # the full-model phase compiles a new optimizer (:228-236)
+            eng.set_iterations(0)
+            eng.lr_dev[1:2].fill_(dec)
+            say('Full model training')
+
+    sched = callbacks[0]
+    sched.on_train_begin()          # like the reference, a resumed run starts a fresh SGDR cycle (the callback is new)
+    monitor = args.snapshot_best
+    best = None
+    for epoch in range(args.initial_epoch, epochs):
+        eng.set_lr(sched.lr)
+        logs = train_epoch()
         val, _ = run_validation(eng, data, ks, None)
         logs.update({'val_' + k: v for k, v in val.items()})
         logs['val_loss'] = val.get('total', val['loss'])

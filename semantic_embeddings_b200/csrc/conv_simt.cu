@@ -644,9 +644,63 @@ static int launch_fwd_stem(const ConvP& p, const float* x, const float* w, const
   return check_launch("conv_fwd_stem_kernel");
 }
 
+// Dense layer on a skinny batch (the 2048 -> 555 'embedding' layer of config 4 at 32 rows: utils.py:242): the generic
+// tile kernel has 9 CTAs walking K = 2048 serially (0.42 ms).  Here a CTA owns 8 output columns and splits K over 32
+// thread groups (each thread 4 consecutive k per step: one 16-byte load of x per row, four of w), 32 rows of fp32
+// accumulators per thread, one shared-memory reduction at the end.  y = x W + b [relu].
+constexpr int DS_COLS = 8, DS_KL = 32, DS_ROWS = 32;
+__global__ void __launch_bounds__(DS_COLS * DS_KL)
+dense_small_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
+                       float* __restrict__ y, int B, int Cin, int Cout, int relu) {
+  pdl_grid_sync();
+  __shared__ float red[DS_KL][DS_ROWS][DS_COLS + 1];
+  const int c = threadIdx.x % DS_COLS, kl = threadIdx.x / DS_COLS;
+  const int col = blockIdx.x * DS_COLS + c;
+  const bool col_ok = col < Cout;
+  for (int r0 = 0; r0 < B; r0 += DS_ROWS) {
+    float acc[DS_ROWS];
+#pragma unroll
+    for (int b = 0; b < DS_ROWS; ++b) acc[b] = 0.f;
+    for (int k = kl * 4; k < Cin; k += DS_KL * 4) {
+      float wv[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) wv[j] = col_ok ? __ldg(w + (long long)(k + j) * Cout + col) : 0.f;
+#pragma unroll
+      for (int b = 0; b < DS_ROWS; ++b) {
+        if (r0 + b < B) {
+          const float4 xv = __ldg(reinterpret_cast<const float4*>(x + (long long)(r0 + b) * Cin + k));
+          acc[b] = fmaf(xv.x, wv[0], acc[b]); acc[b] = fmaf(xv.y, wv[1], acc[b]);
+          acc[b] = fmaf(xv.z, wv[2], acc[b]); acc[b] = fmaf(xv.w, wv[3], acc[b]);
+        }
+      }
+    }
+    __syncthreads();                                   // (the previous row chunk's reduction has been read)
+#pragma unroll
+    for (int b = 0; b < DS_ROWS; ++b) red[kl][b][c] = acc[b];
+    __syncthreads();
+    for (int o = threadIdx.x; o < DS_ROWS * DS_COLS; o += DS_COLS * DS_KL) {
+      const int b = o / DS_COLS, cc = o % DS_COLS, oc = blockIdx.x * DS_COLS + cc;
+      if (r0 + b < B && oc < Cout) {
+        float s = 0.f;
+#pragma unroll 8
+        for (int g = 0; g < DS_KL; ++g) s += red[g][b][cc];
+        if (bias) s += bias[oc];
+        if (relu) s = fmaxf(s, 0.f);
+        y[(long long)(r0 + b) * Cout + oc] = s;
+      }
+    }
+  }
+}
+
 int conv_fwd_simt(const se_conv_desc* d, const float* x, const float* w, const float* bias, const float* residual,
                   float* y, int relu, double* stats, cudaStream_t st) {
   ConvP p = to_p(d);
+  if (p.kh == 1 && p.kw == 1 && p.H == 1 && p.W == 1 && p.Ho == 1 && p.Wo == 1 && p.N <= 64 && p.Cin >= 512 && p.Cin % 4 == 0 &&
+      !residual && !stats && (reinterpret_cast<uintptr_t>(x) & 15) == 0) {
+    launch(dense_small_fwd_kernel, dim3(ceil_div(p.Cout, DS_COLS)), dim3(DS_COLS * DS_KL), 0, st, x, w, bias, y, p.N, p.Cin,
+           p.Cout, relu);
+    return check_launch("dense_small_fwd_kernel");
+  }
   if (p.kh == 3 && p.kw == 3 && p.stride == 1 && p.pad_t == 1 && p.pad_l == 1 && p.Ho == p.H && p.Wo == p.W && p.Cin <= 4 &&
       !residual) {
     int rc = launch_fwd_stem(p, x, w, bias, y, relu, stats, st);

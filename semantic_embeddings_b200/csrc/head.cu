@@ -18,6 +18,7 @@
 namespace se {
 
 constexpr int HEAD_WARPS = 4;
+constexpr int HEAD_WARPS_SPLIT = 8;     // warps of a CTA that share one row's class loop (embed_head_kernel, split mode)
 
 template <bool VEC>
 __device__ __forceinline__ float warp_dot(const float* __restrict__ a_smem, const float* __restrict__ b_gmem, int D,
@@ -36,14 +37,18 @@ __device__ __forceinline__ float warp_dot(const float* __restrict__ a_smem, cons
 }
 
 template <bool VEC>
-__global__ void __launch_bounds__(HEAD_WARPS * 32)
+__global__ void __launch_bounds__(HEAD_WARPS_SPLIT * 32)
 embed_head_kernel(const float* __restrict__ z, int ldz, const int* __restrict__ labels, const float* __restrict__ E,
                   int ldE, int B, int D, int C, int loss_kind, float loss_scale, const float* __restrict__ extra_dx,
                   float* __restrict__ x_out, float* __restrict__ loss, float* __restrict__ acc, float* __restrict__ dz,
-                  float* __restrict__ rank_out, int es_classes) {
+                  float* __restrict__ rank_out, int es_classes, int split) {
+  // split == 0: one row per warp.  split == 1 (large class matrices read from global memory): one row per CTA -- every
+  // warp holds the row, the warps share the class loop of the accuracy metric, warp 0 writes the row's outputs.
   pdl_grid_sync();
   extern __shared__ __align__(16) float smem[];
+  __shared__ float s_red[HEAD_WARPS_SPLIT][4];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nw = blockDim.x >> 5;
   const int Dp = (D + 3) & ~3;
   float* xs = smem + warp * Dp;  // this warp's row (wrapped output x)
   // class matrix staged in shared memory (row pitch D+1: conflict-free when every lane walks its own class row);
@@ -55,8 +60,10 @@ embed_head_kernel(const float* __restrict__ z, int ldz, const int* __restrict__ 
       for (int i = lane; i < D; i += 32) Es[c * (D + 1) + i] = E[(long long)c * ldE + i];
     __syncthreads();
   }
-  const int row = blockIdx.x * HEAD_WARPS + warp;
-  if (row >= B) return;
+  const int row = split ? blockIdx.x : blockIdx.x * HEAD_WARPS + warp;
+  if (row >= B) return;                          // (uniform over the CTA when split)
+  const bool lead = !split || warp == 0;         // this warp writes the row's outputs
+  const int c_first = split ? warp * 32 + lane : lane, c_step = split ? 32 * nw : 32;
   const float* zr = z + (long long)row * ldz;
 
   // ---- load z, sum of squares
@@ -91,7 +98,7 @@ embed_head_kernel(const float* __restrict__ z, int ldz, const int* __restrict__ 
     for (int i = lane; i < D; i += 32) xs[i] *= is;
   }
   __syncwarp();
-  if (x_out) {
+  if (x_out && lead) {
     float* xo = x_out + (long long)row * ldz;
     if (VEC) {
       for (int i = lane; i < (D >> 2); i += 32)
@@ -116,7 +123,7 @@ embed_head_kernel(const float* __restrict__ z, int ldz, const int* __restrict__ 
   } else {
     l = 1.f - true_sim;
   }
-  if (loss && lane == 0) loss[row] = l;
+  if (loss && lane == 0 && lead) loss[row] = l;
 
   // ---- accuracy: nearest class over the whole class matrix (utils.py:73-93)
   if (loss_kind == SE_LOSS_SOFTMAX_CORR) {
@@ -141,103 +148,64 @@ embed_head_kernel(const float* __restrict__ z, int ldz, const int* __restrict__ 
       above = warp_sum(above);
       if (lane == 0) { if (acc) acc[row] = (ax == at) ? 1.f : 0.f; if (rank_out) rank_out[row] = above; }
     }
-  } else if (want_acc && es_classes > 0) {
-    // one class per lane and step: 2 shared loads per FMA, no shuffles inside the loop
+  } else if (want_acc) {
+    // one class per lane and step, no shuffles inside the loop.  The class matrix comes from shared memory when it fits
+    // (2 shared loads per FMA), else every lane streams its own row of E from global memory: a lane's 128-byte line
+    // serves its next 32 steps from L1, and 32 rows are in flight per warp (a warp-per-class loop with a shuffle
+    // reduction per class was latency-bound: 1.6 ms for 32 rows x 555 classes x 555 dimensions)
+    const float* Eb = es_classes > 0 ? Es : E;
+    const long long ep = es_classes > 0 ? (long long)(D + 1) : (long long)ldE;
     float best = (loss_kind == SE_LOSS_MSE) ? FLT_MAX : -FLT_MAX;
     float mine = -FLT_MAX;                          // this row's own class, from the same summation order as `best`
-    for (int c = lane; c < C; c += 32) {
-      const float* e = Es + c * (D + 1);
+    for (int c = c_first; c < C; c += c_step) {
+      const float* e = Eb + c * ep;
       float sim = 0.f, en = 0.f;
+#pragma unroll 8
       for (int i = 0; i < D; ++i) { const float b = e[i]; sim = fmaf(xs[i], b, sim); en = fmaf(b, b, en); }
       if (loss_kind == SE_LOSS_MSE) { const float dist = xnorm2 + en - 2.f * sim; best = fminf(best, dist); if (c == lab) mine = -dist; }
       else { best = fmaxf(best, sim); if (c == lab) mine = sim; }
     }
     best = (loss_kind == SE_LOSS_MSE) ? -warp_max(-best) : warp_max(best);
     mine = warp_max(mine);
+    if (split) {                                  // combine the warps' shares of the class loop
+      if (lane == 0) { s_red[warp][0] = (loss_kind == SE_LOSS_MSE) ? -best : best; s_red[warp][1] = mine; }
+      __syncthreads();
+      float bb = -FLT_MAX, mm = -FLT_MAX;
+      for (int w2 = 0; w2 < nw; ++w2) { bb = fmaxf(bb, s_red[w2][0]); mm = fmaxf(mm, s_red[w2][1]); }
+      best = (loss_kind == SE_LOSS_MSE) ? -bb : bb;
+      mine = mm;
+    }
     // the true class' score comes from the SAME expression as the other classes' (in exact arithmetic it equals
     // utils.py:80,91's separately computed true_dist / true_sim; in fp32 the two differ by more than the 1e-6 threshold
     // for distances of O(10), which would make the metric a coin flip)
     const float ref = (loss_kind == SE_LOSS_MSE) ? -mine : mine;
-    if (acc && lane == 0) acc[row] = (fabsf(best - ref) < 1e-6f) ? 1.f : 0.f;
+    if (acc && lane == 0 && lead) acc[row] = (fabsf(best - ref) < 1e-6f) ? 1.f : 0.f;
     if (rank_out) {
       // top-k form of the metric (utils.py:85,95: any of the k best values within 1e-6 of the true one) for every k at
       // once: with G = classes better than the true value by >= 1e-6 and T = classes within 1e-6 of it, the k best
       // contain a member of T iff G < k (and T is not empty) -> rank = G, or C when T is empty
       float gcnt = 0.f, tcnt = 0.f;
-      for (int c = lane; c < C; c += 32) {
-        const float* e = Es + c * (D + 1);
+      for (int c = c_first; c < C; c += c_step) {
+        const float* e = Eb + c * ep;
         float sim = 0.f, en = 0.f;
+#pragma unroll 8
         for (int i = 0; i < D; ++i) { const float b = e[i]; sim = fmaf(xs[i], b, sim); en = fmaf(b, b, en); }
         const float v = (loss_kind == SE_LOSS_MSE) ? -(xnorm2 + en - 2.f * sim) : sim;      // larger = better
         if (fabsf(v - mine) < 1e-6f) tcnt += 1.f; else if (v > mine) gcnt += 1.f;
       }
       gcnt = warp_sum(gcnt); tcnt = warp_sum(tcnt);
-      if (lane == 0) rank_out[row] = tcnt > 0.f ? gcnt : (float)C;
-    }
-  } else if (want_acc) {
-    float best = (loss_kind == SE_LOSS_MSE) ? FLT_MAX : -FLT_MAX;
-    float gcnt = 0.f, tcnt = 0.f, mine = -FLT_MAX;  // rank of the true class (see the shared-memory path above)
-    // four classes per iteration: independent partial sums keep four rows of E in flight (the loop is latency-bound)
-    for (int c = 0; c < C; c += 4) {
-      float ps[4] = {0.f, 0.f, 0.f, 0.f}, pe[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int cc = min(c + u, C - 1);
-        const float* e = E + (long long)cc * ldE;
-        if (VEC) {
-          for (int i = lane; i < (D >> 2); i += 32) {
-            float4 b = *reinterpret_cast<const float4*>(e + 4 * i);
-            float4 a = *reinterpret_cast<const float4*>(xs + 4 * i);
-            ps[u] = fmaf(a.x, b.x, ps[u]); ps[u] = fmaf(a.y, b.y, ps[u]); ps[u] = fmaf(a.z, b.z, ps[u]); ps[u] = fmaf(a.w, b.w, ps[u]);
-            pe[u] = fmaf(b.x, b.x, pe[u]); pe[u] = fmaf(b.y, b.y, pe[u]); pe[u] = fmaf(b.z, b.z, pe[u]); pe[u] = fmaf(b.w, b.w, pe[u]);
-          }
-        } else {
-          for (int i = lane; i < D; i += 32) { float b = e[i]; ps[u] = fmaf(xs[i], b, ps[u]); pe[u] = fmaf(b, b, pe[u]); }
-        }
+      if (split) {
+        if (lane == 0) { s_red[warp][2] = gcnt; s_red[warp][3] = tcnt; }
+        __syncthreads();
+        gcnt = 0.f; tcnt = 0.f;
+        for (int w2 = 0; w2 < nw; ++w2) { gcnt += s_red[w2][2]; tcnt += s_red[w2][3]; }
       }
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        float sim = warp_sum(ps[u]);
-        float v;
-        if (loss_kind == SE_LOSS_MSE) {
-          float en = warp_sum(pe[u]);                   // centroids_norm (utils.py:76)
-          const float dist = xnorm2 + en - 2.f * sim;
-          best = fminf(best, dist);
-          v = -dist;
-        } else {
-          best = fmaxf(best, sim);
-          v = sim;
-        }
-        // the true class' score from the same expression (see the shared-memory path); classes are visited in ascending
-        // order, so classes before the label are re-examined below once its score is known
-        if (c + u == lab) mine = v;
-      }
-    }
-    const float ref = (loss_kind == SE_LOSS_MSE) ? -mine : mine;
-    if (rank_out) {
-      for (int c = 0; c < C; c += 4) {
-        float ps[4] = {0.f, 0.f, 0.f, 0.f}, pe[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const float* e = E + (long long)min(c + u, C - 1) * ldE;
-          for (int i = lane; i < D; i += 32) { float b = e[i]; ps[u] = fmaf(xs[i], b, ps[u]); pe[u] = fmaf(b, b, pe[u]); }
-        }
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const float sim = warp_sum(ps[u]);
-          const float v = (loss_kind == SE_LOSS_MSE) ? -(xnorm2 + warp_sum(pe[u]) - 2.f * sim) : sim;
-          if (c + u < C) { if (fabsf(v - mine) < 1e-6f) tcnt += 1.f; else if (v > mine) gcnt += 1.f; }
-        }
-      }
-    }
-    if (lane == 0) {
-      if (acc) acc[row] = (fabsf(best - ref) < 1e-6f) ? 1.f : 0.f;
-      if (rank_out) rank_out[row] = tcnt > 0.f ? gcnt : (float)C;
+      if (lane == 0 && lead) rank_out[row] = tcnt > 0.f ? gcnt : (float)C;
     }
   }
 
   // ---- backward
-  if (dz) {
+  if (dz && lead) {
     float* dzr = dz + (long long)row * ldz;
     const float* ex = extra_dx ? extra_dx + (long long)row * ldz : nullptr;
     if (loss_kind == SE_LOSS_INV_CORR) {
@@ -341,18 +309,23 @@ extern "C" int se_embed_head_fwd_bwd_ex(const float* z, int ldz, const int32_t* 
   const int Dp = (D + 3) & ~3;
   size_t smem = (size_t)HEAD_WARPS * Dp * sizeof(float);
   SE_REQUIRE(smem <= 48 * 1024, "D too large for the fused head (max 3072)");
+  int nwarps = HEAD_WARPS, split = 0;
   auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
   bool vec = (D % 4 == 0) && (ldz % 4 == 0) && (ldE % 4 == 0) && al16(z) && al16(E) && (!x_out || al16(x_out));
   int grid = ceil_div(B, HEAD_WARPS);
   int es_classes = 0;
   const size_t es_bytes = (size_t)C * (D + 1) * sizeof(float);
   if ((acc || rank_out) && loss_kind != SE_LOSS_SOFTMAX_CORR && smem + es_bytes <= 48 * 1024) { es_classes = C; smem += es_bytes; }
+  else if ((acc || rank_out) && loss_kind != SE_LOSS_SOFTMAX_CORR && (size_t)HEAD_WARPS_SPLIT * Dp * sizeof(float) <= 48 * 1024) {
+    // the class matrix stays in global memory: the loop over it is latency-bound per warp, so a row gets a whole CTA
+    split = 1; nwarps = HEAD_WARPS_SPLIT; grid = B; smem = (size_t)HEAD_WARPS_SPLIT * Dp * sizeof(float);
+  }
   if (vec)
-    launch(embed_head_kernel<true>, dim3(grid), dim3(HEAD_WARPS * 32), smem, as_stream(stream), z, ldz, labels, E, ldE, B, D, C, loss_kind,
-           loss_scale, extra_dx, x_out, loss, acc, dz, rank_out, es_classes);
+    launch(embed_head_kernel<true>, dim3(grid), dim3(nwarps * 32), smem, as_stream(stream), z, ldz, labels, E, ldE, B, D, C, loss_kind,
+           loss_scale, extra_dx, x_out, loss, acc, dz, rank_out, es_classes, split);
   else
-    launch(embed_head_kernel<false>, dim3(grid), dim3(HEAD_WARPS * 32), smem, as_stream(stream), z, ldz, labels, E, ldE, B, D, C, loss_kind,
-           loss_scale, extra_dx, x_out, loss, acc, dz, rank_out, es_classes);
+    launch(embed_head_kernel<false>, dim3(grid), dim3(nwarps * 32), smem, as_stream(stream), z, ldz, labels, E, ldE, B, D, C, loss_kind,
+           loss_scale, extra_dx, x_out, loss, acc, dz, rank_out, es_classes, split);
   return check_launch("embed_head_kernel");
 }
 

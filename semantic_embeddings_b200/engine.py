@@ -190,6 +190,8 @@ class Engine:
         self.seg_array = (_lib.L2Segment * max(1, len(self.segments)))()
         for k, (b, e, l) in enumerate(self.segments):
             self.seg_array[k].begin, self.seg_array[k].end, self.seg_array[k].l2 = b, e, l
+        self.n_active_segs = len(self.segments)
+        self.frozen_runs = []                 # (offset, length) runs of the flat buffers that set_trainable() froze
         # activations and their gradients
         g = self.g
         self.act, self.grad = {}, {}
@@ -513,11 +515,7 @@ class Engine:
                 da, ba = gb(n.inputs[0])
                 bwd.append(self._op(_lib.OP_ADD_BWD, [1, dY.numel()], [ba, 0.0], [dY, A[n.output.name], da, None]))
         # ---------------- optimizer
-        opt = [self._op(_lib.OP_MEMSET, p=[self.sgd_out, 16]),
-               self._op(_lib.OP_SGD_PREPARE, [len(self.segments)],
-                        p=[self.P, self.G, self.nparams, ctypes.addressof(self.seg_array), self.sgd_out]),
-               self._op(_lib.OP_SGD_APPLY, [1 if self.nesterov else 0], [self.momentum, self.clipnorm],
-                        [self.P, self.G, self.nparams, self.lr_dev, self.sgd_out, self.V])]
+        opt = self._opt_ops()
         ev = []
         for o in inf:                               # validation pass: inference-mode forward that also writes the metrics
             if o.opcode == _lib.OP_HEAD:
@@ -529,9 +527,67 @@ class Engine:
         self.plans = {'fwd': self._pack(fwd), 'bwd': self._pack(bwd), 'opt': self._pack(opt), 'infer': self._pack(inf),
                       'eval': self._pack(ev),
                       'fwdbwd': self._pack(fwd + bwd), 'step': self._pack(fwd + bwd + opt)}
+        self._parts = {'fwd': fwd, 'bwd': bwd, 'final': final}
         if self.world > 1:
             # data parallel: the same step with bucketed all-reduces inside the backward pass (one graph, no host in between)
-            self.plans['step_dp'] = self._pack(fwd + self._with_allreduce(bwd, final) + opt)
+            self._parts['bwd_dp'] = self._with_allreduce(bwd, final)
+            self.plans['step_dp'] = self._pack(fwd + self._parts['bwd_dp'] + opt)
+
+    def _opt_ops(self):
+        """Optimizer ops of a step: [zero the gradients of frozen parameters], global norm + L2 terms, clip + SGD update."""
+        nbytes = lambda t: t.numel() * t.element_size()
+        freeze = [self._op(_lib.OP_MEMSET, p=[self.G[o:o + n], nbytes(self.G[o:o + n])]) for o, n in self.frozen_runs]
+        return freeze + [
+            self._op(_lib.OP_MEMSET, p=[self.sgd_out, 16]),
+            self._op(_lib.OP_SGD_PREPARE, [self.n_active_segs],
+                     p=[self.P, self.G, self.nparams, ctypes.addressof(self.seg_array), self.sgd_out]),
+            self._op(_lib.OP_SGD_APPLY, [1 if self.nesterov else 0], [self.momentum, self.clipnorm],
+                     [self.P, self.G, self.nparams, self.lr_dev, self.sgd_out, self.V])]
+
+    def set_trainable(self, trainable=None):
+        """Keras `layer.trainable` for the optimizer (learn_image_embeddings.py:188-190 freezes everything but the new layers
+        for the first `--finetune_init` epochs, :205-206 thaws): `trainable` is a predicate on parameter names
+        ('<layer>/kernel', ...; None = all).  A frozen parameter gets no update at all -- its data gradient is zeroed before
+        the global clipping norm is taken and its L2 term is left out (Keras differentiates the total loss with respect to
+        the trainable weights only); forward, backward and the BatchNorm moving statistics run as before (Keras 2.2
+        semantics).  Returns the names that are now frozen."""
+        size = lambda n: (int(np.prod(self.offsets[n][1])) + 3) // 4 * 4
+        frozen = [n for n in self.offsets if trainable is not None and not trainable(n)]
+        runs = []
+        for off, sz in sorted((self.offsets[n][0], size(n)) for n in frozen):
+            if runs and runs[-1][0] + runs[-1][1] == off:
+                runs[-1][1] += sz
+            else:
+                runs.append([off, sz])
+        segs = []
+        for b, e, l in self.segments:            # L2 segments minus the frozen runs
+            cur = b
+            for off, sz in runs:
+                lo, hi = max(off, cur), min(off + sz, e)
+                if lo < hi:
+                    if cur < lo:
+                        segs.append((cur, lo, l))
+                    cur = hi
+            if cur < e:
+                segs.append((cur, e, l))
+        if len(segs) > len(self.seg_array):
+            if len(segs) > 8:
+                raise ValueError('the trainable set cuts the L2 segments into %d pieces (at most 8)' % len(segs))
+            self.seg_array = (_lib.L2Segment * len(segs))()
+        for k, (b, e, l) in enumerate(segs):
+            self.seg_array[k].begin, self.seg_array[k].end, self.seg_array[k].l2 = b, e, l
+        self.n_active_segs = len(segs)
+        self.frozen_runs = [tuple(r) for r in runs]
+        for off, sz in self.frozen_runs:          # no momentum carried into (or out of) the frozen phase
+            self.V[off:off + sz].zero_()
+        opt = self._opt_ops()
+        self.plans['opt'] = self._pack(opt)
+        self.plans['step'] = self._pack(self._parts['fwd'] + self._parts['bwd'] + opt)
+        if 'bwd_dp' in self._parts:
+            self.plans['step_dp'] = self._pack(self._parts['fwd'] + self._parts['bwd_dp'] + opt)
+        for k in ('opt', 'step', 'step_dp'):
+            self._graphs.pop(k, None)
+        return frozen
 
     def _with_allreduce(self, bwd, final):
         """Backward plan with SE_OP_ALLREDUCE ops: the flat gradient buffer is cut into `grad_buckets` buckets in the order

