@@ -69,7 +69,11 @@ int se_tc_capabilities(void);
  * Conv2D of models/cifar_resnet.py:96-105,218, models/plainnet.py:52,70,
  * models/wide_residual_network.py:9,20,28,31,46,53 and keras.applications.ResNet50 (utils.py:237).
  * Explicit zero padding (pad_t, pad_l) and output size: the host computes TF 'SAME'
- * (pad_before = total//2, so k=3,s=2 on an even input gives pad 0 before / 1 after). */
+ * (pad_before = total//2, so k=3,s=2 on an even input gives pad 0 before / 1 after).
+ * In SE_MODE_TF32 / SE_MODE_TF32X3 the tcgen05 kernels take: 3x3 / stride 1 / pad 1 on image widths 4..56 (weight
+ * gradient: ..64), 1x1 / stride 1 / pad 0 on any image size (>= 128 pixels per call), 1x1 / stride 2 / pad 0 with
+ * Wo <= 32 -- channel counts in multiples of 16 (the GEMM K dimension: 16 or a multiple of 32).  Every other shape
+ * (3-channel stems, 3x3 / stride 2, 7x7, dense layers) runs on the fp32 kernels in every mode. */
 typedef struct {
   int32_t N, H, W, Cin;   /* input  NHWC */
   int32_t Cout, kh, kw;   /* kernel HWIO */

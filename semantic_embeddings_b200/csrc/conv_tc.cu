@@ -1,7 +1,13 @@
 // tcgen05 (kind::tf32) implicit-GEMM convolution for 3x3 / stride 1 / 'same' layers -- the bulk of every
 // reference architecture (models/cifar_resnet.py:96-105, models/wide_residual_network.py:20-53,
-// models/plainnet.py:52,70) -- forward and data gradient.  fp32 NHWC activations are read as TF32 operands
-// straight from HBM/L2 (no conversion pass), fp32 accumulation in TMEM.
+// models/plainnet.py:52,70) -- and for the 1x1 layers (stride 1 and 2) of keras.applications.ResNet50 (utils.py:237) and
+// of the wide-ResNet shortcuts (wide_residual_network.py:28): forward and data gradient.  fp32 NHWC activations are read
+// as TF32 operands straight from HBM/L2 (no conversion pass), fp32 accumulation in TMEM.
+//
+// The description below is the 3x3 case with image rows that divide 32 (template GEN = 0: every 3x3 layer of the CIFAR
+// networks).  GEN = 1 adds, with the same pipeline: 1x1 as a GEMM over the flat pixel list (one accumulator block, no
+// taps), 1x1 / stride 2 through tensor maps of the sub-sampled view x[:, ::2, ::2, :], and 3x3 on any row width up to 56
+// ("padded row slots" and strips: see ConvTcParams and plan_geometry).
 //
 //   GEMM view   P[m, (s, n)] = sum_{r, k} A_r[m, k] * B_r[(s, n), k]      y[h, w, n] = sum_s P[(h, w + s - 1), (s, n)]
 //     m : 128 output pixels of one tile = a (W x Hb x Nb) box of the NHWC tensor
@@ -150,10 +156,15 @@ __device__ __forceinline__ void tmem_ld_cols<16>(uint32_t taddr, uint32_t (&v)[1
 
 // One block of NC output channels of one pixel: combine the three horizontal partial sums, apply the epilogue
 // ops, store, and (optionally) fold the stored values into the BatchNorm statistics.
-template <int NC>
+template <int NC, int GEN>
 __device__ __forceinline__ void conv_tc_load_combine(const ConvTcParams& p, uint32_t t_addr, int lblk, int c0, bool has_left,
                                                      bool has_right, float (&o)[NC]) {
-  if (p.taps == 1) {                              // 1x1: the accumulator is the result
+  // GEN == 0: the 3x3 layers whose image rows divide 32 (every layer of the CIFAR networks) -- the generic features below
+  // fold to constants and their code disappears from that instantiation
+  const int k_taps = GEN ? p.taps : 3, k_NS = GEN ? p.NS : 1, k_pad = GEN ? p.pad : 1;
+  const bool k_padded = GEN && p.padded, k_flat = GEN && p.flat;
+  (void)k_taps; (void)k_NS; (void)k_pad; (void)k_padded; (void)k_flat;
+  if (k_taps == 1) {                              // 1x1: the accumulator is the result
     uint32_t v1[NC];
     tmem_ld_cols<NC>(t_addr + c0, v1);
     tmem_ld_wait();
@@ -187,19 +198,24 @@ __device__ __forceinline__ void stage_put(uint8_t* sub, int lane, int q, float4 
   *reinterpret_cast<float4*>(sub + lane * 64 + ((q ^ ((lane >> 1) & 3)) << 4)) = val;
 }
 
-template <int NC>
+template <int NC, int GEN>
 __device__ __forceinline__ void conv_tc_epilogue_block(const ConvTcParams& p, const CUtensorMap* map_o, uint32_t t_addr, int lblk,
                                                        int c0, int tn, bool valid, bool has_left, bool has_right, int row0,
                                                        uint8_t* stg, const float* exrow, const float* s_bias, float* sw,
                                                        int lane, long long* dbg = nullptr, int srow = -1, int sc1 = 0,
                                                        int sc3 = 0) {
+  // GEN == 0: the 3x3 layers whose image rows divide 32 (every layer of the CIFAR networks) -- the generic features below
+  // fold to constants and their code disappears from that instantiation
+  const int k_taps = GEN ? p.taps : 3, k_NS = GEN ? p.NS : 1, k_pad = GEN ? p.pad : 1;
+  const bool k_padded = GEN && p.padded, k_flat = GEN && p.flat;
+  (void)k_taps; (void)k_NS; (void)k_pad; (void)k_padded; (void)k_flat;
   // srow: staging row of this lane (-1: none -- a lane outside its strip); padded mode stores at (channel, sc1, row0, sc3)
-  if (!p.padded) srow = lane;
+  if (!k_padded) srow = lane;
   // exrow: residual row of this pixel (forward only)
   const bool live = valid && !(p.debug & 4);
   if (dbg) dbg[0] = clock64();
   float o[NC];
-  conv_tc_load_combine<NC>(p, t_addr, lblk, c0, has_left, has_right, o);
+  conv_tc_load_combine<NC, GEN>(p, t_addr, lblk, c0, has_left, has_right, o);
   if (dbg) dbg[1] = clock64();
 #pragma unroll
   for (int q = 0; q < NC / 4; ++q) {
@@ -223,7 +239,7 @@ __device__ __forceinline__ void conv_tc_epilogue_block(const ConvTcParams& p, co
   if (lane == 0 && !(p.debug & 4)) {
 #pragma unroll
     for (int h = 0; h < NC / 16; ++h) {
-      if (p.padded) {
+      if (k_padded) {
         if (p.beta != 0.f) tma_reduce_add_4d(map_o, stg + h * 2048, tn * p.BN + c0 + 16 * h, sc1, row0, sc3);
         else tma_store_4d(map_o, stg + h * 2048, tn * p.BN + c0 + 16 * h, sc1, row0, sc3);
       } else if (p.beta != 0.f) tma_reduce_add_2d(map_o, stg + h * 2048, tn * p.BN + c0 + 16 * h, row0);   // dgrad accumulate
@@ -256,10 +272,15 @@ __device__ __forceinline__ void conv_tc_epilogue_block(const ConvTcParams& p, co
 // splitter warps (3 and 12) then rewrite the tile IN PLACE as lo, and pass 2 issues A_lo*B_hi.  The MMA thread runs
 // the two passes as two cursors over the same stage sequence (whichever is ready goes next), so pass 1 of the next
 // tile overlaps the split of the previous one.
-template <int X3>
+template <int X3, int GEN>
 __global__ void __maxnreg__(128)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                const __grid_constant__ CUtensorMap map_bl, const __grid_constant__ CUtensorMap map_o, ConvTcParams p) {
+  // GEN == 0: the 3x3 layers whose image rows divide 32 (every layer of the CIFAR networks) -- the generic features below
+  // fold to constants and their code disappears from that instantiation
+  const int k_taps = GEN ? p.taps : 3, k_NS = GEN ? p.NS : 1, k_pad = GEN ? p.pad : 1;
+  const bool k_padded = GEN && p.padded, k_flat = GEN && p.flat;
+  (void)k_taps; (void)k_NS; (void)k_pad; (void)k_padded; (void)k_flat;
   pdl_trigger();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -285,8 +306,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   const int t_end = (p.debug & 1) ? t_begin : min(total_tiles, t_begin + per_cta);
   const int row_bytes = p.cblk * 4;
   const int tiles_per_img = p.tpi;
-  const int strip_bytes = p.a_bytes / p.NS;                 // one strip of a filter row's A slab
-  const int b_rows = p.taps * p.BN;                         // B rows of one filter row: (s, n)
+  const int strip_bytes = p.a_bytes / k_NS;                 // one strip of a filter row's A slab
+  const int b_rows = k_taps * p.BN;                         // B rows of one filter row: (s, n)
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&map_a); prefetch_tmap(&map_b); prefetch_tmap(&map_o);
@@ -339,7 +360,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       uint8_t* sa = tiles + (size_t)stage * p.stage_bytes;
       if (p.single) tma_load_4d(sa, &map_a, &full[stage], 0, 0, h0 - 1, n0);      // rows h0-1 .. h0+Hb: halo rows included
       else for (int r = 0; r < 3; ++r)
-        for (int s = 0; s < p.NS; ++s)
+        for (int s = 0; s < k_NS; ++s)
           tma_load_4d(sa + r * p.a_bytes + s * strip_bytes, &map_a, &full[stage], 0, s * p.Ws - (s > 0), h0 + r - 1, n0);
       CT_TRACE(0, 2);
       if (++stage == p.stages) { stage = 0; phase ^= 1; }
@@ -349,7 +370,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       int n0, h0;
       if (p.Nb == 1) { n0 = tm / tiles_per_img; h0 = (tm % tiles_per_img) * p.Hb; }
       else { n0 = tm * p.Nb; h0 = 0; }
-      for (int rb = 0; rb < p.taps; rb += p.rg) {
+      for (int rb = 0; rb < k_taps; rb += p.rg) {
         for (int kb = 0; kb < p.kblocks; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1);
           CT_TRACE(0, 1);
@@ -358,22 +379,22 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           uint8_t* sb = sa + p.rg * p.a_bytes;
           for (int rr = 0; rr < p.rg; ++rr) {
             const int r = rb + rr;
-            if (p.flat) tma_load_4d(sa + rr * p.a_bytes, &map_a, &full[stage], kb * p.cblk, tm * CT_BM, 0, 0);
+            if (k_flat) tma_load_4d(sa + rr * p.a_bytes, &map_a, &full[stage], kb * p.cblk, tm * CT_BM, 0, 0);
             else if (!(p.debug & 2))
-              for (int s = 0; s < p.NS; ++s)
+              for (int s = 0; s < k_NS; ++s)
                 tma_load_4d(sa + rr * p.a_bytes + s * strip_bytes, &map_a, &full[stage], kb * p.cblk, s * p.Ws - (s > 0),
-                            h0 + r - p.pad, n0);
+                            h0 + r - k_pad, n0);
             uint8_t* sbr = sb + rr * b_rows * row_bytes;
             if (p.b_merged) {
               // one box of 3*BN rows: taps (r,0),(r,1),(r,2) are consecutive row blocks of B.  For dgrad the tap
               // index is reversed, so the box starts at tap 8-(3r+2) and holds the s-blocks in the order 2,1,0.
-              const int tap0 = p.flip ? p.taps * p.taps - 1 - (r * p.taps + p.taps - 1) : r * p.taps;
+              const int tap0 = p.flip ? k_taps * k_taps - 1 - (r * k_taps + k_taps - 1) : r * k_taps;
               tma_load_2d(sbr, &map_b, &full[stage], kb * p.cblk, tap0 * p.Nc);
               if (X3) tma_load_2d(sbr + p.rg * b_rows * row_bytes, &map_bl, &full[stage], kb * p.cblk, tap0 * p.Nc);
             } else {
-              for (int s = 0; s < p.taps; ++s) {
-                const int tap = r * p.taps + s;
-                const int btap = p.flip ? p.taps * p.taps - 1 - tap : tap;
+              for (int s = 0; s < k_taps; ++s) {
+                const int tap = r * k_taps + s;
+                const int btap = p.flip ? k_taps * k_taps - 1 - tap : tap;
                 tma_load_2d(sbr + s * p.BN * row_bytes, &map_b, &full[stage], kb * p.cblk, btap * p.Nc + tn * p.BN);
                 if (X3)
                   tma_load_2d(sbr + p.rg * b_rows * row_bytes + s * p.BN * row_bytes, &map_bl, &full[stage], kb * p.cblk,
@@ -388,7 +409,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     }
   } else if (warp == 1 && elect_one()) {
     // ===================== MMA issuer
-    const uint32_t idesc = umma_idesc(2 /*tf32*/, CT_BM, p.taps * p.BN);
+    const uint32_t idesc = umma_idesc(2 /*tf32*/, CT_BM, k_taps * p.BN);
     const uint32_t sbo = 8 * row_bytes;
     int stage = 0, phase = 0, tr_n = 0;
     CT_TRACE(1, 0);
@@ -403,7 +424,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       const uint32_t bres_lo = ((smem_u32(res_b) & 0x3FFFFu) >> 4) | (1u << 16);
       const int kst = p.cblk / 8;
       const int rows_u = p.res ? 3 : p.rg;                         // filter rows per unit
-      const int upt = p.res ? 1 : (p.taps / p.rg) * p.kblocks;     // units per tile
+      const int upt = p.res ? 1 : (k_taps / p.rg) * p.kblocks;     // units per tile
       const int U = (t_end - t_begin) * upt;
       const uint32_t a_step = (uint32_t)(p.res ? p.a_tap : p.a_bytes) >> 4, b_step = (uint32_t)(b_rows * row_bytes) >> 4;
       const uint32_t stage_step = (uint32_t)p.stage_bytes >> 4;
@@ -495,7 +516,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       fence_after_sync();
       const uint32_t d_tmem = tmem_base + acc * p.acc_stride;
       uint32_t first = 1;
-      for (int it = 0; it < (p.taps / p.rg) * p.kblocks; ++it) {
+      for (int it = 0; it < (k_taps / p.rg) * p.kblocks; ++it) {
         mbar_wait(&full[stage], phase);
         CT_TRACE(1, 2);
         fence_after_sync();
@@ -520,13 +541,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   } else if (X3 && warp == 2 && elect_one()) {
     // ===================== MMA issuer, pass 2 of the error-compensated mode: A_lo * B_hi
     if (t_begin < t_end) {
-      const uint32_t idesc = umma_idesc(2 /*tf32*/, CT_BM, p.taps * p.BN);
+      const uint32_t idesc = umma_idesc(2 /*tf32*/, CT_BM, k_taps * p.BN);
       const uint32_t dhi = umma_desc_hi_kmajor(8 * row_bytes, row_bytes);
       const uint32_t tiles_lo = ((smem_u32(tiles) & 0x3FFFFu) >> 4) | (1u << 16);
       const uint32_t bres_lo = ((smem_u32(res_b) & 0x3FFFFu) >> 4) | (1u << 16);
       const int kst = p.cblk / 8;
       const int rows_u = p.res ? 3 : p.rg;
-      const int upt = p.res ? 1 : (p.taps / p.rg) * p.kblocks;
+      const int upt = p.res ? 1 : (k_taps / p.rg) * p.kblocks;
       const int U = (t_end - t_begin) * upt;
       const uint32_t a_step = (uint32_t)(p.res ? p.a_tap : p.a_bytes) >> 4, b_step = (uint32_t)(b_rows * row_bytes) >> 4;
       const uint32_t stage_step = (uint32_t)p.stage_bytes >> 4;
@@ -555,7 +576,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   } else if (X3 && (warp == 3 || warp >= 12)) {
     // ===================== operand splitters (X3): stage by stage, in the producer's order
     const int tid_c = (warp == 3 ? 0 : 32) + lane;
-    const int upt = p.res ? 1 : (p.taps / p.rg) * p.kblocks;
+    const int upt = p.res ? 1 : (k_taps / p.rg) * p.kblocks;
     const int U = max(0, t_end - t_begin) * upt;
     const int bytes = p.res ? p.a_stage_bytes : p.rg * p.a_bytes;
     int stage = 0, phase = 0;
@@ -591,7 +612,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     const long long total_px = (long long)p.N * p.H * p.W;
     // padded tiles: this lane's row slot, strip and pixel column (see ConvTcParams)
     int pd_hr = 0, pd_img = 0, pd_w = 0, pd_w0 = 0, pd_srow = -1, pd_sub = 0;
-    if (p.padded) {
+    if (k_padded) {
       const int slot = m / p.Wb;
       const int strip = (p.Nb == 1) ? slot / p.Hb : 0;
       pd_hr = slot % p.Hb;
@@ -617,7 +638,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       bool valid = pix < total_px;
       int row0 = tm * CT_BM + q4 * 32;                // first pixel of this warp's 32 rows
       int sc3 = 0;
-      if (p.padded) {
+      if (k_padded) {
         int n, h;
         if (p.Nb == 1) { n = tm / p.tpi; h = (tm - n * p.tpi) * p.Hb + pd_hr; }
         else { n = tm * p.Nb + pd_img; h = pd_hr; }
@@ -636,13 +657,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       if (c0 + 32 <= p.BN) {
         if (lane == 0) tma_store_wait_read<0>();      // the bulk stores that read this warp's staging have drained it
         __syncwarp();
-        conv_tc_epilogue_block<32>(p, &map_o, t_addr, lblk, c0, tn, valid, has_left, has_right, row0, stg_w, rrow, s_bias, sw, lane, dbg,
+        conv_tc_epilogue_block<32, GEN>(p, &map_o, t_addr, lblk, c0, tn, valid, has_left, has_right, row0, stg_w, rrow, s_bias, sw, lane, dbg,
                                    pd_srow, pd_w0, sc3);
         sbuf = 0;
       } else {
         if (lane == 0) { if (two_sub) tma_store_wait_read<1>(); else tma_store_wait_read<0>(); }
         __syncwarp();
-        conv_tc_epilogue_block<16>(p, &map_o, t_addr, lblk, c0, tn, valid, has_left, has_right, row0, stg_w + sbuf * 2048, rrow, s_bias,
+        conv_tc_epilogue_block<16, GEN>(p, &map_o, t_addr, lblk, c0, tn, valid, has_left, has_right, row0, stg_w + sbuf * 2048, rrow, s_bias,
                                    sw, lane, dbg, pd_srow, pd_w0, sc3);
         if (two_sub) sbuf ^= 1;
       }
@@ -940,14 +961,19 @@ static int conv_tc_launch(const se_conv_desc* d, const float* a_tensor, int Kc, 
     set_error("conv_tc: cudaMemsetAsync failed");
     return SE_ERR_CUDA;
   }
-  if (x3) launch(conv_tc_kernel<1>, dim3(grid), dim3(CT_THREADS_X3), smem, st, ma, mb, mbl, mo, p);
-  else launch(conv_tc_kernel<0>, dim3(grid), dim3(CT_THREADS), smem, st, ma, mb, mbl, mo, p);
+  const bool gen = taps != 3 || p.padded || p.flat || p.NS != 1;
+  if (x3 && gen) launch(conv_tc_kernel<1, 1>, dim3(grid), dim3(CT_THREADS_X3), smem, st, ma, mb, mbl, mo, p);
+  else if (x3) launch(conv_tc_kernel<1, 0>, dim3(grid), dim3(CT_THREADS_X3), smem, st, ma, mb, mbl, mo, p);
+  else if (gen) launch(conv_tc_kernel<0, 1>, dim3(grid), dim3(CT_THREADS), smem, st, ma, mb, mbl, mo, p);
+  else launch(conv_tc_kernel<0, 0>, dim3(grid), dim3(CT_THREADS), smem, st, ma, mb, mbl, mo, p);
   return check_launch("conv_tc_kernel");
 }
 
 int init_conv_tc() {
-  if (cudaFuncSetAttribute(conv_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess ||
-      cudaFuncSetAttribute(conv_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) {
+  if (cudaFuncSetAttribute(conv_tc_kernel<0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess ||
+      cudaFuncSetAttribute(conv_tc_kernel<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess ||
+      cudaFuncSetAttribute(conv_tc_kernel<0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess ||
+      cudaFuncSetAttribute(conv_tc_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) {
     set_error("init_conv_tc: cannot raise the shared-memory limit");
     return SE_ERR_CUDA;
   }
