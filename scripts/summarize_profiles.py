@@ -104,9 +104,14 @@ def ncu_report(path, title):
 TRAFFIC_MAP = {
     'pairwise_dist': ('r2_kernels', 'pairwise_tc_kernel<0>', None),
     'conv_wgrad 3x3 s1 16->16 @32x32': ('r2_kernels', 'conv_wgrad_pk_kernel', '148'),
-    'conv_fwd 3x3 s1 16->16 @32x32': ('r2_kernels', 'conv_tc_kernel<1>', '148'),
-    'conv_dgrad 3x3 s1 16->16 @32x32': ('r2_kernels', 'conv_tc_kernel<1>', '148'),
+    'conv_fwd 3x3 s1 16->16 @32x32': ('r2_kernels', 'conv_tc_kernel<1, 0>', '148'),
+    'conv_dgrad 3x3 s1 16->16 @32x32': ('r2_kernels', 'conv_tc_kernel<1, 0>', '148'),
     'conv_wgrad 3x3 s1 32->32 @16x16': ('r2_kernels', 'conv_wgrad_tc_kernel<1>', None),
+    # config 4 (ResNet-50, batch 32): the first conv_tc_kernel<1, 1> launch of scripts/ncu_targets.py is the 1x1 forward
+    'conv_fwd 1x1 s1 256->1024 @14x14': ('r2_kernels', 'conv_tc_kernel<1, 1>', '148'),
+    'conv_dgrad 1x1 s1 256->1024 @14x14': ('r2_kernels', 'conv_tc_kernel<1, 1>', '98'),
+    'conv_wgrad 1x1 s1 256->1024 @14x14': ('r2_kernels', 'conv1x1_wgrad_tc_kernel<1>', None),
+    'conv_wgrad 3x3 s1 128->128 @28x28': ('r2_kernels', 'conv_wgrad_tc_kernel<1>', '37'),
 }
 
 

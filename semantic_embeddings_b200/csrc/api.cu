@@ -402,6 +402,16 @@ static int run_ops_impl(const se_op* ops, int n, int mode, void* stream, bool* f
                                         (float*)p[3], (float*)p[4], (float*)p[5], (float*)p[6], stream);
         break;
       case SE_OP_MEMSET: {
+        if (i[0] & 1) {
+          // a memset of GRADIENT memory (frozen parameters, Engine.set_trainable): the weight-gradient kernels of the side
+          // stream and the all-reduces of the communication stream write that memory -- join them first
+          join_comm(stream);
+          if (*forked) {
+            cudaEventRecord(g_ev_join, g_side);
+            cudaStreamWaitEvent(as_stream(stream), g_ev_join, 0);
+            *forked = false;
+          }
+        }
         cudaError_t e = cudaMemsetAsync(p[0], 0, (size_t)(uintptr_t)p[1], as_stream(stream));
         if (e != cudaSuccess) { set_error("memset: %s", cudaGetErrorString(e)); rc = SE_ERR_CUDA; }
         break;

@@ -20,7 +20,7 @@ enum {
   SE_OP_ADD_BWD = 16,
   SE_OP_HEAD = 17,
   SE_OP_XENT = 18,
-  SE_OP_MEMSET = 19,
+  SE_OP_MEMSET = 19,             /* p[0] = pointer, p[1] = bytes; i[0] bit 0: gradient memory -- join the side / comm streams first */
   SE_OP_SGD_PREPARE = 20,
   SE_OP_SGD_APPLY = 21,
   SE_OP_TRANSPOSE_FILTERS = 22,

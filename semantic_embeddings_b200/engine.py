@@ -536,7 +536,8 @@ class Engine:
     def _opt_ops(self):
         """Optimizer ops of a step: [zero the gradients of frozen parameters], global norm + L2 terms, clip + SGD update."""
         nbytes = lambda t: t.numel() * t.element_size()
-        freeze = [self._op(_lib.OP_MEMSET, p=[self.G[o:o + n], nbytes(self.G[o:o + n])]) for o, n in self.frozen_runs]
+        # i[0] = 1: the runner joins the weight-gradient side stream (and pending all-reduces) before this memset
+        freeze = [self._op(_lib.OP_MEMSET, [1], p=[self.G[o:o + n], nbytes(self.G[o:o + n])]) for o, n in self.frozen_runs]
         return freeze + [
             self._op(_lib.OP_MEMSET, p=[self.sgd_out, 16]),
             self._op(_lib.OP_SGD_PREPARE, [self.n_active_segs],
