@@ -160,11 +160,12 @@ def test_frozen_layers_step_matches_oracle():
     assert all(not vel_e[n].any() for n in frozen)
     report('frozen_step', trainable_weights=worst, frozen=len(frozen))
     assert worst < 1e-4, worst
-    # thaw: every parameter moves again
+    # thaw: every kernel moves again (the biases in front of a BatchNorm have gradients at rounding level: sum of a
+    # normalised gradient -- their updates can vanish in fp32)
     assert eng.set_trainable(None) == []
     eng.train_step(x, y, lr=lr)
     w2 = eng.get_weights()
-    assert all(not np.array_equal(w2[n], w1[n]) for n in eng.offsets)
+    assert all(not np.array_equal(w2[n], w1[n]) for n in eng.offsets if n.endswith('/kernel'))
 
 
 class _relu_probe:

@@ -241,21 +241,41 @@ def test_tf32_operands_are_truncated_by_the_tensor_core():
     assert e_tr < 5e-6 and e_rn > 20 * e_tr, (e_tr, e_rn)
 
 
-def test_conv_epilogue_bias_relu_residual_stats():
+@pytest.mark.parametrize('case', [
+    (3, 8, 8, 16, 32, 3, 1, 0),       # fp32 kernels
+    (3, 8, 8, 16, 32, 3, 1, 2),       # tcgen05, two images per tile
+    (3, 14, 14, 32, 32, 3, 1, 2),     # tcgen05 padded row slots: residual rows / statistics of the valid lanes only
+    (2, 55, 55, 32, 32, 3, 1, 2),     # tcgen05 strips
+    (2, 14, 14, 64, 128, 1, 1, 2),    # tcgen05 1x1 (flat GEMM), ragged last tile
+    (2, 28, 28, 64, 64, 1, 2, 2),     # tcgen05 1x1 / stride 2 (strided view in, padded slots out)
+], ids=lambda c: 'x'.join(str(v) for v in c))
+def test_conv_epilogue_bias_relu_residual_stats(case):
+    """y = relu(conv(x) + bias + residual) and the BatchNorm sums of the stored values, fused in the convolution epilogue."""
+    import ctypes
     from oracle import nn as onn
     L = _lib()
-    g = torch.Generator().manual_seed(5)
-    N, H, W, Cin, Cout = 3, 8, 8, 16, 32
+    N, H, W, Cin, Cout, k, stride, mode = case
+    g = torch.Generator().manual_seed(5 + H + k)
     x = torch.randn(N, H, W, Cin, generator=g, dtype=torch.float64)
-    w = torch.randn(3, 3, Cin, Cout, generator=g, dtype=torch.float64) * 0.1
+    w = torch.randn(k, k, Cin, Cout, generator=g, dtype=torch.float64) * 0.1
     b = torch.randn(Cout, generator=g, dtype=torch.float64)
-    r = torch.randn(N, H, W, Cout, generator=g, dtype=torch.float64)
-    y = torch.relu(onn.conv2d(x, w, b, 1, 'same') + r)
-    d = L.ConvDesc(N, H, W, Cin, Cout, 3, 3, 1, 1, 1, H, W)
-    yd = torch.empty(N, H, W, Cout, device='cuda')
+    y0 = onn.conv2d(x, w, b, stride, 'same' if k == 3 else 'valid')
+    Ho, Wo = y0.shape[1], y0.shape[2]
+    r = torch.randn(N, Ho, Wo, Cout, generator=g, dtype=torch.float64)
+    y = torch.relu(y0 + r)
+    pad = 1 if k == 3 else 0
+    d = L.ConvDesc(N, H, W, Cin, Cout, k, k, stride, pad, pad, Ho, Wo)
+    yd = torch.full((N, Ho, Wo, Cout), 9.0, device='cuda')
     stats = torch.zeros(2 * Cout, dtype=torch.float64, device='cuda')
     xd, wd, bd, rd = dev(x), dev(w), dev(b), dev(r)
-    L.call('se_conv2d_fwd', d, L.ptr(xd), L.ptr(wd), L.ptr(bd), L.ptr(rd), L.ptr(yd), 1, L.ptr(stats), 0, sptr())
+    if mode == 0:
+        L.call('se_conv2d_fwd', d, L.ptr(xd), L.ptr(wd), L.ptr(bd), L.ptr(rd), L.ptr(yd), 1, L.ptr(stats), 0, sptr())
+    else:
+        wtd, wld, wtld = torch.empty_like(wd), torch.empty_like(wd), torch.empty_like(wd)
+        tab = (ctypes.c_int64 * 4)(0, k * k, Cin, Cout)
+        L.call('se_split_filters', L.ptr(wd), L.ptr(wtd), L.ptr(wld), L.ptr(wtld), tab, 1, sptr())
+        aux = L.ConvAux(L.ptr(wtd), L.ptr(wtld), L.ptr(wld))
+        L.call('se_conv2d_fwd_aux', d, L.ptr(xd), L.ptr(wd), aux, L.ptr(bd), L.ptr(rd), L.ptr(yd), 1, L.ptr(stats), mode, sptr())
     assert relerr(yd.cpu(), y) < 2e-5
     ys = y.reshape(-1, Cout)
     assert relerr(stats.cpu()[:Cout], ys.sum(0)) < 1e-5
