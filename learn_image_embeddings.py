@@ -11,9 +11,9 @@ What each part of the reference script maps to:
                                                        and layouts are Keras', so they convert 1:1)
   feature dump (:270-275)                           -> identical pickle: {'feat': {test index: (D,) float32}}
 Deviations, all stated at run time when they apply:
-  * --cls_base raises NotImplementedError (attaching the classifier to an inner layer is not part of the accelerated
-    path); --finetune reads this package's own dumps (pickle / .npz of Keras-named arrays), not Keras HDF5; --log_dir is
-    accepted and ignored with a message;
+  * --cls_base takes a layer name (a feature-vector layer such as avg_pool), not a Keras layer index; --finetune reads
+    this package's own dumps (pickle / .npz of Keras-named arrays), not Keras HDF5; --log_dir is accepted and ignored
+    with a message;
   * --gpus N > 1: launch with `python -m torch.distributed.run --nproc-per-node N learn_image_embeddings.py ...`
     (one process per GPU, NCCL all-reduce; the reference's in-graph towers have the same arithmetic);
   * datasets: 'CIFAR-100' / 'CIFAR-10' (python pickles, datasets/cifar.py) and 'synthetic[:n]';
@@ -132,9 +132,9 @@ def main(argv=None):
     args = build_parser().parse_args(argv)
     if args.val_batch_size is None:
         args.val_batch_size = args.batch_size
-    if args.cls_base is not None:
-        raise NotImplementedError('--cls_base (classifier attached to an inner layer) is outside the accelerated hot path '
-                                  '(SURVEY.md section 8)')
+    if args.cls_base is not None and args.cls_base.lstrip('-').isdigit():
+        raise ValueError('--cls_base takes a layer NAME here (e.g. avg_pool): Keras layer indices count Activation / Add / '
+                         'Lambda layers that this graph fuses into their producers')
 
     import torch
     from semantic_embeddings_b200 import _lib
@@ -178,7 +178,8 @@ def main(argv=None):
     decay = (1.0 / args.max_decay - 1) / (steps_per_epoch * epochs) if args.max_decay > 0 else 0.0
     pb = args.batch_size // world
     eng = Engine(graph, pb, embedding, loss=args.loss, cls_weight=args.cls_weight, num_classes=data.num_classes, mode=mode,
-                 device='cuda:%d' % local, nesterov=args.nesterov, clipnorm=args.clipgrad, world_size=world, decay=decay)
+                 device='cuda:%d' % local, nesterov=args.nesterov, clipnorm=args.clipgrad, world_size=world, decay=decay,
+                 cls_base=args.cls_base if args.cls_weight > 0 else None)
     if args.snapshot and os.path.exists(args.snapshot):
         say('Resuming from snapshot {}'.format(args.snapshot))
         with open(args.snapshot, 'rb') as f:

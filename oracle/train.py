@@ -66,7 +66,7 @@ def per_sample_loss(y_true, y_pred, loss_kind):
 
 
 def train_objective(model, x, labels, embedding, loss_kind='inv_corr', cls=None, cls_weight=0.0,
-                    params=None, updates=None):
+                    params=None, updates=None, cls_base=None):
     """Total Keras training loss for one batch and the metric tensors.
 
     params: dict of ALL weights (model + cls head); defaults to the objects' own.
@@ -74,7 +74,8 @@ def train_objective(model, x, labels, embedding, loss_kind='inv_corr', cls=None,
     p = dict(model.params) if params is None else params
     if cls is not None and params is None:
         p.update(cls.params)
-    z = model.forward(x, training=True, params=p, updates=updates)
+    taps = {} if cls_base is not None else None
+    z = model.forward(x, training=True, params=p, updates=updates, taps=taps)
     emb = head_forward(z, loss_kind)
     y_true = embedding[labels]                          # transform_inputs, :48-50
     ls = per_sample_loss(y_true, emb, loss_kind)
@@ -89,7 +90,9 @@ def train_objective(model, x, labels, embedding, loss_kind='inv_corr', cls=None,
     cls_loss = None
     prob = None
     if cls is not None and cls_weight > 0:
-        prob = cls.forward(p, emb, True, updates)
+        # cls_model(embed_model, num_classes, cls_base) (learn_image_embeddings.py:34-40): the classifier reads the wrapped
+        # embedding output, or the output of the named inner layer
+        prob = cls.forward(p, emb if cls_base is None else taps[cls_base], True, updates)
         onehot = torch.nn.functional.one_hot(labels, prob.shape[-1]).to(prob.dtype)
         cls_loss = nn.categorical_crossentropy(onehot, prob).mean()
         total = total + cls_weight * cls_loss
@@ -127,7 +130,7 @@ def sgd_step(params, grads, velocity, lr, momentum=0.9, nesterov=False, clipnorm
 
 
 def train_step(model, x, labels, embedding, velocity, lr, loss_kind='inv_corr', cls=None,
-               cls_weight=0.0, nesterov=False, clipnorm=10.0, decay=0.0, iterations=0):
+               cls_weight=0.0, nesterov=False, clipnorm=10.0, decay=0.0, iterations=0, cls_base=None):
     """One full reference training step (fwd, autodiff bwd, clip, momentum SGD, BN moving stats).
     Returns (objective dict, grads dict, grad norm)."""
     allp = OrderedDict(model.params)
@@ -137,7 +140,8 @@ def train_step(model, x, labels, embedding, velocity, lr, loss_kind='inv_corr', 
         trainable += cls.trainable
     leaf = {n: allp[n].detach().clone().requires_grad_(n in trainable) for n in allp}
     updates = {}
-    obj = train_objective(model, x, labels, embedding, loss_kind, cls, cls_weight, params=leaf, updates=updates)
+    obj = train_objective(model, x, labels, embedding, loss_kind, cls, cls_weight, params=leaf, updates=updates,
+                          cls_base=cls_base)
     tl = [leaf[n] for n in trainable]
     gl = torch.autograd.grad(obj['total'], tl, allow_unused=True)
     grads = OrderedDict((n, (g if g is not None else torch.zeros_like(leaf[n])).detach())

@@ -34,7 +34,7 @@ class Engine:
     def __init__(self, graph, batch, embedding, loss='inv_corr', cls_weight=0.0, num_classes=None,
                  mode=_lib.SE_MODE_F32, device='cuda:0', momentum=0.9, nesterov=False, clipnorm=10.0,
                  world_size=1, fuse_stats=True, use_cuda_graph=True, seed=0, decay=0.0,
-                 grad_buckets=3, comm='auto'):
+                 grad_buckets=3, comm='auto', cls_base=None):
         if loss not in LOSS_KINDS:
             raise ValueError('unknown loss %r' % loss)
         self.decay = float(decay)
@@ -49,6 +49,7 @@ class Engine:
         self.mode = mode
         self.loss = loss
         self.cls_weight = float(cls_weight)
+        self.cls_base = cls_base          # name of the layer the classifier head reads (None = the wrapped embedding output)
         self.momentum, self.nesterov, self.clipnorm = float(momentum), bool(nesterov), float(clipnorm or 0.0)
         self.world = int(world_size)
         self.grad_buckets = max(1, int(grad_buckets))
@@ -129,10 +130,20 @@ class Engine:
         self.head_node = head
         self.xent_node = None
         if self.cls_weight > 0:
-            # cls_model (learn_image_embeddings.py:16-45): relu -> BatchNormalization() -> Dense(C, softmax, l2 5e-4)
-            sub = Graph('cls', (self.D,))
-            sub.input = x_out
-            r = sub.relu(x_out, 'cls_relu')
+            # cls_model (learn_image_embeddings.py:16-45): relu -> BatchNormalization() -> Dense(C, softmax, l2 5e-4) on the
+            # embedding output, or (--cls_base, :34-40) on the output of a named inner layer
+            base = x_out
+            if self.cls_base is not None:
+                cand = [n for n in g.nodes if n.name == str(self.cls_base)]
+                if not cand:
+                    raise ValueError('cls_base: no layer named %r (layers: %s)' % (self.cls_base, ', '.join(n.name for n in g.nodes)))
+                base = cand[0].output
+                if len(base.shape) != 1:
+                    raise ValueError('cls_base %r has a %d-d output %s: the classifier needs a feature vector (e.g. avg_pool)'
+                                     % (self.cls_base, len(base.shape), tuple(base.shape)))
+            sub = Graph('cls', tuple(base.shape))
+            sub.input = base
+            r = sub.relu(base, 'cls_relu')
             b = sub.bn(r, 'cls_bn')
             logits = sub.dense(b, 'prob', self.num_classes, l2=5e-4)
             self.nodes += sub.nodes

@@ -188,6 +188,34 @@ def test_engine_builds_plans_without_a_gpu(built_lib):
         last_bwd = max(k for k, o in enumerate(e2.plans['step_dp']) if o.opcode in (L.OP_CONV_WGRAD, L.OP_BN_BWD))
         first_opt = min(k for k, o in enumerate(e2.plans['step_dp']) if o.opcode == L.OP_SGD_PREPARE)
         assert pos[0] < last_bwd and last_bwd < pos[-1] < first_opt
+    # --cls_base: the classifier head on the pooled features -- avg_pool then has two consumers, the head has none, so the
+    # forward head op writes dz itself (no separate backward head op) and avg_pool's gradient is written (beta 0) by the
+    # classifier branch, then accumulated into (beta 1) by the embedding layer's data gradient
+    eb = Engine(utils.build_network(100, 'resnet-110-fc'), 2, emb, cls_weight=0.1, num_classes=100, device='cpu',
+                use_cuda_graph=False, cls_base='avg_pool')
+    assert eb.offsets['prob/kernel'][1] == (64, 100) and eb.offsets['cls_bn/gamma'][1] == (64,)
+    assert sum(1 for o in eb.plans['bwd'] if o.opcode == L.OP_HEAD) == 0
+    dg = [o for o in eb.plans['bwd'] if o.opcode == L.OP_CONV_DGRAD]
+    assert dg[0].i[3] == 64 and dg[0].i[4] == 100 and dg[0].f[0] == 0.0        # prob: 64 -> 100, first write of its input gradient
+    assert dg[1].i[3] == 64 and dg[1].i[4] == 100 and dg[1].f[0] == 1.0        # embedding: accumulates into avg_pool's gradient
+    with pytest.raises(ValueError):
+        Engine(utils.build_network(100, 'resnet-110-fc'), 2, emb, cls_weight=0.1, num_classes=100, device='cpu', cls_base='conv0')
+    with pytest.raises(ValueError):
+        Engine(utils.build_network(100, 'resnet-110-fc'), 2, emb, cls_weight=0.1, num_classes=100, device='cpu', cls_base='nope')
+    # set_trainable: frozen runs + the L2 segments that remain partition the regularised range; thawing restores the plan
+    n_opt = len(eng.plans['opt'])
+    frozen = eng.set_trainable(lambda n: n.split('/')[0] == 'embedding')
+    assert len(frozen) == len(eng.offsets) - 2 and eng.frozen_runs
+    fr = sum(sz for _, sz in eng.frozen_runs)
+    tr = sum((int(np.prod(eng.offsets[n][1])) + 3) // 4 * 4 for n in eng.offsets if n.split('/')[0] == 'embedding')
+    assert fr + tr == eng.nparams
+    segs = [(eng.seg_array[k].begin, eng.seg_array[k].end) for k in range(eng.n_active_segs)]
+    assert all(not (b < o + sz and o < e) for b, e in segs for o, sz in eng.frozen_runs)      # no L2 term on frozen weights
+    ek = eng.offsets['embedding/kernel']
+    assert segs == [(ek[0], ek[0] + (int(np.prod(ek[1])) + 3) // 4 * 4)]
+    assert len(eng.plans['opt']) == n_opt + len(eng.frozen_runs)
+    assert all(o.opcode == L.OP_MEMSET and o.i[0] == 1 for o in list(eng.plans['opt'])[:len(eng.frozen_runs)])
+    assert eng.set_trainable(None) == [] and len(eng.plans['opt']) == n_opt and eng.n_active_segs == len(eng.segments)
     # weight I/O round trip keeps Keras names and layouts
     g = utils.build_network(100, 'resnet-32')
     eng = Engine(g, 2, np.eye(64), device='cpu', use_cuda_graph=False)
@@ -320,3 +348,26 @@ def test_augment_oracle_is_the_scipy_transform_keras_delegates_to():
     assert np.allclose(half[:-1], 0.5 * (x[:-1] + x[1:]), atol=1e-4) and np.allclose(half[-1], x[-1], atol=1e-4)
     mean, std = oaug.fit_statistics(np.stack([x, x + 1]))
     assert np.allclose(oaug.standardize(x, mean, std), (x - mean) / (std + 1e-7))
+
+
+def test_finetune_weights_are_loaded_by_name_with_mismatches_skipped(built_lib, tmp_path):
+    """learn_image_embeddings.load_weights_by_name = model.load_weights(by_name=True, skip_mismatch=True) (:185)."""
+    import pickle
+    import learn_image_embeddings as lie
+    from semantic_embeddings_b200 import utils
+    from semantic_embeddings_b200.engine import Engine
+    eng = Engine(utils.build_network(64, 'simple'), 2, np.eye(64), device='cpu', use_cuda_graph=False)
+    ws = utils.build_network(64, 'simple').init_weights(7)
+    ws = {k: np.asarray(v, np.float32) + 1.0 for k, v in ws.items()}
+    ws['embedding/kernel'] = np.zeros((ws['embedding/kernel'].shape[0], 100), np.float32)      # a 100-d head: does not fit
+    ws['not_a_layer/kernel'] = np.zeros((3, 3), np.float32)
+    for path in (tmp_path / 'dump.pickle', tmp_path / 'dump.npz'):
+        if str(path).endswith('.npz'):
+            np.savez(path, **ws)
+        else:
+            with open(path, 'wb') as f:
+                pickle.dump({'architecture': 'simple', 'weights': ws}, f)
+        loaded, skipped = lie.load_weights_by_name(eng, str(path))
+        assert sorted(skipped) == ['embedding/kernel', 'not_a_layer/kernel'] and len(loaded) == len(ws) - 2
+        name = loaded[0]
+        np.testing.assert_array_equal(eng._pview(name).numpy(), ws[name])

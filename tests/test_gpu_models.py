@@ -112,6 +112,52 @@ STEP_CASES = [
 ]
 
 
+def test_cls_base_inner_layer_step_matches_oracle():
+    """--cls_base (learn_image_embeddings.py:34-40): the classifier head (relu -> BatchNorm -> Dense softmax) reads the
+    64-d 'avg_pool' features instead of the embedding output; that tensor then has two consumers (the embedding layer and
+    the classifier) whose gradients accumulate.  One step against the float64 oracle."""
+    import copy
+    from oracle import models as omodels
+    from oracle import train as otrain
+    from semantic_embeddings_b200 import utils
+    from semantic_embeddings_b200.engine import Engine
+    emb = class_matrix('cifar100')
+    C, D = emb.shape
+    B, lr, cw = 8, 0.05, 0.1
+    om = omodels.build_network(D, 'resnet-110-fc', input_channels=3, seed=21)
+    omodels.randomize(om, seed=22)
+    cls = otrain.ClsHead(64, C, seed=23)                     # on the 64-d pooled features
+    omodels.randomize(cls.params, seed=24)
+    to_f32_exact(om, cls)
+    eng = Engine(utils.build_network(D, 'resnet-110-fc', input_channels=3), B, emb, cls_weight=cw, num_classes=C,
+                 clipnorm=10.0, use_cuda_graph=False, cls_base='avg_pool')
+    assert eng.offsets['prob/kernel'][1] == (64, C)
+    eng.set_weights(oracle_weights_np(om, cls))
+    vel = otrain.make_velocity(om, cls)
+    emb_t = torch.as_tensor(emb.astype(np.float32)).double()
+    g = torch.Generator().manual_seed(78)
+    x = torch.randn(B, 32, 32, 3, generator=g, dtype=torch.float64).float()
+    y = torch.randint(0, C, (B,), generator=g)
+    om32, cls32 = copy.deepcopy(om), copy.deepcopy(cls)
+    otrain.cast_model(om32, torch.float32, cls32)
+    _, grads32, _ = otrain.train_step(om32, x, y, emb_t.float(), {k: v.float() for k, v in vel.items()}, lr, 'inv_corr', cls32, cw,
+                                      False, 10.0, cls_base='avg_pool')
+    obj, grads, norm = otrain.train_step(om, x.double(), y, emb_t, vel, lr, 'inv_corr', cls, cw, False, 10.0, cls_base='avg_pool')
+    floor = max(_grad_errors({k: v.numpy() for k, v in grads32.items()}, grads, norm)[:2])
+    eng.train_step(x, y, lr=lr)
+    m = eng.metrics()
+    e_loss = abs(m['loss'] - float(obj['embed_loss'].detach()))
+    e_cls = abs(m['cls_loss'] - float(obj['cls_loss'].detach()))
+    e_emb = rel_max(eng.act['head_out'].cpu().numpy(), obj['emb'].detach().numpy())
+    e_prob = rel_max(eng.act['prob_out'].cpu().numpy(), obj['prob'].detach().numpy())
+    gg, gw, name = _grad_errors(eng.get_grads(), grads, norm)
+    report('cls_base_step', loss=e_loss, cls_loss=e_cls, emb=e_emb, prob=e_prob, grad_global=gg, worst=name, grad_floor_f32_oracle=floor)
+    assert max(e_loss, e_cls, e_emb, e_prob) < 1e-4, (e_loss, e_cls, e_emb, e_prob)
+    assert gg < max(2e-3, 5 * floor), (gg, floor)
+    with pytest.raises(ValueError):
+        Engine(utils.build_network(D, 'resnet-110-fc', input_channels=3), B, emb, cls_weight=cw, num_classes=C, cls_base='conv0')
+
+
 def test_frozen_layers_step_matches_oracle():
     """--finetune_init phase (learn_image_embeddings.py:183-207): only the layers 'embedding' and 'prob' train.  Two steps
     against the float64 oracle restricted to those weights (Keras differentiates only with respect to trainable weights:
