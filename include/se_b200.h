@@ -72,8 +72,10 @@ int se_tc_capabilities(void);
  * (pad_before = total//2, so k=3,s=2 on an even input gives pad 0 before / 1 after).
  * In SE_MODE_TF32 / SE_MODE_TF32X3 the tcgen05 kernels take: 3x3 / stride 1 / pad 1 on image widths 4..56 (weight
  * gradient: ..64), 1x1 / stride 1 / pad 0 on any image size (>= 128 pixels per call), 1x1 / stride 2 / pad 0 with
- * Wo <= 32 -- channel counts in multiples of 16 (the GEMM K dimension: 16 or a multiple of 32).  Every other shape
- * (3-channel stems, 3x3 / stride 2, 7x7, dense layers) runs on the fp32 kernels in every mode. */
+ * Wo <= 32 -- channel counts in multiples of 16 (the GEMM K dimension: 16 or a multiple of 32); backward data and weight
+ * gradient of 3x3 / stride 2 / pad 0 on even image sizes with >= 128 channels on both sides (nine strided 1x1 GEMMs).
+ * Every other shape (3-channel stems, the forward pass and the narrow layers of 3x3 / stride 2, 7x7, dense layers) runs on
+ * the fp32 kernels in every mode; se_conv2d_path() tells which. */
 typedef struct {
   int32_t N, H, W, Cin;   /* input  NHWC */
   int32_t Cout, kh, kw;   /* kernel HWIO */
@@ -115,6 +117,11 @@ int se_conv2d_dgrad(const se_conv_desc* d, const float* dy, const float* w, floa
 /* dw += x (*) dy ; dbias += sum_pixels dy   (dbias may be NULL). Accumulates: caller zeroes. */
 int se_conv2d_wgrad(const se_conv_desc* d, const float* x, const float* dy, float* dw, float* dbias,
                     int mode, void* stream);
+/* Which kernel family takes this layer in `mode` (pure host-side planning: no device work, callable without a GPU):
+ * 1 = a tcgen05 kernel, 0 = an fp32 kernel; direction 0 forward, 1 backward data, 2 weight gradient.  (Forward: given the
+ * auxiliary kernel copies of se_conv_aux; with BatchNorm statistics wider than 384 channels the sums come from a separate
+ * se_bn_stats pass, see se_conv2d_fwd_aux.) */
+int se_conv2d_path(const se_conv_desc* d, int mode, int direction);
 /* Dense (models/cifar_resnet.py:233, plainnet.py:67,76, wide_residual_network.py:96, utils.py:242,
  * learn_image_embeddings.py:44): y = x W + b as a 1x1 convolution over a (B,1,1,Cin) tensor. */
 int se_dense_fwd(const float* x, const float* w, const float* bias, float* y, int B, int Cin, int Cout,

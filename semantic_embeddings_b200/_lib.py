@@ -67,6 +67,7 @@ _SIGS = {
     'se_transpose_filters': (c_int, [_P, _P, POINTER(c_int64), c_int, _P]),
     'se_conv2d_dgrad': (c_int, [POINTER(ConvDesc), _P, _P, _P, c_float, c_int, _P]),
     'se_conv2d_wgrad': (c_int, [POINTER(ConvDesc), _P, _P, _P, _P, c_int, _P]),
+    'se_conv2d_path': (c_int, [POINTER(ConvDesc), c_int, c_int]),
     'se_dense_fwd': (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_int, _P, c_int, _P]),
     'se_dense_bwd': (c_int, [_P, _P, _P, _P, c_float, _P, _P, c_int, c_int, c_int, c_int, _P]),
     'se_bn_stats': (c_int, [_P, c_int64, c_int, _P, _P]),

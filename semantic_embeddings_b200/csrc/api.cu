@@ -173,6 +173,19 @@ extern "C" int se_conv2d_dgrad(const se_conv_desc* d, const float* dy, const flo
   return se_conv2d_dgrad_aux(d, dy, w, nullptr, dx, beta, mode, stream);
 }
 
+namespace se {
+bool conv_tc_would_run(const se_conv_desc* d, int dir, int x3);
+bool conv_wgrad_tc_would_run(const se_conv_desc* d, int x3);
+}
+extern "C" int se_conv2d_path(const se_conv_desc* d, int mode, int direction) {
+  int rc = check_desc(d);
+  if (rc) return rc;
+  SE_REQUIRE(direction >= 0 && direction <= 2, "direction: 0 forward, 1 backward data, 2 weight gradient");
+  if (mode != SE_MODE_TF32 && mode != SE_MODE_TF32X3) return 0;
+  const int x3 = mode == SE_MODE_TF32X3;
+  return (direction == 2 ? conv_wgrad_tc_would_run(d, x3) : conv_tc_would_run(d, direction, x3)) ? 1 : 0;
+}
+
 extern "C" int se_conv2d_wgrad(const se_conv_desc* d, const float* x, const float* dy, float* dw, float* dbias, int mode,
                                void* stream) {
   int rc = check_desc(d);

@@ -798,12 +798,18 @@ constexpr int WG_COOP_SMEM_MAX = 120 * 1024;
 
 static int conv_tc_launch(const se_conv_desc* d, const float* a_tensor, int Kc, const float* bmat, int Nc, int flip,
                           const float* bias, const float* residual, float* out, int relu, float beta, double* stats,
-                          cudaStream_t st, const float* bmat_lo = nullptr, int taps = 3, int s2 = 0) {
+                          cudaStream_t st, const float* bmat_lo = nullptr, int taps = 3, int s2 = 0, int x3_plan = -1,
+                          int out_view_w = 0, int out_view_h = 0) {
+  // out_view_w / out_view_h (s2 backward data only, 0 = Wo x Ho): extent of the sub-sampled output view that starts at
+  // `out` -- a caller that passes dx + (r*W + s)*Cin writes dx[:, r::2, s::2, :], whose last column / row may not exist
+  // (they are clipped by the bulk store): one tap of a 3x3 / stride 2 data gradient, conv_dgrad_tc below
+  // x3_plan >= 0: plan only (se_conv2d_path) -- the shape / shared-memory / TMEM decisions below for arithmetic mode
+  // x3_plan, no pointers touched, nothing launched: SE_OK when this kernel would take the layer
   // s2 (1x1 / stride 2): tiles over the (Ho, Wo) grid; forward reads the sub-sampled view of a_tensor, backward data
   // (flip) writes the sub-sampled view of out (after zeroing it: the other three quarters of dx are zero)
   ConvTcParams p;
   const int gW = s2 ? d->Wo : d->W, gH = s2 ? d->Ho : d->H;      // the grid the pixel tiles cover
-  const int x3 = bmat_lo ? 1 : 0;       // error-compensated mode: bmat_lo = the low parts of bmat (se_split_filters)
+  const int x3 = x3_plan >= 0 ? x3_plan : (bmat_lo ? 1 : 0);   // error-compensated mode: bmat_lo = the low parts of bmat (se_split_filters)
   const long long total_px = (long long)d->N * gH * gW;
   p.taps = taps; p.flat = taps == 1 && !s2; p.pad = taps == 3 ? 1 : 0;
   p.N = d->N; p.H = gH; p.W = gW; p.Kc = Kc; p.Nc = Nc;
@@ -912,6 +918,9 @@ static int conv_tc_launch(const se_conv_desc* d, const float* a_tensor, int Kc, 
   if (stats && (size_t)16 * Nc * sizeof(float) > 24 * 1024) return SE_ERR_UNSUPPORTED;
   if (beta != 0.f && (beta != 1.f || residual || relu)) return SE_ERR_UNSUPPORTED;   // accumulate = bulk reduce-add of the raw result
 
+  const size_t smem = (size_t)p.res_b_bytes + (size_t)p.stages * p.stage_bytes + 8 * p.stage_out + (4 * CT_MAX_STAGES + 2 * CT_MAX_ACC + 4) * 8 + Nc * 4 + (stats ? 16 * Nc * 4 : 0) + 1024 + 64;
+  if (smem > 227 * 1024) return SE_ERR_UNSUPPORTED;
+  if (x3_plan >= 0) return SE_OK;
   CUtensorMap ma, mb, mbl;
   {
     uint64_t dims[4] = {(uint64_t)Kc, (uint64_t)gW, (uint64_t)gH, (uint64_t)d->N};
@@ -943,7 +952,7 @@ static int conv_tc_launch(const se_conv_desc* d, const float* a_tensor, int Kc, 
     uint32_t obox[2] = {16u, 32u};
     if (p.padded) {
       // [N][H][W][channels]: one strip of Ws pixels x rpw rows per warp; pixels / rows / images past the tensor are clipped
-      uint64_t odims4[4] = {(uint64_t)Nc, (uint64_t)gW, (uint64_t)gH, (uint64_t)d->N};
+      uint64_t odims4[4] = {(uint64_t)Nc, (uint64_t)(out_view_w ? out_view_w : gW), (uint64_t)(out_view_h ? out_view_h : gH), (uint64_t)d->N};
       uint64_t ostrides4[3] = {(uint64_t)Nc * 4, (uint64_t)gW * Nc * 4, (uint64_t)gH * gW * Nc * 4};
       if (s2 && flip) {     // backward data: dx[:, ::2, ::2, :]
         ostrides4[0] = (uint64_t)2 * Nc * 4; ostrides4[1] = (uint64_t)2 * d->W * Nc * 4; ostrides4[2] = (uint64_t)d->H * d->W * Nc * 4;
@@ -953,8 +962,6 @@ static int conv_tc_launch(const se_conv_desc* d, const float* a_tensor, int Kc, 
     } else
     if (!make_tmap(&mo, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, out, odims, ostrides, obox, CU_TENSOR_MAP_SWIZZLE_64B)) return SE_ERR_CUDA;
   }
-  const size_t smem = (size_t)p.res_b_bytes + (size_t)p.stages * p.stage_bytes + 8 * p.stage_out + (4 * CT_MAX_STAGES + 2 * CT_MAX_ACC + 4) * 8 + Nc * 4 + (stats ? 16 * Nc * 4 : 0) + 1024 + 64;
-  if (smem > 227 * 1024) return SE_ERR_UNSUPPORTED;
   int grid = min(sm_count(), p.tiles_m * p.tiles_n);
   if (s2 && flip && beta == 0.f &&
       cudaMemsetAsync(out, 0, (size_t)d->N * d->H * d->W * Nc * sizeof(float), st) != cudaSuccess) {
@@ -999,8 +1006,35 @@ int conv_fwd_tc(const se_conv_desc* d, const float* x, const float* w_t, const f
   return conv_tc_launch(d, x, d->Cin, w_t, d->Cout, 0, bias, residual, y, relu, 0.f, stats, st, w_t_lo, k1 ? 1 : 3, k2);
 }
 
+bool conv3x3s2_tc_ok(const se_conv_desc* d);      // conv1x1_wgrad_tc.cu
+
+// 3x3 / stride 2 / no leading padding, wide layers (see conv3x3s2_tc_ok): nine 1x1 / stride 2 data gradients, one per
+// filter tap, each reduce-added into its own sub-sampled view of dx:   dx[:, r::2, s::2, :] += dY W[r, s]^T
+static int conv_dgrad_tc_3x3s2(const se_conv_desc* d, const float* dy, const float* w, const float* w_lo, float* dx, float beta,
+                               cudaStream_t st) {
+  if (beta != 0.f && beta != 1.f) return SE_ERR_UNSUPPORTED;
+  int rc = ensure_init();
+  if (rc) return rc;
+  se_conv_desc d1 = *d;
+  d1.kh = 1; d1.kw = 1;
+  if (!tc_shape_ok_1x1_s2(&d1, d->Cout, d->Cin)) return SE_ERR_UNSUPPORTED;
+  if (beta == 0.f && cudaMemsetAsync(dx, 0, (size_t)d->N * d->H * d->W * d->Cin * sizeof(float), st) != cudaSuccess) {
+    set_error("conv_dgrad_tc: cudaMemsetAsync failed");
+    return SE_ERR_CUDA;
+  }
+  for (int r = 0; r < 3; ++r)
+    for (int s = 0; s < 3; ++s) {
+      const long long woff = (long long)(r * 3 + s) * d->Cin * d->Cout;
+      rc = conv_tc_launch(&d1, dy, d->Cout, w + woff, d->Cin, 1, nullptr, nullptr, dx + ((long long)r * d->W + s) * d->Cin, 0, 1.f,
+                          nullptr, st, w_lo ? w_lo + woff : nullptr, 1, 1, -1, d->Wo - (s == 2), d->Ho - (r == 2));
+      if (rc != SE_OK) return rc;
+    }
+  return SE_OK;
+}
+
 int conv_dgrad_tc(const se_conv_desc* d, const float* dy, const float* w, const float* w_lo, float* dx, float beta,
                   cudaStream_t st) {
+  if (conv3x3s2_tc_ok(d)) return conv_dgrad_tc_3x3s2(d, dy, w, w_lo, dx, beta, st);
   const bool k2 = tc_shape_ok_1x1_s2(d, d->Cout, d->Cin);
   const bool k1 = k2 || tc_shape_ok_1x1(d, d->Cout, d->Cin);
   if (!k1 && !tc_shape_ok(d, d->Cout, d->Cin)) return SE_ERR_UNSUPPORTED;
@@ -1009,6 +1043,21 @@ int conv_dgrad_tc(const se_conv_desc* d, const float* dy, const float* w, const 
   return conv_tc_launch(d, dy, d->Cout, w, d->Cin, 1, nullptr, nullptr, dx, 0, beta, nullptr, st, w_lo, k1 ? 1 : 3, k2);
 }
 
+
+// se_conv2d_path: would the tcgen05 kernel of this file take the layer?  (dir 0 forward, 1 backward data; x3 = 0 / 1)
+bool conv_tc_would_run(const se_conv_desc* d, int dir, int x3) {
+  if (dir == 1 && conv3x3s2_tc_ok(d)) {
+    se_conv_desc d1 = *d;
+    d1.kh = 1; d1.kw = 1;
+    return conv_tc_would_run(&d1, 1, x3);
+  }
+  const int Kc = dir == 0 ? d->Cin : d->Cout, Nc = dir == 0 ? d->Cout : d->Cin;
+  const bool k2 = tc_shape_ok_1x1_s2(d, Kc, Nc);
+  const bool k1 = k2 || tc_shape_ok_1x1(d, Kc, Nc);
+  if (!k1 && !tc_shape_ok(d, Kc, Nc)) return false;
+  return conv_tc_launch(d, nullptr, Kc, nullptr, Nc, dir, nullptr, nullptr, nullptr, 0, 0.f, nullptr, nullptr, nullptr, k1 ? 1 : 3,
+                        k2, x3) == SE_OK;
+}
 
 int transpose_filters(const float* P, float* PT, float* PL, float* PTL, const long long* table, int n, cudaStream_t st) {
   for (int base = 0; base < n; base += TR_MAX) {

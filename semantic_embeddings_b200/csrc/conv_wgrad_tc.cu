@@ -36,7 +36,10 @@ int conv_wgrad_pk(const se_conv_desc* d, const float* x, const float* dy, float*
 // conv1x1_wgrad_tc.cu: 1x1 / stride 1 layers (a GEMM over the flat pixel list)
 int init_conv1x1_wgrad_tc();
 bool conv1x1_wgrad_tc_ok(const se_conv_desc* d);
-int conv1x1_wgrad_tc(const se_conv_desc* d, const float* x, const float* dy, float* dw, float* dbias, int x3, cudaStream_t st);
+int conv1x1_wgrad_tc(const se_conv_desc* d, const float* x, const float* dy, float* dw, float* dbias, int x3, cudaStream_t st,
+                     int x_view_w = 0, int x_view_h = 0);
+bool conv3x3s2_tc_ok(const se_conv_desc* d);
+int conv3x3s2_wgrad_tc(const se_conv_desc* d, const float* x, const float* dy, float* dw, float* dbias, int x3, cudaStream_t st);
 static bool wgrad_is_packed(const se_conv_desc* d, int x3) {
   static const bool no_pack = getenv("SE_WG_NO_PACK") != nullptr;
   return x3 && d->Cin <= 16 && d->Cout <= 16 && !no_pack;
@@ -403,6 +406,15 @@ size_t conv_wgrad_tc_smem(const se_conv_desc* d, int* tmem_cols, int x3) {
   return smem;
 }
 
+// se_conv2d_path: would a tcgen05 weight-gradient kernel take the layer?
+bool conv_wgrad_tc_would_run(const se_conv_desc* d, int x3) {
+  if (conv1x1_wgrad_tc_ok(d) || conv3x3s2_tc_ok(d)) return true;
+  if (wgrad_is_packed(d, x3) && conv_wgrad_pk_smem(d, nullptr) > 0) return true;
+  WgTcParams p;
+  size_t smem = 0;
+  return plan_wgrad(d, true, x3, &p, &smem) == SE_OK;
+}
+
 int conv_wgrad_tc(const se_conv_desc* d, const float* x, const float* dy, float* dw, float* dbias, int x3, cudaStream_t st) {
   if ((reinterpret_cast<uintptr_t>(dw) & 15) != 0 || (dbias && (reinterpret_cast<uintptr_t>(dbias) & 15) != 0))
     return SE_ERR_UNSUPPORTED;
@@ -411,6 +423,7 @@ int conv_wgrad_tc(const se_conv_desc* d, const float* x, const float* dy, float*
   static bool inited = false;
   if (!inited) { int rc0 = init_conv_wgrad_tc(); if (rc0) return rc0; inited = true; }
   if (conv1x1_wgrad_tc_ok(d)) return conv1x1_wgrad_tc(d, x, dy, dw, dbias, x3, st);
+  if (conv3x3s2_tc_ok(d)) return conv3x3s2_wgrad_tc(d, x, dy, dw, dbias, x3, st);
   if (wgrad_is_packed(d, x3)) {
     const int rc_pk = conv_wgrad_pk(d, x, dy, dw, dbias, st);
     if (rc_pk != SE_ERR_UNSUPPORTED) return rc_pk;

@@ -371,3 +371,39 @@ def test_finetune_weights_are_loaded_by_name_with_mismatches_skipped(built_lib, 
         assert sorted(skipped) == ['embedding/kernel', 'not_a_layer/kernel'] and len(loaded) == len(ws) - 2
         name = loaded[0]
         np.testing.assert_array_equal(eng._pview(name).numpy(), ws[name])
+
+
+def test_tensor_core_coverage_of_the_baseline_networks(built_lib):
+    """se_conv2d_path (host-side planning, no GPU): which convolutions of the BASELINE architectures run on the tcgen05
+    kernels in the benchmarked arithmetic, per direction (forward, backward data, weight gradient)."""
+    from semantic_embeddings_b200 import utils
+    from semantic_embeddings_b200.models import resnet50
+    L = built_lib
+    lib = L.load()
+
+    def paths(graph, batch):
+        out = {}
+        for n in graph.nodes:
+            if n.op != 'conv':
+                continue
+            h, w, cin = n.inputs[0].shape
+            ho, wo, cout = n.output.shape
+            a = n.attrs
+            d = L.ConvDesc(batch, h, w, cin, cout, a['k'], a['k'], a['stride'], a['pad_t'], a['pad_l'], ho, wo)
+            out[n.name] = (a['k'], a['stride'], cin) + tuple(lib.se_conv2d_path(d, L.SE_MODE_TF32X3, k) for k in range(3))
+            assert all(lib.se_conv2d_path(d, L.SE_MODE_F32, k) == 0 for k in range(3))
+        return out
+
+    # config 4: every convolution of ResNet-50 at 224 x 224 except the 7x7 / 2 stem on 3 input channels
+    r50 = paths(resnet50.ResNet50(555, input_shape=(224, 224, 3)), 32)
+    assert len(r50) == 53 and [n for n, v in r50.items() if v[3:] != (1, 1, 1)] == ['conv1']
+    assert sum(1 for v in r50.values() if v[0] == 1 and v[1] == 2) == 6             # the strided 1x1 layers are on it too
+    # config 2 (headline): all 3x3 / stride 1 layers; the 3-channel stem and the two narrow 3x3 / stride 2 layers are fp32
+    r110 = paths(utils.build_network(100, 'resnet-110-fc', input_channels=3), 128)
+    off = {n: v for n, v in r110.items() if v[3:] != (1, 1, 1)}
+    assert len(r110) == 109 and sorted(off) == ['conv0', 'res2-1x', 'res3-1x'] and all(v[3:] == (0, 0, 0) for v in off.values())
+    # config 3: the wide 3x3 / stride 2 layers take the nine-tap tensor-core form in the backward pass, fp32 forward
+    wrn = paths(utils.build_network(100, 'wrn-28-10', input_channels=3), 64)
+    s2 = [v for v in wrn.values() if v[0] == 3 and v[1] == 2]
+    assert len(s2) == 2 and all(v[3:] == (0, 1, 1) for v in s2)
+    assert [n for n, v in wrn.items() if v[3:] == (0, 0, 0)] == [next(iter(wrn))]     # only the 3-channel stem

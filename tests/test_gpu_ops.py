@@ -82,6 +82,8 @@ CONV_CASES = [
     (2, 55, 55, 64, 128, 1, 2, 'valid', True),   # tcgen05 1x1 / stride 2 through a strided tensor view: 55 -> 28 (ResNet-50 stage 3)
     (3, 28, 28, 128, 64, 1, 2, 'valid', False),  # tcgen05 1x1 / stride 2: 28 -> 14
     (4, 14, 14, 64, 96, 1, 2, 'valid', True),    # tcgen05 1x1 / stride 2: 14 -> 7, two images per tile
+    (2, 16, 16, 128, 160, 3, 2, 'same', True),   # tcgen05 3x3 / stride 2, wide layer: nine strided 1x1 GEMMs (dgrad, wgrad)
+    (1, 32, 32, 160, 320, 3, 2, 'same', False),  # ... the first down-sampling layer of WRN-28-10
 ]
 TC_PADDED = {(3, 28, 28, 32, 64), (5, 14, 14, 64, 32), (5, 7, 7, 64, 64), (2, 55, 55, 32, 32), (1, 40, 40, 32, 48)}
 
@@ -176,6 +178,8 @@ def test_conv_fwd_dgrad_wgrad(case, mode):
     if mode == 1:
         # the single-pass mode must show tensor-core (10-bit mantissa) error: proof that these layers left the FFMA kernels
         f_tc, d_tc, w_tc = _tc_1x1(case)
+        if k == 3 and stride == 2 and Cin >= 128 and Cout >= 128:
+            d_tc = w_tc = True                               # (forward stays on the fp32 kernel)
         if tuple(case[:5]) in TC_PADDED:
             kok = lambda c: c % 16 == 0 and (c == 16 or c % 32 == 0)      # GEMM K: 16 or whole 32-channel blocks
             f_tc, d_tc, w_tc = kok(Cin), kok(Cout), True
