@@ -181,6 +181,27 @@ def run_reference(args):
 
 
 # ----------------------------------------------------------------------------------------------- GPU arm
+def tc_coverage(graph, batch, mode, L):
+    """How many convolutions of the network run on the tcgen05 kernels in `mode`, per direction (se_conv2d_path: the
+    library's own host-side planning).  Never raises: a reporting extra must not break the bench."""
+    try:
+        lib = L.load()
+        n, cnt = 0, [0, 0, 0]
+        for node in graph.nodes:
+            if node.op != 'conv':
+                continue
+            h, w, cin = node.inputs[0].shape
+            ho, wo, cout = node.output.shape
+            a = node.attrs
+            d = L.ConvDesc(batch, h, w, cin, cout, a['k'], a['k'], a['stride'], a['pad_t'], a['pad_l'], ho, wo)
+            n += 1
+            for k in range(3):
+                cnt[k] += 1 if lib.se_conv2d_path(d, mode, k) == 1 else 0
+        return {'convolutions': n, 'forward': cnt[0], 'backward_data': cnt[1], 'weight_gradient': cnt[2]}
+    except Exception as e:                                   # pragma: no cover
+        return {'error': repr(e)}
+
+
 def op_category(op, L):
     i = op.i
     names = {L.OP_CONV_FWD: 'conv_fwd', L.OP_CONV_DGRAD: 'conv_dgrad', L.OP_CONV_WGRAD: 'conv_wgrad',
@@ -460,7 +481,8 @@ def run_native(args):
             'ms_per_step': ms_res / args.steps, 'higher_is_better': True, 'scaling': args.scaling, 'vs_baseline': None,
             'dtype': (args.mode if tc else 'f32'), 'data': 'synthetic',
             'config': {'workload': wl['name'] if (args.workload != 'config2' or B != PER_GPU_BATCH) else WORKLOAD, 'per_gpu_batch': B, 'global_batch': gb, 'parallelism': 'dp%d' % world,
-                       'arith_mode': args.mode, 'tc_capabilities': caps, 'cuda_graph': not args.no_graph,
+                       'arith_mode': args.mode, 'tc_capabilities': caps, 'tcgen05_layers': tc_coverage(eng.g, B, mode, L),
+                       'cuda_graph': not args.no_graph,
                        'gradient_exchange': ('none' if world == 1 else
                                              ('NCCL inside the library: %d bucketed all-reduces overlapped with the backward '
                                               'pass, captured in the step graph' % eng.grad_buckets) if eng.comm_native

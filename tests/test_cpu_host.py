@@ -394,6 +394,9 @@ def test_tensor_core_coverage_of_the_baseline_networks(built_lib):
             assert all(lib.se_conv2d_path(d, L.SE_MODE_F32, k) == 0 for k in range(3))
         return out
 
+    import bench
+    cov = bench.tc_coverage(utils.build_network(100, 'resnet-110-fc', input_channels=3), 128, L.SE_MODE_TF32X3, L)
+    assert cov == {'convolutions': 109, 'forward': 106, 'backward_data': 106, 'weight_gradient': 106}     # bench.py's config extra
     # config 4: every convolution of ResNet-50 at 224 x 224 except the 7x7 / 2 stem on 3 input channels
     r50 = paths(resnet50.ResNet50(555, input_shape=(224, 224, 3)), 32)
     assert len(r50) == 53 and [n for n, v in r50.items() if v[3:] != (1, 1, 1)] == ['conv1']
